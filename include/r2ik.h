@@ -1,0 +1,190 @@
+/*
+ * r2ik.h -- C ABI of libr2ik.so: B200 (sm_100a) CUDA implementation of the Reachy2
+ * symbolic 7-DoF arm IK hot path of pollen-robotics/reachy2_symbolic_ik.
+ *
+ * The reference is a pure-Python library with no FFI seam; its public surface for this
+ * path is two classes.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout):
+ *
+ *   r2ik_create / r2ik_destroy / r2ik_get_constants
+ *        SymbolicIK.__init__                       src/reachy2_symbolic_ik/symbolic_ik.py:26-83
+ *        (+ get_singularity_position               src/reachy2_symbolic_ik/utils.py:26-43)
+ *   r2ik_symik_solve_f64
+ *        SymbolicIK.is_reachable                   symbolic_ik.py:121-282
+ *        + theta_to_joints_func = get_joints       symbolic_ik.py:697-863
+ *   r2ik_symik_no_limits_f64
+ *        SymbolicIK.is_reachable_no_limits         symbolic_ik.py:85-119  (+ get_joints)
+ *   r2ik_elbow_positions_f64
+ *        SymbolicIK.get_elbow_position             symbolic_ik.py:684-695
+ *   r2ik_ctl_discrete_f64
+ *        ControlIK.symbolic_inverse_kinematics(name, M, "discrete")
+ *                                                  control_ik.py:162-274, 409-462, 464-497
+ *        (get_best_discrete_theta utils.py:334-396, limit_theta_to_interval utils.py:93-112,
+ *         limit_orbita3d_joints_wrist :508-532, allow_multiturn :493-505,
+ *         multiturn_safety_check :535-568)
+ *   r2ik_ctl_continuous_f64
+ *        ControlIK.symbolic_inverse_kinematics(name, M, "continuous") over trajectories
+ *                                                  control_ik.py:276-407
+ *        (get_best_continuous_theta2 utils.py:220-264, tend_to_preferred_theta :115-127,
+ *         get_best_theta_to_current_joints :267-331, continuity_check :571-589)
+ *   r2ik_reach_map_u32
+ *        grid sweep of is_reachable (shape of src/benchmark/ik_comparison.py:137-181)
+ *   r2ik_interval_limit
+ *        interval_limit + l_arm mirroring          control_ik.py:225-252
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless a parameter says "host".
+ *   - Every launch entry takes a cudaStream_t (passed as void*; NULL = legacy default
+ *     stream), is asynchronous with respect to the host and allocates nothing.
+ *   - Return value: 0 = ok, > 0 = argument error (R2IK_ERR_*), < 0 = -(cudaError_t).
+ *   - No exceptions cross this boundary; r2ik_last_error() gives a static message.
+ *   - The library has no CPU implementation of any entry point.
+ */
+#ifndef R2IK_H
+#define R2IK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2IK_ABI_VERSION 1
+
+/* argument errors */
+#define R2IK_ERR_NULL 1
+#define R2IK_ERR_ARG 2
+#define R2IK_ERR_ARM 3
+#define R2IK_ERR_NO_DEVICE 4
+
+/* per-pose state codes; the Python facade maps them to the reference's exact strings */
+#define R2IK_STATE_REACHABLE 0           /* "reachable"                  symbolic_ik.py:234 */
+#define R2IK_STATE_POSE_OUT_OF_REACH 1   /* "Pose out of reach"          symbolic_ik.py:300 */
+#define R2IK_STATE_BACKWARD_POSE 2       /* "Backward pose"              symbolic_ik.py:306 */
+#define R2IK_STATE_WRIST_OUT_OF_RANGE 3  /* "wrist out of range"         symbolic_ik.py:159 */
+#define R2IK_STATE_LIMITED_BY_WRIST 4    /* "limited by wrist"           symbolic_ik.py:262 */
+#define R2IK_STATE_SHOULD_NOT_HAPPEN 5   /* "out of reach - should not happen" :281 */
+#define R2IK_STATE_LIMITED_BY_SHOULDER 6 /* "limited by shoulder"        control_ik.py:363,452 */
+#define R2IK_STATE_EMPTY 7               /* ""                           control_ik.py:297 */
+#define R2IK_STATE_EMERGENCY 8           /* emergency text               utils.py:544-566,584-586 */
+#define R2IK_STATE_INVALID_ROTATION 9    /* scipy from_matrix: det <= 0 (ValueError) */
+
+/* pose layouts */
+#define R2IK_POSE_EULER6 0 /* n x 6 : x y z roll pitch yaw  (the reference's goal_pose, 2x3)     */
+#define R2IK_POSE_MAT4 1   /* n x 16: row-major 4x4; converted like control_ik.py:216 (no snap) */
+
+/* emergency reason bits (utils.py:544-566, 584-586) */
+#define R2IK_EMG_SHOULDER_PITCH 1
+#define R2IK_EMG_ELBOW_YAW 2
+#define R2IK_EMG_WRIST_YAW 4
+#define R2IK_EMG_DISCONTINUITY 8
+
+/* Raw constructor arguments of SymbolicIK for ONE arm (symbolic_ik.py:26-63). */
+typedef struct R2ikArmConfig {
+  double shoulder_position[3];
+  double shoulder_orientation_deg[3]; /* xyz euler, degrees */
+  double upper_arm_size;
+  double forearm_size;
+  double tip_position[3];
+  double elbow_limit_deg;         /* 127   */
+  double wrist_limit_deg;         /* 42.5  */
+  double projection_margin;       /* 1e-8  */
+  double backward_limit;          /* 0.02  */
+  double normal_vector_margin;    /* 1e-7  */
+  double singularity_offset;      /* 0.03; ControlIK: -1.01 (non DVT) / 0.03 (DVT) */
+  double singularity_limit_coeff; /* 1.0   */
+  int32_t side;                   /* +1 = r_arm, -1 = l_arm */
+  int32_t reserved;
+} R2ikArmConfig;
+
+/* Derived per-arm constants, readable by the host facade (attributes of SymbolicIK). */
+typedef struct R2ikArmConstants {
+  double gripper_size;
+  double max_arm_length;
+  double shoulder_wrist_min_distance;
+  double elbow_singularity_position[3];
+  double wrist_singularity_position[3];
+} R2ikArmConstants;
+
+/* Per-call ControlIK parameters (control_ik.py:162-172, 225-252). */
+typedef struct R2ikCtlParams {
+  double preferred_theta;      /* per-call value, already mirrored for l_arm             */
+  double preferred_theta_ctor; /* ControlIK.preferred_theta[arm] (control_ik.py:133-141)  */
+  double interval_limit[2];    /* already mirrored for l_arm (r2ik_interval_limit)        */
+  double d_theta_max;          /* 0.01                                                    */
+  double orbita3d_max_angle;   /* deg2rad(42.5)                                           */
+  int32_t nb_search_points;            /* discrete: 20                                    */
+  int32_t nb_search_points_continuous; /* continuous: 10                                  */
+} R2ikCtlParams;
+
+/* Per-trajectory controller state = ControlIK's previous_theta / previous_sol / init /
+ * emergency_* (control_ik.py:60-84), explicit so trajectories can be chunked and resumed. */
+typedef struct R2ikTrajState {
+  double previous_theta;
+  double previous_sol[7];
+  int32_t has_previous_sol; /* 0: next waypoint re-initialises (first call / timeout) */
+  int32_t init;
+  int32_t emergency_stop;
+  int32_t emergency_bits;
+} R2ikTrajState;
+
+typedef struct r2ik_context *r2ik_handle;
+
+int r2ik_abi_version(void);
+const char *r2ik_last_error(void);
+
+/* cfg: host pointer.  device: CUDA ordinal the handle launches on. */
+int r2ik_create(const R2ikArmConfig *cfg, int device, r2ik_handle *out);
+int r2ik_destroy(r2ik_handle h);
+int r2ik_get_constants(r2ik_handle h, R2ikArmConstants *out /* host */);
+
+/* interval_limit of ControlIK for an arm; out: host double[2]. */
+int r2ik_interval_limit(int side, int low_elbow, double *out);
+
+/* is_reachable + get_joints(theta) for n independent poses (fresh solver state per pose).
+ * theta: nullable; NULL => theta_interval[0].  prev_joints: nullable 7 doubles (device),
+ * broadcast; NULL => zeros (the reference default).  Unreachable poses get NaN interval /
+ * joints / elbow.  Any output pointer except reachable/state may be NULL. */
+int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta,
+                         const double *prev_joints, int64_t n, uint8_t *reachable, uint8_t *state,
+                         double *interval, double *joints, double *elbow, void *stream);
+
+/* is_reachable_no_limits + get_joints(theta[i]). */
+int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta,
+                             int64_t n, double *joints, double *elbow, void *stream);
+
+/* get_elbow_position(thetas[i][k]) after is_reachable(poses[i]); NaN when unreachable. */
+int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, const double *thetas,
+                             int32_t K, int64_t n, double *elbows /* n*K*3 */, void *stream);
+
+/* ControlIK discrete mode for n poses M (n x 16).  prev_joints / current_joints: 7 doubles
+ * each (device), broadcast: ControlIK.previous_sol[arm] and the per-call current_joints.
+ * emergency: nullable, per-pose emergency bits. */
+int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t n,
+                          const double *prev_joints, const double *current_joints, double *joints,
+                          uint8_t *reachable, uint8_t *state, uint8_t *emergency, void *stream);
+
+/* ControlIK continuous mode: T trajectories x W waypoints, M is T x W x 16.  current_joints
+ * (T x 7) and current_pose (T x 16) feed the (re)initialisation; st: T states, in/out. */
+int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
+                            int32_t W, const double *current_joints, const double *current_pose,
+                            R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
+                            void *stream);
+
+/* Workspace reachability map: counts[v] += #orientations o in [ori_begin, ori_end) with
+ * is_reachable(voxel centre, orientations_euler[o]) true.  Voxel (ix,iy,iz) centre =
+ * origin + (ix,iy,iz)*step, v = (ix*dims[1] + iy)*dims[2] + iz.  origin/step/dims: host.
+ * counts must be zero-initialised by the caller (the kernel overwrites, it does not add). */
+int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                       const double *orientations_euler /* device, n_ori x 3 */, int32_t ori_begin,
+                       int32_t ori_end, uint32_t *counts, void *stream);
+
+/* FP64 FMA peak probe used by bench.py for the compute roofline: runs `iters` dependent
+ * DFMA chains (8 per thread) on a full grid and returns elapsed ms / flop count. */
+int r2ik_dfma_probe(int device, int32_t iters, double *out_ms /* host */, double *out_flop /* host */,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2IK_H */

@@ -1,0 +1,394 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+Runs only in the build container, where the reference checkout is mounted read-only at
+/root/reference (it does not exist on the GPU box).  The fixtures pin (a) the CPU oracle
+(oracle/r2ik_oracle.c) and (b) the CUDA library, to the reference's own outputs:
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/gen_golden.py
+
+Oracle of record = reference source + this container's numpy / scipy (versions are stored
+in every file; the reference pins scipy == 1.8.0, this container has scipy 1.18.1).
+
+Reference quirk handled here: ``get_joints`` mutates the solver when the
+elbow projection fires, so every ``get_joints`` below is preceded by a fresh ``is_reachable``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, "/root/reference/src")
+sys.path.insert(0, REPO)
+sys.dont_write_bytecode = True
+warnings.filterwarnings("ignore", message="Gimbal lock detected")
+
+from scipy.spatial.transform import Rotation as R  # noqa: E402
+
+import reachy2_symbolic_ik.control_ik as ref_control  # noqa: E402
+from reachy2_symbolic_ik.control_ik import ControlIK  # noqa: E402
+from reachy2_symbolic_ik.symbolic_ik import SymbolicIK  # noqa: E402
+from reachy2_symbolic_ik.utils import get_ik_parameters_from_urdf  # noqa: E402
+
+from reachy2_symbolic_ik_b200 import fk  # noqa: E402
+
+STATE_CODES = {
+    "reachable": 0,
+    "Pose out of reach": 1,
+    "Backward pose": 2,
+    "wrist out of range": 3,
+    "limited by wrist": 4,
+    "out of reach - should not happen": 5,
+    "limited by shoulder": 6,
+    "": 7,
+}
+META = dict(numpy_version=np.__version__, scipy_version=scipy.__version__, reference="pollen-robotics/reachy2_symbolic_ik")
+URDF_PATH = "/root/reference/src/config_files/reachy2.urdf"
+
+
+class _Quiet:
+    def __enter__(self):
+        self._o = sys.stdout
+        sys.stdout = open(os.devnull, "w")
+
+    def __exit__(self, *a):
+        sys.stdout.close()
+        sys.stdout = self._o
+
+
+def state_code(s: str) -> int:
+    if s.startswith("\nEMERGENCY") or "EMERGENCY" in s:
+        return 8
+    return STATE_CODES[s]
+
+
+def euler_pose_from_matrix(M):
+    return np.array([M[:3, 3], R.from_matrix(M[:3, :3]).as_euler("xyz")])
+
+
+def run_symik(ik: SymbolicIK, goal_poses, thetas=None):
+    """goal_poses: (N,2,3).  Returns flag, state, interval, joints@theta(or interval[0]), elbow."""
+    n = len(goal_poses)
+    flag = np.zeros(n, bool)
+    state = np.zeros(n, np.uint8)
+    interval = np.full((n, 2), np.nan)
+    joints = np.full((n, 7), np.nan)
+    elbow = np.full((n, 3), np.nan)
+    for i, gp in enumerate(goal_poses):
+        ok, itv, fn, st = ik.is_reachable(np.array(gp))
+        flag[i] = ok
+        state[i] = state_code(st)
+        if ok:
+            interval[i] = itv
+            th = itv[0] if thetas is None else thetas[i]
+            j, e = fn(th)
+            joints[i] = j
+            elbow[i] = np.asarray(e)[:3]
+    return flag, state, interval, joints, elbow
+
+
+def named_poses():
+    """Poses named in the reference's tests / docs / examples (euler format), per arm."""
+    rad = np.radians
+    r = [
+        # tests/test_ik.py:15-79
+        [[0.4, 0.2, 0.1], [rad(-60), rad(-90), rad(20)]],
+        [[0.3, -0.2, -0.3], [rad(0), rad(-90), rad(0)]],
+        [[0.02, -0.2, -0.65], [0.0, 0.0, 0.0]],
+        [[0.0, -0.2, -0.65], [0.0, 0.0, 0.0]],
+        [[0.87, -0.2, -0.0], [0.0, -np.pi / 2, 0.0]],
+        [[0.35, -0.2, -0.28], [0.0, -np.pi / 2, 0.0]],
+        # README.md:73-75
+        [[0.55, -0.3, -0.15], [0.0, -np.pi / 2, 0.0]],
+        # src/benchmark/ik_benchmarks.py:13-14
+        [[0.3, -0.1, 0.1], [rad(20), rad(-50), rad(20)]],
+        # src/example/test_go_to.py:169-187
+        [[0.0001, -0.2, -0.6599], [0, 0, 0]],
+        [[0.38, -0.2, -0.28], [0, -np.pi / 2, 0]],
+        [[0.66, -0.2, -0.0], [0, -np.pi / 2, 0]],
+        [[0.30, -0.2, -0.28], [0.0, 0.0, np.pi / 3]],
+        [[0.0, -0.85, -0.0], [-np.pi / 2, 0, 0]],
+        [[0.0, -0.58, -0.28], [-np.pi / 2, -np.pi / 2, 0]],
+        [[0.15, 0.35, -0.10], [np.pi / 3, -np.pi / 2, 0]],
+        [[0.10, 0.20, -0.22], [np.pi / 3, -np.pi / 2, 0]],
+        [[0.0, -0.2, -0.66], [0.0, 0.0, -np.pi / 3]],
+        [[0.001, -0.2, -0.68], [0.0, 0.0, -np.pi / 3]],
+        [[0.001, -0.2, -0.659], [0.0, np.pi / 2, 0.0]],
+        [[0.38, -0.2, -0.28], [0.0, np.pi / 2, 0.0]],
+        [[0.1, -0.2, 0.0], [0.0, np.pi, 0.0]],
+        [[0.38, -0.2, -0.28], [0.0, 0.0, 0.0]],
+        [[0.1, 0.2, -0.1], [0.0, -np.pi / 2, np.pi / 2]],
+        [[0.0, -0.2, -0.66], [0, 0, 0]],
+    ]
+    r = np.array(r, dtype=np.float64)
+    # left arm: the reference's own l_goal_poses (test_go_to.py:189-209) are the y / roll / yaw mirror
+    l = r.copy()
+    l[:, 0, 1] *= -1
+    l[:, 1, 0] *= -1
+    l[:, 1, 2] *= -1
+    return {"r_arm": r, "l_arm": l}
+
+
+def gen_symik_named():
+    out = dict(META)
+    for arm, poses in named_poses().items():
+        with _Quiet():
+            ik = SymbolicIK(arm=arm)
+        flag, state, interval, joints, elbow = run_symik(ik, poses)
+        th0 = np.zeros(len(poses))
+        _, _, _, joints0, elbow0 = run_symik(ik, poses, th0)
+        out.update({
+            f"{arm}_poses": poses, f"{arm}_reachable": flag, f"{arm}_state": state, f"{arm}_interval": interval,
+            f"{arm}_joints": joints, f"{arm}_elbow": elbow, f"{arm}_joints_theta0": joints0, f"{arm}_elbow_theta0": elbow0,
+        })
+    np.savez_compressed(os.path.join(HERE, "symik_named.npz"), **out)
+
+
+def gen_symik_random(n_fk=3000, n_task=3000):
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        M = np.concatenate([
+            fk.sample_fk_poses(n_fk // 2, arm, seed=10 + seed, min_x=None),
+            fk.sample_fk_poses(n_fk - n_fk // 2, arm, seed=20 + seed, min_x=0.05),
+            fk.sample_task_space_poses(n_task, arm, seed=30 + seed),
+        ])
+        gp = np.array([euler_pose_from_matrix(m) for m in M])
+        with _Quiet():
+            ik = SymbolicIK(arm=arm)
+        flag, state, interval, joints, elbow = run_symik(ik, gp)
+        # a second theta per pose: a deterministic point inside the interval (or anywhere if unreachable)
+        rng = np.random.default_rng(100 + seed)
+        u = rng.uniform(0, 1, len(M))
+        width = np.where(interval[:, 0] <= interval[:, 1], interval[:, 1] - interval[:, 0],
+                         interval[:, 1] + 2 * np.pi - interval[:, 0])
+        theta2 = np.where(flag, interval[:, 0] + u * width, 0.0)
+        _, _, _, joints2, elbow2 = run_symik(ik, gp, theta2)
+        np.savez_compressed(
+            os.path.join(HERE, f"symik_random_{arm}.npz"), **META, M=M, goal_pose=gp, reachable=flag, state=state,
+            interval=interval, joints=joints, elbow=elbow, theta2=theta2, joints_theta2=joints2, elbow_theta2=elbow2,
+            n_fk=n_fk, n_task=n_task)
+        print(arm, "symik_random: reachable", flag.mean(), "states", np.bincount(state, minlength=8))
+
+
+def urdf_params():
+    with open(URDF_PATH) as f:
+        urdf = f.read()
+    return get_ik_parameters_from_urdf(urdf, ["r", "l"])
+
+
+def gen_symik_urdf(n=1500):
+    """SymbolicIK as ControlIK configures it (URDF parameters, singularity_offset=-1.01) + no-limits path."""
+    params = urdf_params()
+    out = dict(META)
+    for k, v in params.items():
+        out["param_" + k] = np.asarray(v, dtype=np.float64)
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        M = np.concatenate([fk.sample_fk_poses(n // 2, arm, seed=40 + seed, min_x=None),
+                            fk.sample_task_space_poses(n - n // 2, arm, seed=50 + seed)])
+        gp = np.array([euler_pose_from_matrix(m) for m in M])
+        ik = SymbolicIK(arm=arm, ik_parameters=params, singularity_offset=-1.01, singularity_limit_coeff=1.0)
+        flag, state, interval, joints, elbow = run_symik(ik, gp)
+        # is_reachable_no_limits + get_joints(theta) for every pose (symbolic_ik.py:85-119)
+        rng = np.random.default_rng(200 + seed)
+        th = rng.uniform(-np.pi, np.pi, len(M))
+        nl_joints = np.full((len(M), 7), np.nan)
+        nl_elbow = np.full((len(M), 3), np.nan)
+        for i, g in enumerate(gp):
+            ok, _, fn = ik.is_reachable_no_limits(np.array(g))
+            assert ok
+            j, e = fn(th[i])
+            nl_joints[i] = j
+            nl_elbow[i] = np.asarray(e)[:3]
+        out.update({f"{arm}_M": M, f"{arm}_goal_pose": gp, f"{arm}_reachable": flag, f"{arm}_state": state,
+                    f"{arm}_interval": interval, f"{arm}_joints": joints, f"{arm}_elbow": elbow,
+                    f"{arm}_nl_theta": th, f"{arm}_nl_joints": nl_joints, f"{arm}_nl_elbow": nl_elbow})
+    np.savez_compressed(os.path.join(HERE, "symik_urdf.npz"), **out)
+
+
+def new_control(is_dvt=False):
+    with _Quiet():
+        return ControlIK(urdf_path="../config_files/reachy2.urdf", is_dvt=is_dvt)
+
+
+def run_discrete(ctl, arm, M, constrained_mode="unconstrained"):
+    n = len(M)
+    joints = np.zeros((n, 7))
+    flag = np.zeros(n, bool)
+    state = np.zeros(n, np.uint8)
+    for i in range(n):
+        j, ok, st = ctl.symbolic_inverse_kinematics(arm, M[i], "discrete", constrained_mode=constrained_mode)
+        joints[i] = j
+        flag[i] = ok
+        state[i] = state_code(st)
+        assert not ctl.emergency_stop
+    return joints, flag, state
+
+
+def gen_ctl_discrete(n_fk=1500, n_task=1000, n_k360=600, n_low=500, n_dvt=500):
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        M = np.concatenate([fk.sample_fk_poses(n_fk, arm, seed=60 + seed, min_x=0.0),
+                            fk.sample_task_space_poses(n_task, arm, seed=70 + seed)])
+        # sprinkle identity / near-identity rotations to exercise the allclose() snap (control_ik.py:212)
+        rng = np.random.default_rng(300 + seed)
+        for k in range(0, 40):
+            eps = 10.0 ** rng.uniform(-10, -4)
+            e = rng.normal(size=3) * eps
+            M[k, :3, :3] = R.from_euler("xyz", e).as_matrix() if k % 4 else np.eye(3)
+        out = dict(META, M=M)
+        ctl = new_control()
+        j, f, s = run_discrete(ctl, arm, M)
+        out.update(joints_k20=j, reachable_k20=f, state_k20=s)
+        ctl = new_control()
+        ctl.nb_search_points = 360
+        j, f, s = run_discrete(ctl, arm, M[:n_k360])
+        out.update(joints_k360=j, reachable_k360=f, state_k360=s)
+        ctl = new_control()
+        j, f, s = run_discrete(ctl, arm, M[:n_low], constrained_mode="low_elbow")
+        out.update(joints_low=j, reachable_low=f, state_low=s)
+        ctl = new_control(is_dvt=True)
+        j, f, s = run_discrete(ctl, arm, M[:n_dvt])
+        out.update(joints_dvt=j, reachable_dvt=f, state_dvt=s)
+        np.savez_compressed(os.path.join(HERE, f"ctl_discrete_{arm}.npz"), **out)
+        print(arm, "ctl_discrete: reachable", out["reachable_k20"].mean(), np.bincount(out["state_k20"], minlength=9))
+
+
+class FakeTime:
+    """Deterministic clock for control_ik.time: 1/120 s per call, starting far from 0 so that
+    the first call sees the timeout (control_ik.py:296-304) and later calls never do."""
+
+    def __init__(self):
+        self.t = 1000.0
+
+    def time(self):
+        self.t += 1.0 / 120.0
+        return self.t
+
+
+def run_continuous(arm, Mtraj, is_dvt=False, current_joints=None, current_pose=None):
+    """One fresh ControlIK per trajectory.  Returns joints (W,7), flag (W,), state (W,), emergency flag."""
+    ctl = new_control(is_dvt=is_dvt)
+    W = len(Mtraj)
+    joints = np.zeros((W, 7))
+    flag = np.zeros(W, bool)
+    state = np.zeros(W, np.uint8)
+    kw = {}
+    if current_joints is not None:
+        kw["current_joints"] = list(current_joints)
+        kw["current_pose"] = np.array(current_pose)
+    with _Quiet():
+        for w in range(W):
+            j, ok, st = ctl.symbolic_inverse_kinematics(arm, Mtraj[w], "continuous", **kw)
+            joints[w] = j
+            flag[w] = ok
+            state[w] = state_code(st)
+    return joints, flag, state, ctl.emergency_stop, ctl.previous_theta[arm]
+
+
+def gen_ctl_continuous(T_sin=6, W=300):
+    ref_control.time = FakeTime()
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        Ms, q = fk.sinusoidal_trajectories(T_sin, W, arm, seed=80 + seed)
+        trajs = [Ms[t] for t in range(T_sin)]
+        kinds = ["sin"] * T_sin
+        # trajectories that leave the workspace and come back (unreachable branch, control_ik.py:368-388)
+        side = 1.0 if arm == "r_arm" else -1.0
+        for k in range(2):
+            s = np.linspace(0, 1, W)
+            Mo = np.tile(np.eye(4), (W, 1, 1))
+            ang = np.array([0.0, -np.pi / 2, 0.0]) + np.array([0.3 * side, 0.2, 0.4 * side]) * k
+            Mo[:, :3, :3] = R.from_euler("xyz", ang).as_matrix()
+            Mo[:, 0, 3] = 0.35 + 0.45 * np.sin(np.pi * s) ** 2
+            Mo[:, 1, 3] = -0.25 * side + 0.1 * side * np.sin(2 * np.pi * s)
+            Mo[:, 2, 3] = -0.25 + 0.15 * np.cos(2 * np.pi * s) * (k + 1)
+            trajs.append(Mo)
+            kinds.append("outreach")
+        # a trajectory with a jump (continuity_check -> emergency stop, control_ik.py:395-400)
+        Mj = Ms[0].copy()
+        Mj[W // 2:] = Ms[1][W // 2:][::-1][: W - W // 2] if T_sin > 1 else Mj[W // 2:]
+        Mj[W // 2:, :3, 3] += np.array([0.0, 0.25 * side, 0.3])
+        trajs.append(Mj)
+        kinds.append("jump")
+        trajs = np.array(trajs)
+        T = len(trajs)
+        out = dict(META, M=trajs, kinds=np.array(kinds))
+        J = np.zeros((T, W, 7)); F = np.zeros((T, W), bool); S = np.zeros((T, W), np.uint8)
+        E = np.zeros(T, bool); TH = np.zeros(T)
+        for t in range(T):
+            J[t], F[t], S[t], E[t], TH[t] = run_continuous(arm, trajs[t])
+        out.update(joints=J, reachable=F, state=S, emergency=E, final_theta=TH)
+        # explicit current joints / pose on the (re)initialising call: start from the trajectory's own first sample
+        J2 = np.zeros((T_sin, W, 7)); F2 = np.zeros((T_sin, W), bool); S2 = np.zeros((T_sin, W), np.uint8)
+        E2 = np.zeros(T_sin, bool); TH2 = np.zeros(T_sin)
+        for t in range(T_sin):
+            J2[t], F2[t], S2[t], E2[t], TH2[t] = run_continuous(arm, trajs[t], current_joints=q[t, 0], current_pose=Ms[t, 0])
+        out.update(cj_joints=J2, cj_reachable=F2, cj_state=S2, cj_emergency=E2, cj_final_theta=TH2,
+                   cj_current_joints=q[:, 0], cj_current_pose=Ms[:, 0])
+        # DVT mode (singularity_offset = 0.03: elbow projection + state leak inside the ternary search)
+        nd = 3
+        J3 = np.zeros((nd, W, 7)); F3 = np.zeros((nd, W), bool); S3 = np.zeros((nd, W), np.uint8)
+        E3 = np.zeros(nd, bool); TH3 = np.zeros(nd)
+        for t in range(nd):
+            J3[t], F3[t], S3[t], E3[t], TH3[t] = run_continuous(arm, trajs[t], is_dvt=True)
+        out.update(dvt_joints=J3, dvt_reachable=F3, dvt_state=S3, dvt_emergency=E3, dvt_final_theta=TH3)
+        np.savez_compressed(os.path.join(HERE, f"ctl_continuous_{arm}.npz"), **out)
+        print(arm, "ctl_continuous: emergency", E, "reachable frac", F.mean(axis=1))
+    ref_control.time = time
+
+
+def gen_helpers(n=2000):
+    """Pins of the scipy / utils helpers the kernels restate."""
+    from reachy2_symbolic_ik.utils import (angle_diff, limit_orbita3d_joints, limit_theta_to_interval,
+                                            rotation_matrix_from_vector)
+    rng = np.random.default_rng(7)
+    # matrix -> euler xyz (incl. gimbal lock and truncated / non-orthonormal matrices)
+    e = rng.uniform(-np.pi, np.pi, (n, 3))
+    e[:50, 1] = np.pi / 2
+    e[50:100, 1] = -np.pi / 2
+    e[100:150, 1] = np.pi / 2 - 10.0 ** rng.uniform(-12, -5, 50)
+    Rm = R.from_euler("xyz", e).as_matrix()
+    Rm[150:400] = np.round(Rm[150:400], 5)  # truncated like src/example/test_go_to.py:250-257
+    Rm[400:500] += rng.normal(size=(100, 3, 3)) * 1e-9
+    eul = R.from_matrix(Rm).as_euler("xyz")
+    # orbita3d limit
+    w = rng.uniform(-np.pi, np.pi, (n, 3))
+    w[:100] *= 0.1
+    w[100:120, 1] = 0.0
+    w[120:125] = 0.0
+    orb = np.array([limit_orbita3d_joints(list(x), np.deg2rad(42.5)) for x in w])
+    # angle_diff / limit_theta_to_interval
+    a = rng.uniform(-20, 20, n); b = rng.uniform(-20, 20, n)
+    ad = np.array([angle_diff(x, y) for x, y in zip(a, b)])
+    itv = rng.uniform(-np.pi, np.pi, (n, 2))
+    th = rng.uniform(-10, 10, n)
+    lt = np.array([limit_theta_to_interval(t, 0.0, i)[0] for t, i in zip(th, itv)])
+    # rotation_matrix_from_vector incl. the isclose branches
+    v = rng.normal(size=(n, 3))
+    v[:20] = [1, 0, 0]; v[20:40] = [-1, 0, 0]
+    v[40:80] = np.array([1, 0, 0]) + rng.normal(size=(40, 3)) * 10.0 ** rng.uniform(-10, -6, (40, 1))
+    v[80:120] = np.array([-2, 0, 0]) + rng.normal(size=(40, 3)) * 10.0 ** rng.uniform(-10, -6, (40, 1))
+    rm = np.array([rotation_matrix_from_vector(x) for x in v])
+    np.savez_compressed(os.path.join(HERE, "helpers.npz"), **META, mat=Rm, mat_euler=eul, wrist_in=w, wrist_out=orb,
+                        ad_a=a, ad_b=b, ad=ad, lt_theta=th, lt_interval=itv, lt_out=lt, rmfv_v=v, rmfv=rm)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers"]
+    if "named" in which:
+        gen_symik_named()
+    if "helpers" in which:
+        gen_helpers()
+    if "random" in which:
+        gen_symik_random()
+    if "urdf" in which:
+        gen_symik_urdf()
+    if "discrete" in which:
+        gen_ctl_discrete()
+    if "continuous" in which:
+        gen_ctl_continuous()
+    print(f"done in {time.time() - t0:.1f}s")

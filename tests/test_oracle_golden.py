@@ -1,0 +1,175 @@
+"""Pins the CPU oracle (oracle/r2ik_oracle.c) to the reference's own outputs.
+
+The fixtures under tests/golden/ were produced by the unmodified reference
+(tests/golden/gen_golden.py; numpy / scipy versions stored inside each file).  The
+reference's own CI test (tests/test_ik.py:12-79) only pins flags and shapes on 6 poses; those
+6 poses are the first rows of symik_named.npz and are re-asserted literally below.
+"""
+import numpy as np
+import pytest
+
+from parity import Report, ill_conditioned_mask, load
+
+ARMS = ("r_arm", "l_arm")
+
+
+def test_reference_ci_assertions(oracle):
+    """tests/test_ik.py:12-79 restated against the oracle (default right arm)."""
+    g = load("symik_named.npz")
+    cfg = oracle.arm_config("r_arm")
+    P = g["r_arm_poses"][:6]
+    reach, itv, state, joints, _ = oracle.symik_batch(cfg, P)
+    assert not reach[0] and np.isnan(itv[0]).all()
+    assert reach[1] and itv[1][0] >= -np.pi and itv[1][1] <= np.pi and np.isfinite(joints[1]).all()
+    assert reach[2] and np.all(itv[2] == [-np.pi, np.pi])
+    assert not reach[3]
+    assert not reach[4]
+    assert reach[5]
+    # README.md:73-79 example
+    reach, itv, state, joints, _ = oracle.symik_batch(cfg, g["r_arm_poses"][6:7])
+    assert reach[0] and oracle.STATE_STRINGS[int(state[0])] == "reachable"
+    np.testing.assert_allclose(itv[0], [2.18952378, -0.22393633], atol=1e-8)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_named_poses(oracle, arm):
+    g = load("symik_named.npz")
+    cfg = oracle.arm_config(arm)
+    P = g[f"{arm}_poses"]
+    run = lambda p: oracle.symik_batch(cfg, p.reshape(-1, 2, 3))[:4]  # noqa: E731
+    ill = ill_conditioned_mask(run, P.reshape(len(P), 6))
+    reach, itv, state, joints, elbow = oracle.symik_batch(cfg, P)
+    rep = Report(f"oracle named {arm}", len(P), ill)
+    rep.exact("reachable", reach, g[f"{arm}_reachable"])
+    rep.exact("state", state, g[f"{arm}_state"])
+    rep.close("interval", itv, g[f"{arm}_interval"])
+    rep.close("joints", joints, g[f"{arm}_joints"])
+    rep.close("elbow", elbow, g[f"{arm}_elbow"])
+    _, _, _, j0, e0 = oracle.symik_batch(cfg, P, np.zeros(len(P)))
+    rep.close("joints(theta=0)", j0, g[f"{arm}_joints_theta0"])
+    rep.close("elbow(theta=0)", e0, g[f"{arm}_elbow_theta0"])
+    rep.check(max_ill_fraction=0.1)  # the fully stretched arm (#10) is a true kinematic singularity
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("layout", ["euler", "mat4"])
+def test_random_poses(oracle, arm, layout):
+    g = load(f"symik_random_{arm}.npz")
+    cfg = oracle.arm_config(arm)
+    P = g["goal_pose"] if layout == "euler" else g["M"]
+    flat = P.reshape(len(P), -1)
+    run = lambda p: oracle.symik_batch(cfg, p.reshape(P.shape))[:4]  # noqa: E731
+    ill = ill_conditioned_mask(run, flat)
+    reach, itv, state, joints, elbow = oracle.symik_batch(cfg, P)
+    rep = Report(f"oracle random {arm} {layout}", len(P), ill)
+    rep.exact("reachable", reach, g["reachable"])
+    rep.exact("state", state, g["state"])
+    rep.close("interval", itv, g["interval"])
+    rep.close("joints@interval[0]", joints, g["joints"])
+    rep.close("elbow", elbow, g["elbow"])
+    _, _, _, j2, e2 = oracle.symik_batch(cfg, P, g["theta2"])
+    rep.close("joints@theta2", j2, g["joints_theta2"])
+    rep.close("elbow@theta2", e2, g["elbow_theta2"])
+    rep.check()
+
+
+def _urdf_cfg(oracle, g, arm, singularity_offset=-1.01):
+    params = {k[len("param_"):]: g[k] for k in g.files if k.startswith("param_")}
+    return oracle.arm_config(arm, ik_parameters=params, singularity_offset=singularity_offset)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_urdf_params_and_no_limits(oracle, arm):
+    g = load("symik_urdf.npz")
+    cfg = _urdf_cfg(oracle, g, arm)
+    M = g[f"{arm}_M"]
+    run = lambda p: oracle.symik_batch(cfg, p.reshape(M.shape))[:4] + oracle.symik_no_limits_batch(  # noqa: E731
+        cfg, p.reshape(M.shape), g[f"{arm}_nl_theta"])
+    ill = ill_conditioned_mask(run, M.reshape(len(M), -1))
+    reach, itv, state, joints, elbow = oracle.symik_batch(cfg, M)
+    rep = Report(f"oracle urdf {arm}", len(M), ill)
+    rep.exact("reachable", reach, g[f"{arm}_reachable"])
+    rep.exact("state", state, g[f"{arm}_state"])
+    rep.close("interval", itv, g[f"{arm}_interval"])
+    rep.close("joints", joints, g[f"{arm}_joints"])
+    rep.close("elbow", elbow, g[f"{arm}_elbow"])
+    nj, ne = oracle.symik_no_limits_batch(cfg, M, g[f"{arm}_nl_theta"])
+    rep.close("no_limits joints", nj, g[f"{arm}_nl_joints"])
+    rep.close("no_limits elbow", ne, g[f"{arm}_nl_elbow"])
+    rep.check()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["k20", "k360", "low", "dvt"])
+def test_ctl_discrete(oracle, arm, variant):
+    g = load(f"ctl_discrete_{arm}.npz")
+    u = load("symik_urdf.npz")
+    cfg = _urdf_cfg(oracle, u, arm, singularity_offset=0.03 if variant == "dvt" else -1.01)
+    want_j, want_f, want_s = g[f"joints_{variant}"], g[f"reachable_{variant}"], g[f"state_{variant}"]
+    M = g["M"][: len(want_j)]
+    par = oracle.ControlParams(arm=arm, nb_search_points=360 if variant == "k360" else 20,
+                               constrained_mode="low_elbow" if variant == "low" else "unconstrained")
+    run = lambda p: oracle.ctl_discrete_batch(cfg, par, p.reshape(M.shape))[:3]  # noqa: E731
+    ill = ill_conditioned_mask(run, M.reshape(len(M), -1))
+    joints, reach, state, emg = oracle.ctl_discrete_batch(cfg, par, M)
+    rep = Report(f"oracle ctl discrete {arm} {variant}", len(M), ill)
+    rep.exact("reachable", reach, want_f)
+    rep.exact("state", state, want_s)
+    rep.close("joints", joints, want_j)
+    assert not emg.any()
+    rep.check(max_ill_fraction=0.02)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["default", "cj", "dvt"])
+def test_ctl_continuous(oracle, arm, variant):
+    g = load(f"ctl_continuous_{arm}.npz")
+    u = load("symik_urdf.npz")
+    cfg = _urdf_cfg(oracle, u, arm, singularity_offset=0.03 if variant == "dvt" else -1.01)
+    par = oracle.ControlParams(arm=arm)
+    pre = {"default": "", "cj": "cj_", "dvt": "dvt_"}[variant]
+    want_j, want_f, want_s = g[pre + "joints"], g[pre + "reachable"], g[pre + "state"]
+    T, W = want_j.shape[:2]
+    M = g["M"][:T]
+    kw = {}
+    if variant == "cj":
+        kw = dict(current_joints=g["cj_current_joints"], current_pose=g["cj_current_pose"])
+    joints, reach, state, st = oracle.ctl_continuous_batch(cfg, par, M, **kw)
+    # a trajectory is a sequential recursion: compare every waypoint, report per trajectory
+    for t in range(T):
+        rep = Report(f"oracle ctl continuous {arm} {variant} traj {t}", W)
+        rep.exact("reachable", reach[t], want_f[t])
+        rep.exact("state", state[t], want_s[t])
+        rep.close("joints", joints[t], want_j[t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+
+
+def test_helpers(oracle):
+    h = load("helpers.npz")
+    eul = np.array([oracle.euler_xyz_from_matrix(m) for m in h["mat"]])
+    # orthonormal inputs: 1e-14; truncated (5-digit) matrices go through the polar-factor
+    # projection (scipy: SVD), where the agreement is limited by conditioning to ~1e-12
+    assert np.abs(eul - h["mat_euler"])[:150].max() < 1e-14
+    assert np.abs(eul - h["mat_euler"])[500:].max() < 1e-14
+    assert np.abs(eul - h["mat_euler"]).max() < 1e-11
+    orb = np.array([oracle.limit_orbita3d_joints(w, np.deg2rad(42.5)) for w in h["wrist_in"]])
+    assert np.abs(orb - h["wrist_out"]).max() < 1e-13
+    ad = np.array([oracle.angle_diff(a, b) for a, b in zip(h["ad_a"], h["ad_b"])])
+    assert np.array_equal(ad, h["ad"])
+    lt = np.array([oracle.limit_theta_to_interval(t, 0.0, i) for t, i in zip(h["lt_theta"], h["lt_interval"])])
+    assert np.array_equal(lt, h["lt_out"])
+    rm = np.array([oracle.rotation_matrix_from_vector(v) for v in h["rmfv_v"]])
+    assert np.abs(rm - h["rmfv"]).max() < 1e-14
+
+
+def test_invalid_rotation_is_flagged(oracle):
+    cfg = oracle.arm_config("r_arm")
+    M = np.eye(4)[None].copy()
+    M[0, 0, 0] = -1.0  # det < 0: scipy's from_matrix raises ValueError
+    M[0, :3, 3] = [0.3, -0.2, -0.3]
+    reach, itv, state, joints, _ = oracle.symik_batch(cfg, M)
+    assert not reach[0] and state[0] == 9 and np.isnan(joints).all()
+    with pytest.raises(ValueError):
+        oracle.euler_xyz_from_matrix(M[0, :3, :3])
