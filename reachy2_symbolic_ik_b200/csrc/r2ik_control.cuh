@@ -1,0 +1,184 @@
+// r2ik_control.cuh -- ControlIK policies on top of the per-pose solver: elbow-angle selection
+// (discrete search / rate-limited continuous tracking), (re)initialisation by ternary search,
+// and the safety chain (Orbita3D wrist cone, multi-turn unwrap, +-6pi clamp, continuity check).
+// "ctl" = src/reachy2_symbolic_ik/control_ik.py, "utl" = .../utils.py.
+#pragma once
+
+#include "r2ik_device.cuh"
+
+namespace r2ik {
+
+// Sampling range of get_best_discrete_theta (utl:366-375): full circle uses a vertical
+// symmetry [pi/2, 5pi/2]; a wrapped interval is unrolled past pi.
+R2IK_HD void search_range(double i0, double i1, double &start, double &stop) {
+  if (fabs(fabs(i0) + fabs(i1) - kTwoPi) < 0.00001) { start = kHalfPi; stop = kHalfPi + kTwoPi; }
+  else if (i0 < i1) { start = i0; stop = i1; }
+  else { start = i0; stop = i1 + kTwoPi; }
+}
+
+// One sample of the search loop (utl:381-390): cost = |angle_diff(theta, preferred)| or +inf.
+R2IK_HD double sample_cost(const ArmConst &A, const Solve &S, double theta, double preferred_theta) {
+  double E[3];
+  elbow_position(S, theta, E);
+  if (!is_elbow_ok(A, E)) return INFINITY;
+  return fabs(angle_diff(theta, preferred_theta));
+}
+
+// utl:357-364: preferred_theta is tried first
+R2IK_HD bool preferred_theta_works(const ArmConst &A, const Solve &S, double i0, double i1, double preferred_theta) {
+  if (!is_valid_angle(preferred_theta, i0, i1)) return false;
+  double E[3];
+  elbow_position(S, preferred_theta, E);
+  return is_elbow_ok(A, E);
+}
+
+// utl:334-396 get_best_discrete_theta, serial form (one thread scans all samples; strict <
+// keeps the first minimum).  Returns false when no sample is valid.
+R2IK_HD bool best_discrete_theta(const ArmConst &A, const Solve &S, double i0, double i1, int nb,
+                                 double preferred_theta, double &theta) {
+  if (preferred_theta_works(A, S, i0, i1, preferred_theta)) { theta = preferred_theta; return true; }
+  double start, stop;
+  search_range(i0, i1, start, stop);
+  double best = INFINITY, best_theta = 0.0;
+  for (int i = 0; i < nb; ++i) {
+    double th = linspace_at(start, stop, nb, i);
+    double cost = sample_cost(A, S, th, preferred_theta);
+    if (cost < best) { best = cost; best_theta = th; }
+  }
+  theta = best_theta;
+  return best < INFINITY;
+}
+
+// Step toward a target theta by at most d_theta_max (utl:252-264, utl:123-127)
+R2IK_HD double step_toward(double target, double previous_theta, double d_theta_max) {
+  double ad = angle_diff(target, previous_theta);
+  if (fabs(ad) < d_theta_max) return target;
+  double sign = ad / fabs(ad);
+  return previous_theta + sign * d_theta_max;
+}
+
+// ctl:464-497 safety_checks.  Returns the emergency bits raised by multiturn_safety_check.
+R2IK_HD int safety_checks(double j[7], const double previous_sol[7], double orbita_max) {
+  limit_orbita3d_wrist(j, orbita_max);                      // utl:522-532
+  for (int i = 0; i < 7; ++i)                               // utl:493-505 allow_multiturn
+    j[i] = previous_sol[i] + angle_diff(j[i], previous_sol[i]);
+  int bits = 0;                                             // utl:535-568
+  const double lim = 6.0 * kPi;
+  if (j[0] > lim) { j[0] = lim; bits |= R2IK_EMG_SHOULDER_PITCH; }
+  if (j[0] < -lim) { j[0] = -lim; bits |= R2IK_EMG_SHOULDER_PITCH; }
+  if (j[2] > lim) { j[2] = lim; bits |= R2IK_EMG_ELBOW_YAW; }
+  if (j[2] < -lim) { j[2] = -lim; bits |= R2IK_EMG_ELBOW_YAW; }
+  if (j[6] > lim) { j[6] = lim; bits |= R2IK_EMG_WRIST_YAW; }
+  if (j[6] < -lim) { j[6] = -lim; bits |= R2IK_EMG_WRIST_YAW; }
+  return bits;
+}
+
+R2IK_HD double joints_angle_distance(const double a[7], const double b[7]) {
+  double s = 0.0;
+  for (int i = 0; i < 7; ++i) { double d = angle_diff(a[i], b[i]); s += d * d; }
+  return sqrt(s);
+}
+
+// utl:267-331 get_best_theta_to_current_joints: ternary search of the theta whose joints are
+// closest to current_joints.  get_joints mutates S exactly like the reference (the state leak
+// is part of the reference result when the elbow projection fires).
+R2IK_HD double best_theta_to_current_joints(const ArmConst &A, Solve &S, const double current_joints[7],
+                                            double preferred_theta) {
+  double low = -kPi, high = kPi;
+  if (A.side < 0) { low = 0.0; high = kTwoPi; }
+  const double tolerance = 0.01;
+  double j1[7], j2[7], E[3];
+  get_joints(A, S, preferred_theta, 0.0, 0.0, j1, E);
+  if (joints_angle_distance(j1, current_joints) < tolerance) return preferred_theta;
+  while ((high - low) > tolerance) {
+    double mid1 = low + (high - low) / 3;
+    double mid2 = high - (high - low) / 3;
+    get_joints(A, S, mid1, 0.0, 0.0, j1, E);
+    get_joints(A, S, mid2, 0.0, 0.0, j2, E);
+    double f1 = joints_angle_distance(j1, current_joints);
+    double f2 = joints_angle_distance(j2, current_joints);
+    if (f1 < f2) high = mid2; else low = mid1;
+  }
+  double best = (low + high) / 2;
+  get_joints(A, S, best, 0.0, 0.0, j1, E);  // utl:324: one more call (its state leak is observable)
+  return best;
+}
+
+// Selection + joints + safety for one pose whose is_reachable result is already known.
+// Shared tail of the discrete path (ctl:454-462).
+R2IK_HD int discrete_finish(const ArmConst &A, const R2ikCtlParams &par, Solve &S, bool found, double theta,
+                            const double prev_joints[7], const double current_joints[7], double joints[7]) {
+  if (found) {
+    theta = limit_theta_to_interval(theta, par.interval_limit[0], par.interval_limit[1]);
+    double E[3];
+    get_joints(A, S, theta, prev_joints[0], prev_joints[2], joints, E);
+  } else {
+    for (int i = 0; i < 7; ++i) joints[i] = current_joints[i];
+  }
+  return safety_checks(joints, prev_joints, par.orbita3d_max_angle);
+}
+
+// ctl:276-407 symbolic_inverse_kinematics_continuous for one waypoint of one trajectory.
+R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const double *M,
+                             const double current_joints[7], const double *current_pose, R2ikTrajState &cs,
+                             double joints[7], uint8_t &reachable, uint8_t &state) {
+  if (cs.emergency_stop) {                                   // ctl:205-210
+    for (int i = 0; i < 7; ++i) joints[i] = cs.previous_sol[i];
+    reachable = 0; state = R2IK_STATE_EMERGENCY;
+    return;
+  }
+  double pos[3], eul[3];
+  if (!pose_from_mat4(M, true, pos, eul)) {
+    for (int i = 0; i < 7; ++i) joints[i] = NAN;
+    reachable = 0; state = R2IK_STATE_INVALID_ROTATION;
+    return;
+  }
+  Solve S;
+  int st_out = R2IK_STATE_EMPTY;
+  if (!cs.has_previous_sol) {                                // ctl:306-325
+    for (int i = 0; i < 7; ++i) cs.previous_sol[i] = current_joints[i];
+    cs.has_previous_sol = 1;
+    cs.init = 1;
+    double cpos[3], ceul[3];
+    pose_from_mat4(current_pose, true, cpos, ceul);
+    is_reachable<true>(A, cpos, ceul, S);
+    cs.previous_theta = best_theta_to_current_joints(A, S, current_joints, par.preferred_theta);
+  }
+  Reach rc = is_reachable<false>(A, pos, eul, S);
+  bool ok = rc.state == R2IK_STATE_REACHABLE;
+  double theta;
+  if (ok) {                                                  // ctl:338-366
+    double goal;
+    ok = best_discrete_theta(A, S, rc.i0, rc.i1, par.nb_search_points_continuous, par.preferred_theta_ctor, goal);
+    if (ok) theta = step_toward(goal, cs.previous_theta, par.d_theta_max);
+    else { theta = cs.previous_theta; st_out = R2IK_STATE_LIMITED_BY_SHOULDER; }
+  } else {                                                   // ctl:368-388
+    is_reachable<true>(A, pos, eul, S);
+    theta = step_toward(par.preferred_theta, cs.previous_theta, par.d_theta_max);
+    st_out = rc.state;
+  }
+  theta = limit_theta_to_interval(theta, par.interval_limit[0], par.interval_limit[1]);
+  cs.previous_theta = theta;
+  double E[3];
+  get_joints(A, S, theta, cs.previous_sol[0], cs.previous_sol[2], joints, E);
+  int bits = safety_checks(joints, cs.previous_sol, par.orbita3d_max_angle);   // ctl:393
+  if (bits) { cs.emergency_stop = 1; cs.emergency_bits |= bits; }
+  if (!cs.init) {                                            // ctl:395-400, utl:571-589
+    const double max_step[7] = {0.5, 0.5, 0.5, 0.5, 1.0, 1.0, 1.0};
+    bool discontinuity = false;
+    for (int i = 0; i < 7; ++i)
+      if (fabs(angle_diff(joints[i], cs.previous_sol[i])) > max_step[i]) discontinuity = true;
+    if (discontinuity) {
+      for (int i = 0; i < 7; ++i) joints[i] = cs.previous_sol[i];
+      cs.emergency_stop = 1;
+      cs.emergency_bits |= R2IK_EMG_DISCONTINUITY;
+    }
+  }
+  cs.init = 0;
+  if (!cs.emergency_stop)
+    for (int i = 0; i < 7; ++i) cs.previous_sol[i] = joints[i];
+  reachable = ok ? 1 : 0;
+  state = (uint8_t)st_out;
+}
+
+}  // namespace r2ik

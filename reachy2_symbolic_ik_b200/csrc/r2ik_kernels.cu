@@ -1,0 +1,519 @@
+// r2ik_kernels.cu -- sm_100a kernels and the C ABI of libr2ik.so (include/r2ik.h).
+//
+//   K1 k_symik_solve     one thread / pose   : is_reachable + get_joints
+//   K1b k_symik_no_limits, k_elbow_positions : is_reachable_no_limits, get_elbow_position
+//   K2 k_ctl_discrete    one lane / pose, warp-cooperative K-sample elbow search
+//   K3 k_ctl_continuous  one thread / trajectory, sequential over waypoints
+//   K4 k_reach_map       one thread / voxel, orientation table staged in shared memory
+//
+// The work is scalar FP64 (sincos / atan2 / sqrt / FMA chains): it runs on the FP64 pipe, not on
+// tensor cores; HBM traffic is a few hundred bytes per pose.  There is no host implementation
+// of any entry point in this library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "r2ik_control.cuh"
+#include "r2ik_host.h"
+
+using namespace r2ik;
+
+#define R2IK_BLOCK 128
+
+// ---------------------------------------------------------------------------------------
+// vectorised global memory helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+// 3x4 top of a row-major 4x4 (the last row is never read): 6 x 128-bit loads
+__device__ __forceinline__ void load_mat4(const double *__restrict__ M, double m[16]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double2 a = ldg2(M + 4 * r), b = ldg2(M + 4 * r + 2);
+    m[4 * r] = a.x; m[4 * r + 1] = a.y; m[4 * r + 2] = b.x; m[4 * r + 3] = b.y;
+  }
+  m[12] = 0.0; m[13] = 0.0; m[14] = 0.0; m[15] = 1.0;
+}
+
+template <int KIND>
+__device__ __forceinline__ bool load_pose(const double *__restrict__ poses, int64_t i, bool snap, double pos[3], double eul[3]) {
+  if (KIND == R2IK_POSE_EULER6) {
+    const double *p = poses + 6 * i;
+    double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4);
+    pos[0] = a.x; pos[1] = a.y; pos[2] = b.x;
+    eul[0] = b.y; eul[1] = c.x; eul[2] = c.y;
+    return true;
+  } else {
+    double m[16];
+    load_mat4(poses + 16 * i, m);
+    return pose_from_mat4(m, snap, pos, eul);
+  }
+}
+
+__device__ __forceinline__ void store_nan(double *p, int n) {
+  for (int k = 0; k < n; ++k) p[k] = NAN;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: SymbolicIK.is_reachable + theta_to_joints
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ theta,
+              const double *__restrict__ prev_joints, int64_t n, uint8_t *__restrict__ reachable,
+              uint8_t *__restrict__ state, double *__restrict__ interval, double *__restrict__ joints,
+              double *__restrict__ elbow) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double prev0 = 0.0, prev2 = 0.0;
+  if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
+  double pos[3], eul[3];
+  Solve S;
+  Reach rc;
+  if (load_pose<KIND>(poses, i, false, pos, eul)) {
+    rc = is_reachable<false>(A, pos, eul, S);
+  } else {
+    rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
+  }
+  bool ok = rc.state == R2IK_STATE_REACHABLE;
+  reachable[i] = ok ? 1 : 0;
+  state[i] = (uint8_t)rc.state;
+  if (interval) { interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1; }
+  if (!joints && !elbow) return;
+  double j[7], E[3];
+  if (ok) {
+    double th = theta ? theta[i] : rc.i0;
+    get_joints(A, S, th, prev0, prev2, j, E);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) j[k] = NAN;
+    E[0] = NAN; E[1] = NAN; E[2] = NAN;
+  }
+  if (joints) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+  }
+  if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_symik_no_limits(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ theta,
+                  int64_t n, double *__restrict__ joints, double *__restrict__ elbow) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double pos[3], eul[3], j[7], E[3];
+  Solve S;
+  bool ok = load_pose<KIND>(poses, i, false, pos, eul);
+  if (ok) ok = is_reachable<true>(A, pos, eul, S).state == R2IK_STATE_REACHABLE;
+  if (ok) {
+    get_joints(A, S, theta[i], 0.0, 0.0, j, E);
+  } else {
+    for (int k = 0; k < 7; ++k) j[k] = NAN;
+    E[0] = NAN; E[1] = NAN; E[2] = NAN;
+  }
+  for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+  if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_elbow_positions(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ thetas,
+                  int K, int64_t n, double *__restrict__ elbows) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double pos[3], eul[3];
+  Solve S;
+  bool ok = load_pose<KIND>(poses, i, false, pos, eul);
+  if (ok) ok = is_reachable<false>(A, pos, eul, S).state == R2IK_STATE_REACHABLE;
+  for (int k = 0; k < K; ++k) {
+    double E[3] = {NAN, NAN, NAN};
+    if (ok) elbow_position(S, thetas[(size_t)i * K + k], E);
+    double *o = elbows + ((size_t)i * K + k) * 3;
+    o[0] = E[0]; o[1] = E[1]; o[2] = E[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: ControlIK discrete mode.  Each lane solves its own pose (is_reachable, preferred-theta
+// shortcut); poses that need the K-sample search are then served one at a time by the whole
+// warp: the circle is broadcast with shuffles, lane l evaluates samples l, l+32, ..., and a
+// shuffle arg-min with lowest-index tie-break reproduces the reference's strict-< scan
+// (utl:381-390).  Each lane finally runs get_joints + safety_checks for its own pose.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
+               const double *__restrict__ M, int64_t n, const double *__restrict__ prev_joints,
+               const double *__restrict__ current_joints, double *__restrict__ joints, uint8_t *__restrict__ reachable,
+               uint8_t *__restrict__ state, uint8_t *__restrict__ emergency) {
+  const int lane = threadIdx.x & 31;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  double prev[7], cur[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { prev[k] = prev_joints[k]; cur[k] = current_joints[k]; }
+
+  Solve S;
+  int st = R2IK_STATE_INVALID_ROTATION;
+  bool found = false, need_search = false, valid_pose = false;
+  double theta = 0.0, start = 0.0, stop = 0.0;
+  if (active) {
+    double pos[3], eul[3];
+    valid_pose = load_pose<R2IK_POSE_MAT4>(M, i, true, pos, eul);
+    if (valid_pose) {
+      Reach rc = is_reachable<false>(A, pos, eul, S);
+      st = rc.state;
+      if (st == R2IK_STATE_REACHABLE) {
+        if (preferred_theta_works(A, S, rc.i0, rc.i1, par.preferred_theta)) {
+          theta = par.preferred_theta; found = true;
+        } else {
+          need_search = true;
+          search_range(rc.i0, rc.i1, start, stop);
+        }
+      }
+    }
+  }
+  const int nb = par.nb_search_points;
+  unsigned pending = __ballot_sync(0xffffffffu, need_search);
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    Solve B;  // only the fields elbow_position reads
+    B.c[0] = shfl_d(S.c[0], src); B.c[1] = shfl_d(S.c[1], src); B.c[2] = shfl_d(S.c[2], src);
+    B.a1[0] = shfl_d(S.a1[0], src); B.a1[1] = shfl_d(S.a1[1], src); B.a1[2] = shfl_d(S.a1[2], src);
+    B.a2[0] = shfl_d(S.a2[0], src); B.a2[1] = shfl_d(S.a2[1], src); B.a2[2] = shfl_d(S.a2[2], src);
+    B.r = shfl_d(S.r, src);
+    const double b_start = shfl_d(start, src), b_stop = shfl_d(stop, src);
+    double best = INFINITY;
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < nb; k += 32) {
+      double th = linspace_at(b_start, b_stop, nb, k);
+      double cost = sample_cost(A, B, th, par.preferred_theta);
+      if (cost < best) { best = cost; best_k = k; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      int ok = __shfl_xor_sync(0xffffffffu, best_k, off);
+      if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+    }
+    if (lane == src) {
+      found = best < INFINITY;
+      if (found) theta = linspace_at(start, stop, nb, best_k);
+      else st = R2IK_STATE_LIMITED_BY_SHOULDER;
+    }
+  }
+  if (!active) return;
+  double j[7];
+  int bits = 0;
+  if (valid_pose) {
+    bits = discrete_finish(A, par, S, found, theta, prev, cur, j);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) j[k] = NAN;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+  reachable[i] = found ? 1 : 0;
+  state[i] = (uint8_t)st;
+  if (emergency) emergency[i] = (uint8_t)bits;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: ControlIK continuous mode.  A trajectory is a sequential recursion over its waypoints
+// (previous_theta / previous_sol / init / emergency latch), so one thread owns one trajectory
+// and keeps the controller state in registers; parallelism comes from the trajectories.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
+                 const double *__restrict__ M, int64_t T, int W, const double *__restrict__ current_joints,
+                 const double *__restrict__ current_pose, R2ikTrajState *__restrict__ states,
+                 double *__restrict__ joints, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  R2ikTrajState cs = states[t];
+  double cj[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) cj[k] = current_joints[7 * t + k];
+  for (int w = 0; w < W; ++w) {
+    size_t k = (size_t)t * W + w;
+    double m[16], cp[16];
+    load_mat4(M + 16 * k, m);
+    if (!cs.has_previous_sol && !cs.emergency_stop) load_mat4(current_pose + 16 * t, cp);
+    double j[7];
+    uint8_t r, s;
+    continuous_step(A, par, m, cj, cp, cs, j, r, s);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
+    reachable[k] = r;
+    state[k] = s;
+  }
+  states[t] = cs;
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: workspace reachability map.  One thread per voxel; the rotation-dependent data of the
+// orientation slice (goal rotation matrix) is computed once per block into shared memory.
+// Voxels outside the reach sphere or behind the torso plane leave before the orientation loop
+// (those two states do not depend on the orientation, sik:284-307).
+// ---------------------------------------------------------------------------------------
+#define R2IK_ORI_CHUNK 64
+
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_reach_map(const __grid_constant__ ArmConst A, double ox, double oy, double oz, double sx, double sy, double sz,
+            int d0, int d1, int d2, const double *__restrict__ ori_euler, int ori_begin, int ori_end,
+            uint32_t *__restrict__ counts) {
+  __shared__ double sR[R2IK_ORI_CHUNK][9];
+  const int64_t nv = (int64_t)d0 * d1 * d2;
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_grid = v < nv;
+  double px = 0, py = 0, pz = 0;
+  bool live = false;
+  if (in_grid) {
+    int iz = (int)(v % d2);
+    int iy = (int)((v / d2) % d1);
+    int ix = (int)(v / ((int64_t)d2 * d1));
+    px = ox + ix * sx; py = oy + iy * sy; pz = oz + iz * sz;
+    live = reach_prechecks(A, px, py, pz) < 0;
+  }
+  uint32_t count = 0;
+  for (int base = ori_begin; base < ori_end; base += R2IK_ORI_CHUNK) {
+    int m = min(R2IK_ORI_CHUNK, ori_end - base);
+    __syncthreads();
+    for (int o = threadIdx.x; o < m; o += blockDim.x) {
+      const double *e = ori_euler + 3 * (size_t)(base + o);
+      double R[9];
+      rot_from_euler_xyz(e[0], e[1], e[2], R);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sR[o][k] = R[k];
+    }
+    __syncthreads();
+    if (live) {
+      for (int o = 0; o < m; ++o) {
+        Solve S;
+        S.p[0] = px; S.p[1] = py; S.p[2] = pz;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) S.R[k] = sR[o][k];
+        Reach rc = solve_core<false, true>(A, S);
+        count += (rc.state == R2IK_STATE_REACHABLE) ? 1u : 0u;
+      }
+    }
+  }
+  if (in_grid) counts[v] = count;
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 FMA peak probe (roofline denominator for bench.py; MEASURED_PEAKS.json has no FP64 entry)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_probe(int iters, double seed, double *sink) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+struct r2ik_context {
+  int device;
+  R2ikArmConfig cfg;
+  ArmConst A;
+  R2ikArmConstants pub;
+};
+
+static thread_local char g_err[256] = "";
+
+static int fail_arg(int code, const char *msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return code;
+}
+static int fail_cuda(cudaError_t e, const char *where) {
+  snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(e));
+  return -(int)e;
+}
+#define R2IK_CUDA(call, where)                        \
+  do {                                                \
+    cudaError_t e_ = (call);                          \
+    if (e_ != cudaSuccess) return fail_cuda(e_, where); \
+  } while (0)
+
+static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + R2IK_BLOCK - 1) / R2IK_BLOCK); }
+
+extern "C" {
+
+int r2ik_abi_version(void) { return R2IK_ABI_VERSION; }
+const char *r2ik_last_error(void) { return g_err; }
+
+int r2ik_create(const R2ikArmConfig *cfg, int device, r2ik_handle *out) {
+  if (!cfg || !out) return fail_arg(R2IK_ERR_NULL, "r2ik_create: null argument");
+  if (cfg->side != 1 && cfg->side != -1) return fail_arg(R2IK_ERR_ARM, "r2ik_create: side must be +1 (r_arm) or -1 (l_arm)");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+  if (count == 0 || device < 0 || device >= count) return fail_arg(R2IK_ERR_NO_DEVICE, "r2ik_create: no such CUDA device");
+  r2ik_context *h = new (std::nothrow) r2ik_context;
+  if (!h) return fail_arg(R2IK_ERR_ARG, "r2ik_create: out of host memory");
+  h->device = device;
+  h->cfg = *cfg;
+  derive_constants(*cfg, h->A, h->pub);
+  *out = h;
+  return 0;
+}
+
+int r2ik_destroy(r2ik_handle h) {
+  delete h;
+  return 0;
+}
+
+int r2ik_get_constants(r2ik_handle h, R2ikArmConstants *out) {
+  if (!h || !out) return fail_arg(R2IK_ERR_NULL, "r2ik_get_constants: null argument");
+  *out = h->pub;
+  return 0;
+}
+
+int r2ik_interval_limit(int side, int low_elbow, double *out) {
+  if (!out) return fail_arg(R2IK_ERR_NULL, "r2ik_interval_limit: null argument");
+  // ctl:225-252
+  double il0 = low_elbow ? -4 * kPi / 5 : 3 * kPi / 4;
+  double il1 = low_elbow ? 0.0 : -2 * kPi / 6;
+  if (side < 0) {
+    double a = -kPi - il1, b = -kPi - il0;
+    il0 = a; il1 = b;
+    if (il0 < -kPi) il0 = pymod(il0, kTwoPi);
+    if (il1 < -kPi) il1 = pymod(il1, kTwoPi);
+    if (il0 > kPi) il0 = pymod(il0, -kTwoPi);
+    if (il1 > kPi) il1 = pymod(il1, -kTwoPi);
+  }
+  out[0] = il0; out[1] = il1;
+  return 0;
+}
+
+int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, const double *prev_joints,
+                         int64_t n, uint8_t *reachable, uint8_t *state, double *interval, double *joints, double *elbow,
+                         void *stream) {
+  if (!h || !poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
+  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: bad n or pose_kind");
+  if (n == 0) return 0;
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pose_kind == R2IK_POSE_MAT4)
+    k_symik_solve<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
+  else
+    k_symik_solve<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
+  R2IK_CUDA(cudaGetLastError(), "k_symik_solve launch");
+  return 0;
+}
+
+int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, int64_t n,
+                             double *joints, double *elbow, void *stream) {
+  if (!h || !poses || !theta || !joints) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null argument");
+  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_no_limits_f64: bad n or pose_kind");
+  if (n == 0) return 0;
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pose_kind == R2IK_POSE_MAT4)
+    k_symik_no_limits<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, n, joints, elbow);
+  else
+    k_symik_no_limits<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, n, joints, elbow);
+  R2IK_CUDA(cudaGetLastError(), "k_symik_no_limits launch");
+  return 0;
+}
+
+int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, const double *thetas, int32_t K, int64_t n,
+                             double *elbows, void *stream) {
+  if (!h || !poses || !thetas || !elbows) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null argument");
+  if (n < 0 || K < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_elbow_positions_f64: bad n, K or pose_kind");
+  if (n == 0 || K == 0) return 0;
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pose_kind == R2IK_POSE_MAT4)
+    k_elbow_positions<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows);
+  else
+    k_elbow_positions<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows);
+  R2IK_CUDA(cudaGetLastError(), "k_elbow_positions launch");
+  return 0;
+}
+
+int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n, const double *prev_joints,
+                          const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
+                          uint8_t *emergency, void *stream) {
+  if (!h || !par || !M || !prev_joints || !current_joints || !joints || !reachable || !state)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null argument");
+  if (n < 0 || par->nb_search_points < 2) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_f64: bad n or nb_search_points");
+  if (n == 0) return 0;
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  k_ctl_discrete<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints, joints,
+                                                                        reachable, state, emergency);
+  R2IK_CUDA(cudaGetLastError(), "k_ctl_discrete launch");
+  return 0;
+}
+
+int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                            const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
+                            uint8_t *reachable, uint8_t *state, void *stream) {
+  if (!h || !par || !M || !current_joints || !current_pose || !st || !joints || !reachable || !state)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_f64: null argument");
+  if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_f64: bad T, W or nb_search_points_continuous");
+  if (T == 0 || W == 0) return 0;
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  k_ctl_continuous<<<blocks_for(T), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
+                                                                          joints, reachable, state);
+  R2IK_CUDA(cudaGetLastError(), "k_ctl_continuous launch");
+  return 0;
+}
+
+int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                       const double *orientations_euler, int32_t ori_begin, int32_t ori_end, uint32_t *counts, void *stream) {
+  if (!h || !origin || !step || !dims || !orientations_euler || !counts)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_reach_map_u32: null argument");
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || ori_begin < 0 || ori_end < ori_begin)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_u32: bad dims or orientation range");
+  int64_t nv = (int64_t)dims[0] * dims[1] * dims[2];
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  k_reach_map<<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, origin[0], origin[1], origin[2], step[0], step[1],
+                                                                      step[2], dims[0], dims[1], dims[2], orientations_euler,
+                                                                      ori_begin, ori_end, counts);
+  R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
+  return 0;
+}
+
+int r2ik_dfma_probe(int device, int32_t iters, double *out_ms, double *out_flop, void *stream) {
+  if (!out_ms || !out_flop) return fail_arg(R2IK_ERR_NULL, "r2ik_dfma_probe: null argument");
+  R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  R2IK_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  cudaStream_t s = (cudaStream_t)stream;
+  double *sink = nullptr;
+  R2IK_CUDA(cudaMalloc(&sink, sizeof(double)), "cudaMalloc");
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma_probe<<<blocks, threads, 0, s>>>(iters / 8 + 1, 1.0, sink);  // warm-up
+  cudaEventRecord(e0, s);
+  k_dfma_probe<<<blocks, threads, 0, s>>>(iters, 1.0, sink);
+  cudaEventRecord(e1, s);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) return fail_cuda(e, "k_dfma_probe");
+  *out_ms = (double)ms;
+  *out_flop = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  return 0;
+}
+
+}  // extern "C"

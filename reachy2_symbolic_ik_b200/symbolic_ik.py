@@ -1,0 +1,241 @@
+"""``SymbolicIK`` -- drop-in for ``reachy2_symbolic_ik.symbolic_ik.SymbolicIK`` whose geometry
+runs in the sm_100a CUDA library (``libr2ik.so``), plus batched entry points.
+
+Reference interface mirrored here: constructor ``symbolic_ik.py:26-83``; ``is_reachable``
+``:121-282``; ``is_reachable_no_limits`` ``:85-119``; ``get_joints`` ``:697-863``;
+``get_elbow_position`` ``:684-695``.  The scalar calls are N = 1 launches of the same kernels
+as the batched calls; there is no CPU code path.
+
+Semantics that differ from the reference on purpose: ``get_joints`` of the
+reference mutates the solver when the elbow projection fires, so a second call on the same
+solved pose returns different joints.  Here every ``get_joints`` / closure call is a fresh
+solve of the last pose (the value the reference returns on its *first* call).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+from . import _abi, _native
+from .states import STATE_STRINGS
+
+_ZERO7 = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+
+
+@dataclass
+class BatchResult:
+    """Outputs of a batched solve.  Arrays are torch CUDA tensors when the input was a CUDA
+    tensor, NumPy arrays otherwise."""
+
+    reachable: Any        # (N,) bool
+    theta_interval: Any   # (N, 2) float64, NaN when unreachable; [0] > [1] means wrapped
+    state: Any            # (N,) uint8, see states.STATE_STRINGS
+    joints: Any           # (N, 7) float64, NaN when unreachable
+    elbow: Any            # (N, 3) float64
+
+    def state_strings(self):
+        s = self.state
+        if hasattr(s, "cpu"):
+            s = s.cpu().numpy()
+        return [STATE_STRINGS[int(c)] for c in s]
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+def normalise_poses(torch, poses, device):
+    """Accept (N,4,4) / (N,16) homogeneous matrices or (N,2,3) / (N,6) reference goal poses, as
+    NumPy, CPU tensor or CUDA tensor.  Returns (device tensor (N,k) float64, kind, was_cuda)."""
+    was_cuda = hasattr(poses, "is_cuda") and poses.is_cuda
+    if not hasattr(poses, "is_cuda"):
+        poses = torch.from_numpy(np.ascontiguousarray(poses, dtype=np.float64))
+    if poses.dtype != torch.float64:
+        poses = poses.to(torch.float64)
+    shp = tuple(poses.shape)
+    if len(shp) == 3 and shp[1:] == (4, 4) or len(shp) == 2 and shp[1] == 16:
+        kind, k = _abi.POSE_MAT4, 16
+    elif len(shp) == 3 and shp[1:] == (2, 3) or len(shp) == 2 and shp[1] == 6:
+        kind, k = _abi.POSE_EULER6, 6
+    else:
+        raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6); got {shp}")
+    poses = poses.reshape(shp[0], k).contiguous()
+    if not was_cuda:
+        poses = poses.to(device, non_blocking=True)
+    return poses, kind, was_cuda
+
+
+class SymbolicIK:
+    def __init__(
+        self,
+        arm: str = "r_arm",
+        ik_parameters: dict[str, Any] = {},
+        elbow_limit: int = 127,
+        wrist_limit: np.float64 = np.float64(42.5),
+        projection_margin: float = 1e-8,
+        backward_limit: float = 0.02,
+        normal_vector_margin: float = 1e-7,
+        singularity_offset: float = 0.03,
+        singularity_limit_coeff: float = 1.0,
+        device: Optional[int] = None,
+    ) -> None:
+        if ik_parameters == {}:
+            print("Using default parameters")
+            ik_parameters = _abi.DEFAULT_IK_PARAMETERS
+        if arm not in ["r_arm", "l_arm"]:
+            raise ValueError("arm should be either 'r_arm' or 'l_arm'")
+        self.arm = arm
+        n = arm[0]
+        self.shoulder_position = ik_parameters[f"{n}_shoulder_position"]
+        self.shoulder_orientation_offset = ik_parameters[f"{n}_shoulder_orientation"]
+        self.upper_arm_size = ik_parameters[f"{n}_upper_arm_size"]
+        self.forearm_size = ik_parameters[f"{n}_forearm_size"]
+        self.tip_position = ik_parameters[f"{n}_tip_position"]
+        self.torso_pose = np.array([0.0, 0.0, 0.0])
+        self.projection_margin = projection_margin
+        self.normal_vector_margin = normal_vector_margin
+        self.backward_limit = backward_limit
+        self.elbow_limit = elbow_limit
+        self.wrist_limit = wrist_limit
+        self.singularity_offset = singularity_offset
+        self.singularity_limit_coeff = singularity_limit_coeff
+
+        cfg = _abi.make_arm_config(arm, ik_parameters, elbow_limit, wrist_limit, projection_margin, backward_limit,
+                                   normal_vector_margin, singularity_offset, singularity_limit_coeff)
+        self._torch = _native.require_cuda()
+        self._handle = _native.Handle(cfg, device)
+        self._device = self._torch.device("cuda", self._handle.device)
+        k = self._handle.constants
+        self.gripper_size = np.float64(k.gripper_size)
+        self.max_arm_length = np.float64(k.max_arm_length)
+        self.shoulder_wrist_min_distance = np.float64(k.shoulder_wrist_min_distance)
+        self.elbow_singularity_position = np.array(k.elbow_singularity_position[:])
+        self.wrist_singularity_position = np.array(k.wrist_singularity_position[:])
+
+        # state of the scalar API: the last pose handed to is_reachable / is_reachable_no_limits
+        self.goal_pose: Optional[np.ndarray] = None
+        self.elbow_position: Optional[np.ndarray] = None
+        self._no_limits = False
+
+    # ------------------------------------------------------------------ batched API
+    def is_reachable_batch(self, poses, theta=None, previous_joints=None, want_joints: bool = True) -> BatchResult:
+        """``is_reachable`` + ``theta_to_joints_func(theta)`` for N poses in one launch.
+
+        poses: (N,4,4) homogeneous matrices (converted like the reference's ControlIK front
+        end, ``R.from_matrix(M[:3,:3]).as_euler("xyz")``) or (N,2,3)/(N,6) reference goal poses
+        ``[[x,y,z],[roll,pitch,yaw]]``.  theta: None -> ``theta_interval[0]``; else (N,).
+        """
+        torch = self._torch
+        with torch.cuda.device(self._device):
+            P, kind, was_cuda = normalise_poses(torch, poses, self._device)
+            n = P.shape[0]
+            th = None
+            if theta is not None:
+                th = torch.as_tensor(theta, dtype=torch.float64).to(self._device).reshape(n).contiguous()
+            pj = None
+            if previous_joints is not None:
+                pj = torch.as_tensor(previous_joints, dtype=torch.float64).to(self._device).reshape(7).contiguous()
+            reach = torch.empty(n, dtype=torch.uint8, device=self._device)
+            state = torch.empty(n, dtype=torch.uint8, device=self._device)
+            interval = torch.empty((n, 2), dtype=torch.float64, device=self._device)
+            joints = torch.empty((n, 7), dtype=torch.float64, device=self._device) if want_joints else None
+            elbow = torch.empty((n, 3), dtype=torch.float64, device=self._device) if want_joints else None
+            self.solve_into(P, kind, th, pj, reach, state, interval, joints, elbow)
+            res = BatchResult(reach.bool(), interval, state, joints, elbow)
+            if was_cuda:
+                return res
+            return BatchResult(*[None if x is None else x.cpu().numpy() for x in
+                                 (res.reachable, res.theta_interval, res.state, res.joints, res.elbow)])
+
+    def solve_into(self, poses_dev, kind, theta_dev, prev_dev, reach, state, interval, joints, elbow, stream=None):
+        """Raw launch on device tensors (no allocation, asynchronous): the C-ABI call itself."""
+        torch = self._torch
+        s = torch.cuda.current_stream(self._device).cuda_stream if stream is None else stream
+        rc = self._handle.lib.r2ik_symik_solve_f64(
+            self._handle.h, kind, _ptr(poses_dev), _ptr(theta_dev), _ptr(prev_dev), C.c_int64(poses_dev.shape[0]),
+            _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), C.c_void_p(s))
+        _native.check(rc, "r2ik_symik_solve_f64")
+
+    def is_reachable_no_limits_batch(self, poses, theta):
+        """``is_reachable_no_limits`` + ``get_joints(theta)``: returns (joints (N,7), elbow (N,3))."""
+        torch = self._torch
+        with torch.cuda.device(self._device):
+            P, kind, was_cuda = normalise_poses(torch, poses, self._device)
+            n = P.shape[0]
+            th = torch.as_tensor(theta, dtype=torch.float64).to(self._device).reshape(n).contiguous()
+            joints = torch.empty((n, 7), dtype=torch.float64, device=self._device)
+            elbow = torch.empty((n, 3), dtype=torch.float64, device=self._device)
+            s = torch.cuda.current_stream(self._device).cuda_stream
+            rc = self._handle.lib.r2ik_symik_no_limits_f64(self._handle.h, kind, _ptr(P), _ptr(th), C.c_int64(n),
+                                                           _ptr(joints), _ptr(elbow), C.c_void_p(s))
+            _native.check(rc, "r2ik_symik_no_limits_f64")
+            if was_cuda:
+                return joints, elbow
+            return joints.cpu().numpy(), elbow.cpu().numpy()
+
+    def get_elbow_position_batch(self, poses, thetas):
+        """``get_elbow_position`` for K thetas per pose after ``is_reachable``: (N,K,3), NaN if unreachable."""
+        torch = self._torch
+        with torch.cuda.device(self._device):
+            P, kind, was_cuda = normalise_poses(torch, poses, self._device)
+            n = P.shape[0]
+            th = torch.as_tensor(thetas, dtype=torch.float64).to(self._device).reshape(n, -1).contiguous()
+            K = th.shape[1]
+            out = torch.empty((n, K, 3), dtype=torch.float64, device=self._device)
+            s = torch.cuda.current_stream(self._device).cuda_stream
+            rc = self._handle.lib.r2ik_elbow_positions_f64(self._handle.h, kind, _ptr(P), _ptr(th), C.c_int32(K),
+                                                           C.c_int64(n), _ptr(out), C.c_void_p(s))
+            _native.check(rc, "r2ik_elbow_positions_f64")
+            return out if was_cuda else out.cpu().numpy()
+
+    # ------------------------------------------------------------------ scalar API (reference signatures)
+    @staticmethod
+    def _pose6(goal_pose) -> np.ndarray:
+        gp = np.array([np.asarray(goal_pose[0], dtype=np.float64), np.asarray(goal_pose[1], dtype=np.float64)])
+        return gp.reshape(1, 6)
+
+    def is_reachable(self, goal_pose) -> Tuple[bool, np.ndarray, Optional[Any], str]:
+        """Check if the goal pose ``[[x,y,z],[roll,pitch,yaw]]`` is reachable taking the wrist and
+        elbow limits into account; returns (is_reachable, theta_interval, theta_to_joints_func, state)."""
+        P = self._pose6(goal_pose)
+        res = self.is_reachable_batch(P, want_joints=False)
+        self.goal_pose = P.reshape(2, 3).copy()
+        self._no_limits = False
+        state = STATE_STRINGS[int(res.state[0])]
+        if bool(res.reachable[0]):
+            return True, np.array(res.theta_interval[0]), self.get_joints, state
+        return False, np.array([]), None, state
+
+    def is_reachable_no_limits(self, goal_pose) -> Tuple[bool, np.ndarray, Optional[Any]]:
+        """Reachability without the wrist / elbow limits (unreachable goals are projected);
+        always (True, [-pi, pi], get_joints)."""
+        P = self._pose6(goal_pose)
+        self.goal_pose = P.reshape(2, 3).copy()
+        self._no_limits = True
+        return True, np.array([-np.pi, np.pi]), self.get_joints
+
+    def get_joints(self, theta: float, previous_joints: list = _ZERO7) -> Tuple[np.ndarray, np.ndarray]:
+        """Joints for the elbow angle theta on the last solved pose (fresh solve per call)."""
+        if self.goal_pose is None:
+            raise AttributeError("get_joints called before is_reachable / is_reachable_no_limits")
+        P = self.goal_pose.reshape(1, 6)
+        if self._no_limits:
+            joints, elbow = self.is_reachable_no_limits_batch(P, np.array([float(theta)]))
+            j, e = joints[0], elbow[0]
+        else:
+            res = self.is_reachable_batch(P, theta=np.array([float(theta)]), previous_joints=previous_joints)
+            j, e = res.joints[0], res.elbow[0]
+        self.elbow_position = np.array(e)
+        return np.array(j), self.elbow_position
+
+    def get_elbow_position(self, theta: float) -> np.ndarray:
+        """Elbow position [x, y, z, 1] on the elbow circle of the last solved pose."""
+        if self.goal_pose is None:
+            raise AttributeError("get_elbow_position called before is_reachable")
+        if self._no_limits:
+            raise NotImplementedError("get_elbow_position after is_reachable_no_limits is not exposed")
+        e = self.get_elbow_position_batch(self.goal_pose.reshape(1, 6), np.array([[float(theta)]]))[0, 0]
+        return np.array([e[0], e[1], e[2], 1.0])

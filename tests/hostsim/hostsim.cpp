@@ -1,0 +1,102 @@
+// TEST-ONLY host harness: compiles the device solver source (r2ik_device.cuh /
+// r2ik_control.cuh, all __host__ __device__) with g++ and loops over poses on the CPU, so the
+// kernel *logic* is checked against the golden fixtures in the GPU-less CI.  It is not part
+// of libr2ik.so, is never imported by the package, and is no fallback for anything.
+#include <cstring>
+#include <cstdint>
+
+#include "../../reachy2_symbolic_ik_b200/csrc/r2ik_control.cuh"
+#include "../../reachy2_symbolic_ik_b200/csrc/r2ik_host.h"
+
+using namespace r2ik;
+
+static bool load_pose(int kind, const double *p, double pos[3], double eul[3]) {
+  if (kind == R2IK_POSE_EULER6) {
+    for (int k = 0; k < 3; ++k) { pos[k] = p[k]; eul[k] = p[3 + k]; }
+    return true;
+  }
+  return pose_from_mat4(p, false, pos, eul);
+}
+
+extern "C" {
+
+void hs_constants(const R2ikArmConfig *cfg, R2ikArmConstants *pub) {
+  ArmConst A;
+  derive_constants(*cfg, A, *pub);
+}
+
+void hs_symik_batch(const R2ikArmConfig *cfg, int kind, const double *poses, const double *theta, int64_t n,
+                    uint8_t *reach, uint8_t *state, double *interval, double *joints, double *elbow) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  int stride = kind == R2IK_POSE_EULER6 ? 6 : 16;
+  for (int64_t i = 0; i < n; ++i) {
+    double pos[3], eul[3];
+    for (int k = 0; k < 7; ++k) joints[7 * i + k] = NAN;
+    for (int k = 0; k < 3; ++k) elbow[3 * i + k] = NAN;
+    interval[2 * i] = NAN; interval[2 * i + 1] = NAN;
+    if (!load_pose(kind, poses + i * stride, pos, eul)) { reach[i] = 0; state[i] = R2IK_STATE_INVALID_ROTATION; continue; }
+    Solve S;
+    Reach rc = is_reachable<false>(A, pos, eul, S);
+    state[i] = (uint8_t)rc.state;
+    reach[i] = rc.state == R2IK_STATE_REACHABLE;
+    if (reach[i]) {
+      interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1;
+      get_joints(A, S, theta ? theta[i] : rc.i0, 0.0, 0.0, joints + 7 * i, elbow + 3 * i);
+    }
+  }
+}
+
+void hs_no_limits_batch(const R2ikArmConfig *cfg, int kind, const double *poses, const double *theta, int64_t n,
+                        double *joints, double *elbow) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  int stride = kind == R2IK_POSE_EULER6 ? 6 : 16;
+  for (int64_t i = 0; i < n; ++i) {
+    double pos[3], eul[3];
+    load_pose(kind, poses + i * stride, pos, eul);
+    Solve S;
+    is_reachable<true>(A, pos, eul, S);
+    get_joints(A, S, theta[i], 0.0, 0.0, joints + 7 * i, elbow + 3 * i);
+  }
+}
+
+void hs_ctl_discrete_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t n,
+                           const double *prev, const double *cur, double *joints, uint8_t *reach, uint8_t *state,
+                           uint8_t *emg) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  for (int64_t i = 0; i < n; ++i) {
+    double pos[3], eul[3];
+    if (!pose_from_mat4(M + 16 * i, true, pos, eul)) {
+      for (int k = 0; k < 7; ++k) joints[7 * i + k] = NAN;
+      reach[i] = 0; state[i] = R2IK_STATE_INVALID_ROTATION; emg[i] = 0;
+      continue;
+    }
+    Solve S;
+    Reach rc = is_reachable<false>(A, pos, eul, S);
+    int st = rc.state;
+    bool ok = st == R2IK_STATE_REACHABLE;
+    double theta = 0.0;
+    if (ok) {
+      ok = best_discrete_theta(A, S, rc.i0, rc.i1, par->nb_search_points, par->preferred_theta, theta);
+      if (!ok) st = R2IK_STATE_LIMITED_BY_SHOULDER;
+    }
+    emg[i] = (uint8_t)discrete_finish(A, *par, S, ok, theta, prev, cur, joints + 7 * i);
+    reach[i] = ok; state[i] = (uint8_t)st;
+  }
+}
+
+void hs_ctl_continuous_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                             const double *cur_joints, const double *cur_pose, R2ikTrajState *st, double *joints,
+                             uint8_t *reach, uint8_t *state) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  for (int64_t t = 0; t < T; ++t)
+    for (int32_t w = 0; w < W; ++w) {
+      size_t k = (size_t)t * W + w;
+      continuous_step(A, *par, M + 16 * k, cur_joints + 7 * t, cur_pose + 16 * t, st[t], joints + 7 * k, reach[k], state[k]);
+    }
+}
+
+}  // extern "C"

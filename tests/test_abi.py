@@ -1,0 +1,77 @@
+"""CPU checks of the drop-in boundary: libr2ik.so builds for sm_100a, loads, and exports every
+symbol include/r2ik.h declares; the ctypes structs match the C layouts; the product path refuses
+to run without a GPU (no CPU fallback).  No compute entry is called here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from parity import REPO
+from reachy2_symbolic_ik_b200 import _abi, _native, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _native.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(REPO, "include", "r2ik.h")).read()
+    declared = set(re.findall(r"\b(r2ik_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_abi_version_and_struct_sizes(lib):
+    assert lib.r2ik_abi_version() == _abi.ABI_VERSION
+    assert C.sizeof(_abi.ArmConfig) == 8 * 18 + 8
+    assert C.sizeof(_abi.ArmConstants) == 8 * 9
+    assert C.sizeof(_abi.CtlParams) == 8 * 6 + 8
+    assert C.sizeof(_abi.TrajState) == 80
+
+
+def test_interval_limit_host_entry(lib, oracle):
+    import numpy as np
+    for side in (1, -1):
+        for low in (False, True):
+            got = _native.interval_limit(side, low)
+            want = np.zeros(2)
+            oracle.lib().orc_interval_limit(side, int(low), want.ctypes.data_as(C.POINTER(C.c_double)))
+            assert got == want.tolist()
+    # unconstrained l_arm -> [-2pi/3, pi/4]
+    np.testing.assert_allclose(_native.interval_limit(-1, False), [-2 * np.pi / 3, np.pi / 4], atol=1e-15)
+
+
+def test_argument_errors_do_not_need_a_device(lib):
+    h = C.c_void_p()
+    assert lib.r2ik_create(None, 0, C.byref(h)) == 1  # R2IK_ERR_NULL
+    assert b"null" in lib.r2ik_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from reachy2_symbolic_ik_b200 import SymbolicIK
+
+    with pytest.raises(_native.R2ikError):
+        SymbolicIK(arm="r_arm")
+
+
+def test_sass_is_sm100a_fp64():
+    """The shipped cubin targets sm_100a and the hot kernel is FP64 (DFMA) code."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    build.build()
+    out = subprocess.run([cuobjdump, "-sass", _native.lib_path()], capture_output=True, text=True).stdout
+    assert "arch = sm_100a" in out
+    k1 = out.split("k_symik_solveILi1E")[1].split("Function :")[0]
+    assert k1.count("DFMA") > 500

@@ -1,0 +1,182 @@
+"""GPU parity of K2 (ControlIK discrete) and K3 (ControlIK continuous) through the facade /
+C ABI, against the reference's golden outputs and the CPU oracle."""
+import numpy as np
+import pytest
+
+from parity import Report, ill_conditioned_mask, load
+
+pytestmark = pytest.mark.gpu
+ARMS = ("r_arm", "l_arm")
+
+
+def urdf_params():
+    u = load("symik_urdf.npz")
+    return {k[len("param_"):]: u[k] for k in u.files if k.startswith("param_")}
+
+
+@pytest.fixture(scope="module")
+def controls():
+    from reachy2_symbolic_ik_b200 import ControlIK
+
+    return {False: ControlIK(urdf_path="../config_files/reachy2.urdf"),
+            True: ControlIK(urdf_path="../config_files/reachy2.urdf", is_dvt=True)}
+
+
+def test_constructor_contract():
+    from reachy2_symbolic_ik_b200 import ControlIK
+
+    with pytest.raises(ValueError, match="No URDF provided"):
+        ControlIK()
+    with pytest.raises(ValueError, match="Unknown Reachy model"):
+        ControlIK(urdf_path="../config_files/reachy2.urdf", reachy_model="nope")
+    with pytest.raises(ValueError, match="Error while parsing URDF"):
+        ControlIK(urdf="<robot><joint></robot>")
+    c = ControlIK(urdf_path="../config_files/reachy2.urdf", reachy_model="starter_kit_right")
+    assert list(c.symbolic_ik_solver) == ["r_arm"]
+    with pytest.raises(ValueError, match="Unknown type"):
+        c.symbolic_inverse_kinematics("r_arm", np.eye(4), "bogus")
+    np.testing.assert_allclose(c.preferred_theta["r_arm"], -2 * np.pi / 3)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["k20", "k360", "low", "dvt"])
+def test_discrete_golden(controls, oracle, arm, variant):
+    g = load(f"ctl_discrete_{arm}.npz")
+    params = urdf_params()
+    dvt = variant == "dvt"
+    want_j, want_f, want_s = g[f"joints_{variant}"], g[f"reachable_{variant}"], g[f"state_{variant}"]
+    M = np.ascontiguousarray(g["M"][: len(want_j)])
+    kw = dict(nb_search_points=360 if variant == "k360" else 20,
+              constrained_mode="low_elbow" if variant == "low" else "unconstrained")
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=0.03 if dvt else -1.01)
+    opar = oracle.ControlParams(arm=arm, **kw)
+    ill = ill_conditioned_mask(lambda p: oracle.ctl_discrete_batch(ocfg, opar, p.reshape(M.shape))[:3], M.reshape(len(M), -1))
+    ctl = controls[dvt]
+    ctl.nb_search_points = kw["nb_search_points"]
+    try:
+        joints, reach, state, emg = ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete", constrained_mode=kw["constrained_mode"])
+    finally:
+        ctl.nb_search_points = 20
+    rep = Report(f"gpu ctl discrete {arm} {variant}", len(M), ill)
+    rep.exact("reachable", reach, want_f)
+    rep.exact("state", state, want_s)
+    rep.close("joints", joints, want_j)
+    assert not emg.any()
+    rep.check(max_ill_fraction=0.02)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_discrete_vs_oracle_k360(controls, oracle, arm):
+    """BASELINE config 3 shape (K = 360 samples) at a size the oracle finishes in seconds."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    M = np.concatenate([fk.sample_fk_poses(15000, arm, seed=31, min_x=0.0), fk.sample_task_space_poses(5000, arm, seed=32)])
+    params = urdf_params()
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=-1.01)
+    opar = oracle.ControlParams(arm=arm, nb_search_points=360)
+    ill = ill_conditioned_mask(lambda p: oracle.ctl_discrete_batch(ocfg, opar, p.reshape(M.shape))[:3], M.reshape(len(M), -1), n_trials=2)
+    wj, wr, ws, we = oracle.ctl_discrete_batch(ocfg, opar, M)
+    ctl = controls[False]
+    ctl.nb_search_points = 360
+    try:
+        joints, reach, state, emg = ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete")
+    finally:
+        ctl.nb_search_points = 20
+    rep = Report(f"gpu ctl discrete vs oracle K=360 {arm}", len(M), ill)
+    rep.exact("reachable", reach, wr)
+    rep.exact("state", state, ws)
+    rep.close("joints", joints, wj)
+    rep.check(max_ill_fraction=0.02)
+
+
+def test_discrete_scalar_api_matches_reference_examples(controls):
+    """Survey-session reference outputs for src/example/test_go_to.py pose #1."""
+    g = load("symik_named.npz")
+    ctl = controls[False]
+    pose = g["r_arm_poses"][9]  # [[0.38, -0.2, -0.28], [0, -pi/2, 0]]
+    from oracle import oracle as O
+
+    M = np.eye(4)
+    M[:3, :3] = O.matrix_from_euler_xyz(pose[1])
+    M[:3, 3] = pose[0]
+    joints, ok, state = ctl.symbolic_inverse_kinematics("r_arm", M, "discrete")
+    assert ok and state == "reachable"
+    np.testing.assert_allclose(joints, [-0.00460168557495466, -0.1062724336311957, 0.19960165027845525, -1.5707963267948966,
+                                        -0.3622181452116582, 0.06703749820492533, -0.3622181452116573], atol=1e-9)
+    # unreachable discrete calls return the previous solution (control_ik.py:457-458)
+    M[:3, 3] = [0.0, -0.85, 0.0]
+    joints, ok, state = ctl.symbolic_inverse_kinematics("r_arm", M, "discrete")
+    assert not ok and state in ("Backward pose", "Pose out of reach")
+    np.testing.assert_allclose(joints, [0, 0.2617993877991494, -0.17453292519943295, 0, 0, 0, 0], atol=1e-12)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["default", "cj", "dvt"])
+def test_continuous_golden(controls, oracle, arm, variant):
+    g = load(f"ctl_continuous_{arm}.npz")
+    pre = {"default": "", "cj": "cj_", "dvt": "dvt_"}[variant]
+    want_j, want_f, want_s = g[pre + "joints"], g[pre + "reachable"], g[pre + "state"]
+    T, W = want_j.shape[:2]
+    M = np.ascontiguousarray(g["M"][:T])
+    ctl = controls[variant == "dvt"]
+    kw = {}
+    if variant == "cj":
+        kw = dict(current_joints=g["cj_current_joints"], current_pose=g["cj_current_pose"])
+    joints, reach, state, st = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", **kw)
+    for t in range(T):
+        rep = Report(f"gpu ctl continuous {arm} {variant} traj {t}", W)
+        rep.exact("reachable", reach[t], want_f[t])
+        rep.exact("state", state[t], want_s[t])
+        rep.close("joints", joints[t], want_j[t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+
+
+def test_continuous_resume_is_identical(controls):
+    """Chunked trajectories (state struct passed back in) reproduce the one-shot result bit for bit."""
+    g = load("ctl_continuous_r_arm.npz")
+    M = np.ascontiguousarray(g["M"])
+    ctl = controls[False]
+    j_all, r_all, s_all, st_all = ctl.symbolic_inverse_kinematics_batch("r_arm", M, "continuous")
+    W = M.shape[1]
+    j1, r1, s1, st1 = ctl.symbolic_inverse_kinematics_batch("r_arm", M[:, : W // 3], "continuous")
+    j2, r2, s2, st2 = ctl.symbolic_inverse_kinematics_batch("r_arm", M[:, W // 3:], "continuous", states=st1)
+    np.testing.assert_array_equal(np.concatenate([j1, j2], axis=1), j_all)
+    np.testing.assert_array_equal(np.concatenate([s1, s2], axis=1), s_all)
+    assert st2.tobytes() == st_all.tobytes()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_continuous_vs_oracle_many(controls, oracle, arm):
+    """256 sinusoidal trajectories x 200 waypoints against the oracle; continuity invariant."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    M, q = fk.sinusoidal_trajectories(256, 200, arm, seed=41)
+    params = urdf_params()
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=-1.01)
+    wj, wr, ws, wst = oracle.ctl_continuous_batch(ocfg, oracle.ControlParams(arm=arm), M)
+    joints, reach, state, st = controls[False].symbolic_inverse_kinematics_batch(arm, M, "continuous")
+    assert np.array_equal(reach, wr) and np.array_equal(state, ws)
+    err = np.abs(joints - wj).reshape(256, -1).max(axis=1)
+    # a trajectory is a recursion: an ill-conditioned waypoint would contaminate its tail
+    assert np.quantile(err, 0.99) < 1e-9, np.sort(err)[-5:]
+    assert (err < 1e-9).mean() > 0.99
+    np.testing.assert_array_equal(st["emergency_stop"], wst["emergency_stop"])
+    ok = ~st["emergency_stop"].astype(bool)
+    step = np.abs(np.diff(joints[ok], axis=1))[:, 1:]  # waypoint 0 -> 1 follows the unconstrained init
+    assert (step.max(axis=(0, 1)) <= np.array([0.5, 0.5, 0.5, 0.5, 1.0, 1.0, 1.0])).all()
+
+
+def test_continuous_scalar_api(controls):
+    """Scalar continuous calls (wall-clock timeout logic of control_ik.py:296-304 on the host)
+    walk the same recursion as one batched trajectory."""
+    from reachy2_symbolic_ik_b200 import ControlIK
+
+    g = load("ctl_continuous_r_arm.npz")
+    M = g["M"][0][:40]
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    out = [ctl.symbolic_inverse_kinematics("r_arm", M[w], "continuous") for w in range(len(M))]
+    joints = np.array([o[0] for o in out])
+    np.testing.assert_allclose(joints, g["joints"][0][:40], atol=1e-9)
+    assert all(o[1] for o in out) and all(o[2] == "" for o in out)

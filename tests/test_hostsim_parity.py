@@ -1,0 +1,181 @@
+"""CPU check of the *kernel source logic*: tests/hostsim compiles the device solver headers
+(r2ik_device.cuh, r2ik_control.cuh) for the host and this file compares them with the
+reference's golden outputs.  It exists so that logic regressions are caught in the GPU-less
+CI; the GPU parity tests proper (``-m gpu``, tests/test_gpu_*.py) go through libr2ik.so.
+The harness is test infrastructure: the package never loads it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from parity import REPO, Report, ill_conditioned_mask, load
+from reachy2_symbolic_ik_b200 import _abi
+
+HS_DIR = os.path.join(REPO, "tests", "hostsim")
+ARMS = ("r_arm", "l_arm")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    L = C.CDLL(os.path.join(HS_DIR, "_build", "libr2ik_hostsim.so"))
+    return L
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def cfg_for(arm, params=None, singularity_offset=0.03):
+    return _abi.make_arm_config(arm, params or _abi.DEFAULT_IK_PARAMETERS, 127, 42.5, 1e-8, 0.02, 1e-7,
+                                singularity_offset, 1.0)
+
+
+def hs_symik(hs, cfg, P, theta=None):
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    n = len(P)
+    kind = _abi.POSE_MAT4 if P.shape[1:] == (4, 4) else _abi.POSE_EULER6
+    reach = np.zeros(n, np.uint8); state = np.zeros(n, np.uint8)
+    itv = np.empty((n, 2)); j = np.empty((n, 7)); e = np.empty((n, 3))
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    hs.hs_symik_batch(C.byref(cfg), kind, dp(P), dp(th) if th is not None else None, C.c_int64(n), u8(reach), u8(state),
+                      dp(itv), dp(j), dp(e))
+    return reach.astype(bool), itv, state, j, e
+
+
+def urdf_params():
+    u = load("symik_urdf.npz")
+    return {k[len("param_"):]: u[k] for k in u.files if k.startswith("param_")}
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("layout", ["euler", "mat4"])
+def test_symik_random(hs, oracle, arm, layout):
+    g = load(f"symik_random_{arm}.npz")
+    P = g["goal_pose"] if layout == "euler" else g["M"]
+    ocfg = oracle.arm_config(arm)
+    ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+    cfg = cfg_for(arm)
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg, P)
+    rep = Report(f"hostsim random {arm} {layout}", len(P), ill)
+    rep.exact("reachable", reach, g["reachable"])
+    rep.exact("state", state, g["state"])
+    rep.close("interval", itv, g["interval"])
+    rep.close("joints", joints, g["joints"])
+    rep.close("elbow", elbow, g["elbow"])
+    _, _, _, j2, e2 = hs_symik(hs, cfg, P, g["theta2"])
+    rep.close("joints@theta2", j2, g["joints_theta2"])
+    rep.close("elbow@theta2", e2, g["elbow_theta2"])
+    rep.check()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_named(hs, oracle, arm):
+    g = load("symik_named.npz")
+    P = g[f"{arm}_poses"]
+    ocfg = oracle.arm_config(arm)
+    ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg_for(arm), P)
+    rep = Report(f"hostsim named {arm}", len(P), ill)
+    rep.exact("reachable", reach, g[f"{arm}_reachable"])
+    rep.exact("state", state, g[f"{arm}_state"])
+    rep.close("interval", itv, g[f"{arm}_interval"])
+    rep.close("joints", joints, g[f"{arm}_joints"])
+    rep.check(max_ill_fraction=0.1)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_urdf_and_no_limits(hs, oracle, arm):
+    g = load("symik_urdf.npz")
+    params = urdf_params()
+    M = g[f"{arm}_M"]
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=-1.01)
+    th = g[f"{arm}_nl_theta"]
+    run = lambda p: oracle.symik_batch(ocfg, p.reshape(M.shape))[:4] + oracle.symik_no_limits_batch(  # noqa: E731
+        ocfg, p.reshape(M.shape), th)
+    ill = ill_conditioned_mask(run, M.reshape(len(M), -1))
+    cfg = cfg_for(arm, params, -1.01)
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg, M)
+    rep = Report(f"hostsim urdf {arm}", len(M), ill)
+    rep.exact("reachable", reach, g[f"{arm}_reachable"])
+    rep.exact("state", state, g[f"{arm}_state"])
+    rep.close("interval", itv, g[f"{arm}_interval"])
+    rep.close("joints", joints, g[f"{arm}_joints"])
+    n = len(M)
+    nj = np.empty((n, 7)); ne = np.empty((n, 3))
+    Mc = np.ascontiguousarray(M)
+    hs.hs_no_limits_batch(C.byref(cfg), _abi.POSE_MAT4, dp(Mc), dp(np.ascontiguousarray(th)), C.c_int64(n), dp(nj), dp(ne))
+    rep.close("no_limits joints", nj, g[f"{arm}_nl_joints"])
+    rep.close("no_limits elbow", ne, g[f"{arm}_nl_elbow"])
+    rep.check()
+
+
+def ctl_params(oracle, arm, **kw):
+    """R2ikCtlParams has the oracle's field layout; fill it from the oracle's ControlParams."""
+    op = oracle.ControlParams(arm=arm, **kw)._c
+    p = _abi.CtlParams()
+    C.memmove(C.byref(p), C.byref(op), C.sizeof(p))
+    return p
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["k20", "k360", "low", "dvt"])
+def test_ctl_discrete(hs, oracle, arm, variant):
+    g = load(f"ctl_discrete_{arm}.npz")
+    params = urdf_params()
+    off = 0.03 if variant == "dvt" else -1.01
+    want_j, want_f, want_s = g[f"joints_{variant}"], g[f"reachable_{variant}"], g[f"state_{variant}"]
+    M = np.ascontiguousarray(g["M"][: len(want_j)])
+    kw = dict(nb_search_points=360 if variant == "k360" else 20,
+              constrained_mode="low_elbow" if variant == "low" else "unconstrained")
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=off)
+    opar = oracle.ControlParams(arm=arm, **kw)
+    ill = ill_conditioned_mask(lambda p: oracle.ctl_discrete_batch(ocfg, opar, p.reshape(M.shape))[:3], M.reshape(len(M), -1))
+    cfg = cfg_for(arm, params, off)
+    par = ctl_params(oracle, arm, **kw)
+    n = len(M)
+    prev = np.array(oracle.DEFAULT_PREV_JOINTS[arm])
+    joints = np.empty((n, 7)); reach = np.zeros(n, np.uint8); state = np.zeros(n, np.uint8); emg = np.zeros(n, np.uint8)
+    hs.hs_ctl_discrete_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(n), dp(prev), dp(prev), dp(joints), u8(reach),
+                             u8(state), u8(emg))
+    rep = Report(f"hostsim ctl discrete {arm} {variant}", n, ill)
+    rep.exact("reachable", reach.astype(bool), want_f)
+    rep.exact("state", state, want_s)
+    rep.close("joints", joints, want_j)
+    rep.check(max_ill_fraction=0.02)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["default", "cj", "dvt"])
+def test_ctl_continuous(hs, oracle, arm, variant):
+    g = load(f"ctl_continuous_{arm}.npz")
+    params = urdf_params()
+    off = 0.03 if variant == "dvt" else -1.01
+    pre = {"default": "", "cj": "cj_", "dvt": "dvt_"}[variant]
+    want_j, want_f, want_s = g[pre + "joints"], g[pre + "reachable"], g[pre + "state"]
+    T, W = want_j.shape[:2]
+    M = np.ascontiguousarray(g["M"][:T])
+    cj = np.empty((T, 7)); cp = np.empty((T, 4, 4))
+    cj[:] = g["cj_current_joints"] if variant == "cj" else oracle.DEFAULT_PREV_JOINTS[arm]
+    cp[:] = g["cj_current_pose"] if variant == "cj" else oracle.DEFAULT_CURRENT_POSE[arm]
+    st = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
+    st["init"] = 1
+    joints = np.empty((T, W, 7)); reach = np.zeros((T, W), np.uint8); state = np.zeros((T, W), np.uint8)
+    cfg = cfg_for(arm, params, off)
+    par = ctl_params(oracle, arm)
+    hs.hs_ctl_continuous_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
+                               st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state))
+    for t in range(T):
+        rep = Report(f"hostsim ctl continuous {arm} {variant} traj {t}", W)
+        rep.exact("reachable", reach[t].astype(bool), want_f[t])
+        rep.exact("state", state[t], want_s[t])
+        rep.close("joints", joints[t], want_j[t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
