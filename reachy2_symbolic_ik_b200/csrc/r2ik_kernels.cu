@@ -400,10 +400,11 @@ int r2ik_interval_limit(int side, int low_elbow, double *out) {
 int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, const double *prev_joints,
                          int64_t n, uint8_t *reachable, uint8_t *state, double *interval, double *joints, double *elbow,
                          void *stream) {
-  if (!h || !poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
   if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: bad n or pose_kind");
-  if (n == 0) return 0;
+  if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null handle");
+  if (n == 0) return 0;  // empty batch: nothing to read or write
+  if (!poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
@@ -416,10 +417,11 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
 
 int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, int64_t n,
                              double *joints, double *elbow, void *stream) {
-  if (!h || !poses || !theta || !joints) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null argument");
   if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_no_limits_f64: bad n or pose_kind");
+  if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null handle");
   if (n == 0) return 0;
+  if (!poses || !theta || !joints) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null argument");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
@@ -432,10 +434,11 @@ int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, 
 
 int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, const double *thetas, int32_t K, int64_t n,
                              double *elbows, void *stream) {
-  if (!h || !poses || !thetas || !elbows) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null argument");
   if (n < 0 || K < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
     return fail_arg(R2IK_ERR_ARG, "r2ik_elbow_positions_f64: bad n, K or pose_kind");
+  if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null handle");
   if (n == 0 || K == 0) return 0;
+  if (!poses || !thetas || !elbows) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null argument");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
@@ -449,10 +452,11 @@ int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, 
 int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n, const double *prev_joints,
                           const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
                           uint8_t *emergency, void *stream) {
-  if (!h || !par || !M || !prev_joints || !current_joints || !joints || !reachable || !state)
-    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null argument");
+  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null handle or parameters");
   if (n < 0 || par->nb_search_points < 2) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_f64: bad n or nb_search_points");
   if (n == 0) return 0;
+  if (!M || !prev_joints || !current_joints || !joints || !reachable || !state)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null argument");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   k_ctl_discrete<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints, joints,
                                                                         reachable, state, emergency);
@@ -463,11 +467,12 @@ int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double 
 int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
                             const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
                             uint8_t *reachable, uint8_t *state, void *stream) {
-  if (!h || !par || !M || !current_joints || !current_pose || !st || !joints || !reachable || !state)
-    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_f64: null argument");
+  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_f64: null handle or parameters");
   if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_f64: bad T, W or nb_search_points_continuous");
   if (T == 0 || W == 0) return 0;
+  if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_f64: null argument");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   k_ctl_continuous<<<blocks_for(T), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
                                                                           joints, reachable, state);

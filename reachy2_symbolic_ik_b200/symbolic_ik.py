@@ -159,6 +159,78 @@ class SymbolicIK:
             _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), C.c_void_p(s))
         _native.check(rc, "r2ik_symik_solve_f64")
 
+    # ------------------------------------------------------------------ host-buffer pipeline
+    def alloc_host_outputs(self, n: int) -> BatchResult:
+        """Pinned host output buffers for ``is_reachable_batch_host`` (reusable across calls)."""
+        torch = self._torch
+        return BatchResult(
+            reachable=torch.empty(n, dtype=torch.uint8).pin_memory(),
+            theta_interval=torch.empty((n, 2), dtype=torch.float64).pin_memory(),
+            state=torch.empty(n, dtype=torch.uint8).pin_memory(),
+            joints=torch.empty((n, 7), dtype=torch.float64).pin_memory(),
+            elbow=torch.empty((n, 3), dtype=torch.float64).pin_memory())
+
+    def is_reachable_batch_host(self, poses_host, out: Optional[BatchResult] = None, chunk: int = 1 << 17,
+                                n_streams: int = 3) -> BatchResult:
+        """Host-to-host batched solve: ``poses_host`` is a CPU tensor (N,16)/(N,4,4)/(N,6)/(N,2,3),
+        ideally pinned; results land in ``out`` (pinned CPU tensors; ``reachable`` is uint8 0/1).
+        The batch is cut into chunks that flow H2D -> K1 -> D2H on ``n_streams`` CUDA streams so the
+        PCIe copies in both directions overlap the kernel.  Synchronous on return."""
+        torch = self._torch
+        if not hasattr(poses_host, "is_cuda"):
+            poses_host = torch.from_numpy(np.ascontiguousarray(poses_host, dtype=np.float64))
+        shp = tuple(poses_host.shape)
+        k = 16 if (shp[1:] == (4, 4) or shp[1:] == (16,)) else 6
+        if k == 6 and shp[1:] not in ((2, 3), (6,)):
+            raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6); got {shp}")
+        kind = _abi.POSE_MAT4 if k == 16 else _abi.POSE_EULER6
+        P = poses_host.reshape(shp[0], k)
+        n = shp[0]
+        if out is None:
+            out = self.alloc_host_outputs(n)
+        with torch.cuda.device(self._device):
+            pipe = self._pipeline(chunk, n_streams, k)
+            cur = torch.cuda.current_stream(self._device)
+            for s in pipe["streams"]:
+                s.wait_stream(cur)
+            for ci, lo in enumerate(range(0, n, chunk)):
+                hi = min(n, lo + chunk)
+                m = hi - lo
+                slot = ci % n_streams
+                s = pipe["streams"][slot]
+                b = pipe["bufs"][slot]
+                with torch.cuda.stream(s):
+                    b["poses"][:m].copy_(P[lo:hi], non_blocking=True)
+                    self.solve_into(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
+                                    b["elbow"], stream=s.cuda_stream)
+                    out.reachable[lo:hi].copy_(b["reach"][:m], non_blocking=True)
+                    out.state[lo:hi].copy_(b["state"][:m], non_blocking=True)
+                    out.theta_interval[lo:hi].copy_(b["interval"][:m], non_blocking=True)
+                    out.joints[lo:hi].copy_(b["joints"][:m], non_blocking=True)
+                    out.elbow[lo:hi].copy_(b["elbow"][:m], non_blocking=True)
+            for s in pipe["streams"]:
+                s.synchronize()
+        return out
+
+    def _pipeline(self, chunk: int, n_streams: int, k: int):
+        key = (chunk, n_streams, k)
+        cache = getattr(self, "_pipe_cache", None)
+        if cache is None:
+            cache = self._pipe_cache = {}
+        if key not in cache:
+            torch = self._torch
+            d = self._device
+            cache[key] = {
+                "streams": [torch.cuda.Stream(device=d) for _ in range(n_streams)],
+                "bufs": [dict(poses=torch.empty((chunk, k), dtype=torch.float64, device=d),
+                              reach=torch.empty(chunk, dtype=torch.uint8, device=d),
+                              state=torch.empty(chunk, dtype=torch.uint8, device=d),
+                              interval=torch.empty((chunk, 2), dtype=torch.float64, device=d),
+                              joints=torch.empty((chunk, 7), dtype=torch.float64, device=d),
+                              elbow=torch.empty((chunk, 3), dtype=torch.float64, device=d)) for _ in range(n_streams)],
+            }
+        return cache[key]
+
     def is_reachable_no_limits_batch(self, poses, theta):
         """``is_reachable_no_limits`` + ``get_joints(theta)``: returns (joints (N,7), elbow (N,3))."""
         torch = self._torch

@@ -118,7 +118,10 @@ def test_continuous_golden(controls, oracle, arm, variant):
     want_j, want_f, want_s = g[pre + "joints"], g[pre + "reachable"], g[pre + "state"]
     T, W = want_j.shape[:2]
     M = np.ascontiguousarray(g["M"][:T])
-    ctl = controls[variant == "dvt"]
+    from reachy2_symbolic_ik_b200 import ControlIK
+
+    # fresh controller: previous_pose / previous_sol are per-instance state, like the reference's
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf", is_dvt=(variant == "dvt"))
     kw = {}
     if variant == "cj":
         kw = dict(current_joints=g["cj_current_joints"], current_pose=g["cj_current_pose"])
@@ -136,8 +139,10 @@ def test_continuous_golden(controls, oracle, arm, variant):
 def test_continuous_resume_is_identical(controls):
     """Chunked trajectories (state struct passed back in) reproduce the one-shot result bit for bit."""
     g = load("ctl_continuous_r_arm.npz")
+    from reachy2_symbolic_ik_b200 import ControlIK
+
     M = np.ascontiguousarray(g["M"])
-    ctl = controls[False]
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
     j_all, r_all, s_all, st_all = ctl.symbolic_inverse_kinematics_batch("r_arm", M, "continuous")
     W = M.shape[1]
     j1, r1, s1, st1 = ctl.symbolic_inverse_kinematics_batch("r_arm", M[:, : W // 3], "continuous")
@@ -156,7 +161,10 @@ def test_continuous_vs_oracle_many(controls, oracle, arm):
     params = urdf_params()
     ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=-1.01)
     wj, wr, ws, wst = oracle.ctl_continuous_batch(ocfg, oracle.ControlParams(arm=arm), M)
-    joints, reach, state, st = controls[False].symbolic_inverse_kinematics_batch(arm, M, "continuous")
+    from reachy2_symbolic_ik_b200 import ControlIK
+
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    joints, reach, state, st = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous")
     assert np.array_equal(reach, wr) and np.array_equal(state, ws)
     err = np.abs(joints - wj).reshape(256, -1).max(axis=1)
     # a trajectory is a recursion: an ill-conditioned waypoint would contaminate its tail
