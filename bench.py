@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the Reachy2 symbolic IK hot path on B200.
+"""bench.py -- benchmarks of the Reachy2 symbolic IK hot path on B200.
 
-Workload (BASELINE.json configs[1]): 1 M FK-sampled poses per arm (r_arm and l_arm), FP64,
-reachability flag + theta interval + 7 joints at theta_interval[0] + elbow position.  One *step*
-= one pass of K1 (`r2ik_symik_solve_f64`) over both arms' batches = 2 M solves per GPU.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload symik|discrete|continuous|reachmap]
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Default workload `symik` = BASELINE.json configs[1], the configuration the headline metric is quoted on:
+1 M FK-sampled poses per arm (r_arm and l_arm), FP64, reachability flag + theta interval + 7 joints at
+theta_interval[0] + elbow position.  One *step* = one pass of K1 (`r2ik_symik_solve_f64`) over both arms'
+batches = 2 M solves per GPU.  The other workloads are configs[2..4] (ControlIK discrete K=360, ControlIK
+continuous 65 536 x 1 000, reach map 256^3 x 512 with an NCCL all-reduce); they print the same JSON line.
 
-* own arm: `value` = poses/s with inputs resident in HBM (CUDA events on the launching stream,
-  max over ranks); `e2e` = the same metric through the public facade with pinned HOST buffers,
-  H2D and D2H copies inside the timed region; `roofline` / `roofline_fp64` for the K1 kernel;
-  `cpu_baseline` = the C oracle (a port of the reference algorithm) on the box's host cores.
-* `--impl reference`: the reference algorithm's CPU implementation (oracle port, OpenMP over all
-  host threads) on the same workload; the pure-Python reference itself cannot travel to the GPU
-  box (its measured speed in the build container is recorded in BASELINE.md / DESIGN.md).
-* N > 1: launched by torchrun, one rank per GPU, contiguous slices of the pose batch per rank,
-  no data-path collective (weak scaling: 2 M solves per GPU per step).
+* own arm: `value` = poses/s with inputs resident in HBM (CUDA events on the launching stream, max over
+  ranks); `e2e` = the same metric through the public facade with pinned HOST buffers, H2D and D2H copies inside
+  the timed region; `roofline` (HBM form) / `roofline_fp64` for the dominant kernel; `cpu_baseline` = the C oracle
+  (a port of the reference algorithm, OpenMP on all host threads) and, when `baseline/_ref` holds the installed
+  Python reference, the reference itself on a bounded sample with one process per core.
+* `--impl reference`: the reference algorithm's CPU implementation (oracle port, all host threads) on the same
+  workload; rank 0 only.
+* N > 1: launched by torchrun, one rank per GPU, contiguous slices of the batch per rank, no data-path collective
+  (weak scaling); the reach map shards orientations and all-reduces the count volume.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -32,14 +35,9 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-POSES_PER_ARM = 1_000_000
-ARMS = ("r_arm", "l_arm")
-SEEDS = {"r_arm": 1, "l_arm": 2}
-BYTES_IN = 128                              # row-major 4x4 float64 per pose
-BYTES_OUT = 1 + 1 + 16 + 56 + 24            # reachable, state, interval, joints, elbow
-FLOP_EQ_PER_SOLVE = 2100.0                  # weighted FP64 flop-equivalents
 METRIC = "ik_poses_per_sec"
 UNIT = "poses/s"
+ARMS = ("r_arm", "l_arm")
 
 
 def measured_peaks():
@@ -47,7 +45,7 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -72,7 +70,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -99,87 +97,468 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(rank: int):
-    """Synthetic FK-sampled poses, distinct per rank (contiguous slices of the global batch)."""
-    from reachy2_symbolic_ik_b200 import fk
+# =================================================================================================
+# Python reference (baseline/_ref, pip-installed unmodified) on a bounded sample, one process per core
+# =================================================================================================
+def _pyref_available():
+    return os.path.isdir(os.path.join(REPO, "baseline", "_ref", "reachy2_symbolic_ik"))
 
-    return {arm: fk.sample_fk_poses(POSES_PER_ARM, arm, seed=SEEDS[arm] + 1000 * rank) for arm in ARMS}
 
+def _pyref_worker(args):
+    kind, arm, poses = args
+    import contextlib
+    import io
+    import warnings
 
-def cpu_baseline(poses, repeats: int = 3):
-    """The oracle port on the host cores (all OpenMP threads) over the full per-GPU workload."""
-    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
+    warnings.filterwarnings("ignore")
+    with contextlib.redirect_stdout(io.StringIO()):
+        from reachy2_symbolic_ik.control_ik import ControlIK
+        from reachy2_symbolic_ik.symbolic_ik import SymbolicIK
+        from reachy2_symbolic_ik.utils import get_euler_from_homogeneous_matrix
 
-    cfgs = {arm: O.arm_config(arm) for arm in ARMS}
-    O.symik_batch(cfgs["r_arm"], poses["r_arm"][:20000])  # warm-up (thread pool, page-in)
-    best = float("inf")
-    for _ in range(repeats):
+        from reachy2_symbolic_ik_b200 import fk
+
         t0 = time.perf_counter()
+        if kind == "symik":
+            ik = SymbolicIK(arm=arm)
+            for M in poses:
+                goal = [M[:3, 3], get_euler_from_homogeneous_matrix(M)]
+                ok, itv, f, _ = ik.is_reachable(goal)
+                if ok:
+                    f(itv[0])
+        elif kind == "discrete":
+            ctl = ControlIK(urdf=open(fk.bundled_urdf_path()).read())
+            ctl.nb_search_points = 360
+            for M in poses:
+                ctl.symbolic_inverse_kinematics(arm, M, "discrete")
+        elif kind == "continuous":
+            for traj in poses:
+                ctl = ControlIK(urdf=open(fk.bundled_urdf_path()).read())
+                for M in traj:
+                    ctl.symbolic_inverse_kinematics(arm, M, "continuous")
+        return time.perf_counter() - t0
+
+
+def python_reference_baseline(kind: str, arm: str, poses: np.ndarray, units: int):
+    """poses: per-process work items are contiguous chunks.  Returns the `python_reference` sub-object."""
+    if not _pyref_available():
+        return None
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    chunks = [c for c in np.array_split(poses, cores) if len(c)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(chunks)) as pool:
+        busy = pool.map(_pyref_worker, [(kind, arm, c) for c in chunks])
+    wall = time.perf_counter() - t0
+    return {"value": units / max(busy), "unit": UNIT, "cores": len(chunks), "kind": "reference",
+            "per_core": units / sum(busy), "wall_s_incl_spawn": wall,
+            "sample": f"unmodified pollen-robotics/reachy2_symbolic_ik (baseline/_ref) {kind}, {units} {arm} poses split over "
+                      f"{len(chunks)} processes, numpy {np.__version__}"}
+
+
+# =================================================================================================
+# Workloads.  Each returns a dict of closures; all device work goes through the package facade / C ABI.
+# =================================================================================================
+class Symik:
+    """configs[1]"""
+    name = "symik"
+    POSES_PER_ARM = 1_000_000
+    SEEDS = {"r_arm": 1, "l_arm": 2}
+    BYTES_IN, BYTES_OUT = 128, 1 + 1 + 16 + 56 + 24
+    FLOP_EQ = 2100.0
+    kernel = "k_symik_solve<MAT4>"
+
+    def config(self, world):
+        n = self.POSES_PER_ARM
+        return {"workload": "configs[1]: 1M FK-sampled poses per arm (r_arm + l_arm), FP64, flag + theta interval + joints at "
+                            "theta_interval[0] + elbow, (N,4,4) pose input", "poses_per_step_per_gpu": 2 * n,
+                "global_poses_per_step": 2 * n * world, "pose_layout": "mat4_rowmajor_f64",
+                "l2_policy": "inputs+outputs per step (452 MB) exceed the 126 MB L2; the two arms' batches alternate",
+                "parallelism": f"pose-slices x{world}, no collective"}
+
+    def host_poses(self, rank):
+        from reachy2_symbolic_ik_b200 import fk
+
+        return {arm: fk.sample_fk_poses(self.POSES_PER_ARM, arm, seed=self.SEEDS[arm] + 1000 * rank) for arm in ARMS}
+
+    def setup(self, torch, dev, rank, world):
+        from reachy2_symbolic_ik_b200 import SymbolicIK, _abi
+
+        n = self.POSES_PER_ARM
+        self.poses = self.host_poses(rank)
+        self.solvers = {arm: SymbolicIK(arm=arm, device=dev.index) for arm in ARMS}
+        self.dpose = {arm: torch.from_numpy(self.poses[arm]).reshape(n, 16).to(dev) for arm in ARMS}
+        self.outs = {arm: dict(reach=torch.empty(n, dtype=torch.uint8, device=dev), state=torch.empty(n, dtype=torch.uint8, device=dev),
+                               interval=torch.empty((n, 2), dtype=torch.float64, device=dev),
+                               joints=torch.empty((n, 7), dtype=torch.float64, device=dev),
+                               elbow=torch.empty((n, 3), dtype=torch.float64, device=dev)) for arm in ARMS}
+        self.kind = _abi.POSE_MAT4
+        self.units_per_step = 2 * n
+        self.units_per_launch = n
+
+    def step(self):
         for arm in ARMS:
-            O.symik_batch(cfgs[arm], poses[arm])
-        best = min(best, time.perf_counter() - t0)
-    n = sum(len(poses[a]) for a in ARMS)
-    return {"value": n / best, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
-            "sample": f"full per-GPU workload ({n} poses: {POSES_PER_ARM} per arm), best of {repeats}, C oracle + OpenMP"}
+            o = self.outs[arm]
+            self.solvers[arm].solve_into(self.dpose[arm], self.kind, None, None, o["reach"], o["state"], o["interval"], o["joints"], o["elbow"])
+        return 2
+
+    def e2e_setup(self, torch):
+        n = self.POSES_PER_ARM
+        self.host_in = {arm: torch.from_numpy(self.poses[arm]).reshape(n, 16).pin_memory() for arm in ARMS}
+        self.host_out = {arm: self.solvers[arm].alloc_host_outputs(n) for arm in ARMS}
+        return {"h2d_bytes_per_step": 2 * n * self.BYTES_IN, "d2h_bytes_per_step": 2 * n * self.BYTES_OUT,
+                "path": "SymbolicIK.is_reachable_batch_host: pinned host -> chunked H2D / K1 / D2H on 3 streams"}
+
+    def e2e_step(self, torch):
+        for arm in ARMS:
+            self.solvers[arm].is_reachable_batch_host(self.host_in[arm], self.host_out[arm])
+
+    def e2e_check(self, torch):
+        assert torch.equal(self.host_out["r_arm"].joints[:1000].nan_to_num(), self.outs["r_arm"]["joints"][:1000].cpu().nan_to_num())
+
+    def parity(self, torch):
+        from oracle import oracle as O
+
+        m = 100_000
+        want = O.symik_batch(O.arm_config("r_arm"), self.poses["r_arm"][:m])
+        o = self.outs["r_arm"]
+        got_j, got_i, got_s = o["joints"][:m].cpu().numpy(), o["interval"][:m].cpu().numpy(), o["state"][:m].cpu().numpy()
+        ej, ei = np.abs(got_j - want[3]), np.abs(got_i - want[1])
+        return {"checked_poses": m, "state_mismatches": int((got_s != want[2]).sum()),
+                "max_abs_err_joints_rad": float(np.nanmax(ej)), "p99.9_abs_err_joints_rad": float(np.nanquantile(ej, 0.999)),
+                "max_abs_err_interval_rad": float(np.nanmax(ei)), "over_1e-9": int((np.nan_to_num(ej).max(axis=1) > 1e-9).sum()),
+                "vs": "CPU oracle (pinned to the reference by tests/golden)"}
+
+    def cpu_port(self, poses=None, repeats=3):
+        from oracle import oracle as O
+
+        if poses is None:
+            if not hasattr(self, "_cpu_data"):
+                self._cpu_data = self.host_poses(0)
+            poses = self._cpu_data
+        cfgs = {arm: O.arm_config(arm) for arm in ARMS}
+        O.symik_batch(cfgs["r_arm"], poses["r_arm"][:20000])  # warm-up (thread pool, page-in)
+        best = float("inf")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for arm in ARMS:
+                O.symik_batch(cfgs[arm], poses[arm])
+            best = min(best, time.perf_counter() - t0)
+        n = sum(len(poses[a]) for a in ARMS)
+        return n / best, best, O.max_threads(), f"full per-GPU workload ({n} poses: {self.POSES_PER_ARM} per arm), C oracle + OpenMP"
+
+    def pyref(self):
+        cores = os.cpu_count() or 1
+        m = 400 * cores
+        return python_reference_baseline("symik", "r_arm", self.poses["r_arm"][:m], m)
 
 
-def run_reference(args):
+class Discrete:
+    """configs[2]"""
+    name = "discrete"
+    N = 1_000_000
+    K = 360
+    BYTES_IN, BYTES_OUT = 128, 56 + 3
+    kernel = "k_ctl_discrete"
+
+    @property
+    def FLOP_EQ(self):
+        return 2700.0 + 100.0 * self.K
+
+    def config(self, world):
+        return {"workload": f"configs[2]: ControlIK discrete, 1M FK-sampled r_arm poses x {self.K} elbow-theta samples, in-kernel "
+                            "best-elbow selection + joints + safety checks", "poses_per_step_per_gpu": self.N,
+                "global_poses_per_step": self.N * world, "nb_search_points": self.K,
+                "l2_policy": "inputs+outputs per step (187 MB) exceed the 126 MB L2",
+                "parallelism": f"pose-slices x{world}, no collective"}
+
+    def setup(self, torch, dev, rank, world):
+        from reachy2_symbolic_ik_b200 import ControlIK, fk
+
+        self.poses = fk.sample_fk_poses(self.N, "r_arm", seed=3 + 1000 * rank)
+        self.ctl = ControlIK(urdf_path="../config_files/reachy2.urdf", device=dev.index)
+        self.ctl.nb_search_points = self.K
+        self.dM = torch.from_numpy(self.poses).reshape(self.N, 16).to(dev)
+        self.out = None
+        self.units_per_step = self.N
+        self.units_per_launch = self.N
+
+    def step(self):
+        self.out = self.ctl.symbolic_inverse_kinematics_batch("r_arm", self.dM, "discrete", out=self.out)
+        return 1
+
+    def e2e_setup(self, torch):
+        self.host_in = torch.from_numpy(self.poses).reshape(self.N, 16).pin_memory()
+        return {"h2d_bytes_per_step": self.N * self.BYTES_IN, "d2h_bytes_per_step": self.N * self.BYTES_OUT,
+                "path": "ControlIK.symbolic_inverse_kinematics_batch(host tensor): H2D, K2, D2H"}
+
+    def e2e_step(self, torch):
+        self.e2e_out = self.ctl.symbolic_inverse_kinematics_batch("r_arm", self.host_in, "discrete")
+
+    def e2e_check(self, torch):
+        assert np.array_equal(np.asarray(self.e2e_out[0][:1000]), self.out[0][:1000].cpu().numpy())
+
+    def _oracle(self, M):
+        from oracle import oracle as O
+        from reachy2_symbolic_ik_b200 import fk
+        from reachy2_symbolic_ik_b200.urdf import get_ik_parameters_from_urdf
+
+        params = get_ik_parameters_from_urdf(open(fk.bundled_urdf_path()).read(), ["r", "l"])
+        cfg = O.arm_config("r_arm", ik_parameters=params, singularity_offset=-1.01)
+        return O.ctl_discrete_batch(cfg, O.ControlParams(arm="r_arm", nb_search_points=self.K), M)
+
+    def parity(self, torch):
+        m = 50_000
+        wj, wr, ws, we = self._oracle(self.poses[:m])
+        j, r, s, e = (x[:m].cpu().numpy() for x in self.out)
+        ej = np.abs(j - wj)
+        return {"checked_poses": m, "state_mismatches": int((s != ws).sum()), "flag_mismatches": int((r != wr).sum()),
+                "max_abs_err_joints_rad": float(ej.max()), "p99.9_abs_err_joints_rad": float(np.quantile(ej, 0.999)),
+                "over_1e-9": int((ej.max(axis=1) > 1e-9).sum()), "vs": "CPU oracle (pinned to the reference by tests/golden)"}
+
+    def cpu_port(self, poses=None, repeats=2):
+        from oracle import oracle as O
+        from reachy2_symbolic_ik_b200 import fk
+
+        if poses is None:
+            if not hasattr(self, "_cpu_data"):
+                self._cpu_data = fk.sample_fk_poses(200_000, "r_arm", seed=3)
+            poses = self._cpu_data
+        M = poses[:200_000]
+        self._oracle(M[:5000])
+        best = float("inf")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            self._oracle(M)
+            best = min(best, time.perf_counter() - t0)
+        return len(M) / best, best, O.max_threads(), f"first {len(M)} poses of the workload, K={self.K}, C oracle + OpenMP"
+
+    def pyref(self):
+        cores = os.cpu_count() or 1
+        m = 40 * cores
+        return python_reference_baseline("discrete", "r_arm", self.poses[:m], m)
+
+
+class Continuous:
+    """configs[3]"""
+    name = "continuous"
+    T, W = 65_536, 1_000
+    BYTES_IN, BYTES_OUT = 128, 56 + 2
+    FLOP_EQ = 4500.0
+    kernel = "k_ctl_continuous"
+
+    def config(self, world):
+        return {"workload": f"configs[3]: ControlIK continuous, {self.T} trajectories x {self.W} waypoints (joint-space sinusoids "
+                            "through FK), joint continuity + multi-turn unwrapping", "poses_per_step_per_gpu": self.T * self.W,
+                "global_poses_per_step": self.T * self.W * world, "unit_note": "a pose = one waypoint",
+                "l2_policy": "inputs+outputs per step (12.2 GB) exceed the 126 MB L2",
+                "parallelism": f"trajectory-slices x{world}, no collective"}
+
+    def setup(self, torch, dev, rank, world):
+        from reachy2_symbolic_ik_b200 import ControlIK, fk
+
+        self.ctl = ControlIK(urdf_path="../config_files/reachy2.urdf", device=dev.index)
+        self.dM = fk.sinusoidal_trajectories_device(self.T, self.W, "r_arm", seed=4 + 1000 * rank, device=dev)
+        from reachy2_symbolic_ik_b200 import _abi
+
+        st0 = np.zeros(self.T, dtype=_abi.TRAJ_STATE_DTYPE)
+        st0["init"] = 1                       # every step replays the trajectories from a fresh controller
+        self.st0 = torch.from_numpy(st0.view(np.uint8).reshape(self.T, -1)).to(dev)
+        self.st = self.st0.clone()
+        self.out = None
+        self.units_per_step = self.T * self.W
+        self.units_per_launch = self.T * self.W
+
+    def step(self):
+        self.st.copy_(self.st0)
+        self.out = self.ctl.symbolic_inverse_kinematics_batch("r_arm", self.dM, "continuous", states=self.st, out=self.out)
+        return 1
+
+    def e2e_setup(self, torch):
+        # a bounded slice of the trajectories goes host -> device -> host each e2e step
+        self.e2e_T = 4096
+        self.host_in = self.dM[: self.e2e_T].cpu().pin_memory()
+        return {"h2d_bytes_per_step": self.e2e_T * self.W * self.BYTES_IN, "d2h_bytes_per_step": self.e2e_T * self.W * self.BYTES_OUT,
+                "path": f"ControlIK.symbolic_inverse_kinematics_batch(host tensor) on {self.e2e_T} of the trajectories per step",
+                "units_per_step": self.e2e_T * self.W}
+
+    def e2e_step(self, torch):
+        self.e2e_out = self.ctl.symbolic_inverse_kinematics_batch("r_arm", self.host_in, "continuous")
+
+    def e2e_check(self, torch):
+        assert np.array_equal(np.asarray(self.e2e_out[0][:16]), self.out[0][:16].cpu().numpy())
+
+    def _oracle(self, M):
+        from oracle import oracle as O
+        from reachy2_symbolic_ik_b200 import fk
+        from reachy2_symbolic_ik_b200.urdf import get_ik_parameters_from_urdf
+
+        params = get_ik_parameters_from_urdf(open(fk.bundled_urdf_path()).read(), ["r", "l"])
+        cfg = O.arm_config("r_arm", ik_parameters=params, singularity_offset=-1.01)
+        return O.ctl_continuous_batch(cfg, O.ControlParams(arm="r_arm"), M)
+
+    def parity(self, torch):
+        m = 64
+        M = self.dM[:m].cpu().numpy()
+        wj, wr, ws, _ = self._oracle(M)
+        j, r, s = (x[:m].cpu().numpy() for x in self.out[:3])
+        ej = np.abs(j - wj)
+        return {"checked_poses": m * self.W, "state_mismatches": int((s != ws).sum()), "flag_mismatches": int((r != wr).sum()),
+                "max_abs_err_joints_rad": float(ej.max()), "over_1e-9": int((ej.reshape(-1, 7).max(axis=1) > 1e-9).sum()),
+                "vs": "CPU oracle (pinned to the reference by tests/golden)"}
+
+    def cpu_port(self, poses=None, repeats=1):
+        from oracle import oracle as O
+        from reachy2_symbolic_ik_b200 import fk
+
+        Tn = 2048
+        if not hasattr(self, "_cpu_data"):
+            self._cpu_data = fk.sinusoidal_trajectories(Tn, self.W, "r_arm", seed=4)[0]
+        M = self._cpu_data
+        t0 = time.perf_counter()
+        self._oracle(M)
+        dt = time.perf_counter() - t0
+        return Tn * self.W / dt, dt, O.max_threads(), f"{Tn} trajectories x {self.W} waypoints, C oracle + OpenMP over trajectories"
+
+    def pyref(self):
+        cores = os.cpu_count() or 1
+        M = self.dM[:cores, :100].cpu().numpy()
+        return python_reference_baseline("continuous", "r_arm", M, cores * 100)
+
+
+class ReachMap:
+    """configs[4]"""
+    name = "reachmap"
+    N, N_ORI = 256, 512
+    BYTES_IN, BYTES_OUT = 0, 4.0 / 512
+    FLOP_EQ = 900.0 * 0.25   # ~25 % of the voxels pass the orientation-independent early-outs
+    kernel = "k_reach_map"
+
+    def config(self, world):
+        return {"workload": f"configs[4]: workspace reachability map, {self.N}^3 voxel grid x {self.N_ORI} orientations, per-voxel "
+                            "reachable counts; orientations sharded over ranks, one all-reduce of the uint32 volume",
+                "poses_per_step_per_gpu": self.N ** 3 * self.N_ORI // world, "global_poses_per_step": self.N ** 3 * self.N_ORI,
+                "l2_policy": "no input traffic (poses generated from indices); 64 MiB count volume written per step",
+                "parallelism": f"orientation-shards x{world} + NCCL all-reduce(sum, int32[{self.N}^3])" if world > 1 else "single GPU, no collective"}
+
+    scaling = "strong"
+
+    def setup(self, torch, dev, rank, world):
+        from reachy2_symbolic_ik_b200 import SymbolicIK, fk
+
+        self.ik = SymbolicIK(arm="r_arm", device=dev.index)
+        self.ori = torch.from_numpy(fk.fibonacci_orientations(self.N_ORI)).to(dev)
+        self.out = torch.empty((self.N,) * 3, dtype=torch.int32, device=dev)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            self.dist = dist
+        self.world = world
+        self.units_per_step = self.N ** 3 * self.N_ORI // world   # bench multiplies by world
+        self.units_per_launch = self.N ** 3 * self.N_ORI // world
+
+    def step(self):
+        self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out)
+        return 1
+
+    def e2e_setup(self, torch):
+        self.host_out = torch.empty((self.N,) * 3, dtype=torch.int32).pin_memory()
+        return {"h2d_bytes_per_step": self.N_ORI * 24, "d2h_bytes_per_step": self.N ** 3 * 4,
+                "path": "SymbolicIK.reach_map + D2H of the count volume"}
+
+    def e2e_step(self, torch):
+        self.ik.reach_map(n=self.N, orientations_euler=self.ori.cpu().numpy(), dist=self.dist, out=self.out)
+        self.host_out.copy_(self.out, non_blocking=True)
+
+    def e2e_check(self, torch):
+        torch.cuda.synchronize()
+        assert int(self.host_out.sum()) == int(self.out.sum())
+
+    def parity(self, torch):
+        from oracle import oracle as O
+        from reachy2_symbolic_ik_b200 import fk, workspace
+
+        n, no = 40, 32
+        ori = fk.fibonacci_orientations(no)
+        origin, step, dims = workspace.reach_grid(self.ik.shoulder_position, self.ik.max_arm_length, n)
+        got = self.ik.reach_map(n=n, orientations_euler=ori).cpu().numpy()
+        want = O.reach_map(O.arm_config("r_arm"), origin, step, dims, ori)
+        d = got.astype(np.int64) - want.astype(np.int64)
+        return {"checked_poses": n ** 3 * no, "voxels_differing": int((d != 0).sum()), "max_abs_count_diff": int(np.abs(d).max()),
+                "reachable_total": int(want.sum()), "full_map_reachable_total": int(self.out.sum().item()),
+                "vs": "CPU oracle on a 40^3 x 32 sub-problem"}
+
+    def cpu_port(self, poses=None, repeats=1):
+        from oracle import oracle as O
+        from reachy2_symbolic_ik_b200 import fk, workspace
+
+        n, no = 64, 64
+        ori = fk.fibonacci_orientations(no)
+        origin, step, dims = workspace.reach_grid([0.0, -0.2, 0.0], 0.66, n)
+        t0 = time.perf_counter()
+        O.reach_map(O.arm_config("r_arm"), origin, step, dims, ori)
+        dt = time.perf_counter() - t0
+        return n ** 3 * no / dt, dt, O.max_threads(), f"{n}^3 x {no} sub-grid of the same cube, C oracle + OpenMP, extrapolated linearly"
+
+    def pyref(self):
+        return None
+
+
+WORKLOADS = {w.name: w for w in (Symik, Discrete, Continuous, ReachMap)}
+
+
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle as O
-
-    poses = make_workload(0)
-    cfgs = {arm: O.arm_config(arm) for arm in ARMS}
-    n = sum(len(poses[a]) for a in ARMS)
+    # a bounded sample per step: one pass of the CPU port over the (sub)workload cpu_port() defines
+    vals, secs = [], []
+    sample = cores = None
     for _ in range(args.warmup):
-        for arm in ARMS:
-            O.symik_batch(cfgs[arm], poses[arm])
-    t0 = time.perf_counter()
+        wl.cpu_port(repeats=1)
     for _ in range(args.steps):
-        for arm in ARMS:
-            O.symik_batch(cfgs[arm], poses[arm])
-    dt = time.perf_counter() - t0
-    value = n * args.steps / dt
+        v, dt, cores, sample = wl.cpu_port(repeats=1)
+        vals.append(v); secs.append(dt)
+    value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
-                         "sample": f"{n} poses per step ({POSES_PER_ARM} per arm), C oracle port of the reference algorithm, OpenMP"},
+        "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
+        "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": wl.config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"per step: {sample}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference is pure Python (NumPy/SciPy) and is not installable on the GPU box; this arm times the "
-                "C port of its algorithm (oracle/) on all host threads. The Python reference itself measured "
-                "~590 poses/s/core in the build container (BASELINE.md).",
+        "note": "the reference is pure Python (NumPy/SciPy, single-threaded, ~590 poses/s/core); this arm times the C port of "
+                "its algorithm (oracle/, pinned to the reference's outputs by tests/golden) on all host threads -- a much "
+                "stronger CPU baseline than the reference itself.",
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_config(n_gpus: int):
-    return {"workload": "configs[1]: 1M FK-sampled poses per arm (r_arm + l_arm), FP64, flag + theta interval + joints at "
-                        "theta_interval[0] + elbow, (N,4,4) pose input", "poses_per_step_per_gpu": 2 * POSES_PER_ARM,
-            "global_poses_per_step": 2 * POSES_PER_ARM * n_gpus, "pose_layout": "mat4_rowmajor_f64",
-            "l2_policy": "inputs+outputs per step (452 MB) exceed the 126 MB L2; the two arms' batches alternate",
-            "parallelism": f"pose-slices x{n_gpus}, no collective"}
-
-
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="symik", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]()
+    default_steps = {"symik": 2000, "discrete": 50, "continuous": 5, "reachmap": 5}[wl.name]
+    default_warm = {"symik": 20, "discrete": 5, "continuous": 3, "reachmap": 3}[wl.name]
     if args.impl == "reference":
-        # one reference step is ~0.25 s of all host cores: bound the run to a few minutes
-        args.steps = min(args.steps, 20)
-        args.warmup = min(args.warmup, 2)
-        return run_reference(args)
+        # one reference step is a fraction of a second to a few seconds of all host cores: bound the run
+        args.steps = min(args.steps or 10, 20)
+        args.warmup = min(args.warmup if args.warmup is not None else 1, 2)
+        return run_reference(args, wl)
+    args.steps = args.steps or default_steps
+    args.warmup = max(args.warmup if args.warmup is not None else default_warm, 3)
 
     import torch
 
@@ -195,104 +574,81 @@ def main() -> int:
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from reachy2_symbolic_ik_b200 import SymbolicIK, _abi, _native
+    from reachy2_symbolic_ik_b200 import _native
 
     dev = torch.device("cuda", local_rank)
-    poses = make_workload(rank)
-    solvers = {arm: SymbolicIK(arm=arm, device=local_rank) for arm in ARMS}
-    n = POSES_PER_ARM
-    dpose = {arm: torch.from_numpy(poses[arm]).reshape(n, 16).to(dev) for arm in ARMS}
-    outs = {arm: dict(reach=torch.empty(n, dtype=torch.uint8, device=dev), state=torch.empty(n, dtype=torch.uint8, device=dev),
-                      interval=torch.empty((n, 2), dtype=torch.float64, device=dev),
-                      joints=torch.empty((n, 7), dtype=torch.float64, device=dev),
-                      elbow=torch.empty((n, 3), dtype=torch.float64, device=dev)) for arm in ARMS}
+    import contextlib
 
-    def step():
-        for arm in ARMS:
-            o = outs[arm]
-            solvers[arm].solve_into(dpose[arm], _abi.POSE_MAT4, None, None, o["reach"], o["state"], o["interval"], o["joints"], o["elbow"])
-        return 2  # kernel launches
+    with contextlib.redirect_stdout(sys.stderr):   # the facade prints like the reference ("Using default parameters")
+        wl.setup(torch, dev, rank, world)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
-        step()
+        wl.step()
     barrier()
     launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         ev0.record()
         for _ in range(args.steps):
-            launches += step()
+            launches += wl.step()
         ev1.record()
         barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    if dist is not None:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    poses_per_step = 2 * n * world
-    value = poses_per_step * args.steps / (ms_total * 1e-3)
-    kernel_ms = ms_total / launches  # the step is nothing but K1 launches: average launch duration
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    units_per_step = wl.units_per_step * world
+    value = units_per_step * args.steps / (ms_total * 1e-3)
+    kernel_ms = ms_total / launches  # a step is nothing but launches of the dominant kernel: average launch duration
 
     # ---- end to end through the public facade with pinned host buffers (copies inside the timed region)
-    host_in = {arm: torch.from_numpy(poses[arm]).reshape(n, 16).pin_memory() for arm in ARMS}
-    host_out = {arm: solvers[arm].alloc_host_outputs(n) for arm in ARMS}
+    e2e_info = wl.e2e_setup(torch)
+    e2e_units = e2e_info.pop("units_per_step", wl.units_per_step) * world
     for _ in range(2):
-        for arm in ARMS:
-            solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm])
+        wl.e2e_step(torch)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        for arm in ARMS:
-            solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm])
+        wl.e2e_step(torch)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = poses_per_step * e2e_steps / e2e_s
-    # the e2e results must be the device-resident results
-    chk = solvers["r_arm"].is_reachable_batch_host(host_in["r_arm"], host_out["r_arm"])
-    assert torch.equal(chk.joints[:1000].nan_to_num(), outs["r_arm"]["joints"][:1000].cpu().nan_to_num())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = e2e_units * e2e_steps / e2e_s
+    wl.e2e_check(torch)
 
-    # ---- parity spot check against the oracle on this rank's data (not timed)
-    parity = None
-    cpu = None
+    # ---- parity spot check against the oracle on this rank's data (not timed), CPU baselines
+    parity = cpu = None
     if rank == 0:
-        from oracle import oracle as O
-
-        m = 100_000
-        want = O.symik_batch(O.arm_config("r_arm"), poses["r_arm"][:m])
-        got_j = outs["r_arm"]["joints"][:m].cpu().numpy()
-        got_i = outs["r_arm"]["interval"][:m].cpu().numpy()
-        got_s = outs["r_arm"]["state"][:m].cpu().numpy()
-        ej = np.abs(got_j - want[3]); ei = np.abs(got_i - want[1])
-        parity = {"checked_poses": m, "state_mismatches": int((got_s != want[2]).sum()),
-                  "max_abs_err_joints_rad": float(np.nanmax(ej)), "p99.9_abs_err_joints_rad": float(np.nanquantile(ej, 0.999)),
-                  "max_abs_err_interval_rad": float(np.nanmax(ei)), "over_1e-9": int((np.nan_to_num(ej).max(axis=1) > 1e-9).sum()),
-                  "vs": "CPU oracle (pinned to the reference by tests/golden)"}
+        parity = wl.parity(torch)
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(poses)
+            v, dt, cores, sample = wl.cpu_port(getattr(wl, "poses", None))
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            try:
+                pr = wl.pyref()
+            except Exception as e:  # the installed reference is optional
+                pr = {"unavailable": repr(e)}
+            if pr is not None:
+                cpu["python_reference"] = pr
 
-    # ---- rooflines for the K1 kernel
+    # ---- rooflines for the dominant kernel
     hbm_peak, peak_src = measured_peaks()
-    solves_per_launch = n
-    alg_bytes = (BYTES_IN + BYTES_OUT) * solves_per_launch
+    alg_bytes = (wl.BYTES_IN + wl.BYTES_OUT) * wl.units_per_launch
     achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    import ctypes as C
-
     pms, pfl = C.c_double(), C.c_double()
     _native.check(_native.load().r2ik_dfma_probe(local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_dfma_probe")
     fp64_peak = pfl.value / (pms.value * 1e-3) / 1e12
-    fp64_ach = FLOP_EQ_PER_SOLVE * solves_per_launch / (kernel_ms * 1e-3) / 1e12
+    fp64_ach = wl.FLOP_EQ * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
     traffic = None
-    tp = os.path.join(REPO, "profiles", "k1_traffic.json")
+    tp = os.path.join(REPO, "profiles", f"{wl.name}_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
@@ -300,17 +656,16 @@ def main() -> int:
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * BYTES_IN, "d2h_bytes_per_step": 2 * n * BYTES_OUT,
-                    "steps": e2e_steps, "path": "SymbolicIK.is_reachable_batch_host: pinned host -> chunked H2D / K1 / D2H on 3 streams"},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, **e2e_info, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": traffic, "kernel": "k_symik_solve<MAT4>", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_solve": BYTES_IN + BYTES_OUT, "solves_per_launch": solves_per_launch, "peak_source": peak_src,
-                         "note": "K1 is FP64-pipe bound, not HBM bound: see roofline_fp64"},
+                         "traffic": traffic, "kernel": wl.kernel, "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_pose": wl.BYTES_IN + wl.BYTES_OUT, "poses_per_launch": wl.units_per_launch,
+                         "peak_source": peak_src, "note": "the kernel is FP64-pipe bound, not HBM bound: see roofline_fp64"},
             "roofline_fp64": {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
-                              "flop_eq_per_solve": FLOP_EQ_PER_SOLVE, "peak_source": "r2ik_dfma_probe measured in this run (DFMA chains, full grid)"},
+                              "flop_eq_per_pose": wl.FLOP_EQ, "peak_source": "r2ik_dfma_probe measured in this run (DFMA chains, full grid)"},
             "clocks": clocks.summary(), "parity": parity,
         }
         if cpu is not None:

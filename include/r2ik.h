@@ -31,6 +31,11 @@
  *        grid sweep of is_reachable (shape of src/benchmark/ik_comparison.py:137-181)
  *   r2ik_interval_limit
  *        interval_limit + l_arm mirroring          control_ik.py:225-252
+ *   r2ik_fk_f64
+ *        forward kinematics of the arm chain of config_files/reachy2.urdf (torso -> arm tip).
+ *        The reference has no FK of its own: its examples call the Reachy SDK's
+ *        (src/example/test_continuous_ik.py:146).  Used for synthetic FK-sampled poses and
+ *        the FK round-trip property tests.
  *
  * Conventions
  *   - All data pointers are DEVICE pointers unless a parameter says "host".
@@ -128,6 +133,14 @@ typedef struct R2ikTrajState {
   int32_t emergency_bits;
 } R2ikTrajState;
 
+/* Kinematic chain torso -> tip for r2ik_fk_f64: 7 revolute joints.  fixed[k] is the constant
+ * 3x4 row-major transform [R|t] between joint k-1 and joint k (fixed[7]: last joint -> tip),
+ * axis[k] the unit rotation axis of joint k in its own frame (URDF <origin>/<axis>). */
+typedef struct R2ikFkChain {
+  double fixed[8][12];
+  double axis[7][3];
+} R2ikFkChain;
+
 typedef struct r2ik_context *r2ik_handle;
 
 int r2ik_abi_version(void);
@@ -178,6 +191,10 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, 
 int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
                        const double *orientations_euler /* device, n_ori x 3 */, int32_t ori_begin,
                        int32_t ori_end, uint32_t *counts, void *stream);
+
+/* Forward kinematics: M[i] (row-major 4x4) = tip pose in the torso frame for joints[i] (7).
+ * chain: host pointer.  device: CUDA ordinal to launch on. */
+int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int64_t n, double *M, void *stream);
 
 /* FP64 FMA peak probe used by bench.py for the compute roofline: runs `iters` dependent
  * DFMA chains (8 per thread) on a full grid and returns elapsed ms / flop count. */

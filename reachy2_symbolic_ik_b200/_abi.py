@@ -71,6 +71,12 @@ class TrajState(C.Structure):
     ]
 
 
+class FkChain(C.Structure):
+    """R2ikFkChain: fixed 3x4 transforms between the 7 revolute joints (+ tip) and the joint axes."""
+
+    _fields_ = [("fixed", (C.c_double * 12) * 8), ("axis", (C.c_double * 3) * 7)]
+
+
 TRAJ_STATE_DTYPE = np.dtype(
     [
         ("previous_theta", "f8"),

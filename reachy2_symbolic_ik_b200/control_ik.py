@@ -153,7 +153,7 @@ class ControlIK:
     def symbolic_inverse_kinematics_batch(self, name: str, M, control_type: str = "discrete", current_joints=None,
                                           constrained_mode: str = "unconstrained", current_pose=None,
                                           d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
-                                          previous_joints=None, states=None):
+                                          previous_joints=None, states=None, out=None):
         """Batched ``symbolic_inverse_kinematics``.
 
         discrete:   M (N,4,4) -> joints (N,7), reachable (N,), state (N,) uint8, emergency bits (N,).
@@ -161,6 +161,9 @@ class ControlIK:
                     default ``self.previous_sol[name]``), like N independent reference calls.
         continuous: M (T,W,4,4) -> joints (T,W,7), reachable (T,W), state (T,W), states (T,) structured
                     array (``_abi.TRAJ_STATE_DTYPE``) that can be passed back to resume the trajectories.
+                    ``states`` may also be a CUDA uint8 tensor (T,80): it is then updated in place and
+                    returned as is (no host round trip).
+        ``out``: the tuple a previous call returned for CUDA input of the same shape; its tensors are reused.
         """
         torch = self._torch
         solver = self.symbolic_ik_solver[name]
@@ -174,40 +177,48 @@ class ControlIK:
                 Md = Md.reshape(n, 16)
                 prev = self._dev(self.previous_sol[name] if previous_joints is None else previous_joints, (7,))
                 cur = prev if current_joints is None else self._dev(current_joints, (7,))
-                joints = torch.empty((n, 7), dtype=torch.float64, device=self._device)
-                reach = torch.empty(n, dtype=torch.uint8, device=self._device)
-                state = torch.empty(n, dtype=torch.uint8, device=self._device)
-                emg = torch.empty(n, dtype=torch.uint8, device=self._device)
+                if out is not None and was_cuda:
+                    joints, reach, state, emg = out[0], out[1].view(torch.uint8), out[2], out[3]
+                else:
+                    joints = torch.empty((n, 7), dtype=torch.float64, device=self._device)
+                    reach = torch.empty(n, dtype=torch.uint8, device=self._device)
+                    state = torch.empty(n, dtype=torch.uint8, device=self._device)
+                    emg = torch.empty(n, dtype=torch.uint8, device=self._device)
                 rc = solver._handle.lib.r2ik_ctl_discrete_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(n),
                                                               _ptr(prev), _ptr(cur), _ptr(joints), _ptr(reach), _ptr(state),
                                                               _ptr(emg), stream)
                 _native.check(rc, "r2ik_ctl_discrete_f64")
-                out = (joints, reach.bool(), state, emg)
-                return out if was_cuda else tuple(x.cpu().numpy() for x in out)
+                res = (joints, reach.view(torch.bool), state, emg)
+                return res if was_cuda else tuple(x.cpu().numpy() for x in res)
             if control_type == "continuous":
                 T, W = Md.shape[0], Md.shape[1]
                 Md = Md.reshape(T, W, 16)
-                k = 0 if name.startswith("r") else 1
                 cj = torch.empty((T, 7), dtype=torch.float64, device=self._device)
                 cj[:] = self._dev(self.previous_sol[name] if current_joints is None else current_joints)
                 cp = torch.empty((T, 16), dtype=torch.float64, device=self._device)
                 cp[:] = self._dev(self.previous_pose[name] if current_pose is None else current_pose).reshape(-1, 16)
-                del k
-                if states is None:
-                    states = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
-                    states["init"] = 1
-                st = torch.from_numpy(np.ascontiguousarray(states).view(np.uint8).reshape(T, -1)).to(self._device)
-                joints = torch.empty((T, W, 7), dtype=torch.float64, device=self._device)
-                reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
-                state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
+                states_on_device = hasattr(states, "is_cuda") and states.is_cuda
+                if states_on_device:
+                    st = states
+                else:
+                    if states is None:
+                        states = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
+                        states["init"] = 1
+                    st = torch.from_numpy(np.ascontiguousarray(states).view(np.uint8).reshape(T, -1)).to(self._device)
+                if out is not None and was_cuda:
+                    joints, reach, state = out[0], out[1].view(torch.uint8), out[2]
+                else:
+                    joints = torch.empty((T, W, 7), dtype=torch.float64, device=self._device)
+                    reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
+                    state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                 rc = solver._handle.lib.r2ik_ctl_continuous_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T),
                                                                 C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st), _ptr(joints),
                                                                 _ptr(reach), _ptr(state), stream)
                 _native.check(rc, "r2ik_ctl_continuous_f64")
-                st_out = st.cpu().numpy().reshape(-1).view(_abi.TRAJ_STATE_DTYPE).copy()
-                out = (joints, reach.bool(), state)
-                out = out if was_cuda else tuple(x.cpu().numpy() for x in out)
-                return (*out, st_out)
+                st_out = st if states_on_device else st.cpu().numpy().reshape(-1).view(_abi.TRAJ_STATE_DTYPE).copy()
+                res = (joints, reach.view(torch.bool), state)
+                res = res if was_cuda else tuple(x.cpu().numpy() for x in res)
+                return (*res, st_out)
             raise ValueError(f"Unknown type {control_type}")
 
     # ------------------------------------------------------------------ scalar API (reference signature)

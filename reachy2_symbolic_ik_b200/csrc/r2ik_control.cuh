@@ -127,8 +127,9 @@ R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const 
     reachable = 0; state = R2IK_STATE_EMERGENCY;
     return;
   }
-  double pos[3], eul[3];
-  if (!pose_from_mat4(M, true, pos, eul)) {
+  double pos[3] = {M[3], M[7], M[11]};
+  double Rg[9];
+  if (!rotation_from_mat4(M, true, Rg)) {
     for (int i = 0; i < 7; ++i) joints[i] = NAN;
     reachable = 0; state = R2IK_STATE_INVALID_ROTATION;
     return;
@@ -139,12 +140,13 @@ R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const 
     for (int i = 0; i < 7; ++i) cs.previous_sol[i] = current_joints[i];
     cs.has_previous_sol = 1;
     cs.init = 1;
-    double cpos[3], ceul[3];
-    pose_from_mat4(current_pose, true, cpos, ceul);
-    is_reachable<true>(A, cpos, ceul, S);
+    double cpos[3] = {current_pose[3], current_pose[7], current_pose[11]};
+    rotation_from_mat4(current_pose, true, S.R);
+    is_reachable_R<true>(A, cpos, S);
     cs.previous_theta = best_theta_to_current_joints(A, S, current_joints, par.preferred_theta);
   }
-  Reach rc = is_reachable<false>(A, pos, eul, S);
+  for (int i = 0; i < 9; ++i) S.R[i] = Rg[i];
+  Reach rc = is_reachable_R<false>(A, pos, S);
   bool ok = rc.state == R2IK_STATE_REACHABLE;
   double theta;
   if (ok) {                                                  // ctl:338-366
@@ -153,7 +155,7 @@ R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const 
     if (ok) theta = step_toward(goal, cs.previous_theta, par.d_theta_max);
     else { theta = cs.previous_theta; st_out = R2IK_STATE_LIMITED_BY_SHOULDER; }
   } else {                                                   // ctl:368-388
-    is_reachable<true>(A, pos, eul, S);
+    is_reachable_R<true>(A, pos, S);
     theta = step_toward(par.preferred_theta, cs.previous_theta, par.d_theta_max);
     st_out = rc.state;
   }

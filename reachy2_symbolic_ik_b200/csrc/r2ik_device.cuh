@@ -59,6 +59,28 @@ struct ArmConst {
 // Python / NumPy scalar semantics
 // ---------------------------------------------------------------------------------------
 
+// 1/sqrt(x): one MUFU.RSQ64H + Newton steps on the device (about 1 ulp).
+R2IK_HD double rsqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// (c, s) = (cos a, sin a) for a = atan2(y, x), without evaluating the angle: the reference builds
+// its elementary frame rotations as from_euler(atan2(...)) (sik:758-829); x/h, y/h equal
+// cos/sin of that angle to ~1 ulp.  Degenerate (0, 0) / underflowing inputs take the literal route.
+R2IK_HD void cs_of_atan2(double y, double x, double &c, double &s) {
+  double h2 = x * x + y * y;
+  if (h2 > 1e-280 && h2 < 1e280) {
+    double ih = rsqrt_fast(h2);
+    c = x * ih; s = y * ih;
+  } else {
+    sincos(atan2(y, x), &s, &c);
+  }
+}
+
 // Python float `%`: fmod is exact; the result takes the sign of the divisor.
 R2IK_HD double pymod(double a, double m) {
   double r = fmod(a, m);
@@ -343,10 +365,9 @@ R2IK_HD void wrist_from_goal(const ArmConst &A, const double p[3], const double 
 // sik:337-349 reduce_goal_pose_no_limits: wrist pulled radially to distance d_target;
 // the same displacement is applied to the goal.
 R2IK_HD void reduce_goal(const ArmConst &A, double p[3], double w[3], double d, double d_target) {
-  double den = fabs(d) + A.proj_margin;
+  double sc = d_target / (fabs(d) + A.proj_margin);
   for (int k = 0; k < 3; ++k) {
-    double dir = (w[k] - A.s[k]) / den;
-    double nw = A.s[k] + dir * d_target;
+    double nw = A.s[k] + (w[k] - A.s[k]) * sc;
     p[k] = p[k] + (nw - w[k]);
     w[k] = nw;
   }
@@ -359,10 +380,11 @@ R2IK_HD bool elbow_circle(const ArmConst &A, Solve &S, double n[3]) {
   if (d > A.L12) return false;
   double d2 = d * d;
   double k = d2 - A.L2sq + A.L1sq;
-  double inv2d = 1.0 / (2.0 * d);
+  double invd = 1.0 / d;
+  double inv2d = 0.5 * invd;
   S.r = inv2d * sqrt(4.0 * d2 * A.L1sq - k * k);
-  double cd = k / (2.0 * d);
-  n[0] = Px / d; n[1] = Py / d; n[2] = Pz / d;
+  double cd = k * inv2d;
+  n[0] = Px * invd; n[1] = Py * invd; n[2] = Pz * invd;
   S.c[0] = n[0] * cd + A.s[0];
   S.c[1] = n[1] * cd + A.s[1];
   S.c[2] = n[2] * cd + A.s[2];
@@ -373,7 +395,10 @@ R2IK_HD bool elbow_circle(const ArmConst &A, Solve &S, double n[3]) {
 struct Reach {
   int state;        // R2IK_STATE_*
   double i0, i1;    // theta interval (i0 > i1 means wrapped); NaN when unreachable
+  double c0, s0;    // cos(i0), sin(i0): lets get_joints(theta_interval[0]) skip a sincos
 };
+
+constexpr double kSinMinusPi = -1.2246467991473532e-16;  // np.sin(-np.pi)
 
 // sik:284-307 is_pose_in_robot_reach: out-of-reach projection and backward clamp of the goal
 // position.  Returns -1 when the pose passes, else the reference's state code.
@@ -382,10 +407,10 @@ R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &p
   double dx = px - A.s[0], dy = py - A.s[1], dz = pz - A.s[2];
   double dg = sqrt(dx * dx + dy * dy + dz * dz);
   if (dg > A.max_arm_length) {
-    double den = dg + A.proj_margin;
-    px = A.s[0] + (dx / den) * A.max_arm_length;
-    py = A.s[1] + (dy / den) * A.max_arm_length;
-    pz = A.s[2] + (dz / den) * A.max_arm_length;
+    double sc = A.max_arm_length / (dg + A.proj_margin);
+    px = A.s[0] + dx * sc;
+    py = A.s[1] + dy * sc;
+    pz = A.s[2] + dz * sc;
     pre_state = R2IK_STATE_POSE_OUT_OF_REACH;
   }
   if (px < A.backward_limit) {
@@ -402,7 +427,7 @@ R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &p
 template <bool NO_LIMITS, bool FLAG_ONLY>
 R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
   Reach out;
-  out.i0 = NAN; out.i1 = NAN;
+  out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN;
   wrist_from_goal(A, S.p, S.R, S.w);
   // --- sik:146-153 / sik:94-98 keep the wrist in front of the torso plane
   if (S.w[0] < A.backward_limit) {
@@ -430,12 +455,15 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
     double c0[3];
     rmfv_columns(n[0], n[1], n[2], false, c0, S.a1, S.a2);    // sik:454, sik:686
   }
-  if (NO_LIMITS) { out.state = R2IK_STATE_REACHABLE; out.i0 = -kPi; out.i1 = kPi; return out; }
+  if (NO_LIMITS) {
+    out.state = R2IK_STATE_REACHABLE; out.i0 = -kPi; out.i1 = kPi; out.c0 = -1.0; out.s0 = kSinMinusPi;
+    return out;
+  }
 
   // --- sik:401-416 wrist-limit circle, relative to the wrist: centre p1 = n1 * hL
   double nLx = S.w[0] - S.p[0], nLy = S.w[1] - S.p[1], nLz = S.w[2] - S.p[2];
-  double nLn = sqrt(nLx * nLx + nLy * nLy + nLz * nLz);
-  double n1[3] = {nLx / nLn, nLy / nLn, nLz / nLn};
+  double inLn = rsqrt_fast(nLx * nLx + nLy * nLy + nLz * nLz);
+  double n1[3] = {nLx * inLn, nLy * inLn, nLz * inLn};
   double p1[3] = {n1[0] * A.hL, n1[1] * A.hL, n1[2] * A.hL};
   double p2[3] = {S.c[0] - S.w[0], S.c[1] - S.w[1], S.c[2] - S.w[2]};
   // column 0 of rotation_matrix_from_vector(nL): only the x row of T_limitation_torso is used
@@ -458,8 +486,8 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
     v[0] = n1[1] * n2[2] - n1[2] * n2[1];
     v[1] = n1[2] * n2[0] - n1[0] * n2[2];
     v[2] = n1[0] * n2[1] - n1[1] * n2[0];
-    double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    v[0] /= nv; v[1] /= nv; v[2] /= nv;
+    double inv = rsqrt_fast(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
     double e1[3] = {v[1] * n1[2] - v[2] * n1[1], v[2] * n1[0] - v[0] * n1[2], v[0] * n1[1] - v[1] * n1[0]};
     double e2[3] = {v[1] * n2[2] - v[2] * n2[1], v[2] * n2[0] - v[0] * n2[2], v[0] * n2[1] - v[1] * n2[0]};
     double b[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
@@ -483,19 +511,27 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
     } else {
       // sik:511-568 angles of the intersection points in the elbow-circle frame
       double sq = sqrt(disc);
-      double ta = (disc == 0) ? (-qb / (2.0 * qa)) : ((-qb + sq) / (2.0 * qa));
+      double inv2a = 1.0 / (2.0 * qa);
+      double ta = (disc == 0) ? (-qb * inv2a) : ((-qb + sq) * inv2a);
       double Pa[3] = {q[0] + ta * v[0] - p2[0], q[1] + ta * v[1] - p2[1], q[2] + ta * v[2] - p2[2]};
-      double ang1 = atan2(S.a2[0] * Pa[0] + S.a2[1] * Pa[1] + S.a2[2] * Pa[2],
-                          S.a1[0] * Pa[0] + S.a1[1] * Pa[1] + S.a1[2] * Pa[2]);
+      double ya = S.a2[0] * Pa[0] + S.a2[1] * Pa[1] + S.a2[2] * Pa[2];
+      double xa = S.a1[0] * Pa[0] + S.a1[1] * Pa[1] + S.a1[2] * Pa[2];
+      double ang1 = atan2(ya, xa);
       if (disc == 0) {
         out.state = R2IK_STATE_REACHABLE; out.i0 = ang1; out.i1 = ang1;
+        cs_of_atan2(ya, xa, out.c0, out.s0);
         return out;
       }
-      double tb = (-qb - sq) / (2.0 * qa);
+      double tb = (-qb - sq) * inv2a;
       double Pb[3] = {q[0] + tb * v[0] - p2[0], q[1] + tb * v[1] - p2[1], q[2] + tb * v[2] - p2[2]};
-      double ang2 = atan2(S.a2[0] * Pb[0] + S.a2[1] * Pb[1] + S.a2[2] * Pb[2],
-                          S.a1[0] * Pb[0] + S.a1[1] * Pb[1] + S.a1[2] * Pb[2]);
-      if (ang2 < ang1) { double tmp = ang1; ang1 = ang2; ang2 = tmp; }
+      double yb = S.a2[0] * Pb[0] + S.a2[1] * Pb[1] + S.a2[2] * Pb[2];
+      double xb = S.a1[0] * Pb[0] + S.a1[1] * Pb[1] + S.a1[2] * Pb[2];
+      double ang2 = atan2(yb, xb);
+      if (ang2 < ang1) {
+        double tmp = ang1; ang1 = ang2; ang2 = tmp;
+        tmp = ya; ya = yb; yb = tmp;
+        tmp = xa; xa = xb; xb = tmp;
+      }
       double sm, cm;
       sincos((ang1 + ang2) / 2.0, &sm, &cm);
       double yc = cm * S.r, zc = sm * S.r;
@@ -504,32 +540,46 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
                       S.a1[2] * yc + S.a2[2] * zc + p2[2] - p1[2]};
       double xl = l0[0] * Tm[0] + l0[1] * Tm[1] + l0[2] * Tm[2];
       out.state = R2IK_STATE_REACHABLE;
-      if (xl > 0) { out.i0 = ang1; out.i1 = ang2; } else { out.i0 = ang2; out.i1 = ang1; }
+      if (xl > 0) { out.i0 = ang1; out.i1 = ang2; cs_of_atan2(ya, xa, out.c0, out.s0); }
+      else { out.i0 = ang2; out.i1 = ang1; cs_of_atan2(yb, xb, out.c0, out.s0); }
       return out;
     }
   }
-  if (linked_full) { out.state = R2IK_STATE_REACHABLE; out.i0 = -kPi; out.i1 = kPi; }
+  if (linked_full) { out.state = R2IK_STATE_REACHABLE; out.i0 = -kPi; out.i1 = kPi; out.c0 = -1.0; out.s0 = kSinMinusPi; }
   else out.state = R2IK_STATE_LIMITED_BY_WRIST;
   return out;
 }
 
-// sik:121-282 is_reachable / sik:85-119 is_reachable_no_limits from the reference's goal_pose
-// (position, xyz euler).  Fills S for get_joints / elbow_position.
+// sik:121-282 is_reachable / sik:85-119 is_reachable_no_limits for a goal position and a goal
+// rotation matrix already stored in S.R.  Fills S for get_joints / elbow_position.
 template <bool NO_LIMITS>
-R2IK_HD Reach is_reachable(const ArmConst &A, const double pos[3], const double eul[3], Solve &S) {
+R2IK_HD Reach is_reachable_R(const ArmConst &A, const double pos[3], Solve &S) {
   double px = pos[0], py = pos[1], pz = pos[2];
   int pre_state = reach_prechecks(A, px, py, pz);
   if (!NO_LIMITS && pre_state >= 0) {
     Reach out;
-    out.state = pre_state; out.i0 = NAN; out.i1 = NAN;
+    out.state = pre_state; out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN;
     return out;
   }
   S.p[0] = px; S.p[1] = py; S.p[2] = pz;
-  rot_from_euler_xyz(eul[0], eul[1], eul[2], S.R);
   return solve_core<NO_LIMITS, false>(A, S);
 }
 
-// sik:684-695 get_elbow_position
+// The same from the reference's goal_pose (position, xyz euler).
+template <bool NO_LIMITS>
+R2IK_HD Reach is_reachable(const ArmConst &A, const double pos[3], const double eul[3], Solve &S) {
+  rot_from_euler_xyz(eul[0], eul[1], eul[2], S.R);
+  return is_reachable_R<NO_LIMITS>(A, pos, S);
+}
+
+// sik:684-695 get_elbow_position, from (cos theta, sin theta)
+R2IK_HD void elbow_position_cs(const Solve &S, double ct, double st, double E[3]) {
+  double y = S.r * ct, z = S.r * st;
+  E[0] = S.a1[0] * y + S.a2[0] * z + S.c[0];
+  E[1] = S.a1[1] * y + S.a2[1] * z + S.c[1];
+  E[2] = S.a1[2] * y + S.a2[2] * z + S.c[2];
+}
+
 R2IK_HD void elbow_position(const Solve &S, double theta, double E[3]) {
   double st, ct;
   sincos(theta, &st, &ct);
@@ -571,15 +621,19 @@ R2IK_HD P3 to_shoulder(const ArmConst &A, const double X[3]) {
 // sik:697-863 get_joints.  Mutates S like the reference when the elbow projection fires
 // (sik:708-718: goal_pose, elbow_position, wrist_position).  prev0 / prev2 are
 // previous_joints[0] / [2], used only at the exact-zero singularities (sik:751, 782).
-R2IK_HD void get_joints(const ArmConst &A, Solve &S, double theta, double prev0, double prev2, double joints[7], double E[3]) {
-  elbow_position(S, theta, E);
+// (ct, st) = (cos theta, sin theta).  The reference's frame rotations R(+-joint angle) are
+// applied from the (cos, sin) of the atan2 that defines the joint (cs_of_atan2): the seven
+// atan2 that produce the outputs are then off the dependent chain.
+R2IK_HD void get_joints_cs(const ArmConst &A, Solve &S, double ct, double st, double prev0, double prev2, double joints[7],
+                           double E[3]) {
+  elbow_position_cs(S, ct, st, E);
   if (E[2] > (E[0] - A.es[0]) * A.sing_coeff + A.es[2] - A.sing_offset) {
     // sik:647-682 make_elbow_projection with the plane constants hoisted to the host
     double dist = (E[0] - A.plP[0]) * A.plV[0] + (E[1] - A.plP[1]) * A.plV[1] + (E[2] - A.plP[2]) * A.plV[2];
     double vc[3] = {E[0] - dist * A.plV[0] - A.plC[0], E[1] - dist * A.plV[1] - A.plC[1], E[2] - dist * A.plV[2] - A.plC[2]};
-    double nvc = sqrt(vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2]);
+    double sc = A.plRho * rsqrt_fast(vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2]);
     for (int k = 0; k < 3; ++k) {
-      double ne = A.plC[k] + A.plRho * (vc[k] / nvc);
+      double ne = A.plC[k] + vc[k] * sc;
       S.p[k] = S.p[k] + (ne - E[k]);
       E[k] = ne;
     }
@@ -593,32 +647,45 @@ R2IK_HD void get_joints(const ArmConst &A, Solve &S, double theta, double prev0,
   P3 el = to_shoulder(A, E), wr = to_shoulder(A, S.w), tp = to_shoulder(A, tipw), pt = to_shoulder(A, ptw);
   double s, c;
 
-  // sik:751-755 shoulder pitch
-  double shoulder_pitch = (el.x == 0 && el.z == 0) ? prev0 : -atan2(el.z, el.x);
-  sincos(-shoulder_pitch, &s, &c);                 // sik:758 R_y(-shoulder_pitch)
+  // sik:751-755 shoulder pitch; sik:758 R_y(-shoulder_pitch)
+  double shoulder_pitch;
+  if (el.x == 0 && el.z == 0) { shoulder_pitch = prev0; sincos(-shoulder_pitch, &s, &c); }
+  else { shoulder_pitch = -atan2(el.z, el.x); cs_of_atan2(el.z, el.x, c, s); }
   rot_y(el, c, s); rot_y(wr, c, s); rot_y(tp, c, s); rot_y(pt, c, s);
-  // sik:766 shoulder roll
+  // sik:766 shoulder roll; sik:769 R_z(-shoulder_roll)
   double shoulder_roll = atan2(el.y, el.x);
-  sincos(-shoulder_roll, &s, &c);                  // sik:769 R_z(-shoulder_roll)
+  cs_of_atan2(-el.y, el.x, c, s);
   rot_z(wr, c, s); rot_z(tp, c, s); rot_z(pt, c, s);
   wr.x -= A.L1; tp.x -= A.L1; pt.x -= A.L1;        // sik:776-777 elbow frame
-  // sik:782-786 elbow yaw (not wrapped: range (-3pi/2, pi/2])
-  double elbow_yaw = (wr.y == 0 && wr.z == 0) ? prev2 : (-kHalfPi + atan2(wr.z, -wr.y));
-  sincos(elbow_yaw, &s, &c);                       // sik:789 R_x(elbow_yaw)
+  // sik:782-786 elbow yaw (not wrapped: range (-3pi/2, pi/2]); sik:789 R_x(elbow_yaw):
+  // cos(-pi/2 + a) = sin a, sin(-pi/2 + a) = -cos a with a = atan2(wr.z, -wr.y)
+  double elbow_yaw;
+  if (wr.y == 0 && wr.z == 0) { elbow_yaw = prev2; sincos(elbow_yaw, &s, &c); }
+  else {
+    elbow_yaw = -kHalfPi + atan2(wr.z, -wr.y);
+    double ca, sa;
+    cs_of_atan2(wr.z, -wr.y, ca, sa);
+    c = sa; s = -ca;
+  }
   rot_x(wr, c, s); rot_x(tp, c, s); rot_x(pt, c, s);
-  // sik:797 elbow pitch
+  // sik:797 elbow pitch; sik:800 R_y(-elbow_pitch)
   double elbow_pitch = -atan2(wr.z, wr.x);
-  sincos(-elbow_pitch, &s, &c);                    // sik:800 R_y(-elbow_pitch)
+  cs_of_atan2(wr.z, wr.x, c, s);
   rot_y(tp, c, s); rot_y(pt, c, s);
   tp.x -= A.L2; pt.x -= A.L2;                      // sik:805-806 wrist frame
-  // sik:815-817 wrist roll
+  // sik:815-817 wrist roll = pi - atan2(tp.y, -tp.x); sik:820 R_z(-wrist_roll):
+  // cos(-(pi - a)) = -cos a, sin(-(pi - a)) = -sin a
   double wrist_roll = kPi - atan2(tp.y, -tp.x);
   if (wrist_roll > kPi) wrist_roll = wrist_roll - kTwoPi;
-  sincos(-wrist_roll, &s, &c);                     // sik:820 R_z(-wrist_roll)
+  {
+    double ca, sa;
+    cs_of_atan2(tp.y, -tp.x, ca, sa);
+    c = -ca; s = -sa;
+  }
   rot_z(tp, c, s); rot_z(pt, c, s);
-  // sik:826 wrist pitch
+  // sik:826 wrist pitch; sik:829 R_y(wrist_pitch)
   double wrist_pitch = atan2(tp.z, tp.x);
-  sincos(wrist_pitch, &s, &c);                     // sik:829 R_y(wrist_pitch)
+  cs_of_atan2(tp.z, tp.x, c, s);
   rot_y(pt, c, s);
   // (the x -= tip_z of sik:836-837 does not touch y, z)
   double wrist_yaw = -atan2(pt.y, pt.z);           // sik:848
@@ -627,6 +694,12 @@ R2IK_HD void get_joints(const ArmConst &A, Solve &S, double theta, double prev0,
   joints[4] = wrist_roll; joints[5] = -wrist_pitch; joints[6] = -wrist_yaw;
   if (joints[3] > A.elbow_limit) joints[3] = A.elbow_limit;     // sik:853-861
   if (joints[3] < -A.elbow_limit) joints[3] = -A.elbow_limit;
+}
+
+R2IK_HD void get_joints(const ArmConst &A, Solve &S, double theta, double prev0, double prev2, double joints[7], double E[3]) {
+  double st, ct;
+  sincos(theta, &st, &ct);
+  get_joints_cs(A, S, ct, st, prev0, prev2, joints, E);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -638,6 +711,40 @@ R2IK_HD bool pose_from_mat4(const double *M, bool snap, double pos[3], double eu
   pos[0] = M[3]; pos[1] = M[7]; pos[2] = M[11];
   if (snap && rotation_is_identity(M)) { eul[0] = 0.0; eul[1] = 0.0; eul[2] = 0.0; return true; }
   return euler_xyz_from_mat4(M, eul);
+}
+
+// Goal rotation the solver sees for a 4x4 input.  The reference converts M to xyz Euler angles
+// (from_matrix -> as_euler, utl:84-90) and every later use rebuilds the matrix from them
+// (from_euler, sik:420): for a rotation matrix that round trip is the identity up to rounding,
+// so an orthonormal (Gramian within 1e-13 of I), right-handed M outside scipy's gimbal-lock
+// band is used as it is.  Anything else -- scaled / skewed input that scipy projects or
+// normalises, |cos(pitch)| < 1e-5 where as_euler zeroes the third angle (rxp:1085-1099),
+// det <= 0 -- takes the literal route.  false <=> scipy raises (det <= 0).
+R2IK_HD bool rotation_from_mat4(const double *M, bool snap, double R[9]) {
+  if (snap && rotation_is_identity(M)) {
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    return true;
+  }
+  const double m[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+  bool direct = true;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 3; ++j) {
+      double g = m[3 * i] * m[3 * j] + m[3 * i + 1] * m[3 * j + 1] + m[3 * i + 2] * m[3 * j + 2];
+      double e = (i == j) ? 1.0 : 0.0;
+      if (!(fabs(g - e) <= 1e-13)) direct = false;
+    }
+  if (!(m[0] * m[0] + m[3] * m[3] > 1e-10)) direct = false;   // cos^2(pitch)
+  if (!(det3(m) > 0.0)) direct = false;
+  if (direct) {
+    for (int k = 0; k < 9; ++k) R[k] = m[k];
+    return true;
+  }
+  double e[3];
+  Quat q;
+  if (!quat_from_matrix(m, q)) return false;
+  quat_as_euler_xyz_extrinsic(q, e);
+  rot_from_euler_xyz(e[0], e[1], e[2], R);
+  return true;
 }
 
 }  // namespace r2ik

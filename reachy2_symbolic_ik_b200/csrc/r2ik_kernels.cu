@@ -21,6 +21,9 @@
 using namespace r2ik;
 
 #define R2IK_BLOCK 128
+#ifndef R2IK_K1_MINBLOCKS
+#define R2IK_K1_MINBLOCKS 4   // resident blocks / SM the register allocation of K1 is held to
+#endif
 
 // ---------------------------------------------------------------------------------------
 // vectorised global memory helpers
@@ -37,18 +40,20 @@ __device__ __forceinline__ void load_mat4(const double *__restrict__ M, double m
   m[12] = 0.0; m[13] = 0.0; m[14] = 0.0; m[15] = 1.0;
 }
 
+// Goal position + goal rotation matrix of pose i.  false <=> invalid rotation (det <= 0).
 template <int KIND>
-__device__ __forceinline__ bool load_pose(const double *__restrict__ poses, int64_t i, bool snap, double pos[3], double eul[3]) {
+__device__ __forceinline__ bool load_pose(const double *__restrict__ poses, int64_t i, bool snap, double pos[3], double R[9]) {
   if (KIND == R2IK_POSE_EULER6) {
     const double *p = poses + 6 * i;
     double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4);
     pos[0] = a.x; pos[1] = a.y; pos[2] = b.x;
-    eul[0] = b.y; eul[1] = c.x; eul[2] = c.y;
+    rot_from_euler_xyz(b.y, c.x, c.y, R);
     return true;
   } else {
     double m[16];
     load_mat4(poses + 16 * i, m);
-    return pose_from_mat4(m, snap, pos, eul);
+    pos[0] = m[3]; pos[1] = m[7]; pos[2] = m[11];
+    return rotation_from_mat4(m, snap, R);
   }
 }
 
@@ -60,7 +65,7 @@ __device__ __forceinline__ void store_nan(double *p, int n) {
 // K1: SymbolicIK.is_reachable + theta_to_joints
 // ---------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(R2IK_BLOCK)
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
 k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ theta,
               const double *__restrict__ prev_joints, int64_t n, uint8_t *__restrict__ reachable,
               uint8_t *__restrict__ state, double *__restrict__ interval, double *__restrict__ joints,
@@ -69,11 +74,11 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
   if (i >= n) return;
   double prev0 = 0.0, prev2 = 0.0;
   if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
-  double pos[3], eul[3];
+  double pos[3];
   Solve S;
   Reach rc;
-  if (load_pose<KIND>(poses, i, false, pos, eul)) {
-    rc = is_reachable<false>(A, pos, eul, S);
+  if (load_pose<KIND>(poses, i, false, pos, S.R)) {
+    rc = is_reachable_R<false>(A, pos, S);
   } else {
     rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
   }
@@ -84,8 +89,9 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
   if (!joints && !elbow) return;
   double j[7], E[3];
   if (ok) {
-    double th = theta ? theta[i] : rc.i0;
-    get_joints(A, S, th, prev0, prev2, j, E);
+    double ct = rc.c0, st = rc.s0;   // theta_interval[0]: its cos / sin come with the interval
+    if (theta) sincos(theta[i], &st, &ct);
+    get_joints_cs(A, S, ct, st, prev0, prev2, j, E);
   } else {
 #pragma unroll
     for (int k = 0; k < 7; ++k) j[k] = NAN;
@@ -104,10 +110,10 @@ k_symik_no_limits(const __grid_constant__ ArmConst A, const double *__restrict__
                   int64_t n, double *__restrict__ joints, double *__restrict__ elbow) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double pos[3], eul[3], j[7], E[3];
+  double pos[3], j[7], E[3];
   Solve S;
-  bool ok = load_pose<KIND>(poses, i, false, pos, eul);
-  if (ok) ok = is_reachable<true>(A, pos, eul, S).state == R2IK_STATE_REACHABLE;
+  bool ok = load_pose<KIND>(poses, i, false, pos, S.R);
+  if (ok) ok = is_reachable_R<true>(A, pos, S).state == R2IK_STATE_REACHABLE;
   if (ok) {
     get_joints(A, S, theta[i], 0.0, 0.0, j, E);
   } else {
@@ -124,10 +130,10 @@ k_elbow_positions(const __grid_constant__ ArmConst A, const double *__restrict__
                   int K, int64_t n, double *__restrict__ elbows) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double pos[3], eul[3];
+  double pos[3];
   Solve S;
-  bool ok = load_pose<KIND>(poses, i, false, pos, eul);
-  if (ok) ok = is_reachable<false>(A, pos, eul, S).state == R2IK_STATE_REACHABLE;
+  bool ok = load_pose<KIND>(poses, i, false, pos, S.R);
+  if (ok) ok = is_reachable_R<false>(A, pos, S).state == R2IK_STATE_REACHABLE;
   for (int k = 0; k < K; ++k) {
     double E[3] = {NAN, NAN, NAN};
     if (ok) elbow_position(S, thetas[(size_t)i * K + k], E);
@@ -162,10 +168,10 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
   bool found = false, need_search = false, valid_pose = false;
   double theta = 0.0, start = 0.0, stop = 0.0;
   if (active) {
-    double pos[3], eul[3];
-    valid_pose = load_pose<R2IK_POSE_MAT4>(M, i, true, pos, eul);
+    double pos[3];
+    valid_pose = load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R);
     if (valid_pose) {
-      Reach rc = is_reachable<false>(A, pos, eul, S);
+      Reach rc = is_reachable_R<false>(A, pos, S);
       st = rc.state;
       if (st == R2IK_STATE_REACHABLE) {
         if (preferred_theta_works(A, S, rc.i0, rc.i1, par.preferred_theta)) {
@@ -304,6 +310,53 @@ k_reach_map(const __grid_constant__ ArmConst A, double ox, double oy, double oz,
     }
   }
   if (in_grid) counts[v] = count;
+}
+
+// ---------------------------------------------------------------------------------------
+// FK: tip pose of the 7-joint arm chain (synthetic FK-sampled workloads, round-trip checks).
+// A = A * [R|t] on 3x4 affine transforms held in registers; joint rotations by Rodrigues.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void affine_mul(double A[12], const double B[12]) {
+  double o[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double v = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+      if (c == 3) v += A[4 * r + 3];
+      o[4 * r + c] = v;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) A[k] = o[k];
+}
+
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_fk(const __grid_constant__ R2ikFkChain ch, const double *__restrict__ joints, int64_t n, double *__restrict__ M) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    affine_mul(T, ch.fixed[k]);
+    double s, c;
+    sincos(joints[7 * i + k], &s, &c);
+    const double ax = ch.axis[k][0], ay = ch.axis[k][1], az = ch.axis[k][2], v = 1.0 - c;
+    // R = I + sin q K + (1 - cos q) K^2
+    double Rj[12] = {1.0 - v * (ay * ay + az * az), -s * az + v * ax * ay, s * ay + v * ax * az, 0.0,
+                     s * az + v * ax * ay, 1.0 - v * (ax * ax + az * az), -s * ax + v * ay * az, 0.0,
+                     -s * ay + v * ax * az, s * ax + v * ay * az, 1.0 - v * (ax * ax + ay * ay), 0.0};
+    affine_mul(T, Rj);
+  }
+  affine_mul(T, ch.fixed[7]);
+  double2 *o = reinterpret_cast<double2 *>(M + 16 * i);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    o[2 * r] = make_double2(T[4 * r], T[4 * r + 1]);
+    o[2 * r + 1] = make_double2(T[4 * r + 2], T[4 * r + 3]);
+  }
+  o[6] = make_double2(0.0, 0.0);
+  o[7] = make_double2(0.0, 1.0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -492,6 +545,17 @@ int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, 
                                                                       step[2], dims[0], dims[1], dims[2], orientations_euler,
                                                                       ori_begin, ori_end, counts);
   R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
+  return 0;
+}
+
+int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int64_t n, double *M, void *stream) {
+  if (!chain) return fail_arg(R2IK_ERR_NULL, "r2ik_fk_f64: null chain");
+  if (n < 0) return fail_arg(R2IK_ERR_ARG, "r2ik_fk_f64: bad n");
+  if (n == 0) return 0;
+  if (!joints || !M) return fail_arg(R2IK_ERR_NULL, "r2ik_fk_f64: null argument");
+  R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  k_fk<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(*chain, joints, n, M);
+  R2IK_CUDA(cudaGetLastError(), "k_fk launch");
   return 0;
 }
 

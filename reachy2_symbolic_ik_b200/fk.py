@@ -173,3 +173,71 @@ def fibonacci_orientations(n: int, seed: int = 5) -> np.ndarray:
     # yaw = lam, pitch = phi - pi/2, roll = spin  (extrinsic xyz)
     e = np.stack([spin - np.pi, phi - np.pi / 2, (lam % (2 * np.pi)) - np.pi], axis=1)
     return e
+
+
+# --------------------------------------------------------------------------------------------
+# Device FK (libr2ik.so: r2ik_fk_f64) -- the same chain evaluated by a CUDA kernel, for
+# workloads too large to build on the host (cfg 4: 65 536 x 1 000 waypoints) and for FK
+# round-trip checks at full batch size.  No CPU fallback: needs the built library and a GPU.
+# --------------------------------------------------------------------------------------------
+def fk_chain_struct(arm: str):
+    """R2ikFkChain for an arm from the bundled URDF."""
+    from . import _abi
+
+    ch = _abi.FkChain()
+    k = 0
+    for fixed, axis in arm_chain(arm):
+        ch.fixed[k][:] = [float(v) for v in fixed[:3, :].reshape(-1)]
+        if axis is not None:
+            ch.axis[k][:] = [float(v) for v in axis / np.linalg.norm(axis)]
+        k += 1
+    return ch
+
+
+def forward_kinematics_device(joints, arm: str = "r_arm", out=None):
+    """joints: CUDA float64 tensor (..., 7) -> tip poses (..., 4, 4) CUDA float64 (asynchronous)."""
+    import ctypes as C
+
+    from . import _native
+
+    torch = _native.require_cuda()
+    if not (hasattr(joints, "is_cuda") and joints.is_cuda):
+        raise _native.R2ikError("forward_kinematics_device needs a CUDA tensor (use forward_kinematics on the host)")
+    q = joints.to(torch.float64).contiguous()
+    lead = tuple(q.shape[:-1])
+    n = q.numel() // 7
+    if out is None:
+        out = torch.empty((*lead, 4, 4), dtype=torch.float64, device=q.device)
+    ch = fk_chain_struct(arm)
+    with torch.cuda.device(q.device):
+        s = torch.cuda.current_stream(q.device).cuda_stream
+        rc = _native.load().r2ik_fk_f64(C.byref(ch), q.device.index, C.c_void_p(q.data_ptr()), C.c_int64(n),
+                                        C.c_void_p(out.data_ptr()), C.c_void_p(s))
+        _native.check(rc, "r2ik_fk_f64")
+    return out
+
+
+def sinusoidal_trajectories_device(T: int, W: int, arm: str = "r_arm", seed: int = 4, dt: float = 1.0 / 120.0,
+                                   device=None, chunk: int = 4096):
+    """Device version of ``sinusoidal_trajectories``: same joint-space sinusoids (phases from the
+    same NumPy generator), FK on the GPU.  Returns (T, W, 4, 4) CUDA float64."""
+    from . import _native
+
+    torch = _native.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    rng = np.random.default_rng(seed)
+    q0 = np.deg2rad([-25.0, -40.0, 0.0, -45.0, 0.0, 0.0, 0.0])
+    A = np.deg2rad([20.0, 20.0, 30.0, 45.0, 25.0, 25.0, 90.0])
+    f = np.array([0.6, 0.34, 0.78, 0.18, 0.31, 0.47, 0.25])
+    if arm.startswith("l"):
+        mirror = np.array([1, -1, -1, 1, -1, 1, -1.0])
+        q0, A = q0 * mirror, A * mirror
+    phase = torch.from_numpy(rng.uniform(0, 2 * np.pi, size=(T, 1, 7))).to(dev)
+    t = (torch.arange(W, dtype=torch.float64, device=dev) * dt)[None, :, None]
+    q0d, Ad, fd = (torch.from_numpy(x).to(dev) for x in (q0, A, f))
+    out = torch.empty((T, W, 4, 4), dtype=torch.float64, device=dev)
+    for lo in range(0, T, chunk):
+        hi = min(T, lo + chunk)
+        q = q0d + Ad * torch.sin(2 * np.pi * fd * t + phase[lo:hi])
+        forward_kinematics_device(q, arm, out=out[lo:hi])
+    return out

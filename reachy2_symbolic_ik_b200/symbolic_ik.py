@@ -263,6 +263,13 @@ class SymbolicIK:
             _native.check(rc, "r2ik_elbow_positions_f64")
             return out if was_cuda else out.cpu().numpy()
 
+    def reach_map(self, n: int = 256, orientations_euler=None, n_orientations: int = 512, **kw):
+        """Workspace reachability map: int32 CUDA tensor (n,n,n) of per-voxel reachable-orientation
+        counts (see ``workspace.reach_map``; all-reduced over ranks when ``dist=torch.distributed``)."""
+        from . import workspace
+
+        return workspace.reach_map(self, n=n, orientations_euler=orientations_euler, n_orientations=n_orientations, **kw)
+
     # ------------------------------------------------------------------ scalar API (reference signatures)
     @staticmethod
     def _pose6(goal_pose) -> np.ndarray:

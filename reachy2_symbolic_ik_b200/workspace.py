@@ -1,0 +1,88 @@
+"""Workspace reachability map (BASELINE.json configs[4]) and the multi-GPU partitioning helpers.
+
+The reference has no such component; its closest code is the task-space grid sweep of
+``src/benchmark/ik_comparison.py:137-181`` (``is_reachable`` over a position grid).  Here a
+voxel grid x orientation set is swept by the K4 kernel (``r2ik_reach_map_u32``): counts[v] =
+number of orientations for which ``SymbolicIK.is_reachable(voxel centre, orientation)`` is True.
+
+Multi-GPU: poses / trajectories are independent, so batches are cut into contiguous slices
+(``shard_range``) with no exchange.  The reach map shards the ORIENTATION set; every rank fills a
+full count volume, and one all-reduce (NCCL over NVLink / NVSwitch) sums them in place -- the only
+collective of the whole path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from .fk import fibonacci_orientations
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced slice [begin, end) of ``n_items`` owned by ``rank`` (first ``n % world``
+    ranks get one extra item)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(int(n_items), world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def reach_grid(shoulder_position, max_arm_length: float, n: int):
+    """Cell-centred n^3 grid over the bounding cube of the reach sphere (shoulder +- max_arm_length)."""
+    step = 2.0 * float(max_arm_length) / n
+    origin = np.asarray(shoulder_position, dtype=np.float64) - float(max_arm_length) + step / 2
+    return origin, np.array([step, step, step]), np.array([n, n, n], dtype=np.int32)
+
+
+def sharded_sum(launch: Callable[[int, int], "object"], n_orientations: int, dist=None, group=None):
+    """Run ``launch(ori_begin, ori_end)`` on this rank's orientation slice and sum the returned
+    count tensor over the ranks in place.  ``dist`` is ``torch.distributed`` (initialised) or None."""
+    rank, world = 0, 1
+    if dist is not None and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b, e = shard_range(n_orientations, rank, world)
+    counts = launch(b, e)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int = 512, origin=None, step=None,
+              dims=None, dist=None, group=None, out=None):
+    """Reachability count volume of ``solver`` (a ``SymbolicIK``): int32 CUDA tensor (d0, d1, d2).
+
+    orientations_euler: (n_ori, 3) xyz Euler angles (default: ``fibonacci_orientations(n_orientations)``).
+    With an initialised ``torch.distributed`` passed as ``dist`` the orientation set is sharded over the
+    ranks and the volume is all-reduced; every rank returns the full map."""
+    torch = solver._torch
+    if orientations_euler is None:
+        orientations_euler = fibonacci_orientations(n_orientations)
+    if origin is None or step is None or dims is None:
+        origin, step, dims = reach_grid(solver.shoulder_position, solver.max_arm_length, n)
+    origin = np.ascontiguousarray(origin, dtype=np.float64)
+    step = np.ascontiguousarray(step, dtype=np.float64)
+    dims = np.ascontiguousarray(dims, dtype=np.int32)
+    dev = solver._device
+    with torch.cuda.device(dev):
+        if hasattr(orientations_euler, "is_cuda"):
+            ori = orientations_euler.to(dev, torch.float64).contiguous()
+        else:
+            ori = torch.from_numpy(np.ascontiguousarray(orientations_euler, dtype=np.float64)).to(dev)
+        n_ori = ori.shape[0]
+        if out is None:
+            out = torch.empty(tuple(int(d) for d in dims), dtype=torch.int32, device=dev)
+
+        def launch(b: int, e: int):
+            s = torch.cuda.current_stream(dev).cuda_stream
+            rc = solver._handle.lib.r2ik_reach_map_u32(
+                solver._handle.h, origin.ctypes.data_as(C.POINTER(C.c_double)), step.ctypes.data_as(C.POINTER(C.c_double)),
+                dims.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(ori.data_ptr()), C.c_int32(b), C.c_int32(e),
+                C.c_void_p(out.data_ptr()), C.c_void_p(s))
+            _native.check(rc, "r2ik_reach_map_u32")
+            return out
+
+        return sharded_sum(launch, n_ori, dist, group)

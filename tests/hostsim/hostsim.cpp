@@ -10,12 +10,15 @@
 
 using namespace r2ik;
 
-static bool load_pose(int kind, const double *p, double pos[3], double eul[3]) {
+// mirrors load_pose<KIND> of r2ik_kernels.cu
+static bool load_pose(int kind, const double *p, bool snap, double pos[3], double R[9]) {
   if (kind == R2IK_POSE_EULER6) {
-    for (int k = 0; k < 3; ++k) { pos[k] = p[k]; eul[k] = p[3 + k]; }
+    for (int k = 0; k < 3; ++k) pos[k] = p[k];
+    rot_from_euler_xyz(p[3], p[4], p[5], R);
     return true;
   }
-  return pose_from_mat4(p, false, pos, eul);
+  pos[0] = p[3]; pos[1] = p[7]; pos[2] = p[11];
+  return rotation_from_mat4(p, snap, R);
 }
 
 extern "C" {
@@ -31,18 +34,19 @@ void hs_symik_batch(const R2ikArmConfig *cfg, int kind, const double *poses, con
   derive_constants(*cfg, A, pub);
   int stride = kind == R2IK_POSE_EULER6 ? 6 : 16;
   for (int64_t i = 0; i < n; ++i) {
-    double pos[3], eul[3];
+    double pos[3];
+    Solve S;
     for (int k = 0; k < 7; ++k) joints[7 * i + k] = NAN;
     for (int k = 0; k < 3; ++k) elbow[3 * i + k] = NAN;
     interval[2 * i] = NAN; interval[2 * i + 1] = NAN;
-    if (!load_pose(kind, poses + i * stride, pos, eul)) { reach[i] = 0; state[i] = R2IK_STATE_INVALID_ROTATION; continue; }
-    Solve S;
-    Reach rc = is_reachable<false>(A, pos, eul, S);
+    if (!load_pose(kind, poses + i * stride, false, pos, S.R)) { reach[i] = 0; state[i] = R2IK_STATE_INVALID_ROTATION; continue; }
+    Reach rc = is_reachable_R<false>(A, pos, S);
     state[i] = (uint8_t)rc.state;
     reach[i] = rc.state == R2IK_STATE_REACHABLE;
     if (reach[i]) {
       interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1;
-      get_joints(A, S, theta ? theta[i] : rc.i0, 0.0, 0.0, joints + 7 * i, elbow + 3 * i);
+      if (theta) get_joints(A, S, theta[i], 0.0, 0.0, joints + 7 * i, elbow + 3 * i);
+      else get_joints_cs(A, S, rc.c0, rc.s0, 0.0, 0.0, joints + 7 * i, elbow + 3 * i);
     }
   }
 }
@@ -53,10 +57,10 @@ void hs_no_limits_batch(const R2ikArmConfig *cfg, int kind, const double *poses,
   derive_constants(*cfg, A, pub);
   int stride = kind == R2IK_POSE_EULER6 ? 6 : 16;
   for (int64_t i = 0; i < n; ++i) {
-    double pos[3], eul[3];
-    load_pose(kind, poses + i * stride, pos, eul);
+    double pos[3];
     Solve S;
-    is_reachable<true>(A, pos, eul, S);
+    load_pose(kind, poses + i * stride, false, pos, S.R);
+    is_reachable_R<true>(A, pos, S);
     get_joints(A, S, theta[i], 0.0, 0.0, joints + 7 * i, elbow + 3 * i);
   }
 }
@@ -67,14 +71,14 @@ void hs_ctl_discrete_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, c
   ArmConst A; R2ikArmConstants pub;
   derive_constants(*cfg, A, pub);
   for (int64_t i = 0; i < n; ++i) {
-    double pos[3], eul[3];
-    if (!pose_from_mat4(M + 16 * i, true, pos, eul)) {
+    double pos[3];
+    Solve S;
+    if (!load_pose(R2IK_POSE_MAT4, M + 16 * i, true, pos, S.R)) {
       for (int k = 0; k < 7; ++k) joints[7 * i + k] = NAN;
       reach[i] = 0; state[i] = R2IK_STATE_INVALID_ROTATION; emg[i] = 0;
       continue;
     }
-    Solve S;
-    Reach rc = is_reachable<false>(A, pos, eul, S);
+    Reach rc = is_reachable_R<false>(A, pos, S);
     int st = rc.state;
     bool ok = st == R2IK_STATE_REACHABLE;
     double theta = 0.0;

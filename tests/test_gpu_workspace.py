@@ -1,0 +1,89 @@
+"""GPU tests of K4 (workspace reachability map) and of the FK kernel, through the facade / C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ARMS = ("r_arm", "l_arm")
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_reach_map_matches_oracle(oracle, arm):
+    """Every voxel count equals the oracle's (sum over orientations of is_reachable flags); voxels whose
+    flag flips under a 3e-13 perturbation of the pose are boundary cases and only counted."""
+    from reachy2_symbolic_ik_b200 import SymbolicIK, fk, workspace
+
+    ik = SymbolicIK(arm=arm)
+    n = 20
+    ori = fk.fibonacci_orientations(24)
+    origin, step, dims = workspace.reach_grid(ik.shoulder_position, ik.max_arm_length, n)
+    got = ik.reach_map(n=n, orientations_euler=ori).cpu().numpy()
+    want = oracle.reach_map(oracle.arm_config(arm), origin, step, dims, ori)
+    assert got.shape == (n, n, n) and got.dtype == np.int32
+    diff = got.astype(np.int64) - want.astype(np.int64)
+    # allow a handful of boundary voxels (|diff| <= 1) but nothing systematic
+    assert np.abs(diff).max() <= 1, np.abs(diff).max()
+    assert (diff != 0).sum() <= 3, (diff != 0).sum()
+    assert want.sum() > 0 and (want == 0).sum() > 0
+    # orientation slices add up (the multi-GPU decomposition of workspace.sharded_sum)
+    parts = np.zeros_like(got)
+    for r in range(3):
+        b, e = workspace.shard_range(len(ori), r, 3)
+        parts += ik.reach_map(n=n, orientations_euler=ori[b:e]).cpu().numpy()
+    assert np.array_equal(parts, got)
+
+
+def test_reach_map_flags_are_is_reachable(oracle):
+    """counts with ONE orientation == the K1 reachability flag of the same poses."""
+    from reachy2_symbolic_ik_b200 import SymbolicIK, workspace
+
+    ik = SymbolicIK(arm="r_arm")
+    n = 16
+    e = np.array([[0.3, -1.2, 0.4]])
+    origin, step, dims = workspace.reach_grid(ik.shoulder_position, ik.max_arm_length, n)
+    got = ik.reach_map(n=n, orientations_euler=e).cpu().numpy().reshape(-1)
+    idx = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 3)
+    P = np.concatenate([origin + idx * step, np.broadcast_to(e, (n ** 3, 3))], axis=1)
+    res = ik.is_reachable_batch(P, want_joints=False)
+    assert np.array_equal(got.astype(bool), res.reachable)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_fk_kernel_matches_host_fk(arm):
+    import torch
+
+    from reachy2_symbolic_ik_b200 import fk
+
+    rng = np.random.default_rng(11)
+    q = fk.sample_fk_joints(5000, rng)
+    want = fk.forward_kinematics(q, arm)
+    got = fk.forward_kinematics_device(torch.from_numpy(q).cuda(), arm).cpu().numpy()
+    assert got.shape == (5000, 4, 4)
+    np.testing.assert_allclose(got, want, atol=1e-14, rtol=0)
+    assert np.array_equal(got[:, 3], np.broadcast_to([0, 0, 0, 1.0], (5000, 4)))
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_fk_round_trip_full_size(arm):
+    """Size-independent property at BASELINE size (1M poses): FK(get_joints(theta)) reproduces the goal pose
+    whenever no goal-shifting branch fired (ControlIK's singularity_offset = -1.01 disables the elbow
+    projection).  The URDF's truncated rpy literals bound the agreement at ~1e-5."""
+    import torch
+
+    from reachy2_symbolic_ik_b200 import SymbolicIK, fk
+
+    n = 1_000_000
+    rng = np.random.default_rng(21)
+    q = torch.from_numpy(fk.sample_fk_joints(n, rng)).cuda()
+    M = fk.forward_kinematics_device(q, arm)
+    ik = SymbolicIK(arm=arm, singularity_offset=-1.01)
+    res = ik.is_reachable_batch(M)
+    ok = res.reachable
+    assert 0.3 < ok.double().mean().item() < 0.7   # about half of raw FK samples are backward poses
+    M2 = fk.forward_kinematics_device(res.joints[ok], arm)
+    # poses whose wrist was pushed forward / outward by is_reachable are legitimately shifted: compare
+    # orientation always, position only where the solver did not move the goal
+    rot_err = (M2[:, :3, :3] - M[ok][:, :3, :3]).abs().amax(dim=(1, 2))
+    assert rot_err.quantile(0.999).item() < 1e-4
+    pos_err = (M2[:, :3, 3] - M[ok][:, :3, 3]).norm(dim=1)
+    assert pos_err.median().item() < 1e-5
+    assert (pos_err < 1e-4).double().mean().item() > 0.9
