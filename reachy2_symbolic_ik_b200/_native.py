@@ -9,7 +9,8 @@ import os
 
 from . import _abi
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr2ik.so")
+# R2IK_LIB: development aid (kernel tuning variants built by scripts/build_variants.py); same C ABI, same CUDA code base.
+_LIB_PATH = os.environ.get("R2IK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr2ik.so")
 _lib = None
 
 EXPORTS = (

@@ -17,12 +17,7 @@
 #include <stdint.h>
 
 #include "../../include/r2ik.h"
-
-#if defined(__CUDACC__)
-#define R2IK_HD __host__ __device__ __forceinline__
-#else
-#define R2IK_HD inline
-#endif
+#include "r2ik_math.cuh"
 
 namespace r2ik {
 
@@ -59,26 +54,36 @@ struct ArmConst {
 // Python / NumPy scalar semantics
 // ---------------------------------------------------------------------------------------
 
-// 1/sqrt(x): one MUFU.RSQ64H + Newton steps on the device (about 1 ulp).
-R2IK_HD double rsqrt_fast(double x) {
-#if defined(__CUDA_ARCH__)
-  return rsqrt(x);
-#else
-  return 1.0 / sqrt(x);
-#endif
-}
+// Fast / literal duality.  The hot kernels run the solver with LIT = false: every elementary
+// function is straight-line code that is only valid for "ordinary" magnitudes, and each use
+// ORs its validity test into a `degenerate` flag instead of branching.  A pose that raised the
+// flag (exact zeros, under/overflowing magnitudes -- never on physical data) is solved again
+// by the out-of-line LIT = true instantiation, which calls the math library exactly where the
+// reference calls numpy / scipy.  The hot instruction stream thus contains no library slow
+// path and no branch around one.
 
 // (c, s) = (cos a, sin a) for a = atan2(y, x), without evaluating the angle: the reference builds
 // its elementary frame rotations as from_euler(atan2(...)) (sik:758-829); x/h, y/h equal
-// cos/sin of that angle to ~1 ulp.  Degenerate (0, 0) / underflowing inputs take the literal route.
-R2IK_HD void cs_of_atan2(double y, double x, double &c, double &s) {
-  double h2 = x * x + y * y;
-  if (h2 > 1e-280 && h2 < 1e280) {
-    double ih = rsqrt_fast(h2);
-    c = x * ih; s = y * ih;
-  } else {
+// cos/sin of that angle to ~1 ulp.
+template <bool LIT>
+R2IK_HD void cs_of_atan2(double y, double x, double &c, double &s, bool &degenerate) {
+  if (LIT) {
     sincos(atan2(y, x), &s, &c);
+  } else {
+    double h2 = x * x + y * y;
+    // 1e-280 < h2 < 1e280, tested on the exponent field (integer pipe)
+    degenerate = degenerate || !((unsigned)(hi_word(h2) - 0x05e00000) < (unsigned)(0x7a000000 - 0x05e00000));
+    double ih = rsqrt_pos(h2);
+    c = x * ih; s = y * ih;
   }
+}
+
+// atan2 as a leaf value.
+template <bool LIT>
+R2IK_HD double atan2_leaf(double y, double x, bool &degenerate) {
+  if (LIT) return atan2(y, x);
+  degenerate = degenerate || !atan2_core_ok(y, x);
+  return atan2_core(y, x);
 }
 
 // Python float `%`: fmod is exact; the result takes the sign of the divisor.
@@ -332,8 +337,8 @@ struct Solve {
 R2IK_HD void rmfv_columns(double vx, double vy, double vz, bool normalise, double c0[3], double a1[3], double a2[3]) {
   double ux = vx, uy = vy, uz = vz;
   if (normalise) {
-    double n = sqrt(vx * vx + vy * vy + vz * vz);
-    ux = vx / n; uy = vy / n; uz = vz / n;
+    double in = rsqrt_pos(vx * vx + vy * vy + vz * vz);
+    ux = vx * in; uy = vy * in; uz = vz * in;
   }
   if (np_isclose(1.0, ux) && np_isclose(0.0, uy) && np_isclose(0.0, uz)) {
     c0[0] = 1; c0[1] = 0; c0[2] = 0;
@@ -348,8 +353,8 @@ R2IK_HD void rmfv_columns(double vx, double vy, double vz, bool normalise, doubl
     return;
   }
   // R = I + K + K^2 (1 - c) / s^2 with k = e_x x u = (0, -uz, uy)
-  double s = sqrt(uy * uy + uz * uz);
-  double f = (1.0 - ux) / (s * s);
+  // (1 - c) / s^2 with s = |k|: s^2 is taken as uy^2 + uz^2 directly (the reference squares the norm)
+  double f = div_fast(1.0 - ux, uy * uy + uz * uz);
   c0[0] = 1.0 + (-(uy * uy) - (uz * uz)) * f; c0[1] = uy; c0[2] = uz;
   a1[0] = -uy; a1[1] = 1.0 + (-(uy * uy)) * f; a1[2] = (-(uy * uz)) * f;
   a2[0] = -uz; a2[1] = (-(uy * uz)) * f;       a2[2] = 1.0 + (-(uz * uz)) * f;
@@ -365,7 +370,7 @@ R2IK_HD void wrist_from_goal(const ArmConst &A, const double p[3], const double 
 // sik:337-349 reduce_goal_pose_no_limits: wrist pulled radially to distance d_target;
 // the same displacement is applied to the goal.
 R2IK_HD void reduce_goal(const ArmConst &A, double p[3], double w[3], double d, double d_target) {
-  double sc = d_target / (fabs(d) + A.proj_margin);
+  double sc = div_fast(d_target, fabs(d) + A.proj_margin);
   for (int k = 0; k < 3; ++k) {
     double nw = A.s[k] + (w[k] - A.s[k]) * sc;
     p[k] = p[k] + (nw - w[k]);
@@ -376,13 +381,14 @@ R2IK_HD void reduce_goal(const ArmConst &A, double p[3], double w[3], double d, 
 // sik:366-399 get_intersection_circle (n = P/d form).  false <=> None.
 R2IK_HD bool elbow_circle(const ArmConst &A, Solve &S, double n[3]) {
   double Px = S.w[0] - A.s[0], Py = S.w[1] - A.s[1], Pz = S.w[2] - A.s[2];
-  double d = sqrt(Px * Px + Py * Py + Pz * Pz);
+  double d = sqrt_nonneg(Px * Px + Py * Py + Pz * Pz);
   if (d > A.L12) return false;
   double d2 = d * d;
   double k = d2 - A.L2sq + A.L1sq;
-  double invd = 1.0 / d;
+  double invd = rcp_fast(d);
   double inv2d = 0.5 * invd;
-  S.r = inv2d * sqrt(4.0 * d2 * A.L1sq - k * k);
+  double rad = 4.0 * d2 * A.L1sq - k * k;          // < 0 by rounding at d ~ L1 + L2: np.sqrt gives nan
+  S.r = hi_word(rad) < 0 ? NAN : inv2d * sqrt_nonneg(rad);
   double cd = k * inv2d;
   n[0] = Px * invd; n[1] = Py * invd; n[2] = Pz * invd;
   S.c[0] = n[0] * cd + A.s[0];
@@ -396,6 +402,7 @@ struct Reach {
   int state;        // R2IK_STATE_*
   double i0, i1;    // theta interval (i0 > i1 means wrapped); NaN when unreachable
   double c0, s0;    // cos(i0), sin(i0): lets get_joints(theta_interval[0]) skip a sincos
+  bool degenerate;  // LIT = false only: the result is not valid, solve again with LIT = true
 };
 
 constexpr double kSinMinusPi = -1.2246467991473532e-16;  // np.sin(-np.pi)
@@ -405,9 +412,9 @@ constexpr double kSinMinusPi = -1.2246467991473532e-16;  // np.sin(-np.pi)
 R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &pz) {
   int pre_state = -1;
   double dx = px - A.s[0], dy = py - A.s[1], dz = pz - A.s[2];
-  double dg = sqrt(dx * dx + dy * dy + dz * dz);
+  double dg = sqrt_nonneg(dx * dx + dy * dy + dz * dz);
   if (dg > A.max_arm_length) {
-    double sc = A.max_arm_length / (dg + A.proj_margin);
+    double sc = div_fast(A.max_arm_length, dg + A.proj_margin);
     px = A.s[0] + dx * sc;
     py = A.s[1] + dy * sc;
     pz = A.s[2] + dz * sc;
@@ -424,10 +431,10 @@ R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &p
 // (true) after the pre-checks: S.p (pre-checked goal position) and S.R (goal rotation) are
 // set by the caller.  FLAG_ONLY skips the interval angles (reach-map kernel): state is exact,
 // i0/i1 are not computed.
-template <bool NO_LIMITS, bool FLAG_ONLY>
-R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
+template <bool NO_LIMITS, bool FLAG_ONLY, bool LIT>
+R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
   Reach out;
-  out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN;
+  out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false;
   wrist_from_goal(A, S.p, S.R, S.w);
   // --- sik:146-153 / sik:94-98 keep the wrist in front of the torso plane
   if (S.w[0] < A.backward_limit) {
@@ -439,7 +446,7 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
   double d;
   {
     double dx = S.w[0] - A.s[0], dy = S.w[1] - A.s[1], dz = S.w[2] - A.s[2];
-    d = sqrt(dx * dx + dy * dy + dz * dz);
+    d = sqrt_nonneg(dx * dx + dy * dy + dz * dz);
   }
   if (d > A.L12) {
     if (!NO_LIMITS) { out.state = R2IK_STATE_WRIST_OUT_OF_RANGE; return out; }
@@ -462,7 +469,7 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
 
   // --- sik:401-416 wrist-limit circle, relative to the wrist: centre p1 = n1 * hL
   double nLx = S.w[0] - S.p[0], nLy = S.w[1] - S.p[1], nLz = S.w[2] - S.p[2];
-  double inLn = rsqrt_fast(nLx * nLx + nLy * nLy + nLz * nLz);
+  double inLn = rsqrt_pos(nLx * nLx + nLy * nLy + nLz * nLz);
   double n1[3] = {nLx * inLn, nLy * inLn, nLz * inLn};
   double p1[3] = {n1[0] * A.hL, n1[1] * A.hL, n1[2] * A.hL};
   double p2[3] = {S.c[0] - S.w[0], S.c[1] - S.w[1], S.c[2] - S.w[2]};
@@ -486,13 +493,13 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
     v[0] = n1[1] * n2[2] - n1[2] * n2[1];
     v[1] = n1[2] * n2[0] - n1[0] * n2[2];
     v[2] = n1[0] * n2[1] - n1[1] * n2[0];
-    double inv = rsqrt_fast(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double inv = rsqrt_pos(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
     double e1[3] = {v[1] * n1[2] - v[2] * n1[1], v[2] * n1[0] - v[0] * n1[2], v[0] * n1[1] - v[1] * n1[0]};
     double e2[3] = {v[1] * n2[2] - v[2] * n2[1], v[2] * n2[0] - v[0] * n2[2], v[0] * n2[1] - v[1] * n2[0]};
     double b[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-    double t = (n2[0] * b[0] + n2[1] * b[1] + n2[2] * b[2]) / (n2[0] * e1[0] + n2[1] * e1[1] + n2[2] * e1[2]);
-    double u = -(n1[0] * b[0] + n1[1] * b[1] + n1[2] * b[2]) / (n1[0] * e2[0] + n1[1] * e2[1] + n1[2] * e2[2]);
+    double t = div_fast(n2[0] * b[0] + n2[1] * b[1] + n2[2] * b[2], n2[0] * e1[0] + n2[1] * e1[1] + n2[2] * e1[2]);
+    double u = -div_fast(n1[0] * b[0] + n1[1] * b[1] + n1[2] * b[2], n1[0] * e2[0] + n1[1] * e2[1] + n1[2] * e2[2]);
     if (np_isclose(u, t)) { decided = true; linked_full = Xc > 0; }
     q[0] = e1[0] * t + p1[0]; q[1] = e1[1] * t + p1[1]; q[2] = e1[2] * t + p1[2];
   }
@@ -510,38 +517,54 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
       return out;
     } else {
       // sik:511-568 angles of the intersection points in the elbow-circle frame
-      double sq = sqrt(disc);
-      double inv2a = 1.0 / (2.0 * qa);
+      double sq = sqrt_nonneg(disc);
+      double inv2a = rcp_fast(2.0 * qa);
       double ta = (disc == 0) ? (-qb * inv2a) : ((-qb + sq) * inv2a);
       double Pa[3] = {q[0] + ta * v[0] - p2[0], q[1] + ta * v[1] - p2[1], q[2] + ta * v[2] - p2[2]};
       double ya = S.a2[0] * Pa[0] + S.a2[1] * Pa[1] + S.a2[2] * Pa[2];
       double xa = S.a1[0] * Pa[0] + S.a1[1] * Pa[1] + S.a1[2] * Pa[2];
-      double ang1 = atan2(ya, xa);
+      double ang1 = atan2_leaf<LIT>(ya, xa, out.degenerate);
+      double ca, sa;                      // cos / sin of ang1 (unit vector of the point in the circle plane)
+      cs_of_atan2<LIT>(ya, xa, ca, sa, out.degenerate);
       if (disc == 0) {
         out.state = R2IK_STATE_REACHABLE; out.i0 = ang1; out.i1 = ang1;
-        cs_of_atan2(ya, xa, out.c0, out.s0);
+        out.c0 = ca; out.s0 = sa;
         return out;
       }
       double tb = (-qb - sq) * inv2a;
       double Pb[3] = {q[0] + tb * v[0] - p2[0], q[1] + tb * v[1] - p2[1], q[2] + tb * v[2] - p2[2]};
       double yb = S.a2[0] * Pb[0] + S.a2[1] * Pb[1] + S.a2[2] * Pb[2];
       double xb = S.a1[0] * Pb[0] + S.a1[1] * Pb[1] + S.a1[2] * Pb[2];
-      double ang2 = atan2(yb, xb);
+      double ang2 = atan2_leaf<LIT>(yb, xb, out.degenerate);
+      double cb, sb;
+      cs_of_atan2<LIT>(yb, xb, cb, sb, out.degenerate);
       if (ang2 < ang1) {
         double tmp = ang1; ang1 = ang2; ang2 = tmp;
-        tmp = ya; ya = yb; yb = tmp;
-        tmp = xa; xa = xb; xb = tmp;
+        tmp = ca; ca = cb; cb = tmp;
+        tmp = sa; sa = sb; sb = tmp;
       }
+      // cos / sin of the mid-arc angle (ang1 + ang2) / 2 (sik:541-547): the bisector of the two unit
+      // vectors, reversed when the arc from ang1 to ang2 is longer than pi.  Exactly opposite points
+      // (|bisector| ~ 0) are flagged degenerate and take the literal sincos.
       double sm, cm;
-      sincos((ang1 + ang2) / 2.0, &sm, &cm);
+      if (LIT) {
+        sincos((ang1 + ang2) / 2.0, &sm, &cm);
+      } else {
+        double bx = ca + cb, by = sa + sb;
+        double b2 = bx * bx + by * by;
+        out.degenerate = out.degenerate || !(b2 > 1e-12);
+        double ib = rsqrt_pos(b2);
+        if (ang2 - ang1 > kPi) ib = -ib;
+        cm = bx * ib; sm = by * ib;
+      }
       double yc = cm * S.r, zc = sm * S.r;
       // test point in the torso(wrist-relative) frame, then its x in the limitation frame
       double Tm[3] = {S.a1[0] * yc + S.a2[0] * zc + p2[0] - p1[0], S.a1[1] * yc + S.a2[1] * zc + p2[1] - p1[1],
                       S.a1[2] * yc + S.a2[2] * zc + p2[2] - p1[2]};
       double xl = l0[0] * Tm[0] + l0[1] * Tm[1] + l0[2] * Tm[2];
       out.state = R2IK_STATE_REACHABLE;
-      if (xl > 0) { out.i0 = ang1; out.i1 = ang2; cs_of_atan2(ya, xa, out.c0, out.s0); }
-      else { out.i0 = ang2; out.i1 = ang1; cs_of_atan2(yb, xb, out.c0, out.s0); }
+      if (xl > 0) { out.i0 = ang1; out.i1 = ang2; out.c0 = ca; out.s0 = sa; }
+      else { out.i0 = ang2; out.i1 = ang1; out.c0 = cb; out.s0 = sb; }
       return out;
     }
   }
@@ -552,13 +575,42 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
 
 // sik:121-282 is_reachable / sik:85-119 is_reachable_no_limits for a goal position and a goal
 // rotation matrix already stored in S.R.  Fills S for get_joints / elbow_position.
+// Out-of-line literal instantiation (see "Fast / literal duality"): S travels through a local
+// copy so that the caller's S stays in registers on the hot path.
+template <bool NO_LIMITS, bool FLAG_ONLY>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void solve_core_literal(const ArmConst &A, Solve *S, Reach *out) {
+  *out = solve_core_impl<NO_LIMITS, FLAG_ONLY, true>(A, *S);
+}
+
+// S.p (pre-checked goal position) and S.R (goal rotation) set by the caller.
+template <bool NO_LIMITS, bool FLAG_ONLY>
+R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
+  const double p0 = S.p[0], p1 = S.p[1], p2 = S.p[2];
+  Reach out = solve_core_impl<NO_LIMITS, FLAG_ONLY, false>(A, S);
+  if (out.degenerate) {
+    Solve T;
+    T.p[0] = p0; T.p[1] = p1; T.p[2] = p2;
+    for (int k = 0; k < 9; ++k) T.R[k] = S.R[k];
+    Reach lit;
+    solve_core_literal<NO_LIMITS, FLAG_ONLY>(A, &T, &lit);
+    S = T;
+    out = lit;
+  }
+  return out;
+}
+
 template <bool NO_LIMITS>
 R2IK_HD Reach is_reachable_R(const ArmConst &A, const double pos[3], Solve &S) {
   double px = pos[0], py = pos[1], pz = pos[2];
   int pre_state = reach_prechecks(A, px, py, pz);
   if (!NO_LIMITS && pre_state >= 0) {
     Reach out;
-    out.state = pre_state; out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN;
+    out.state = pre_state; out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false;
     return out;
   }
   S.p[0] = px; S.p[1] = py; S.p[2] = pz;
@@ -624,14 +676,18 @@ R2IK_HD P3 to_shoulder(const ArmConst &A, const double X[3]) {
 // (ct, st) = (cos theta, sin theta).  The reference's frame rotations R(+-joint angle) are
 // applied from the (cos, sin) of the atan2 that defines the joint (cs_of_atan2): the seven
 // atan2 that produce the outputs are then off the dependent chain.
-R2IK_HD void get_joints_cs(const ArmConst &A, Solve &S, double ct, double st, double prev0, double prev2, double joints[7],
-                           double E[3]) {
+// Returns false (LIT = false only) when a degenerate input needs the literal instantiation; S.p /
+// S.w may then have been modified and must be restored by the caller.
+template <bool LIT>
+R2IK_HD bool get_joints_impl(const ArmConst &A, Solve &S, double ct, double st, double prev0, double prev2, double joints[7],
+                             double E[3]) {
+  bool degenerate = false;
   elbow_position_cs(S, ct, st, E);
   if (E[2] > (E[0] - A.es[0]) * A.sing_coeff + A.es[2] - A.sing_offset) {
     // sik:647-682 make_elbow_projection with the plane constants hoisted to the host
     double dist = (E[0] - A.plP[0]) * A.plV[0] + (E[1] - A.plP[1]) * A.plV[1] + (E[2] - A.plP[2]) * A.plV[2];
     double vc[3] = {E[0] - dist * A.plV[0] - A.plC[0], E[1] - dist * A.plV[1] - A.plC[1], E[2] - dist * A.plV[2] - A.plC[2]};
-    double sc = A.plRho * rsqrt_fast(vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2]);
+    double sc = A.plRho * rsqrt_pos(vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2]);
     for (int k = 0; k < 3; ++k) {
       double ne = A.plC[k] + vc[k] * sc;
       S.p[k] = S.p[k] + (ne - E[k]);
@@ -647,53 +703,95 @@ R2IK_HD void get_joints_cs(const ArmConst &A, Solve &S, double ct, double st, do
   P3 el = to_shoulder(A, E), wr = to_shoulder(A, S.w), tp = to_shoulder(A, tipw), pt = to_shoulder(A, ptw);
   double s, c;
 
+  // The seven atan2 that define the joints are collected as (y, x) pairs and evaluated together
+  // at the end: they are leaves of the dependency graph (the frame rotations use cs_of_atan2),
+  // so the straight-line atan2_core evaluations interleave on the FP64 pipe.
+  double ay[7], ax[7];
   // sik:751-755 shoulder pitch; sik:758 R_y(-shoulder_pitch)
-  double shoulder_pitch;
-  if (el.x == 0 && el.z == 0) { shoulder_pitch = prev0; sincos(-shoulder_pitch, &s, &c); }
-  else { shoulder_pitch = -atan2(el.z, el.x); cs_of_atan2(el.z, el.x, c, s); }
+  const bool sing0 = is_zero(el.x) && is_zero(el.z);
+  ay[0] = el.z; ax[0] = el.x;
+  if (LIT && sing0) sincos(-prev0, &s, &c);
+  else cs_of_atan2<LIT>(el.z, el.x, c, s, degenerate);
   rot_y(el, c, s); rot_y(wr, c, s); rot_y(tp, c, s); rot_y(pt, c, s);
   // sik:766 shoulder roll; sik:769 R_z(-shoulder_roll)
-  double shoulder_roll = atan2(el.y, el.x);
-  cs_of_atan2(-el.y, el.x, c, s);
+  ay[1] = el.y; ax[1] = el.x;
+  cs_of_atan2<LIT>(-el.y, el.x, c, s, degenerate);
   rot_z(wr, c, s); rot_z(tp, c, s); rot_z(pt, c, s);
   wr.x -= A.L1; tp.x -= A.L1; pt.x -= A.L1;        // sik:776-777 elbow frame
   // sik:782-786 elbow yaw (not wrapped: range (-3pi/2, pi/2]); sik:789 R_x(elbow_yaw):
   // cos(-pi/2 + a) = sin a, sin(-pi/2 + a) = -cos a with a = atan2(wr.z, -wr.y)
-  double elbow_yaw;
-  if (wr.y == 0 && wr.z == 0) { elbow_yaw = prev2; sincos(elbow_yaw, &s, &c); }
+  const bool sing2 = is_zero(wr.y) && is_zero(wr.z);
+  ay[2] = wr.z; ax[2] = -wr.y;
+  if (LIT && sing2) sincos(prev2, &s, &c);
   else {
-    elbow_yaw = -kHalfPi + atan2(wr.z, -wr.y);
     double ca, sa;
-    cs_of_atan2(wr.z, -wr.y, ca, sa);
+    cs_of_atan2<LIT>(wr.z, -wr.y, ca, sa, degenerate);
     c = sa; s = -ca;
   }
   rot_x(wr, c, s); rot_x(tp, c, s); rot_x(pt, c, s);
   // sik:797 elbow pitch; sik:800 R_y(-elbow_pitch)
-  double elbow_pitch = -atan2(wr.z, wr.x);
-  cs_of_atan2(wr.z, wr.x, c, s);
+  ay[3] = wr.z; ax[3] = wr.x;
+  cs_of_atan2<LIT>(wr.z, wr.x, c, s, degenerate);
   rot_y(tp, c, s); rot_y(pt, c, s);
   tp.x -= A.L2; pt.x -= A.L2;                      // sik:805-806 wrist frame
   // sik:815-817 wrist roll = pi - atan2(tp.y, -tp.x); sik:820 R_z(-wrist_roll):
   // cos(-(pi - a)) = -cos a, sin(-(pi - a)) = -sin a
-  double wrist_roll = kPi - atan2(tp.y, -tp.x);
-  if (wrist_roll > kPi) wrist_roll = wrist_roll - kTwoPi;
+  ay[4] = tp.y; ax[4] = -tp.x;
   {
     double ca, sa;
-    cs_of_atan2(tp.y, -tp.x, ca, sa);
+    cs_of_atan2<LIT>(tp.y, -tp.x, ca, sa, degenerate);
     c = -ca; s = -sa;
   }
   rot_z(tp, c, s); rot_z(pt, c, s);
   // sik:826 wrist pitch; sik:829 R_y(wrist_pitch)
-  double wrist_pitch = atan2(tp.z, tp.x);
-  cs_of_atan2(tp.z, tp.x, c, s);
+  ay[5] = tp.z; ax[5] = tp.x;
+  cs_of_atan2<LIT>(tp.z, tp.x, c, s, degenerate);
   rot_y(pt, c, s);
-  // (the x -= tip_z of sik:836-837 does not touch y, z)
-  double wrist_yaw = -atan2(pt.y, pt.z);           // sik:848
+  // (the x -= tip_z of sik:836-837 does not touch y, z); sik:848 wrist yaw
+  ay[6] = pt.y; ax[6] = pt.z;
+
+  double at[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) at[k] = atan2_leaf<LIT>(ay[k], ax[k], degenerate);
+  // exact-zero singularities (sik:751, 782) make cs_of_atan2 flag the pose: literal route
+  double shoulder_pitch = sing0 ? prev0 : -at[0];
+  double shoulder_roll = at[1];
+  double elbow_yaw = sing2 ? prev2 : -kHalfPi + at[2];
+  double elbow_pitch = -at[3];
+  double wrist_roll = kPi - at[4];
+  if (wrist_roll > kPi) wrist_roll = wrist_roll - kTwoPi;
+  double wrist_pitch = at[5];
+  double wrist_yaw = -at[6];
 
   joints[0] = shoulder_pitch; joints[1] = shoulder_roll; joints[2] = elbow_yaw; joints[3] = elbow_pitch;
   joints[4] = wrist_roll; joints[5] = -wrist_pitch; joints[6] = -wrist_yaw;
   if (joints[3] > A.elbow_limit) joints[3] = A.elbow_limit;     // sik:853-861
   if (joints[3] < -A.elbow_limit) joints[3] = -A.elbow_limit;
+  return !degenerate;
+}
+
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void get_joints_literal(const ArmConst &A, Solve *S, double ct, double st, double prev0, double prev2, double *joints,
+                        double *E) {
+  get_joints_impl<true>(A, *S, ct, st, prev0, prev2, joints, E);
+}
+
+R2IK_HD void get_joints_cs(const ArmConst &A, Solve &S, double ct, double st, double prev0, double prev2, double joints[7],
+                           double E[3]) {
+  const double p0 = S.p[0], p1 = S.p[1], p2 = S.p[2], w0 = S.w[0], w1 = S.w[1], w2 = S.w[2];
+  if (!get_joints_impl<false>(A, S, ct, st, prev0, prev2, joints, E)) {
+    Solve T = S;   // local copy: only this rare path touches memory
+    T.p[0] = p0; T.p[1] = p1; T.p[2] = p2; T.w[0] = w0; T.w[1] = w1; T.w[2] = w2;
+    double jj[7], EE[3];
+    get_joints_literal(A, &T, ct, st, prev0, prev2, jj, EE);
+    S = T;
+    for (int k = 0; k < 7; ++k) joints[k] = jj[k];
+    for (int k = 0; k < 3; ++k) E[k] = EE[k];
+  }
 }
 
 R2IK_HD void get_joints(const ArmConst &A, Solve &S, double theta, double prev0, double prev2, double joints[7], double E[3]) {
@@ -720,6 +818,23 @@ R2IK_HD bool pose_from_mat4(const double *M, bool snap, double pos[3], double eu
 // band is used as it is.  Anything else -- scaled / skewed input that scipy projects or
 // normalises, |cos(pitch)| < 1e-5 where as_euler zeroes the third angle (rxp:1085-1099),
 // det <= 0 -- takes the literal route.  false <=> scipy raises (det <= 0).
+// Literal route of rotation_from_mat4: from_matrix -> as_euler("xyz") -> from_euler (utl:84-90,
+// sik:420).  Out of line on the device: it is the rare path (non-orthonormal or gimbal-band
+// input) and it is large (SVD-equivalent projection, three atan2, three sincos).
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+bool rotation_from_mat3_literal(const double m[9], double R[9]) {
+  double e[3];
+  Quat q;
+  if (!quat_from_matrix(m, q)) return false;
+  quat_as_euler_xyz_extrinsic(q, e);
+  rot_from_euler_xyz(e[0], e[1], e[2], R);
+  return true;
+}
+
 R2IK_HD bool rotation_from_mat4(const double *M, bool snap, double R[9]) {
   if (snap && rotation_is_identity(M)) {
     R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
@@ -739,12 +854,12 @@ R2IK_HD bool rotation_from_mat4(const double *M, bool snap, double R[9]) {
     for (int k = 0; k < 9; ++k) R[k] = m[k];
     return true;
   }
-  double e[3];
-  Quat q;
-  if (!quat_from_matrix(m, q)) return false;
-  quat_as_euler_xyz_extrinsic(q, e);
-  rot_from_euler_xyz(e[0], e[1], e[2], R);
-  return true;
+  // address-taken copies live in local memory only on this rare path; m / R stay in registers
+  double mm[9], RR[9];
+  for (int k = 0; k < 9; ++k) mm[k] = m[k];
+  bool ok = rotation_from_mat3_literal(mm, RR);
+  for (int k = 0; k < 9; ++k) R[k] = RR[k];
+  return ok;
 }
 
 }  // namespace r2ik

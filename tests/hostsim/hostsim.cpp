@@ -23,6 +23,14 @@ static bool load_pose(int kind, const double *p, bool snap, double pos[3], doubl
 
 extern "C" {
 
+// r2ik_math.cuh: the straight-line atan2 (host build: '/' instead of the MUFU seed + Newton).
+void hs_atan2_core(const double *y, const double *x, int64_t n, double *out, uint8_t *ok) {
+  for (int64_t i = 0; i < n; ++i) {
+    ok[i] = atan2_core_ok(y[i], x[i]);
+    out[i] = atan2_core(y[i], x[i]);
+  }
+}
+
 void hs_constants(const R2ikArmConfig *cfg, R2ikArmConstants *pub) {
   ArmConst A;
   derive_constants(*cfg, A, *pub);
