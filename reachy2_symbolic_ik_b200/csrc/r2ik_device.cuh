@@ -78,6 +78,15 @@ R2IK_HD void cs_of_atan2(double y, double x, double &c, double &s, bool &degener
   }
 }
 
+// (c, s) as above AND the angle a = atan2(y, x) itself: the fast route reads the angle off the unit
+// vector (angle_of_unit, no division).
+template <bool LIT>
+R2IK_HD double cs_and_angle(double y, double x, double &c, double &s, bool &degenerate) {
+  cs_of_atan2<LIT>(y, x, c, s, degenerate);
+  if (LIT) return atan2(y, x);
+  return angle_of_unit(c, s);
+}
+
 // atan2 as a leaf value.
 template <bool LIT>
 R2IK_HD double atan2_leaf(double y, double x, bool &degenerate) {
@@ -379,13 +388,12 @@ R2IK_HD void reduce_goal(const ArmConst &A, double p[3], double w[3], double d, 
 }
 
 // sik:366-399 get_intersection_circle (n = P/d form).  false <=> None.
-R2IK_HD bool elbow_circle(const ArmConst &A, Solve &S, double n[3]) {
+// (d, invd) = |w - s| and its reciprocal, computed by the caller from the current S.w.
+R2IK_HD bool elbow_circle(const ArmConst &A, Solve &S, double d, double invd, double n[3]) {
   double Px = S.w[0] - A.s[0], Py = S.w[1] - A.s[1], Pz = S.w[2] - A.s[2];
-  double d = sqrt_nonneg(Px * Px + Py * Py + Pz * Pz);
   if (d > A.L12) return false;
   double d2 = d * d;
   double k = d2 - A.L2sq + A.L1sq;
-  double invd = rcp_fast(d);
   double inv2d = 0.5 * invd;
   double rad = 4.0 * d2 * A.L1sq - k * k;          // < 0 by rounding at d ~ L1 + L2: np.sqrt gives nan
   S.r = hi_word(rad) < 0 ? NAN : inv2d * sqrt_nonneg(rad);
@@ -412,8 +420,12 @@ constexpr double kSinMinusPi = -1.2246467991473532e-16;  // np.sin(-np.pi)
 R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &pz) {
   int pre_state = -1;
   double dx = px - A.s[0], dy = py - A.s[1], dz = pz - A.s[2];
-  double dg = sqrt_nonneg(dx * dx + dy * dy + dz * dz);
-  if (dg > A.max_arm_length) {
+  // dg > max_arm_length decided on the squares; only a pose within 1e-12 of the sphere takes the root
+  const double dg2 = dx * dx + dy * dy + dz * dz, L2 = A.max_arm_length * A.max_arm_length;
+  bool outside = dg2 > L2;
+  if (fabs(dg2 - L2) <= 1e-12) outside = sqrt(dg2) > A.max_arm_length;
+  if (outside) {
+    double dg = sqrt_nonneg(dg2);
     double sc = div_fast(A.max_arm_length, dg + A.proj_margin);
     px = A.s[0] + dx * sc;
     py = A.s[1] + dy * sc;
@@ -443,21 +455,28 @@ R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
     if (NO_LIMITS) wrist_from_goal(A, S.p, S.R, S.w);
     else S.w[0] = S.w[0] + diff;
   }
-  double d;
+  double d, invd;
   {
     double dx = S.w[0] - A.s[0], dy = S.w[1] - A.s[1], dz = S.w[2] - A.s[2];
-    d = sqrt_nonneg(dx * dx + dy * dy + dz * dz);
+    d = sqrt_rsqrt_nonneg(dx * dx + dy * dy + dz * dz, invd);
   }
+  bool moved = false;
   if (d > A.L12) {
     if (!NO_LIMITS) { out.state = R2IK_STATE_WRIST_OUT_OF_RANGE; return out; }
     reduce_goal(A, S.p, S.w, d, A.L12);                       // sik:102-105
+    moved = true;
   }
   if (d < A.d_min) {                                          // sik:166-171 / sik:107-112
     reduce_goal(A, S.p, S.w, d, A.d_min);
     wrist_from_goal(A, S.p, S.R, S.w);
+    moved = true;
+  }
+  if (moved) {   // rare: the wrist was pulled in / pushed out, its distance is recomputed (sik:376)
+    double dx = S.w[0] - A.s[0], dy = S.w[1] - A.s[1], dz = S.w[2] - A.s[2];
+    d = sqrt_rsqrt_nonneg(dx * dx + dy * dy + dz * dz, invd);
   }
   double n[3];
-  if (!elbow_circle(A, S, n)) { out.state = R2IK_STATE_SHOULD_NOT_HAPPEN; return out; }
+  if (!elbow_circle(A, S, d, invd, n)) { out.state = R2IK_STATE_SHOULD_NOT_HAPPEN; return out; }
   if (!FLAG_ONLY) {
     double c0[3];
     rmfv_columns(n[0], n[1], n[2], false, c0, S.a1, S.a2);    // sik:454, sik:686
@@ -496,10 +515,12 @@ R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
     double inv = rsqrt_pos(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
     double e1[3] = {v[1] * n1[2] - v[2] * n1[1], v[2] * n1[0] - v[0] * n1[2], v[0] * n1[1] - v[1] * n1[0]};
-    double e2[3] = {v[1] * n2[2] - v[2] * n2[1], v[2] * n2[0] - v[0] * n2[2], v[0] * n2[1] - v[1] * n2[0]};
     double b[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-    double t = div_fast(n2[0] * b[0] + n2[1] * b[1] + n2[2] * b[2], n2[0] * e1[0] + n2[1] * e1[1] + n2[2] * e1[2]);
-    double u = -div_fast(n1[0] * b[0] + n1[1] * b[1] + n1[2] * b[2], n1[0] * e2[0] + n1[1] * e2[1] + n1[2] * e2[2]);
+    // Line parameters of the consistent 3x2 system [e1 -e2](t, u)^T = b with e_i = v x n_i:
+    //   t = (n2 . b) / (n2 . e1),  u = -(n1 . b) / (n1 . e2),  and  n2 . e1 = -(n1 . e2) = v . (n1 x n2)
+    //   = |n1 x n2| = 1 / inv: both share the reciprocal that normalised v.
+    double t = (n2[0] * b[0] + n2[1] * b[1] + n2[2] * b[2]) * inv;
+    double u = (n1[0] * b[0] + n1[1] * b[1] + n1[2] * b[2]) * inv;
     if (np_isclose(u, t)) { decided = true; linked_full = Xc > 0; }
     q[0] = e1[0] * t + p1[0]; q[1] = e1[1] * t + p1[1]; q[2] = e1[2] * t + p1[2];
   }
@@ -523,9 +544,8 @@ R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
       double Pa[3] = {q[0] + ta * v[0] - p2[0], q[1] + ta * v[1] - p2[1], q[2] + ta * v[2] - p2[2]};
       double ya = S.a2[0] * Pa[0] + S.a2[1] * Pa[1] + S.a2[2] * Pa[2];
       double xa = S.a1[0] * Pa[0] + S.a1[1] * Pa[1] + S.a1[2] * Pa[2];
-      double ang1 = atan2_leaf<LIT>(ya, xa, out.degenerate);
       double ca, sa;                      // cos / sin of ang1 (unit vector of the point in the circle plane)
-      cs_of_atan2<LIT>(ya, xa, ca, sa, out.degenerate);
+      double ang1 = cs_and_angle<LIT>(ya, xa, ca, sa, out.degenerate);
       if (disc == 0) {
         out.state = R2IK_STATE_REACHABLE; out.i0 = ang1; out.i1 = ang1;
         out.c0 = ca; out.s0 = sa;
@@ -535,9 +555,8 @@ R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
       double Pb[3] = {q[0] + tb * v[0] - p2[0], q[1] + tb * v[1] - p2[1], q[2] + tb * v[2] - p2[2]};
       double yb = S.a2[0] * Pb[0] + S.a2[1] * Pb[1] + S.a2[2] * Pb[2];
       double xb = S.a1[0] * Pb[0] + S.a1[1] * Pb[1] + S.a1[2] * Pb[2];
-      double ang2 = atan2_leaf<LIT>(yb, xb, out.degenerate);
       double cb, sb;
-      cs_of_atan2<LIT>(yb, xb, cb, sb, out.degenerate);
+      double ang2 = cs_and_angle<LIT>(yb, xb, cb, sb, out.degenerate);
       if (ang2 < ang1) {
         double tmp = ang1; ang1 = ang2; ang2 = tmp;
         tmp = ca; ca = cb; cb = tmp;
@@ -703,56 +722,47 @@ R2IK_HD bool get_joints_impl(const ArmConst &A, Solve &S, double ct, double st, 
   P3 el = to_shoulder(A, E), wr = to_shoulder(A, S.w), tp = to_shoulder(A, tipw), pt = to_shoulder(A, ptw);
   double s, c;
 
-  // The seven atan2 that define the joints are collected as (y, x) pairs and evaluated together
-  // at the end: they are leaves of the dependency graph (the frame rotations use cs_of_atan2),
-  // so the straight-line atan2_core evaluations interleave on the FP64 pipe.
-  double ay[7], ax[7];
+  // Six of the seven joint angles are atan2 of a pair whose (cos, sin) also drives the next frame
+  // rotation: cs_and_angle normalises once and reads the angle off the unit vector.  The angles are
+  // leaves of the dependency graph (nothing downstream consumes them), so their polynomial
+  // evaluations interleave with the frame chain on the FP64 pipe.
+  double at[7];
   // sik:751-755 shoulder pitch; sik:758 R_y(-shoulder_pitch)
   const bool sing0 = is_zero(el.x) && is_zero(el.z);
-  ay[0] = el.z; ax[0] = el.x;
-  if (LIT && sing0) sincos(-prev0, &s, &c);
-  else cs_of_atan2<LIT>(el.z, el.x, c, s, degenerate);
+  if (LIT && sing0) { at[0] = 0.0; sincos(-prev0, &s, &c); }
+  else at[0] = cs_and_angle<LIT>(el.z, el.x, c, s, degenerate);
   rot_y(el, c, s); rot_y(wr, c, s); rot_y(tp, c, s); rot_y(pt, c, s);
-  // sik:766 shoulder roll; sik:769 R_z(-shoulder_roll)
-  ay[1] = el.y; ax[1] = el.x;
-  cs_of_atan2<LIT>(-el.y, el.x, c, s, degenerate);
+  // sik:766 shoulder roll = atan2(el.y, el.x); sik:769 R_z(-shoulder_roll)
+  at[1] = -cs_and_angle<LIT>(-el.y, el.x, c, s, degenerate);
   rot_z(wr, c, s); rot_z(tp, c, s); rot_z(pt, c, s);
   wr.x -= A.L1; tp.x -= A.L1; pt.x -= A.L1;        // sik:776-777 elbow frame
   // sik:782-786 elbow yaw (not wrapped: range (-3pi/2, pi/2]); sik:789 R_x(elbow_yaw):
   // cos(-pi/2 + a) = sin a, sin(-pi/2 + a) = -cos a with a = atan2(wr.z, -wr.y)
   const bool sing2 = is_zero(wr.y) && is_zero(wr.z);
-  ay[2] = wr.z; ax[2] = -wr.y;
-  if (LIT && sing2) sincos(prev2, &s, &c);
+  if (LIT && sing2) { at[2] = 0.0; sincos(prev2, &s, &c); }
   else {
     double ca, sa;
-    cs_of_atan2<LIT>(wr.z, -wr.y, ca, sa, degenerate);
+    at[2] = cs_and_angle<LIT>(wr.z, -wr.y, ca, sa, degenerate);
     c = sa; s = -ca;
   }
   rot_x(wr, c, s); rot_x(tp, c, s); rot_x(pt, c, s);
   // sik:797 elbow pitch; sik:800 R_y(-elbow_pitch)
-  ay[3] = wr.z; ax[3] = wr.x;
-  cs_of_atan2<LIT>(wr.z, wr.x, c, s, degenerate);
+  at[3] = cs_and_angle<LIT>(wr.z, wr.x, c, s, degenerate);
   rot_y(tp, c, s); rot_y(pt, c, s);
   tp.x -= A.L2; pt.x -= A.L2;                      // sik:805-806 wrist frame
   // sik:815-817 wrist roll = pi - atan2(tp.y, -tp.x); sik:820 R_z(-wrist_roll):
   // cos(-(pi - a)) = -cos a, sin(-(pi - a)) = -sin a
-  ay[4] = tp.y; ax[4] = -tp.x;
   {
     double ca, sa;
-    cs_of_atan2<LIT>(tp.y, -tp.x, ca, sa, degenerate);
+    at[4] = cs_and_angle<LIT>(tp.y, -tp.x, ca, sa, degenerate);
     c = -ca; s = -sa;
   }
   rot_z(tp, c, s); rot_z(pt, c, s);
   // sik:826 wrist pitch; sik:829 R_y(wrist_pitch)
-  ay[5] = tp.z; ax[5] = tp.x;
-  cs_of_atan2<LIT>(tp.z, tp.x, c, s, degenerate);
+  at[5] = cs_and_angle<LIT>(tp.z, tp.x, c, s, degenerate);
   rot_y(pt, c, s);
   // (the x -= tip_z of sik:836-837 does not touch y, z); sik:848 wrist yaw
-  ay[6] = pt.y; ax[6] = pt.z;
-
-  double at[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) at[k] = atan2_leaf<LIT>(ay[k], ax[k], degenerate);
+  at[6] = atan2_leaf<LIT>(pt.y, pt.z, degenerate);
   // exact-zero singularities (sik:751, 782) make cs_of_atan2 flag the pose: literal route
   double shoulder_pitch = sing0 ? prev0 : -at[0];
   double shoulder_roll = at[1];

@@ -12,8 +12,12 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "r2ik_control.cuh"
 #include "r2ik_host.h"
@@ -28,6 +32,7 @@ using namespace r2ik;
 // ---------------------------------------------------------------------------------------
 // vectorised global memory helpers
 // ---------------------------------------------------------------------------------------
+// 128-bit read-only load: pose buffers must be 16-byte aligned (checked by the C entry points)
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 // 3x4 top of a row-major 4x4 (the last row is never read): 6 x 128-bit loads
@@ -72,6 +77,12 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
               double *__restrict__ elbow) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+#ifdef R2IK_K1_PREFETCH
+  {  // pull the pose a later wave of blocks will read into L2
+    const int64_t pf = i + (int64_t)R2IK_K1_PREFETCH * R2IK_BLOCK;
+    if (pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(poses + (KIND == R2IK_POSE_MAT4 ? 16 : 6) * pf));
+  }
+#endif
   double prev0 = 0.0, prev2 = 0.0;
   if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
   double pos[3];
@@ -102,6 +113,166 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
     for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
   }
   if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1, streaming form (MAT4 poses, all outputs, theta_interval[0]): persistent warps, each
+// owning tiles of 32 consecutive poses.
+//   in : one TMA bulk copy (cp.async.bulk, 4 KB contiguous) per tile into the warp's shared
+//        buffer, completion on the warp's mbarrier; the copy of the warp's NEXT tile is issued
+//        as soon as the current poses are in registers, so it lands during the solve;
+//   out: results are staged in shared memory and leave as five contiguous TMA bulk stores per
+//        tile (joints 1792 B, interval 512 B, elbow 768 B, flags 2 x 32 B).
+// No thread waits on a global load or drains global stores; the only synchronisation is
+// __syncwarp (no block barrier, so warps with early-out poses do not wait for their neighbours).
+// The same kernel runs with pinned HOST pointers (UVA): bulk copies are the PCIe-friendly
+// access pattern, which is the zero-copy end-to-end path of SymbolicIK.is_reachable_batch_host.
+// ---------------------------------------------------------------------------------------
+#define R2IK_TILE 32
+#define R2IK_STREAM_WARPS (R2IK_BLOCK / 32)
+
+struct __align__(128) R2ikWarpStage {
+  double in[R2IK_TILE * 16];       // 4096 B  poses of the tile, row-major 4x4
+  double joints[R2IK_TILE * 7];    // 1792 B
+  double interval[R2IK_TILE * 2];  //  512 B
+  double elbow[R2IK_TILE * 3];     //  768 B
+  uint8_t reach[R2IK_TILE];        //   32 B
+  uint8_t state[R2IK_TILE];        //   32 B
+  unsigned long long bar;          // mbarrier of the input buffer
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Tile scheduler: sched[0] = next tile to hand out, sched[1] = warps that have finished.  Warps
+// draw tiles with an atomic (one draw ahead, so its latency is hidden by the solve); the last warp
+// to finish zeroes both words, so the slot is ready for the next launch on the same stream.
+__device__ __forceinline__ int draw_tile(unsigned *sched, int lane) {
+  unsigned t = 0;
+  if (lane == 0) t = atomicAdd(sched, 1u);
+  return (int)__shfl_sync(0xffffffffu, t, 0);
+}
+
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
+k_symik_solve_stream(const __grid_constant__ ArmConst A, const double *__restrict__ poses, int64_t n, int n_tiles,
+                     unsigned *__restrict__ sched, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state,
+                     double *__restrict__ interval, double *__restrict__ joints, double *__restrict__ elbow) {
+  __shared__ R2ikWarpStage stage[R2IK_STREAM_WARPS];
+  const int lane = threadIdx.x & 31;
+  R2ikWarpStage &W = stage[threadIdx.x >> 5];
+  const uint32_t bar = smem_u32(&W.bar), in_s = smem_u32(W.in);
+  const int last_m = (int)(n - (int64_t)(n_tiles - 1) * R2IK_TILE);   // poses in the last tile (1..32)
+
+  int tile = draw_tile(sched, lane);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_async_smem();   // make the initialised barrier visible to the async proxy
+    if (tile < n_tiles) {
+      const uint32_t bytes = (uint32_t)(tile == n_tiles - 1 ? last_m : R2IK_TILE) * 128u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(in_s, poses + (size_t)tile * (R2IK_TILE * 16), bytes, bar);
+    }
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+#pragma unroll 1
+  while (tile < n_tiles) {
+    const int next = draw_tile(sched, lane);   // consumed after the solve: the atomic's latency is hidden
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    double mm[16];
+    {
+      const double2 *src = reinterpret_cast<const double2 *>(W.in + lane * 16);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        double2 a = src[2 * r], b = src[2 * r + 1];
+        mm[4 * r] = a.x; mm[4 * r + 1] = a.y; mm[4 * r + 2] = b.x; mm[4 * r + 3] = b.y;
+      }
+      mm[12] = 0.0; mm[13] = 0.0; mm[14] = 0.0; mm[15] = 1.0;
+    }
+    __syncwarp();   // every lane holds its pose: the input buffer is free for the next tile
+    if (lane == 0 && next < n_tiles) {
+      const uint32_t bytes = (uint32_t)(next == n_tiles - 1 ? last_m : R2IK_TILE) * 128u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(in_s, poses + (size_t)next * (R2IK_TILE * 16), bytes, bar);
+    }
+    const int m = tile == n_tiles - 1 ? last_m : R2IK_TILE;
+    // ---- solve
+    Reach rc;
+    double j[7], E[3];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) j[k] = NAN;
+    E[0] = NAN; E[1] = NAN; E[2] = NAN;
+    rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
+    if (lane < m) {
+      Solve S;
+      double pos[3] = {mm[3], mm[7], mm[11]};
+      if (rotation_from_mat4(mm, false, S.R)) rc = is_reachable_R<false>(A, pos, S);
+      if (rc.state == R2IK_STATE_REACHABLE) get_joints_cs(A, S, rc.c0, rc.s0, 0.0, 0.0, j, E);
+    }
+    const bool ok = rc.state == R2IK_STATE_REACHABLE;
+    // ---- results
+    if (m == R2IK_TILE) {
+      if (lane == 0) bulk_wait_read0();   // the previous tile's bulk stores have read the staging area
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 7; ++k) W.joints[lane * 7 + k] = j[k];
+      *reinterpret_cast<double2 *>(W.interval + lane * 2) = make_double2(rc.i0, rc.i1);
+      W.elbow[lane * 3] = E[0]; W.elbow[lane * 3 + 1] = E[1]; W.elbow[lane * 3 + 2] = E[2];
+      W.reach[lane] = ok ? 1 : 0;
+      W.state[lane] = (uint8_t)rc.state;
+      fence_async_smem();   // generic-proxy writes -> visible to the bulk-copy engine
+      __syncwarp();
+      if (lane == 0) {
+        const size_t base = (size_t)tile * R2IK_TILE;
+        bulk_s2g(joints + base * 7, smem_u32(W.joints), R2IK_TILE * 56);
+        bulk_s2g(interval + base * 2, smem_u32(W.interval), R2IK_TILE * 16);
+        bulk_s2g(elbow + base * 3, smem_u32(W.elbow), R2IK_TILE * 24);
+        bulk_s2g(reachable + base, smem_u32(W.reach), R2IK_TILE);
+        bulk_s2g(state + base, smem_u32(W.state), R2IK_TILE);
+        bulk_commit();
+      }
+    } else if (lane < m) {   // ragged last tile: plain stores
+      const size_t i = (size_t)tile * R2IK_TILE + lane;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+      interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1;
+      elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2];
+      reachable[i] = ok ? 1 : 0;
+      state[i] = (uint8_t)rc.state;
+    }
+    tile = next;
+  }
+  if (lane == 0) {
+    bulk_wait_read0();   // shared memory must outlive the bulk stores that read it
+    const unsigned total = gridDim.x * R2IK_STREAM_WARPS;
+    if (atomicAdd(sched + 1, 1u) == total - 1) {   // last warp out: re-arm the slot
+      sched[0] = 0u;
+      sched[1] = 0u;
+    }
+  }
 }
 
 template <int KIND>
@@ -381,7 +552,24 @@ struct r2ik_context {
   R2ikArmConfig cfg;
   ArmConst A;
   R2ikArmConstants pub;
+  int stream_blocks;   // persistent grid of k_symik_solve_stream: SMs x resident blocks (0: kernel unavailable)
+  int force_generic;   // R2IK_K1_GENERIC=1: always use the one-thread-per-pose kernel (A/B timing)
+  // tile-scheduler slots of k_symik_solve_stream, one per CUDA stream that has launched it (launches on
+  // one stream are ordered, so a slot is never shared by two running kernels); 2 x u32 each, self-resetting
+  std::mutex sched_mutex;
+  std::vector<std::pair<cudaStream_t, unsigned *>> sched_slots;
 };
+
+static unsigned *sched_slot_for(r2ik_context *h, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(h->sched_mutex);
+  for (auto &e : h->sched_slots)
+    if (e.first == s) return e.second;
+  unsigned *p = nullptr;
+  if (cudaMalloc(&p, 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+  if (cudaMemset(p, 0, 2 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p); return nullptr; }
+  h->sched_slots.emplace_back(s, p);
+  return p;
+}
 
 static thread_local char g_err[256] = "";
 
@@ -399,6 +587,7 @@ static int fail_cuda(cudaError_t e, const char *where) {
     if (e_ != cudaSuccess) return fail_cuda(e_, where); \
   } while (0)
 
+static inline bool misaligned16(const void *p) { return ((uintptr_t)p & 15) != 0; }
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + R2IK_BLOCK - 1) / R2IK_BLOCK); }
 
 extern "C" {
@@ -418,11 +607,28 @@ int r2ik_create(const R2ikArmConfig *cfg, int device, r2ik_handle *out) {
   h->device = device;
   h->cfg = *cfg;
   derive_constants(*cfg, h->A, h->pub);
+  {
+    // size the persistent grid of the streaming K1 from the occupancy the driver reports
+    h->stream_blocks = 0;
+    const char *g = getenv("R2IK_K1_GENERIC");
+    h->force_generic = (g && g[0] == '1') ? 1 : 0;
+    int sms = 0, per_sm = 0;
+    if (cudaSetDevice(device) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_symik_solve_stream, R2IK_BLOCK, 0) == cudaSuccess)
+      h->stream_blocks = sms * per_sm;
+    (void)cudaGetLastError();
+  }
   *out = h;
   return 0;
 }
 
 int r2ik_destroy(r2ik_handle h) {
+  if (h) {
+    if (!h->sched_slots.empty() && cudaSetDevice(h->device) == cudaSuccess)
+      for (auto &e : h->sched_slots) cudaFree(e.second);
+    (void)cudaGetLastError();
+  }
   delete h;
   return 0;
 }
@@ -458,8 +664,23 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null handle");
   if (n == 0) return 0;  // empty batch: nothing to read or write
   if (!poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
+  if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
+  // Streaming form: the common full-output call on 16-byte aligned buffers (TMA bulk copies).
+  const uintptr_t align_or = (uintptr_t)reachable | (uintptr_t)state | (uintptr_t)interval | (uintptr_t)joints | (uintptr_t)elbow;
+  if (pose_kind == R2IK_POSE_MAT4 && !theta && !prev_joints && interval && joints && elbow && (align_or & 15) == 0 &&
+      h->stream_blocks > 0 && !h->force_generic) {
+    const int64_t n_tiles = (n + R2IK_TILE - 1) / R2IK_TILE;
+    unsigned *sched = n_tiles < (int64_t)1 << 30 ? sched_slot_for(h, s) : nullptr;
+    if (sched) {
+      const int64_t want = (n_tiles + R2IK_STREAM_WARPS - 1) / R2IK_STREAM_WARPS;
+      const unsigned blocks = (unsigned)(want < (int64_t)h->stream_blocks ? want : (int64_t)h->stream_blocks);
+      k_symik_solve_stream<<<blocks, R2IK_BLOCK, 0, s>>>(h->A, poses, n, (int)n_tiles, sched, reachable, state, interval, joints, elbow);
+      R2IK_CUDA(cudaGetLastError(), "k_symik_solve_stream launch");
+      return 0;
+    }
+  }
   if (pose_kind == R2IK_POSE_MAT4)
     k_symik_solve<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
   else
@@ -475,6 +696,7 @@ int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, 
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null handle");
   if (n == 0) return 0;
   if (!poses || !theta || !joints) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null argument");
+  if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_no_limits_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
@@ -492,6 +714,7 @@ int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, 
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null handle");
   if (n == 0 || K == 0) return 0;
   if (!poses || !thetas || !elbows) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null argument");
+  if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_elbow_positions_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
@@ -510,6 +733,7 @@ int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double 
   if (n == 0) return 0;
   if (!M || !prev_joints || !current_joints || !joints || !reachable || !state)
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null argument");
+  if (misaligned16(M)) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_f64: M must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   k_ctl_discrete<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints, joints,
                                                                         reachable, state, emergency);
@@ -526,6 +750,8 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const doubl
   if (T == 0 || W == 0) return 0;
   if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state)
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_f64: null argument");
+  if (misaligned16(M) || misaligned16(current_pose))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_f64: M and current_pose must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   k_ctl_continuous<<<blocks_for(T), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
                                                                           joints, reachable, state);

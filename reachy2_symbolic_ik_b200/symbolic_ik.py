@@ -65,6 +65,8 @@ def normalise_poses(torch, poses, device):
     poses = poses.reshape(shp[0], k).contiguous()
     if not was_cuda:
         poses = poses.to(device, non_blocking=True)
+    elif poses.data_ptr() % 16:
+        poses = poses.clone()   # the C ABI reads poses with 128-bit loads
     return poses, kind, was_cuda
 
 

@@ -60,7 +60,10 @@ def cmd_sweep():
         env = dict(os.environ)
         if lib:
             env["R2IK_LIB"] = lib
-        subprocess.run([sys.executable, __file__, "time"], env=env)
+        for generic in (("0", "1") if lib is None else ("1",)):
+            env["R2IK_K1_GENERIC"] = generic
+            print("generic" if generic == "1" else "stream ", end=" ", flush=True)
+            subprocess.run([sys.executable, __file__, "time"], env=env)
 
 
 def cmd_zerocopy():

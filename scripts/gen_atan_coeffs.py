@@ -1,11 +1,13 @@
-"""Generate the polynomial coefficients of the device atan kernel (csrc/r2ik_math.cuh).
+"""Generate the polynomial coefficients of the device atan / asin kernels (csrc/r2ik_math.cuh).
 
-atan(q) = q * P(q^2) on q in [0, qmax]: P is the Chebyshev interpolant (near-minimax) of
-f(s) = atan(sqrt(s)) / sqrt(s) on s in [0, qmax^2], computed with mpmath at 60 digits and rounded
-to double.  Prints the monomial coefficients (c0 first) and the max relative error of the
-double-rounded polynomial evaluated in exact arithmetic.
+g(q) = q * P(q^2) on q in [0, qmax] for g = atan (default) or asin: P is the Chebyshev interpolant
+(near-minimax) of f(s) = g(sqrt(s)) / sqrt(s) on s in [0, qmax^2], computed with mpmath at 60
+digits and rounded to double.  Prints the monomial coefficients (c0 first) and the max relative
+error of the double-rounded polynomial evaluated in exact arithmetic.
 
-    python scripts/gen_atan_coeffs.py [qmax] [n_terms]
+    python scripts/gen_atan_coeffs.py [qmax] [n_terms] [atan|asin]
+    python scripts/gen_atan_coeffs.py 0.41421356237309515 12 atan    # tan(pi/8)
+    python scripts/gen_atan_coeffs.py 0.3826834323650898 12 asin     # sin(pi/8)
 """
 import sys
 
@@ -14,11 +16,14 @@ import mpmath as mp
 mp.mp.dps = 60
 
 
+G = mp.asin if (len(sys.argv) > 3 and sys.argv[3] == "asin") else mp.atan
+
+
 def f(s):
     if s == 0:
         return mp.mpf(1)
     r = mp.sqrt(s)
-    return mp.atan(r) / r
+    return G(r) / r
 
 
 def fit(qmax, n):

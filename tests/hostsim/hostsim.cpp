@@ -31,6 +31,16 @@ void hs_atan2_core(const double *y, const double *x, int64_t n, double *out, uin
   }
 }
 
+// angle_of_unit on (x, y) / |(x, y)| normalised the way cs_of_atan2 does
+void hs_angle_of_unit(const double *y, const double *x, int64_t n, double *out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double c, s;
+    bool degenerate = false;
+    cs_of_atan2<false>(y[i], x[i], c, s, degenerate);
+    out[i] = degenerate ? NAN : angle_of_unit(c, s);
+  }
+}
+
 void hs_constants(const R2ikArmConfig *cfg, R2ikArmConstants *pub) {
   ArmConst A;
   derive_constants(*cfg, A, *pub);

@@ -217,3 +217,78 @@ def test_mirror_symmetry(solvers):
     sign = np.array([1, -1, -1, 1, -1, 1, -1.0])
     d = np.abs(np.angle(np.exp(1j * (l.joints[both] - r.joints[both] * sign))))
     assert np.quantile(d.max(axis=1), 0.999) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 4099, 200_001])
+def test_stream_kernel_matches_generic_kernel(solvers, n):
+    """The streaming K1 (TMA bulk tiles, chosen for aligned full-output calls) and the one-thread-per-pose
+    K1 (misaligned output buffers, optional outputs, theta given) must agree bit for bit, incl. ragged tails."""
+    import torch
+
+    from reachy2_symbolic_ik_b200 import _abi, fk
+
+    ik = solvers["r_arm"]
+    M = np.concatenate([fk.sample_fk_poses(n - n // 3, "r_arm", seed=n), fk.sample_task_space_poses(n // 3, "r_arm", seed=n + 1)])
+    dev = torch.device("cuda", 0)
+
+    def run(offset):
+        # offset = 1 element: every OUTPUT buffer starts 8 bytes (1 byte for the flags) off a 16-byte
+        # boundary (poses must be 16-byte aligned by contract)
+        P = torch.from_numpy(M).reshape(-1).to(dev)
+        reach = torch.zeros(n + 16, dtype=torch.uint8, device=dev)[offset:offset + n]
+        state = torch.zeros(n + 16, dtype=torch.uint8, device=dev)[offset:offset + n]
+        itv = torch.zeros(n * 2 + 2, dtype=torch.float64, device=dev)[offset:offset + 2 * n]
+        j = torch.zeros(n * 7 + 2, dtype=torch.float64, device=dev)[offset:offset + 7 * n]
+        e = torch.zeros(n * 3 + 2, dtype=torch.float64, device=dev)[offset:offset + 3 * n]
+
+        class V:   # solve_into only needs data_ptr() / shape[0]
+            def __init__(s, t, rows): s.t, s.shape = t, (rows,)
+            def data_ptr(s): return s.t.data_ptr()
+        ik.solve_into(V(P, n), _abi.POSE_MAT4, None, None, reach, state, itv, j, e)
+        torch.cuda.synchronize()
+        return [x.cpu().numpy().copy() for x in (reach, state, itv, j, e)]
+
+    aligned, misaligned = run(0), run(1)
+    for a, b in zip(aligned, misaligned):
+        np.testing.assert_array_equal(a, b)
+    assert aligned[0].sum() > 0 or n < 4
+
+
+def test_stream_kernel_zero_copy_pinned_host(solvers):
+    """The same launch with pinned HOST buffers (UVA): results identical to the device-resident call."""
+    import torch
+
+    from reachy2_symbolic_ik_b200 import _abi, fk
+
+    ik = solvers["l_arm"]
+    n = 50_000
+    M = fk.sample_fk_poses(n, "l_arm", seed=5)
+    want = ik.is_reachable_batch(M)
+    hin = torch.from_numpy(M).reshape(n, 16).pin_memory()
+    out = ik.alloc_host_outputs(n)
+    ik.solve_into(hin, _abi.POSE_MAT4, None, None, out.reachable, out.state, out.theta_interval, out.joints, out.elbow)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.state.numpy(), want.state)
+    np.testing.assert_array_equal(out.joints.numpy(), want.joints)
+    np.testing.assert_array_equal(out.theta_interval.numpy(), want.theta_interval)
+    np.testing.assert_array_equal(out.elbow.numpy(), want.elbow)
+
+
+def test_misaligned_pose_pointer_is_an_argument_error(solvers):
+    import torch
+
+    from reachy2_symbolic_ik_b200 import _abi, _native
+
+    ik = solvers["r_arm"]
+    buf = torch.zeros(16 * 4 + 1, dtype=torch.float64, device="cuda")
+    P = buf[1:]
+
+    class V:
+        shape = (4,)
+        def data_ptr(self): return P.data_ptr()
+    o = ik.alloc_host_outputs(4)
+    with pytest.raises(_native.R2ikError, match="16-byte aligned"):
+        ik.solve_into(V(), _abi.POSE_MAT4, None, None, o.reachable, o.state, o.theta_interval, o.joints, o.elbow)
+    # the facade re-aligns such a view instead of failing
+    res = ik.is_reachable_batch(P.reshape(4, 16))
+    assert res.state.shape == (4,)

@@ -74,3 +74,34 @@ def test_atan2_core_ok_rejects_out_of_range(hs):
     x = np.array([0.0, 1e-312, 1e308, 1.0, 1.0, np.inf])
     _, ok = run(hs, y, x)
     assert not ok.any()
+
+
+def test_angle_of_unit_vs_mpmath(hs):
+    """atan2 of a normalised vector without the division (used for the angles whose (cos, sin) the
+    solver needs anyway): a few 1e-16 rad absolute against the true atan2 of the un-normalised input."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(1)
+    ang = rng.uniform(-np.pi, np.pi, 20000)
+    r = 10.0 ** rng.uniform(-6, 2, ang.size)
+    y, x = r * np.sin(ang), r * np.cos(ang)
+    y = np.concatenate([y, [0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1.0, 1.0, 0.38268343236508978, 1e-9]])
+    x = np.concatenate([x, [1.0, 1.0, -1.0, -1.0, 0.0, 0.0, 1.0, -1.0, 0.92387953251128674, 1.0]])
+    out = np.empty_like(y)
+    dp = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(C.c_double))
+    y = np.ascontiguousarray(y); x = np.ascontiguousarray(x)
+    hs.hs_angle_of_unit(dp(y), dp(x), C.c_int64(len(y)), dp(out))
+    want = np.arctan2(y, x)
+    assert np.array_equal(np.signbit(out), np.signbit(want))
+    worst_abs, worst_rel = 0.0, 0.0
+    assert np.max(np.abs(out - want)) < 1e-15          # incl. the signed-zero cases (+-pi, +-0)
+    for yi, xi, gi in zip(y, x, out):
+        if yi == 0.0:
+            continue                                     # mpmath has no signed zero
+        w = mp.atan2(mp.mpf(float(yi)), mp.mpf(float(xi)))
+        e = float(abs(mp.mpf(float(gi)) - w))
+        worst_abs = max(worst_abs, e)
+        if w != 0:
+            worst_rel = max(worst_rel, e / float(abs(w)))
+    assert worst_abs < 1e-15, worst_abs
+    assert worst_rel < 2e-15, worst_rel     # small angles keep relative accuracy (asin(u) ~ u)
