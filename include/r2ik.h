@@ -38,15 +38,11 @@
  *        the FK round-trip property tests.
  *
  * Conventions
- *   - All data pointers are DEVICE-ACCESSIBLE pointers unless a parameter says "host": device
- *     memory, or pinned host memory under unified addressing (zero-copy over PCIe /
- *     NVLink-C2C; r2ik_symik_solve_f64 then moves whole 32-pose tiles with TMA bulk copies).
+ *   - All data pointers are DEVICE pointers unless a parameter says "host".
  *   - Pose buffers (poses / M / current_pose) must be 16-byte aligned (128-bit loads);
  *     a misaligned pointer is R2IK_ERR_ARG.
  *   - Every launch entry takes a cudaStream_t (passed as void*; NULL = legacy default
- *     stream) and is asynchronous with respect to the host.  No entry allocates per call;
- *     the first r2ik_symik_solve_f64 on a given stream allocates that stream's 8-byte
- *     tile-scheduler slot (freed by r2ik_destroy).
+ *     stream), is asynchronous with respect to the host and allocates nothing.
  *   - Return value: 0 = ok, > 0 = argument error (R2IK_ERR_*), < 0 = -(cudaError_t).
  *   - No exceptions cross this boundary; r2ik_last_error() gives a static message.
  *   - The library has no CPU implementation of any entry point.

@@ -16,12 +16,56 @@ R2IK_HD void search_range(double i0, double i1, double &start, double &stop) {
   else { start = i0; stop = i1 + kTwoPi; }
 }
 
-// One sample of the search loop (utl:381-390): cost = |angle_diff(theta, preferred)| or +inf.
-R2IK_HD double sample_cost(const ArmConst &A, const Solve &S, double theta, double preferred_theta) {
-  double E[3];
-  elbow_position(S, theta, E);
-  if (!is_elbow_ok(A, E)) return INFINITY;
-  return fabs(angle_diff(theta, preferred_theta));
+// is_elbow_ok(get_elbow_position(theta)) (utl:443-465 on sik:684-695) as two half-plane tests in
+// (cos theta, sin theta): the elbow point is c + a1 r cos + a2 r sin, and both conditions of the
+// predicate are linear in it:
+//   E.y side < -0.2                                   <=>  C1 + A1 cos + B1 sin < 0
+//   E.z < (E.x - es.x) coeff + es.z - offset          <=>  C2 + A2 cos + B2 sin < 0
+// Hoisting the six coefficients out of the K-sample loop leaves 4 FMA + 2 compares per sample
+// (algebraically the same predicate; it can differ from the literal evaluation only for an elbow
+// within rounding of a limit plane).
+struct ElbowTest { double A1, B1, C1, A2, B2, C2; };
+
+R2IK_HD ElbowTest make_elbow_test(const ArmConst &A, const Solve &S) {
+  ElbowTest T;
+  T.A1 = A.side * S.a1[1] * S.r;
+  T.B1 = A.side * S.a2[1] * S.r;
+  T.C1 = A.side * S.c[1] + 0.2;
+  T.A2 = (S.a1[2] - A.sing_coeff * S.a1[0]) * S.r;
+  T.B2 = (S.a2[2] - A.sing_coeff * S.a2[0]) * S.r;
+  T.C2 = (S.c[2] - A.sing_coeff * S.c[0]) + (A.sing_coeff * A.es[0] - A.es[2] + A.sing_offset);
+  return T;
+}
+R2IK_HD bool elbow_ok_cs(const ElbowTest &T, double c, double s) {
+  return (T.C1 + T.A1 * c + T.B1 * s < 0.0) && (T.C2 + T.A2 * c + T.B2 * s < 0.0);
+}
+
+// The K samples of the search (utl:366-390) for one pose: theta_k = linspace(start, stop, K)[k].
+// cos / sin of the samples a thread visits (k0, k0 + stride, ...) follow from one sincos and a
+// fixed rotation by stride * step per sample instead of a sincos each.
+struct SearchPlan {
+  Linspace L;
+  ElbowTest T;
+  double preferred_theta;
+};
+
+// Lowest cost among samples k0, k0 + stride, ... < nb (strict <: the first minimum wins, utl:386).
+R2IK_HD void search_strided(const SearchPlan &P, int nb, int k0, int stride, double &best, int &best_k) {
+  best = INFINITY;
+  best_k = 0x7fffffff;
+  if (k0 >= nb) return;
+  double c, s, cd, sd;
+  sincos(linspace_value(P.L, k0), &s, &c);
+  sincos((double)stride * P.L.step, &sd, &cd);
+  for (int k = k0; k < nb; k += stride) {
+    if (elbow_ok_cs(P.T, c, s)) {
+      double cost = fabs(angle_diff(linspace_value(P.L, k), P.preferred_theta));
+      if (cost < best) { best = cost; best_k = k; }
+    }
+    double cn = c * cd - s * sd;
+    s = s * cd + c * sd;
+    c = cn;
+  }
 }
 
 // utl:357-364: preferred_theta is tried first
@@ -39,14 +83,16 @@ R2IK_HD bool best_discrete_theta(const ArmConst &A, const Solve &S, double i0, d
   if (preferred_theta_works(A, S, i0, i1, preferred_theta)) { theta = preferred_theta; return true; }
   double start, stop;
   search_range(i0, i1, start, stop);
-  double best = INFINITY, best_theta = 0.0;
-  for (int i = 0; i < nb; ++i) {
-    double th = linspace_at(start, stop, nb, i);
-    double cost = sample_cost(A, S, th, preferred_theta);
-    if (cost < best) { best = cost; best_theta = th; }
-  }
-  theta = best_theta;
-  return best < INFINITY;
+  SearchPlan P;
+  P.L = make_linspace(start, stop, nb);
+  P.T = make_elbow_test(A, S);
+  P.preferred_theta = preferred_theta;
+  double best;
+  int best_k;
+  search_strided(P, nb, 0, 1, best, best_k);
+  if (!(best < INFINITY)) { theta = 0.0; return false; }
+  theta = linspace_value(P.L, best_k);
+  return true;
 }
 
 // Step toward a target theta by at most d_theta_max (utl:252-264, utl:123-127)

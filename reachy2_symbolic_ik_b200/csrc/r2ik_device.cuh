@@ -106,22 +106,37 @@ R2IK_HD double pymod(double a, double m) {
   return r;
 }
 
+// pymod(x, 2 pi) for the arguments the controller produces.  Python's float % is fmod (exact) plus at
+// most one rounded `+ m`.  For -2 pi <= x < 8 pi the exact remainder is reached by subtracting 4 pi /
+// 2 pi when x is at least that: 2 pi and 4 pi are exact multiples of the same double and every
+// difference below is exactly representable (both operands are multiples of the ulp of the result
+// range), so each step is error-free and the value is bit-identical to fmod's.  Negative x in
+// [-2 pi, 0) is Python's `fmod(x) + m`, one rounded add, as here.  Anything else takes pymod().
+R2IK_HD double pymod_2pi(double x) {
+  if (!(x >= -kTwoPi && x < 4.0 * kTwoPi)) return pymod(x, kTwoPi);
+  if (x < 0.0) return x + kTwoPi;
+  double r = x;
+  if (r >= 2.0 * kTwoPi) r -= 2.0 * kTwoPi;
+  if (r >= kTwoPi) r -= kTwoPi;
+  return r;
+}
+
 // utl:486-490
-R2IK_HD double angle_diff(double a, double b) { return pymod((a - b) + kPi, kTwoPi) - kPi; }
+R2IK_HD double angle_diff(double a, double b) { return pymod_2pi((a - b) + kPi) - kPi; }
 
 // np.isclose(a, b), rtol 1e-5, atol 1e-8 (asymmetric in b)
 R2IK_HD bool np_isclose(double a, double b) { return fabs(a - b) <= 1e-8 + 1e-5 * fabs(b); }
 
 // utl:468-474
 R2IK_HD bool is_valid_angle(double angle, double i0, double i1) {
-  if (pymod(i0, kTwoPi) == pymod(i1, kTwoPi)) return true;
+  if (pymod_2pi(i0) == pymod_2pi(i1)) return true;
   if (i0 < i1) return (i0 <= angle) && (angle <= i1);
   return (i0 <= angle) || (angle <= i1);
 }
 
 // utl:93-112 (previous_theta is normalised but never used by the reference)
 R2IK_HD double limit_theta_to_interval(double theta, double i0, double i1) {
-  theta = pymod(theta, kTwoPi);
+  theta = pymod_2pi(theta);
   if (theta > kPi) theta -= kTwoPi;
   if (is_valid_angle(theta, i0, i1)) return theta;
   double pos_diff = angle_diff(theta, i1);
@@ -130,15 +145,31 @@ R2IK_HD double limit_theta_to_interval(double theta, double i0, double i1) {
   return i0;
 }
 
-// np.linspace(start, stop, num)[i], endpoint=True
-R2IK_HD double linspace_at(double start, double stop, int num, int i) {
-  int div = num - 1;
-  if (div <= 0) return start;
-  if (i == div) return stop;
-  double delta = stop - start;
-  double step = delta / (double)div;
-  if (step == 0.0) return ((double)i / (double)div) * delta + start;
-  return (double)i * step + start;
+// a * b + c with two roundings (numpy evaluates linspace as arange * step + start, unfused)
+R2IK_HD double mul_add_unfused(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(__dmul_rn(a, b), c);
+#else
+  return a * b + c;
+#endif
+}
+
+// np.linspace(start, stop, num) with the per-array quantities hoisted out of the sample loop
+struct Linspace {
+  double start, stop, delta, step;
+  int div;
+};
+R2IK_HD Linspace make_linspace(double start, double stop, int num) {
+  Linspace L;
+  L.start = start; L.stop = stop; L.div = num - 1; L.delta = stop - start;
+  L.step = L.div > 0 ? L.delta / (double)L.div : 0.0;
+  return L;
+}
+R2IK_HD double linspace_value(const Linspace &L, int i) {
+  if (L.div <= 0) return L.start;
+  if (i == L.div) return L.stop;
+  if (L.step == 0.0) return mul_add_unfused((double)i / (double)L.div, L.delta, L.start);
+  return mul_add_unfused((double)i, L.step, L.start);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -281,9 +312,9 @@ R2IK_HD void get_angles(bool extrinsic, bool symmetric, double sign, double a, d
     ang1 = ang1 - kHalfPi;
   }
   if (extrinsic) { ang0 = first; ang2 = third; } else { ang2 = first; ang0 = third; }
-  out[0] = pymod(ang0 + kPi, kTwoPi) - kPi;
-  out[1] = pymod(ang1 + kPi, kTwoPi) - kPi;
-  out[2] = pymod(ang2 + kPi, kTwoPi) - kPi;
+  out[0] = pymod_2pi(ang0 + kPi) - kPi;
+  out[1] = pymod_2pi(ang1 + kPi) - kPi;
+  out[2] = pymod_2pi(ang2 + kPi) - kPi;
 }
 
 // rxp:365-404 as_euler for the three sequences the reference uses
@@ -319,6 +350,40 @@ R2IK_HD bool rotation_is_identity(const double *M) {
 
 // utl:508-519 limit_orbita3d_joints on joints[4:7]
 R2IK_HD void limit_orbita3d_wrist(double j[7], double max_angle) {
+  // Algebraic route.  For R = Rx(a) Ry(b) Rz(c) = Rz(alpha) Ry(beta) Rz(gamma):
+  //   cos(beta) = R22 = cos a cos b,   (cos alpha, sin alpha) sin(beta) = (R02, R12) = (sin b, -sin a cos b),
+  //   (-cos gamma, sin gamma) sin(beta) = (R20, R21).
+  // Inside the cone (beta <= max) with (a, b, c) in as_euler's canonical ranges the four conversions
+  // are the identity (to rounding).  Outside, the clamped rotation Rz(alpha) Ry(max) Rz(gamma) is built
+  // from those unit vectors and read back as XYZ angles (a' = atan2(-R12, R22), b' = asin(R02),
+  // c' = atan2(-R01, R00)): three small sincos, one rsqrt, three atan2, all straight-line.  Inputs in
+  // a gimbal band of either sequence (where scipy zeroes an angle) or outside the canonical ranges take
+  // the literal conversions below.
+  {
+    const double a = j[4], b = j[5], c = j[6];
+    if (fabs(a) <= kPi && fabs(c) <= kPi && fabs(b) < kHalfPi - 1e-3 && sincos_small_ok(max_angle)) {
+      double sa, ca, sb, cb, sm, cm;
+      sincos_small(a, sa, ca);
+      sincos_small(b, sb, cb);
+      sincos_small(max_angle, sm, cm);
+      const double cbeta = ca * cb;
+      if (cbeta < 1.0 - 1e-12) {          // beta > ~1.4e-6: outside scipy's ZYZ gimbal band (1e-7)
+        if (cbeta >= cm) return;          // inside the cone
+        double sc, cc;
+        sincos_small(c, sc, cc);
+        const double r02 = sb, r12 = -sa * cb;
+        const double r20 = sa * sc - ca * sb * cc, r21 = sa * cc + ca * sb * sc;
+        const double isb = rsqrt_pos(r02 * r02 + r12 * r12);
+        const double cal = r02 * isb, sal = r12 * isb, cga = -r20 * isb, sga = r21 * isb;
+        const double q02 = cal * sm, q12 = sal * sm, q22 = cm;
+        const double q00 = cal * cm * cga - sal * sga, q01 = -(cal * cm) * sga - sal * cga;
+        j[4] = atan2_core(-q12, q22);
+        j[5] = atan2_core(q02, sqrt_nonneg(q12 * q12 + q22 * q22));
+        j[6] = atan2_core(-q01, q00);
+        return;
+      }
+    }
+  }
   Quat q = quat_from_euler(0, 1, 2, true, j[4], j[5], j[6]);   // from_euler("XYZ")
   double zyz[3];
   quat_as_euler_ZYZ_intrinsic(q, zyz);

@@ -12,12 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
-#include <utility>
-#include <vector>
 
 #include "r2ik_control.cuh"
 #include "r2ik_host.h"
@@ -115,166 +111,6 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
   if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
 }
 
-// ---------------------------------------------------------------------------------------
-// K1, streaming form (MAT4 poses, all outputs, theta_interval[0]): persistent warps, each
-// owning tiles of 32 consecutive poses.
-//   in : one TMA bulk copy (cp.async.bulk, 4 KB contiguous) per tile into the warp's shared
-//        buffer, completion on the warp's mbarrier; the copy of the warp's NEXT tile is issued
-//        as soon as the current poses are in registers, so it lands during the solve;
-//   out: results are staged in shared memory and leave as five contiguous TMA bulk stores per
-//        tile (joints 1792 B, interval 512 B, elbow 768 B, flags 2 x 32 B).
-// No thread waits on a global load or drains global stores; the only synchronisation is
-// __syncwarp (no block barrier, so warps with early-out poses do not wait for their neighbours).
-// The same kernel runs with pinned HOST pointers (UVA): bulk copies are the PCIe-friendly
-// access pattern, which is the zero-copy end-to-end path of SymbolicIK.is_reachable_batch_host.
-// ---------------------------------------------------------------------------------------
-#define R2IK_TILE 32
-#define R2IK_STREAM_WARPS (R2IK_BLOCK / 32)
-
-struct __align__(128) R2ikWarpStage {
-  double in[R2IK_TILE * 16];       // 4096 B  poses of the tile, row-major 4x4
-  double joints[R2IK_TILE * 7];    // 1792 B
-  double interval[R2IK_TILE * 2];  //  512 B
-  double elbow[R2IK_TILE * 3];     //  768 B
-  uint8_t reach[R2IK_TILE];        //   32 B
-  uint8_t state[R2IK_TILE];        //   32 B
-  unsigned long long bar;          // mbarrier of the input buffer
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Tile scheduler: sched[0] = next tile to hand out, sched[1] = warps that have finished.  Warps
-// draw tiles with an atomic (one draw ahead, so its latency is hidden by the solve); the last warp
-// to finish zeroes both words, so the slot is ready for the next launch on the same stream.
-__device__ __forceinline__ int draw_tile(unsigned *sched, int lane) {
-  unsigned t = 0;
-  if (lane == 0) t = atomicAdd(sched, 1u);
-  return (int)__shfl_sync(0xffffffffu, t, 0);
-}
-
-__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
-k_symik_solve_stream(const __grid_constant__ ArmConst A, const double *__restrict__ poses, int64_t n, int n_tiles,
-                     unsigned *__restrict__ sched, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state,
-                     double *__restrict__ interval, double *__restrict__ joints, double *__restrict__ elbow) {
-  __shared__ R2ikWarpStage stage[R2IK_STREAM_WARPS];
-  const int lane = threadIdx.x & 31;
-  R2ikWarpStage &W = stage[threadIdx.x >> 5];
-  const uint32_t bar = smem_u32(&W.bar), in_s = smem_u32(W.in);
-  const int last_m = (int)(n - (int64_t)(n_tiles - 1) * R2IK_TILE);   // poses in the last tile (1..32)
-
-  int tile = draw_tile(sched, lane);
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    fence_async_smem();   // make the initialised barrier visible to the async proxy
-    if (tile < n_tiles) {
-      const uint32_t bytes = (uint32_t)(tile == n_tiles - 1 ? last_m : R2IK_TILE) * 128u;
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s(in_s, poses + (size_t)tile * (R2IK_TILE * 16), bytes, bar);
-    }
-  }
-  __syncwarp();
-  uint32_t parity = 0;
-#pragma unroll 1
-  while (tile < n_tiles) {
-    const int next = draw_tile(sched, lane);   // consumed after the solve: the atomic's latency is hidden
-    mbar_wait(bar, parity);
-    parity ^= 1u;
-    double mm[16];
-    {
-      const double2 *src = reinterpret_cast<const double2 *>(W.in + lane * 16);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        double2 a = src[2 * r], b = src[2 * r + 1];
-        mm[4 * r] = a.x; mm[4 * r + 1] = a.y; mm[4 * r + 2] = b.x; mm[4 * r + 3] = b.y;
-      }
-      mm[12] = 0.0; mm[13] = 0.0; mm[14] = 0.0; mm[15] = 1.0;
-    }
-    __syncwarp();   // every lane holds its pose: the input buffer is free for the next tile
-    if (lane == 0 && next < n_tiles) {
-      const uint32_t bytes = (uint32_t)(next == n_tiles - 1 ? last_m : R2IK_TILE) * 128u;
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s(in_s, poses + (size_t)next * (R2IK_TILE * 16), bytes, bar);
-    }
-    const int m = tile == n_tiles - 1 ? last_m : R2IK_TILE;
-    // ---- solve
-    Reach rc;
-    double j[7], E[3];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) j[k] = NAN;
-    E[0] = NAN; E[1] = NAN; E[2] = NAN;
-    rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
-    if (lane < m) {
-      Solve S;
-      double pos[3] = {mm[3], mm[7], mm[11]};
-      if (rotation_from_mat4(mm, false, S.R)) rc = is_reachable_R<false>(A, pos, S);
-      if (rc.state == R2IK_STATE_REACHABLE) get_joints_cs(A, S, rc.c0, rc.s0, 0.0, 0.0, j, E);
-    }
-    const bool ok = rc.state == R2IK_STATE_REACHABLE;
-    // ---- results
-    if (m == R2IK_TILE) {
-      if (lane == 0) bulk_wait_read0();   // the previous tile's bulk stores have read the staging area
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 7; ++k) W.joints[lane * 7 + k] = j[k];
-      *reinterpret_cast<double2 *>(W.interval + lane * 2) = make_double2(rc.i0, rc.i1);
-      W.elbow[lane * 3] = E[0]; W.elbow[lane * 3 + 1] = E[1]; W.elbow[lane * 3 + 2] = E[2];
-      W.reach[lane] = ok ? 1 : 0;
-      W.state[lane] = (uint8_t)rc.state;
-      fence_async_smem();   // generic-proxy writes -> visible to the bulk-copy engine
-      __syncwarp();
-      if (lane == 0) {
-        const size_t base = (size_t)tile * R2IK_TILE;
-        bulk_s2g(joints + base * 7, smem_u32(W.joints), R2IK_TILE * 56);
-        bulk_s2g(interval + base * 2, smem_u32(W.interval), R2IK_TILE * 16);
-        bulk_s2g(elbow + base * 3, smem_u32(W.elbow), R2IK_TILE * 24);
-        bulk_s2g(reachable + base, smem_u32(W.reach), R2IK_TILE);
-        bulk_s2g(state + base, smem_u32(W.state), R2IK_TILE);
-        bulk_commit();
-      }
-    } else if (lane < m) {   // ragged last tile: plain stores
-      const size_t i = (size_t)tile * R2IK_TILE + lane;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
-      interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1;
-      elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2];
-      reachable[i] = ok ? 1 : 0;
-      state[i] = (uint8_t)rc.state;
-    }
-    tile = next;
-  }
-  if (lane == 0) {
-    bulk_wait_read0();   // shared memory must outlive the bulk stores that read it
-    const unsigned total = gridDim.x * R2IK_STREAM_WARPS;
-    if (atomicAdd(sched + 1, 1u) == total - 1) {   // last warp out: re-arm the slot
-      sched[0] = 0u;
-      sched[1] = 0u;
-    }
-  }
-}
-
 template <int KIND>
 __global__ void __launch_bounds__(R2IK_BLOCK)
 k_symik_no_limits(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ theta,
@@ -322,7 +158,10 @@ k_elbow_positions(const __grid_constant__ ArmConst A, const double *__restrict__
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-__global__ void __launch_bounds__(R2IK_BLOCK)
+#ifndef R2IK_K2_MINBLOCKS
+#define R2IK_K2_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K2_MINBLOCKS)
 k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
                const double *__restrict__ M, int64_t n, const double *__restrict__ prev_joints,
                const double *__restrict__ current_joints, double *__restrict__ joints, uint8_t *__restrict__ reachable,
@@ -337,7 +176,10 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
   Solve S;
   int st = R2IK_STATE_INVALID_ROTATION;
   bool found = false, need_search = false, valid_pose = false;
-  double theta = 0.0, start = 0.0, stop = 0.0;
+  double theta = 0.0;
+  const int nb = par.nb_search_points;
+  SearchPlan plan;
+  plan.preferred_theta = par.preferred_theta;
   if (active) {
     double pos[3];
     valid_pose = load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R);
@@ -349,29 +191,28 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
           theta = par.preferred_theta; found = true;
         } else {
           need_search = true;
+          double start, stop;
           search_range(rc.i0, rc.i1, start, stop);
+          plan.L = make_linspace(start, stop, nb);
+          plan.T = make_elbow_test(A, S);
         }
       }
     }
   }
-  const int nb = par.nb_search_points;
   unsigned pending = __ballot_sync(0xffffffffu, need_search);
   while (pending) {
     const int src = __ffs(pending) - 1;
     pending &= pending - 1;
-    Solve B;  // only the fields elbow_position reads
-    B.c[0] = shfl_d(S.c[0], src); B.c[1] = shfl_d(S.c[1], src); B.c[2] = shfl_d(S.c[2], src);
-    B.a1[0] = shfl_d(S.a1[0], src); B.a1[1] = shfl_d(S.a1[1], src); B.a1[2] = shfl_d(S.a1[2], src);
-    B.a2[0] = shfl_d(S.a2[0], src); B.a2[1] = shfl_d(S.a2[1], src); B.a2[2] = shfl_d(S.a2[2], src);
-    B.r = shfl_d(S.r, src);
-    const double b_start = shfl_d(start, src), b_stop = shfl_d(stop, src);
-    double best = INFINITY;
-    int best_k = 0x7fffffff;
-    for (int k = lane; k < nb; k += 32) {
-      double th = linspace_at(b_start, b_stop, nb, k);
-      double cost = sample_cost(A, B, th, par.preferred_theta);
-      if (cost < best) { best = cost; best_k = k; }
-    }
+    SearchPlan B;   // the plan of lane `src`, broadcast
+    B.preferred_theta = par.preferred_theta;
+    B.L.div = nb - 1;
+    B.L.start = shfl_d(plan.L.start, src); B.L.stop = shfl_d(plan.L.stop, src);
+    B.L.delta = shfl_d(plan.L.delta, src); B.L.step = shfl_d(plan.L.step, src);
+    B.T.A1 = shfl_d(plan.T.A1, src); B.T.B1 = shfl_d(plan.T.B1, src); B.T.C1 = shfl_d(plan.T.C1, src);
+    B.T.A2 = shfl_d(plan.T.A2, src); B.T.B2 = shfl_d(plan.T.B2, src); B.T.C2 = shfl_d(plan.T.C2, src);
+    double best;
+    int best_k;
+    search_strided(B, nb, lane, 32, best, best_k);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       double ob = __shfl_xor_sync(0xffffffffu, best, off);
@@ -380,7 +221,7 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
     }
     if (lane == src) {
       found = best < INFINITY;
-      if (found) theta = linspace_at(start, stop, nb, best_k);
+      if (found) theta = linspace_value(plan.L, best_k);
       else st = R2IK_STATE_LIMITED_BY_SHOULDER;
     }
   }
@@ -405,7 +246,17 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
 // (previous_theta / previous_sol / init / emergency latch), so one thread owns one trajectory
 // and keeps the controller state in registers; parallelism comes from the trajectories.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(R2IK_BLOCK)
+// Launch shape of K3: 65 536 trajectories are only 2 048 warps, 13.8 per SM.  Blocks of 64 threads held
+// to 128 registers (7 blocks = 14 warps per SM) make the whole batch resident in one wave and spread
+// it evenly over the 148 SMs; the unconstrained allocation (240 registers, 8 warps / SM) needed two
+// waves, the second 73 % full: 49 ms vs 32 ms for cfg 4 (profiles/r1_experiments.md).
+#ifndef R2IK_K3_BLOCK
+#define R2IK_K3_BLOCK 64
+#endif
+#ifndef R2IK_K3_MINBLOCKS
+#define R2IK_K3_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
 k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
                  const double *__restrict__ M, int64_t T, int W, const double *__restrict__ current_joints,
                  const double *__restrict__ current_pose, R2ikTrajState *__restrict__ states,
@@ -552,24 +403,7 @@ struct r2ik_context {
   R2ikArmConfig cfg;
   ArmConst A;
   R2ikArmConstants pub;
-  int stream_blocks;   // persistent grid of k_symik_solve_stream: SMs x resident blocks (0: kernel unavailable)
-  int force_generic;   // R2IK_K1_GENERIC=1: always use the one-thread-per-pose kernel (A/B timing)
-  // tile-scheduler slots of k_symik_solve_stream, one per CUDA stream that has launched it (launches on
-  // one stream are ordered, so a slot is never shared by two running kernels); 2 x u32 each, self-resetting
-  std::mutex sched_mutex;
-  std::vector<std::pair<cudaStream_t, unsigned *>> sched_slots;
 };
-
-static unsigned *sched_slot_for(r2ik_context *h, cudaStream_t s) {
-  std::lock_guard<std::mutex> lock(h->sched_mutex);
-  for (auto &e : h->sched_slots)
-    if (e.first == s) return e.second;
-  unsigned *p = nullptr;
-  if (cudaMalloc(&p, 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
-  if (cudaMemset(p, 0, 2 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p); return nullptr; }
-  h->sched_slots.emplace_back(s, p);
-  return p;
-}
 
 static thread_local char g_err[256] = "";
 
@@ -607,28 +441,11 @@ int r2ik_create(const R2ikArmConfig *cfg, int device, r2ik_handle *out) {
   h->device = device;
   h->cfg = *cfg;
   derive_constants(*cfg, h->A, h->pub);
-  {
-    // size the persistent grid of the streaming K1 from the occupancy the driver reports
-    h->stream_blocks = 0;
-    const char *g = getenv("R2IK_K1_GENERIC");
-    h->force_generic = (g && g[0] == '1') ? 1 : 0;
-    int sms = 0, per_sm = 0;
-    if (cudaSetDevice(device) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_symik_solve_stream, R2IK_BLOCK, 0) == cudaSuccess)
-      h->stream_blocks = sms * per_sm;
-    (void)cudaGetLastError();
-  }
   *out = h;
   return 0;
 }
 
 int r2ik_destroy(r2ik_handle h) {
-  if (h) {
-    if (!h->sched_slots.empty() && cudaSetDevice(h->device) == cudaSuccess)
-      for (auto &e : h->sched_slots) cudaFree(e.second);
-    (void)cudaGetLastError();
-  }
   delete h;
   return 0;
 }
@@ -667,20 +484,6 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
-  // Streaming form: the common full-output call on 16-byte aligned buffers (TMA bulk copies).
-  const uintptr_t align_or = (uintptr_t)reachable | (uintptr_t)state | (uintptr_t)interval | (uintptr_t)joints | (uintptr_t)elbow;
-  if (pose_kind == R2IK_POSE_MAT4 && !theta && !prev_joints && interval && joints && elbow && (align_or & 15) == 0 &&
-      h->stream_blocks > 0 && !h->force_generic) {
-    const int64_t n_tiles = (n + R2IK_TILE - 1) / R2IK_TILE;
-    unsigned *sched = n_tiles < (int64_t)1 << 30 ? sched_slot_for(h, s) : nullptr;
-    if (sched) {
-      const int64_t want = (n_tiles + R2IK_STREAM_WARPS - 1) / R2IK_STREAM_WARPS;
-      const unsigned blocks = (unsigned)(want < (int64_t)h->stream_blocks ? want : (int64_t)h->stream_blocks);
-      k_symik_solve_stream<<<blocks, R2IK_BLOCK, 0, s>>>(h->A, poses, n, (int)n_tiles, sched, reachable, state, interval, joints, elbow);
-      R2IK_CUDA(cudaGetLastError(), "k_symik_solve_stream launch");
-      return 0;
-    }
-  }
   if (pose_kind == R2IK_POSE_MAT4)
     k_symik_solve<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
   else
@@ -753,7 +556,7 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const doubl
   if (misaligned16(M) || misaligned16(current_pose))
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_f64: M and current_pose must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
-  k_ctl_continuous<<<blocks_for(T), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
+  k_ctl_continuous<<<(unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK), R2IK_K3_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
                                                                           joints, reachable, state);
   R2IK_CUDA(cudaGetLastError(), "k_ctl_continuous launch");
   return 0;

@@ -22,7 +22,7 @@ for name, p in procs:
     log = p.communicate()[0]
     lines = log.splitlines()
     for i, l in enumerate(lines):
-        if "k_symik_solveILi1" in l and "Compiling" in l:
+        if os.environ.get("R2IK_VARIANT_KERNEL", "k_symik_solveILi1") in l and "Compiling" in l:
             print(name, "|", lines[i + 2].strip(), "|", lines[i + 3].strip())
     if p.returncode != 0:
         print(name, "FAILED\n", log[-2000:])

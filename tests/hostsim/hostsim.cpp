@@ -41,6 +41,19 @@ void hs_angle_of_unit(const double *y, const double *x, int64_t n, double *out) 
   }
 }
 
+void hs_sincos_small(const double *x, int64_t n, double *sn, double *cs) {
+  for (int64_t i = 0; i < n; ++i) sincos_small(x[i], sn[i], cs[i]);
+}
+
+// utl:508-519 on n wrist triples (joints[4:7])
+void hs_limit_orbita3d(const double *w, int64_t n, double max_angle, double *out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double j[7] = {0, 0, 0, 0, w[3 * i], w[3 * i + 1], w[3 * i + 2]};
+    limit_orbita3d_wrist(j, max_angle);
+    out[3 * i] = j[4]; out[3 * i + 1] = j[5]; out[3 * i + 2] = j[6];
+  }
+}
+
 void hs_constants(const R2ikArmConfig *cfg, R2ikArmConstants *pub) {
   ArmConst A;
   derive_constants(*cfg, A, *pub);

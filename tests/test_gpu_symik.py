@@ -219,10 +219,10 @@ def test_mirror_symmetry(solvers):
     assert np.quantile(d.max(axis=1), 0.999) < 1e-9
 
 
-@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 4099, 200_001])
-def test_stream_kernel_matches_generic_kernel(solvers, n):
-    """The streaming K1 (TMA bulk tiles, chosen for aligned full-output calls) and the one-thread-per-pose
-    K1 (misaligned output buffers, optional outputs, theta given) must agree bit for bit, incl. ragged tails."""
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 4099, 200_001])
+def test_ragged_sizes_and_misaligned_outputs(solvers, n):
+    """Ragged batch sizes; output buffers that start off a 16-byte boundary (only the pose buffer has an
+    alignment contract) must give the same results as aligned ones."""
     import torch
 
     from reachy2_symbolic_ik_b200 import _abi, fk
@@ -232,8 +232,6 @@ def test_stream_kernel_matches_generic_kernel(solvers, n):
     dev = torch.device("cuda", 0)
 
     def run(offset):
-        # offset = 1 element: every OUTPUT buffer starts 8 bytes (1 byte for the flags) off a 16-byte
-        # boundary (poses must be 16-byte aligned by contract)
         P = torch.from_numpy(M).reshape(-1).to(dev)
         reach = torch.zeros(n + 16, dtype=torch.uint8, device=dev)[offset:offset + n]
         state = torch.zeros(n + 16, dtype=torch.uint8, device=dev)[offset:offset + n]
@@ -252,26 +250,6 @@ def test_stream_kernel_matches_generic_kernel(solvers, n):
     for a, b in zip(aligned, misaligned):
         np.testing.assert_array_equal(a, b)
     assert aligned[0].sum() > 0 or n < 4
-
-
-def test_stream_kernel_zero_copy_pinned_host(solvers):
-    """The same launch with pinned HOST buffers (UVA): results identical to the device-resident call."""
-    import torch
-
-    from reachy2_symbolic_ik_b200 import _abi, fk
-
-    ik = solvers["l_arm"]
-    n = 50_000
-    M = fk.sample_fk_poses(n, "l_arm", seed=5)
-    want = ik.is_reachable_batch(M)
-    hin = torch.from_numpy(M).reshape(n, 16).pin_memory()
-    out = ik.alloc_host_outputs(n)
-    ik.solve_into(hin, _abi.POSE_MAT4, None, None, out.reachable, out.state, out.theta_interval, out.joints, out.elbow)
-    torch.cuda.synchronize()
-    np.testing.assert_array_equal(out.state.numpy(), want.state)
-    np.testing.assert_array_equal(out.joints.numpy(), want.joints)
-    np.testing.assert_array_equal(out.theta_interval.numpy(), want.theta_interval)
-    np.testing.assert_array_equal(out.elbow.numpy(), want.elbow)
 
 
 def test_misaligned_pose_pointer_is_an_argument_error(solvers):

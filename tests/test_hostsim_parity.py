@@ -179,3 +179,43 @@ def test_ctl_continuous(hs, oracle, arm, variant):
         rep.check()
     np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
     np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+
+
+def test_limit_orbita3d_wrist_fast_route(hs):
+    """utl:508-532: the algebraic clamp of the kernels against (i) the reference outputs in the helper
+    fixtures and (ii) scipy's own conversions on random wrists, incl. near the cone boundary."""
+    from scipy.spatial.transform import Rotation as R
+
+    def run(w, max_angle):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.empty_like(w)
+        hs.hs_limit_orbita3d(dp(w), C.c_int64(len(w)), C.c_double(max_angle), dp(out))
+        return out
+
+    h = load("helpers.npz")
+    mx = np.deg2rad(42.5)
+    assert np.abs(run(h["wrist_in"], mx) - h["wrist_out"]).max() < 1e-12
+
+    def ref(w, max_angle):   # the reference function, restated with scipy
+        zyz = R.from_euler("XYZ", w).as_euler("ZYZ")
+        zyz[:, 1] = np.clip(zyz[:, 1], -max_angle, max_angle)
+        return R.from_euler("ZYZ", zyz).as_euler("XYZ")
+
+    rng = np.random.default_rng(0)
+    w = np.concatenate([rng.uniform(-1.2, 1.2, (20000, 3)), rng.uniform(-np.pi, np.pi, (20000, 3))])
+    # wrists right at the cone boundary: beta = max +- 1e-9 .. 1e-3
+    al, ga = rng.uniform(-np.pi, np.pi, (2, 2000))
+    be = mx + rng.choice([-1, 1], 2000) * 10.0 ** rng.uniform(-9, -3, 2000)
+    w = np.concatenate([w, R.from_euler("ZYZ", np.stack([al, be, ga], 1)).as_euler("XYZ")])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = ref(w, mx)
+    got = run(w, mx)
+    # compare as rotations (angle triples near +-pi wrap) and as angles away from the wrap
+    err_rot = (R.from_euler("XYZ", got).inv() * R.from_euler("XYZ", want)).magnitude()
+    assert err_rot.max() < 1e-12, err_rot.max()
+    d = np.abs(np.angle(np.exp(1j * (got - want))))
+    assert d.max() < 1e-11, d.max()
+    exact = np.abs(got - want) < 1e-11
+    assert exact.mean() > 0.999      # the rest sit at the +-pi wrap of an output angle
