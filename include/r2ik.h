@@ -198,6 +198,13 @@ int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, 
  * chain: host pointer.  device: CUDA ordinal to launch on. */
 int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int64_t n, double *M, void *stream);
 
+/* Strided copy (cudaMemcpy2DAsync, direction inferred from the pointers): `rows` rows of `width_bytes`
+ * between buffers of the given pitches.  Plumbing for the waypoint-chunked host pipeline of the
+ * continuous mode (a chunk of waypoints of every trajectory is a strided block of the (T, W, 16)
+ * host array).  Host memory should be pinned for the copy to be asynchronous. */
+int r2ik_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                      size_t rows, void *stream);
+
 /* FP64 FMA peak probe used by bench.py for the compute roofline: runs `iters` dependent
  * DFMA chains (8 per thread) on a full grid and returns elapsed ms / flop count. */
 int r2ik_dfma_probe(int device, int32_t iters, double *out_ms /* host */, double *out_flop /* host */,

@@ -221,6 +221,146 @@ class ControlIK:
                 return (*res, st_out)
             raise ValueError(f"Unknown type {control_type}")
 
+    # ------------------------------------------------------------------ host-buffer pipelines
+    def alloc_host_outputs(self, control_type: str, shape) -> tuple:
+        """Pinned host output buffers for ``symbolic_inverse_kinematics_batch_host`` (reusable across calls).
+        discrete: shape = N -> (joints (N,7), reachable (N,) u8, state (N,) u8, emergency (N,) u8);
+        continuous: shape = (T, W) -> (joints (T,W,7), reachable (T,W) u8, state (T,W) u8, states (T,80) u8)."""
+        torch = self._torch
+        pin = lambda *sz, dt=torch.uint8: torch.empty(sz, dtype=dt).pin_memory()
+        if control_type == "discrete":
+            n = int(shape)
+            return (pin(n, 7, dt=torch.float64), pin(n), pin(n), pin(n))
+        if control_type == "continuous":
+            T, W = shape
+            return (pin(T, W, 7, dt=torch.float64), pin(T, W), pin(T, W), pin(T, _abi.TRAJ_STATE_DTYPE.itemsize))
+        raise ValueError(f"Unknown type {control_type}")
+
+    def symbolic_inverse_kinematics_batch_host(self, name: str, M_host, control_type: str = "discrete", out=None,
+                                               chunk: int | None = None, n_streams: int = 3, current_joints=None,
+                                               constrained_mode: str = "unconstrained", current_pose=None,
+                                               d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
+                                               previous_joints=None, states=None):
+        """Host-to-host ``symbolic_inverse_kinematics_batch``: ``M_host`` is a CPU tensor (ideally pinned),
+        (N,4,4)/(N,16) for discrete mode or (T,W,4,4)/(T,W,16) for continuous mode; the results land in
+        ``out`` (pinned CPU tensors from ``alloc_host_outputs``).  The batch is cut into chunks -- ``chunk``
+        poses in discrete mode, ``chunk`` waypoints of every trajectory in continuous mode -- that flow
+        H2D -> kernel -> D2H on CUDA streams, so both PCIe directions overlap the kernels.  Synchronous on
+        return."""
+        torch = self._torch
+        solver = self.symbolic_ik_solver[name]
+        par = self._ctl_params(name, constrained_mode, preferred_theta, d_theta_max)
+        lib, h = solver._handle.lib, solver._handle.h
+        if not hasattr(M_host, "is_cuda"):
+            M_host = torch.from_numpy(np.ascontiguousarray(M_host, dtype=np.float64))
+        dev = self._device
+        f64, u8 = torch.float64, torch.uint8
+        with torch.cuda.device(dev):
+            cur_stream = torch.cuda.current_stream(dev)
+            if control_type == "discrete":
+                n = M_host.shape[0]
+                P = M_host.reshape(n, 16)
+                chunk = chunk or (1 << 17)
+                if out is None:
+                    out = self.alloc_host_outputs("discrete", n)
+                prev = self._dev(self.previous_sol[name] if previous_joints is None else previous_joints, (7,))
+                cur = prev if current_joints is None else self._dev(current_joints, (7,))
+                pipe = self._pipeline(("discrete", chunk, n_streams), lambda: dict(
+                    M=torch.empty((chunk, 16), dtype=f64, device=dev), joints=torch.empty((chunk, 7), dtype=f64, device=dev),
+                    reach=torch.empty(chunk, dtype=u8, device=dev), state=torch.empty(chunk, dtype=u8, device=dev),
+                    emg=torch.empty(chunk, dtype=u8, device=dev)), n_streams)
+                for s in pipe["streams"]:
+                    s.wait_stream(cur_stream)
+                for ci, lo in enumerate(range(0, n, chunk)):
+                    hi = min(n, lo + chunk)
+                    m = hi - lo
+                    s, b = pipe["streams"][ci % n_streams], pipe["bufs"][ci % n_streams]
+                    with torch.cuda.stream(s):
+                        b["M"][:m].copy_(P[lo:hi], non_blocking=True)
+                        rc = lib.r2ik_ctl_discrete_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(m), _ptr(prev), _ptr(cur),
+                                                       _ptr(b["joints"]), _ptr(b["reach"]), _ptr(b["state"]), _ptr(b["emg"]),
+                                                       C.c_void_p(s.cuda_stream))
+                        _native.check(rc, "r2ik_ctl_discrete_f64")
+                        out[0][lo:hi].copy_(b["joints"][:m], non_blocking=True)
+                        out[1][lo:hi].copy_(b["reach"][:m], non_blocking=True)
+                        out[2][lo:hi].copy_(b["state"][:m], non_blocking=True)
+                        out[3][lo:hi].copy_(b["emg"][:m], non_blocking=True)
+            elif control_type == "continuous":
+                # A trajectory is a recursion over its waypoints, so K3's run time is set by W, not by T: the
+                # pipeline therefore cuts the WAYPOINT axis.  Chunk c = waypoints [w0, w1) of every trajectory
+                # (a strided block of the (T, W, 16) host array, moved by 2-D copies); the controller states
+                # stay on the device between chunks (R2ikTrajState is the resume point).  Copies in, kernels
+                # and copies out run on three streams chained by events.
+                T, W = M_host.shape[0], M_host.shape[1]
+                P = M_host.reshape(T, W, 16)
+                wc = chunk or max(1, min(W, (1 << 18) // max(T, 1)))          # waypoints per chunk
+                if out is None:
+                    out = self.alloc_host_outputs("continuous", (T, W))
+                cj = torch.empty((T, 7), dtype=f64, device=dev)
+                cj[:] = self._dev(self.previous_sol[name] if current_joints is None else current_joints)
+                cp = torch.empty((T, 16), dtype=f64, device=dev)
+                cp[:] = self._dev(self.previous_pose[name] if current_pose is None else current_pose).reshape(-1, 16)
+                if states is None:
+                    states = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
+                    states["init"] = 1
+                st = torch.from_numpy(np.ascontiguousarray(states).view(np.uint8).reshape(T, -1)).to(dev)
+                n_slots = max(2, n_streams)
+                pipe = self._pipeline(("continuous", T, wc, n_slots), lambda: dict(
+                    M=torch.empty((T, wc, 16), dtype=f64, device=dev), joints=torch.empty((T, wc, 7), dtype=f64, device=dev),
+                    reach=torch.empty((T, wc), dtype=u8, device=dev), state=torch.empty((T, wc), dtype=u8, device=dev)),
+                    max(3, n_slots))
+                s_in, s_k, s_out = pipe["streams"][:3]
+                for s in (s_in, s_k, s_out):
+                    s.wait_stream(cur_stream)
+                ev = [dict(h2d=torch.cuda.Event(), k=None, d2h=None) for _ in range(n_slots)]
+
+                def copy2d(dst_ptr, dpitch, src_ptr, spitch, width, stream):
+                    rc = lib.r2ik_copy2d_async(C.c_void_p(dst_ptr), dpitch, C.c_void_p(src_ptr), spitch, width, T,
+                                               C.c_void_p(stream.cuda_stream))
+                    _native.check(rc, "r2ik_copy2d_async")
+
+                for ci, w0 in enumerate(range(0, W, wc)):
+                    w1 = min(W, w0 + wc)
+                    m = w1 - w0
+                    e, b = ev[ci % n_slots], pipe["bufs"][ci % n_slots]
+                    if e["k"] is not None:
+                        s_in.wait_event(e["k"])                   # the kernel that read this slot's poses is done
+                    copy2d(b["M"].data_ptr(), m * 128, P.data_ptr() + w0 * 128, W * 128, m * 128, s_in)
+                    e["h2d"].record(s_in)
+                    s_k.wait_event(e["h2d"])
+                    if e["d2h"] is not None:
+                        s_k.wait_event(e["d2h"])                  # this slot's previous results have left
+                    rc = lib.r2ik_ctl_continuous_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
+                                                     _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]), _ptr(b["state"]),
+                                                     C.c_void_p(s_k.cuda_stream))
+                    _native.check(rc, "r2ik_ctl_continuous_f64")
+                    e["k"] = torch.cuda.Event()
+                    e["k"].record(s_k)
+                    s_out.wait_event(e["k"])
+                    copy2d(out[0].data_ptr() + w0 * 56, W * 56, b["joints"].data_ptr(), m * 56, m * 56, s_out)
+                    copy2d(out[1].data_ptr() + w0, W, b["reach"].data_ptr(), m, m, s_out)
+                    copy2d(out[2].data_ptr() + w0, W, b["state"].data_ptr(), m, m, s_out)
+                    e["d2h"] = torch.cuda.Event()
+                    e["d2h"].record(s_out)
+                s_out.wait_stream(s_k)
+                with torch.cuda.stream(s_out):
+                    out[3].copy_(st, non_blocking=True)
+            else:
+                raise ValueError(f"Unknown type {control_type}")
+            for s in pipe["streams"]:
+                s.synchronize()
+        return out
+
+    def _pipeline(self, key, make_bufs, n_streams: int):
+        cache = getattr(self, "_pipe_cache", None)
+        if cache is None:
+            cache = self._pipe_cache = {}
+        if key not in cache:
+            torch = self._torch
+            cache[key] = {"streams": [torch.cuda.Stream(device=self._device) for _ in range(n_streams)],
+                          "bufs": [make_bufs() for _ in range(n_streams)]}
+        return cache[key]
+
     # ------------------------------------------------------------------ scalar API (reference signature)
     def symbolic_inverse_kinematics(  # noqa: C901
         self,

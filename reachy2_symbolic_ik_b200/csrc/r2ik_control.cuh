@@ -55,8 +55,9 @@ R2IK_HD void search_strided(const SearchPlan &P, int nb, int k0, int stride, dou
   best_k = 0x7fffffff;
   if (k0 >= nb) return;
   double c, s, cd, sd;
-  sincos(linspace_value(P.L, k0), &s, &c);
-  sincos((double)stride * P.L.step, &sd, &cd);
+  const double th0 = linspace_value(P.L, k0), dth = (double)stride * P.L.step;
+  sincos_any(th0, s, c);
+  sincos_any(dth, sd, cd);
   for (int k = k0; k < nb; k += stride) {
     if (elbow_ok_cs(P.T, c, s)) {
       double cost = fabs(angle_diff(linspace_value(P.L, k), P.preferred_theta));

@@ -95,6 +95,25 @@ R2IK_HD double atan2_leaf(double y, double x, bool &degenerate) {
   return atan2_core(y, x);
 }
 
+// sin / cos of an arbitrary angle: the straight-line kernel for moderate arguments, the library (out of
+// line on the device) beyond.
+#if defined(__CUDACC__)
+__device__ __noinline__ double2 sincos_library_dev(double a) {
+  double s, c;
+  sincos(a, &s, &c);
+  return make_double2(s, c);
+}
+#endif
+R2IK_HD void sincos_any(double a, double &s, double &c) {
+  if (sincos_small_ok(a)) { sincos_small(a, s, c); return; }
+#if defined(__CUDA_ARCH__)
+  double2 r = sincos_library_dev(a);
+  s = r.x; c = r.y;
+#else
+  sincos(a, &s, &c);
+#endif
+}
+
 // Python float `%`: fmod is exact; the result takes the sign of the divisor.
 R2IK_HD double pymod(double a, double m) {
   double r = fmod(a, m);
@@ -217,9 +236,9 @@ R2IK_HD void quat_to_matrix(const Quat &q, double m[9]) {
 // R.from_euler("xyz", e).as_matrix(), specialised: q = qz o (qy o qx)
 R2IK_HD void rot_from_euler_xyz(double e0, double e1, double e2, double m[9]) {
   double sx, cx, sy, cy, sz, cz;
-  sincos(e0 / 2.0, &sx, &cx);
-  sincos(e1 / 2.0, &sy, &cy);
-  sincos(e2 / 2.0, &sz, &cz);
+  sincos_any(e0 / 2.0, sx, cx);
+  sincos_any(e1 / 2.0, sy, cy);
+  sincos_any(e2 / 2.0, sz, cz);
   // qy o qx with p = (0,sy,0,cy), q = (sx,0,0,cx)
   Quat a = {cy * sx, cx * sy, -(sy * sx), cy * cx};
   // qz o a with p = (0,0,sz,cz)
@@ -718,7 +737,7 @@ R2IK_HD void elbow_position_cs(const Solve &S, double ct, double st, double E[3]
 
 R2IK_HD void elbow_position(const Solve &S, double theta, double E[3]) {
   double st, ct;
-  sincos(theta, &st, &ct);
+  sincos_any(theta, st, ct);
   double y = S.r * ct, z = S.r * st;
   E[0] = S.a1[0] * y + S.a2[0] * z + S.c[0];
   E[1] = S.a1[1] * y + S.a2[1] * z + S.c[1];
@@ -871,7 +890,7 @@ R2IK_HD void get_joints_cs(const ArmConst &A, Solve &S, double ct, double st, do
 
 R2IK_HD void get_joints(const ArmConst &A, Solve &S, double theta, double prev0, double prev2, double joints[7], double E[3]) {
   double st, ct;
-  sincos(theta, &st, &ct);
+  sincos_any(theta, st, ct);
   get_joints_cs(A, S, ct, st, prev0, prev2, joints, E);
 }
 

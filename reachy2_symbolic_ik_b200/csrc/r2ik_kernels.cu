@@ -158,8 +158,12 @@ k_elbow_positions(const __grid_constant__ ArmConst A, const double *__restrict__
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// K2 spends most of its time in the warp-serial K-sample search, a short dependent chain per lane that
+// only more resident warps can overlap: holding the kernel to 64 registers (8 blocks / SM; the solve
+// phases spill ~1.1 KB to L1-resident local memory) measured 0.89 ms per 1M poses x 360 samples against
+// 1.18 ms at 128 registers and 1.77 ms unconstrained (176 registers), profiles/r1_experiments.md.
 #ifndef R2IK_K2_MINBLOCKS
-#define R2IK_K2_MINBLOCKS 1
+#define R2IK_K2_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K2_MINBLOCKS)
 k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
@@ -585,6 +589,16 @@ int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int6
   R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
   k_fk<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(*chain, joints, n, M);
   R2IK_CUDA(cudaGetLastError(), "k_fk launch");
+  return 0;
+}
+
+int r2ik_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t rows,
+                      void *stream) {
+  if (!dst || !src) return fail_arg(R2IK_ERR_NULL, "r2ik_copy2d_async: null argument");
+  if (width_bytes > dst_pitch || width_bytes > src_pitch) return fail_arg(R2IK_ERR_ARG, "r2ik_copy2d_async: width exceeds a pitch");
+  if (width_bytes == 0 || rows == 0) return 0;
+  R2IK_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream),
+            "cudaMemcpy2DAsync");
   return 0;
 }
 

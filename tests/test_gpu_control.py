@@ -188,3 +188,29 @@ def test_continuous_scalar_api(controls):
     joints = np.array([o[0] for o in out])
     np.testing.assert_allclose(joints, g["joints"][0][:40], atol=1e-9)
     assert all(o[1] for o in out) and all(o[2] == "" for o in out)
+
+
+def test_host_pipelines_match_device_calls(controls):
+    """symbolic_inverse_kinematics_batch_host (pinned host in / out, chunked over 3 streams) returns exactly
+    what the device-resident batched call returns, for ragged chunk counts, in both modes."""
+    import torch
+
+    from reachy2_symbolic_ik_b200 import fk
+
+    ctl = controls[False]
+    M = fk.sample_fk_poses(10_001, "r_arm", seed=31)
+    want = ctl.symbolic_inverse_kinematics_batch("r_arm", M, "discrete")
+    hin = torch.from_numpy(M).reshape(-1, 16).pin_memory()
+    got = ctl.symbolic_inverse_kinematics_batch_host("r_arm", hin, "discrete", chunk=3000)
+    np.testing.assert_array_equal(got[0].numpy(), want[0])
+    np.testing.assert_array_equal(got[1].numpy().astype(bool), want[1])
+    np.testing.assert_array_equal(got[2].numpy(), want[2])
+    np.testing.assert_array_equal(got[3].numpy(), want[3])
+
+    Mt = fk.sinusoidal_trajectories(37, 50, "l_arm", seed=32)[0]
+    want = ctl.symbolic_inverse_kinematics_batch("l_arm", Mt, "continuous")
+    got = ctl.symbolic_inverse_kinematics_batch_host("l_arm", torch.from_numpy(Mt).pin_memory(), "continuous", chunk=8)
+    np.testing.assert_array_equal(got[0].numpy(), want[0])
+    np.testing.assert_array_equal(got[1].numpy().astype(bool), want[1])
+    np.testing.assert_array_equal(got[2].numpy(), want[2])
+    np.testing.assert_array_equal(got[3].numpy().reshape(-1).view(want[3].dtype), want[3])

@@ -111,7 +111,7 @@ def test_sincos_small_vs_mpmath(hs):
     mp = pytest.importorskip("mpmath")
     mp.mp.dps = 40
     rng = np.random.default_rng(2)
-    x = np.concatenate([rng.uniform(-4, 4, 20000), [0.0, -0.0, np.pi, -np.pi, np.pi / 2, -np.pi / 2, np.pi / 4, 3 * np.pi / 4,
+    x = np.concatenate([rng.uniform(-4, 4, 20000), rng.uniform(-40, 40, 5000), rng.uniform(-1000, 1000, 2000), [0.0, -0.0, np.pi, -np.pi, np.pi / 2, -np.pi / 2, np.pi / 4, 3 * np.pi / 4,
                                                      1e-300, 1e-9, 4.0, -4.0, 0.7417649320975901]])
     x = np.ascontiguousarray(x)
     sn = np.empty_like(x); cs = np.empty_like(x)
