@@ -73,12 +73,6 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
               double *__restrict__ elbow) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-#ifdef R2IK_K1_PREFETCH
-  {  // pull the pose a later wave of blocks will read into L2
-    const int64_t pf = i + (int64_t)R2IK_K1_PREFETCH * R2IK_BLOCK;
-    if (pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(poses + (KIND == R2IK_POSE_MAT4 ? 16 : 6) * pf));
-  }
-#endif
   double prev0 = 0.0, prev2 = 0.0;
   if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
   double pos[3];
@@ -97,7 +91,7 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
   double j[7], E[3];
   if (ok) {
     double ct = rc.c0, st = rc.s0;   // theta_interval[0]: its cos / sin come with the interval
-    if (theta) sincos(theta[i], &st, &ct);
+    if (theta) sincos_any(theta[i], st, ct);
     get_joints_cs(A, S, ct, st, prev0, prev2, j, E);
   } else {
 #pragma unroll
