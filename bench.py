@@ -534,6 +534,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from oracle import oracle as O
+
+    O.use_all_host_threads()   # torchrun exports OMP_NUM_THREADS=1
     # a bounded sample per step: one pass of the CPU port over the (sub)workload cpu_port() defines
     vals, secs = [], []
     sample = cores = None
@@ -649,6 +652,9 @@ def main() -> int:
     if rank == 0:
         parity = wl.parity(torch)
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+
+            O.use_all_host_threads()
             v, dt, cores, sample = wl.cpu_port(getattr(wl, "poses", None))
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
             try:

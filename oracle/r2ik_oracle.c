@@ -1220,3 +1220,12 @@ int orc_max_threads(void) {
   return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arms of bench.py ask for the host's threads explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

@@ -147,6 +147,7 @@ void orc_limit_theta_to_interval(double theta, double previous_theta, const doub
 void orc_rotation_matrix_from_vector(const double v[3], double m9[9]);
 void orc_interval_limit(int side, int low_elbow, double out[2]);
 int orc_max_threads(void);
+void orc_set_threads(int n);
 
 #ifdef __cplusplus
 }
