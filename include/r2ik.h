@@ -186,6 +186,15 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, 
                             R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
                             void *stream);
 
+/* The same computation as r2ik_ctl_continuous_f64 (bit-identical outputs), cut at its data dependences:
+ * the per-waypoint work (reachability, target theta, joints for a given theta, Orbita3D limit) runs with one
+ * thread per waypoint, and only the rate-limited theta and the unwrap / continuity / emergency chain run as
+ * per-trajectory scans.  workspace: T*W doubles of device scratch (theta per waypoint), caller-owned. */
+int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
+                                   int32_t W, const double *current_joints, const double *current_pose,
+                                   R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
+                                   double *workspace, void *stream);
+
 /* Workspace reachability map: counts[v] += #orientations o in [ori_begin, ori_end) with
  * is_reachable(voxel centre, orientations_euler[o]) true.  Voxel (ix,iy,iz) centre =
  * origin + (ix,iy,iz)*step, v = (ix*dims[1] + iy)*dims[2] + iz.  origin/step/dims: host.

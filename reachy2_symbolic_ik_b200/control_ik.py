@@ -153,7 +153,7 @@ class ControlIK:
     def symbolic_inverse_kinematics_batch(self, name: str, M, control_type: str = "discrete", current_joints=None,
                                           constrained_mode: str = "unconstrained", current_pose=None,
                                           d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
-                                          previous_joints=None, states=None, out=None):
+                                          previous_joints=None, states=None, out=None, phased: bool = True):
         """Batched ``symbolic_inverse_kinematics``.
 
         discrete:   M (N,4,4) -> joints (N,7), reachable (N,), state (N,) uint8, emergency bits (N,).
@@ -164,6 +164,8 @@ class ControlIK:
                     ``states`` may also be a CUDA uint8 tensor (T,80): it is then updated in place and
                     returned as is (no host round trip).
         ``out``: the tuple a previous call returned for CUDA input of the same shape; its tensors are reused.
+        ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans (needs T*W doubles of device
+        scratch, allocated here); False = the single one-thread-per-trajectory kernel.  Same outputs, bit for bit.
         """
         torch = self._torch
         solver = self.symbolic_ik_solver[name]
@@ -211,15 +213,30 @@ class ControlIK:
                     joints = torch.empty((T, W, 7), dtype=torch.float64, device=self._device)
                     reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                     state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
-                rc = solver._handle.lib.r2ik_ctl_continuous_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T),
-                                                                C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st), _ptr(joints),
-                                                                _ptr(reach), _ptr(state), stream)
-                _native.check(rc, "r2ik_ctl_continuous_f64")
+                if phased:
+                    ws = self._scratch(T * W)
+                    rc = solver._handle.lib.r2ik_ctl_continuous_phased_f64(
+                        solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
+                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), stream)
+                    _native.check(rc, "r2ik_ctl_continuous_phased_f64")
+                else:
+                    rc = solver._handle.lib.r2ik_ctl_continuous_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T),
+                                                                    C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st), _ptr(joints),
+                                                                    _ptr(reach), _ptr(state), stream)
+                    _native.check(rc, "r2ik_ctl_continuous_f64")
                 st_out = st if states_on_device else st.cpu().numpy().reshape(-1).view(_abi.TRAJ_STATE_DTYPE).copy()
                 res = (joints, reach.view(torch.bool), state)
                 res = res if was_cuda else tuple(x.cpu().numpy() for x in res)
                 return (*res, st_out)
             raise ValueError(f"Unknown type {control_type}")
+
+    def _scratch(self, n: int):
+        """Device scratch of n doubles for the phased continuous kernels (grown on demand, reused across calls)."""
+        torch = self._torch
+        buf = getattr(self, "_scratch_buf", None)
+        if buf is None or buf.numel() < n or buf.device != self._device:
+            buf = self._scratch_buf = torch.empty(n, dtype=torch.float64, device=self._device)
+        return buf
 
     # ------------------------------------------------------------------ host-buffer pipelines
     def alloc_host_outputs(self, control_type: str, shape) -> tuple:
@@ -307,7 +324,8 @@ class ControlIK:
                 n_slots = max(2, n_streams)
                 pipe = self._pipeline(("continuous", T, wc, n_slots), lambda: dict(
                     M=torch.empty((T, wc, 16), dtype=f64, device=dev), joints=torch.empty((T, wc, 7), dtype=f64, device=dev),
-                    reach=torch.empty((T, wc), dtype=u8, device=dev), state=torch.empty((T, wc), dtype=u8, device=dev)),
+                    reach=torch.empty((T, wc), dtype=u8, device=dev), state=torch.empty((T, wc), dtype=u8, device=dev),
+                    ws=torch.empty((T, wc), dtype=f64, device=dev)),
                     max(3, n_slots))
                 s_in, s_k, s_out = pipe["streams"][:3]
                 for s in (s_in, s_k, s_out):
@@ -330,10 +348,10 @@ class ControlIK:
                     s_k.wait_event(e["h2d"])
                     if e["d2h"] is not None:
                         s_k.wait_event(e["d2h"])                  # this slot's previous results have left
-                    rc = lib.r2ik_ctl_continuous_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
-                                                     _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]), _ptr(b["state"]),
-                                                     C.c_void_p(s_k.cuda_stream))
-                    _native.check(rc, "r2ik_ctl_continuous_f64")
+                    rc = lib.r2ik_ctl_continuous_phased_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
+                                                            _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]),
+                                                            _ptr(b["state"]), _ptr(b["ws"]), C.c_void_p(s_k.cuda_stream))
+                    _native.check(rc, "r2ik_ctl_continuous_phased_f64")
                     e["k"] = torch.cuda.Event()
                     e["k"].record(s_k)
                     s_out.wait_event(e["k"])

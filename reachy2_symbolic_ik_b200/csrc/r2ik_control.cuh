@@ -104,9 +104,9 @@ R2IK_HD double step_toward(double target, double previous_theta, double d_theta_
   return previous_theta + sign * d_theta_max;
 }
 
-// ctl:464-497 safety_checks.  Returns the emergency bits raised by multiturn_safety_check.
-R2IK_HD int safety_checks(double j[7], const double previous_sol[7], double orbita_max) {
-  limit_orbita3d_wrist(j, orbita_max);                      // utl:522-532
+// ctl:464-497 safety_checks after the (stateless) Orbita3D limit: multi-turn unwrap against the previous
+// solution and the +-6 pi clamp.  Returns the emergency bits raised by multiturn_safety_check.
+R2IK_HD int safety_multiturn(double j[7], const double previous_sol[7]) {
   for (int i = 0; i < 7; ++i)                               // utl:493-505 allow_multiturn
     j[i] = previous_sol[i] + angle_diff(j[i], previous_sol[i]);
   int bits = 0;                                             // utl:535-568
@@ -118,6 +118,12 @@ R2IK_HD int safety_checks(double j[7], const double previous_sol[7], double orbi
   if (j[6] > lim) { j[6] = lim; bits |= R2IK_EMG_WRIST_YAW; }
   if (j[6] < -lim) { j[6] = -lim; bits |= R2IK_EMG_WRIST_YAW; }
   return bits;
+}
+
+// ctl:464-497 safety_checks
+R2IK_HD int safety_checks(double j[7], const double previous_sol[7], double orbita_max) {
+  limit_orbita3d_wrist(j, orbita_max);                      // utl:522-532
+  return safety_multiturn(j, previous_sol);
 }
 
 R2IK_HD double joints_angle_distance(const double a[7], const double b[7]) {
@@ -165,52 +171,71 @@ R2IK_HD int discrete_finish(const ArmConst &A, const R2ikCtlParams &par, Solve &
   return safety_checks(joints, prev_joints, par.orbita3d_max_angle);
 }
 
-// ctl:276-407 symbolic_inverse_kinematics_continuous for one waypoint of one trajectory.
-R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const double *M,
-                             const double current_joints[7], const double *current_pose, R2ikTrajState &cs,
-                             double joints[7], uint8_t &reachable, uint8_t &state) {
-  if (cs.emergency_stop) {                                   // ctl:205-210
-    for (int i = 0; i < 7; ++i) joints[i] = cs.previous_sol[i];
-    reachable = 0; state = R2IK_STATE_EMERGENCY;
-    return;
-  }
-  double pos[3] = {M[3], M[7], M[11]};
-  double Rg[9];
-  if (!rotation_from_mat4(M, true, Rg)) {
-    for (int i = 0; i < 7; ++i) joints[i] = NAN;
-    reachable = 0; state = R2IK_STATE_INVALID_ROTATION;
-    return;
-  }
-  Solve S;
-  int st_out = R2IK_STATE_EMPTY;
-  if (!cs.has_previous_sol) {                                // ctl:306-325
-    for (int i = 0; i < 7; ++i) cs.previous_sol[i] = current_joints[i];
-    cs.has_previous_sol = 1;
-    cs.init = 1;
-    double cpos[3] = {current_pose[3], current_pose[7], current_pose[11]};
-    rotation_from_mat4(current_pose, true, S.R);
-    is_reachable_R<true>(A, cpos, S);
-    cs.previous_theta = best_theta_to_current_joints(A, S, current_joints, par.preferred_theta);
-  }
-  for (int i = 0; i < 9; ++i) S.R[i] = Rg[i];
+// ---------------------------------------------------------------------------------------
+// Continuous mode (ctl:276-407), cut at its data dependences.  Of one waypoint's work only two thin
+// strands depend on the trajectory's past: the rate-limited elbow angle (previous_theta) and the
+// unwrap / continuity / emergency chain (previous_sol).  Everything else -- the goal rotation,
+// is_reachable, the 10-sample search for the target theta, get_joints for a GIVEN theta, the Orbita3D
+// limit -- is a function of the waypoint alone.  The four pieces below are exactly the statements of
+// the reference's function, regrouped; continuous_step composes them for one waypoint (serial kernel,
+// host harness) and the phased kernels run (1) and (3) over all waypoints in parallel and (2), (4) as
+// short per-trajectory scans, with bit-identical results.
+// ---------------------------------------------------------------------------------------
+#define R2IK_WP_INVALID 0        // rotation block with det <= 0
+#define R2IK_WP_TARGET 1         // reachable, a target theta was found                       (ctl:350-361)
+#define R2IK_WP_NO_SAMPLE 2      // reachable, no valid sample: theta = previous, "limited by shoulder" (ctl:362-363)
+#define R2IK_WP_UNREACHABLE 3    // not reachable: no-limits solve, tend to preferred_theta   (ctl:368-388)
+#define R2IK_WP_SERIAL 0x80      // get_joints hit a degenerate input: phase (4) redoes this waypoint in order
+
+// (1) stateless: classify the waypoint and find its target theta.  S holds the goal rotation on exit
+// (and the is_reachable solve for codes 1, 2).
+R2IK_HD int cont_target(const ArmConst &A, const R2ikCtlParams &par, const double *M, Solve &S, double pos[3], double &goal,
+                        int &st_out) {
+  pos[0] = M[3]; pos[1] = M[7]; pos[2] = M[11];
+  goal = 0.0;
+  if (!rotation_from_mat4(M, true, S.R)) { st_out = R2IK_STATE_INVALID_ROTATION; return R2IK_WP_INVALID; }
   Reach rc = is_reachable_R<false>(A, pos, S);
-  bool ok = rc.state == R2IK_STATE_REACHABLE;
-  double theta;
-  if (ok) {                                                  // ctl:338-366
-    double goal;
-    ok = best_discrete_theta(A, S, rc.i0, rc.i1, par.nb_search_points_continuous, par.preferred_theta_ctor, goal);
-    if (ok) theta = step_toward(goal, cs.previous_theta, par.d_theta_max);
-    else { theta = cs.previous_theta; st_out = R2IK_STATE_LIMITED_BY_SHOULDER; }
-  } else {                                                   // ctl:368-388
-    is_reachable_R<true>(A, pos, S);
-    theta = step_toward(par.preferred_theta, cs.previous_theta, par.d_theta_max);
-    st_out = rc.state;
+  if (rc.state != R2IK_STATE_REACHABLE) { st_out = rc.state; return R2IK_WP_UNREACHABLE; }
+  if (best_discrete_theta(A, S, rc.i0, rc.i1, par.nb_search_points_continuous, par.preferred_theta_ctor, goal)) {
+    st_out = R2IK_STATE_EMPTY;
+    return R2IK_WP_TARGET;
   }
-  theta = limit_theta_to_interval(theta, par.interval_limit[0], par.interval_limit[1]);
-  cs.previous_theta = theta;
+  st_out = R2IK_STATE_LIMITED_BY_SHOULDER;
+  return R2IK_WP_NO_SAMPLE;
+}
+
+// (2) scan over previous_theta: ctl:306-325 (re)initialisation
+R2IK_HD double cont_initial_theta(const ArmConst &A, const R2ikCtlParams &par, const double current_joints[7],
+                                  const double *current_pose) {
+  Solve S;
+  double cpos[3] = {current_pose[3], current_pose[7], current_pose[11]};
+  rotation_from_mat4(current_pose, true, S.R);
+  is_reachable_R<true>(A, cpos, S);
+  return best_theta_to_current_joints(A, S, current_joints, par.preferred_theta);
+}
+// ... and the step of the scan (ctl:350-366, 379-381)
+R2IK_HD double cont_next_theta(const R2ikCtlParams &par, int code, double goal, double previous_theta) {
+  double theta;
+  if (code == R2IK_WP_TARGET) theta = step_toward(goal, previous_theta, par.d_theta_max);
+  else if (code == R2IK_WP_NO_SAMPLE) theta = previous_theta;
+  else theta = step_toward(par.preferred_theta, previous_theta, par.d_theta_max);
+  return limit_theta_to_interval(theta, par.interval_limit[0], par.interval_limit[1]);
+}
+
+// (3) stateless for a given theta: joints + Orbita3D limit.  S.R / pos as left by cont_target; an
+// unreachable waypoint is solved without limits first (ctl:369).  prev0 / prev2 only matter at the exact
+// singularities of get_joints.
+R2IK_HD void cont_raw_joints(const ArmConst &A, const R2ikCtlParams &par, int code, const double pos[3], Solve &S, double theta,
+                             double prev0, double prev2, double joints[7]) {
+  if (code == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S);
   double E[3];
-  get_joints(A, S, theta, cs.previous_sol[0], cs.previous_sol[2], joints, E);
-  int bits = safety_checks(joints, cs.previous_sol, par.orbita3d_max_angle);   // ctl:393
+  get_joints(A, S, theta, prev0, prev2, joints, E);
+  limit_orbita3d_wrist(joints, par.orbita3d_max_angle);                        // ctl:393, first link of safety_checks
+}
+
+// (4) scan over previous_sol: unwrap + clamp, continuity check, emergency latch (ctl:393-405)
+R2IK_HD void cont_finish(R2ikTrajState &cs, double joints[7]) {
+  int bits = safety_multiturn(joints, cs.previous_sol);
   if (bits) { cs.emergency_stop = 1; cs.emergency_bits |= bits; }
   if (!cs.init) {                                            // ctl:395-400, utl:571-589
     const double max_step[7] = {0.5, 0.5, 0.5, 0.5, 1.0, 1.0, 1.0};
@@ -226,7 +251,37 @@ R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const 
   cs.init = 0;
   if (!cs.emergency_stop)
     for (int i = 0; i < 7; ++i) cs.previous_sol[i] = joints[i];
-  reachable = ok ? 1 : 0;
+}
+
+// ctl:276-407 symbolic_inverse_kinematics_continuous for one waypoint of one trajectory.
+R2IK_HD void continuous_step(const ArmConst &A, const R2ikCtlParams &par, const double *M,
+                             const double current_joints[7], const double *current_pose, R2ikTrajState &cs,
+                             double joints[7], uint8_t &reachable, uint8_t &state) {
+  if (cs.emergency_stop) {                                   // ctl:205-210
+    for (int i = 0; i < 7; ++i) joints[i] = cs.previous_sol[i];
+    reachable = 0; state = R2IK_STATE_EMERGENCY;
+    return;
+  }
+  Solve S;
+  double pos[3], goal;
+  int st_out;
+  const int code = cont_target(A, par, M, S, pos, goal, st_out);
+  if (code == R2IK_WP_INVALID) {
+    for (int i = 0; i < 7; ++i) joints[i] = NAN;
+    reachable = 0; state = R2IK_STATE_INVALID_ROTATION;
+    return;
+  }
+  if (!cs.has_previous_sol) {                                // ctl:306-325
+    for (int i = 0; i < 7; ++i) cs.previous_sol[i] = current_joints[i];
+    cs.has_previous_sol = 1;
+    cs.init = 1;
+    cs.previous_theta = cont_initial_theta(A, par, current_joints, current_pose);
+  }
+  const double theta = cont_next_theta(par, code, goal, cs.previous_theta);
+  cs.previous_theta = theta;
+  cont_raw_joints(A, par, code, pos, S, theta, cs.previous_sol[0], cs.previous_sol[2], joints);
+  cont_finish(cs, joints);
+  reachable = code == R2IK_WP_TARGET ? 1 : 0;
   state = (uint8_t)st_out;
 }
 

@@ -282,6 +282,137 @@ k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2i
 }
 
 // ---------------------------------------------------------------------------------------
+// K3, phased form (needs a T x W double workspace).  See r2ik_control.cuh "Continuous mode, cut at its
+// data dependences":
+//   k_cont_targets     1 thread / waypoint    classify + target theta            -> code, state, ws = goal
+//   k_cont_thetas      1 thread / trajectory  rate-limited theta scan            -> ws = theta
+//   k_cont_raw_joints  1 thread / waypoint    get_joints(theta) + Orbita3D limit -> joints (raw)
+//   k_cont_finish      1 thread / trajectory  unwrap / continuity / emergency scan -> joints, reachable, state, states
+// The two per-waypoint kernels hold ~85 % of the arithmetic and run at full parallelism (T x W threads); the
+// two scans are a few dozen FP64 operations per waypoint.  `reachable` carries the waypoint code and
+// `state` the reference state between the phases, so the only scratch is the theta workspace.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
+k_cont_targets(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
+               int64_t n_wp, double *__restrict__ ws, uint8_t *__restrict__ code, uint8_t *__restrict__ state) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_wp) return;
+  double m[16], pos[3], goal;
+  load_mat4(M + 16 * k, m);
+  Solve S;
+  int st;
+  const int c = cont_target(A, par, m, S, pos, goal, st);
+  ws[k] = goal;
+  code[k] = (uint8_t)c;
+  state[k] = (uint8_t)st;
+}
+
+__global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
+k_cont_thetas(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, int64_t T, int W,
+              const double *__restrict__ current_joints, const double *__restrict__ current_pose,
+              const R2ikTrajState *__restrict__ states, double *__restrict__ ws, const uint8_t *__restrict__ code) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  if (states[t].emergency_stop) return;   // every waypoint will answer with the latched solution
+  double theta = states[t].previous_theta;
+  bool has = states[t].has_previous_sol != 0;
+  const size_t base = (size_t)t * W;
+  for (int w = 0; w < W; ++w) {
+    const int c = code[base + w];
+    if (c == R2IK_WP_INVALID) continue;
+    if (!has) {                                                // ctl:306-325, at the first valid waypoint
+      double cj[7], cp[16];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) cj[q] = current_joints[7 * t + q];
+      load_mat4(current_pose + 16 * t, cp);
+      theta = cont_initial_theta(A, par, cj, cp);
+      has = true;
+    }
+    theta = cont_next_theta(par, c, ws[base + w], theta);
+    ws[base + w] = theta;
+  }
+}
+
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
+k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
+                  int64_t n_wp, const double *__restrict__ ws, uint8_t *__restrict__ code, double *__restrict__ joints) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_wp) return;
+  const int c = code[k];
+  double j[7];
+  bool serial = false;
+  if (c == R2IK_WP_INVALID) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) j[q] = NAN;
+  } else {
+    double m[16];
+    load_mat4(M + 16 * k, m);
+    Solve S;
+    double pos[3] = {m[3], m[7], m[11]};
+    rotation_from_mat4(m, true, S.R);
+    if (c == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S);
+    else is_reachable_R<false>(A, pos, S);
+    double st, ct, E[3];
+    sincos_any(ws[k], st, ct);
+    // straight-line get_joints only; a degenerate input (exact singularity: needs previous_sol) is left to the scan
+    serial = !get_joints_impl<false>(A, S, ct, st, 0.0, 0.0, j, E);
+    if (!serial) limit_orbita3d_wrist(j, par.orbita3d_max_angle);
+  }
+  if (serial) { code[k] = (uint8_t)(c | R2IK_WP_SERIAL); return; }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
+}
+
+__global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
+k_cont_finish(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
+              int64_t T, int W, const double *__restrict__ current_joints, R2ikTrajState *__restrict__ states,
+              const double *__restrict__ ws, double *__restrict__ joints, uint8_t *__restrict__ reachable,
+              uint8_t *__restrict__ state) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  R2ikTrajState cs = states[t];
+  const size_t base = (size_t)t * W;
+  for (int w = 0; w < W; ++w) {
+    const size_t k = base + w;
+    double j[7];
+    if (cs.emergency_stop) {                                   // ctl:205-210
+#pragma unroll
+      for (int q = 0; q < 7; ++q) joints[7 * k + q] = cs.previous_sol[q];
+      reachable[k] = 0;
+      state[k] = R2IK_STATE_EMERGENCY;
+      continue;
+    }
+    const int c = reachable[k];
+    const int kind = c & 0x7f;
+    if (kind == R2IK_WP_INVALID) { reachable[k] = 0; continue; }   // joints are NaN, state is INVALID_ROTATION already
+    if (!cs.has_previous_sol) {                                // ctl:306-313
+#pragma unroll
+      for (int q = 0; q < 7; ++q) cs.previous_sol[q] = current_joints[7 * t + q];
+      cs.has_previous_sol = 1;
+      cs.init = 1;
+    }
+    cs.previous_theta = ws[k];
+    if (c & R2IK_WP_SERIAL) {                                  // exact singularity of get_joints: redo it with previous_sol
+      double m[16];
+      load_mat4(M + 16 * k, m);
+      Solve S;
+      double pos[3] = {m[3], m[7], m[11]};
+      rotation_from_mat4(m, true, S.R);
+      if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
+      cont_raw_joints(A, par, kind, pos, S, cs.previous_theta, cs.previous_sol[0], cs.previous_sol[2], j);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 7; ++q) j[q] = joints[7 * k + q];
+    }
+    cont_finish(cs, j);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
+    reachable[k] = kind == R2IK_WP_TARGET ? 1 : 0;
+  }
+  states[t] = cs;
+}
+
+// ---------------------------------------------------------------------------------------
 // K4: workspace reachability map.  One thread per voxel; the rotation-dependent data of the
 // orientation slice (goal rotation matrix) is computed once per block into shared memory.
 // Voxels outside the reach sphere or behind the torso plane leave before the orientation loop
@@ -557,6 +688,29 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const doubl
   k_ctl_continuous<<<(unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK), R2IK_K3_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
                                                                           joints, reachable, state);
   R2IK_CUDA(cudaGetLastError(), "k_ctl_continuous launch");
+  return 0;
+}
+
+int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                                   const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
+                                   uint8_t *reachable, uint8_t *state, double *workspace, void *stream) {
+  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_phased_f64: null handle or parameters");
+  if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: bad T, W or nb_search_points_continuous");
+  if (T == 0 || W == 0) return 0;
+  if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state || !workspace)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_phased_f64: null argument");
+  if (misaligned16(M) || misaligned16(current_pose))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: M and current_pose must be 16-byte aligned");
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_wp = T * (int64_t)W;
+  const unsigned tb = (unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK);
+  k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
+  k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
+  k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints);
+  k_cont_finish<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state);
+  R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
   return 0;
 }
 

@@ -134,4 +134,82 @@ void hs_ctl_continuous_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par,
     }
 }
 
+// Mirrors the four phased kernels of r2ik_kernels.cu (k_cont_targets / k_cont_thetas / k_cont_raw_joints /
+// k_cont_finish) statement by statement, phase after phase over the whole batch.
+void hs_ctl_continuous_phased_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                                    const double *cur_joints, const double *cur_pose, R2ikTrajState *st, double *joints,
+                                    uint8_t *reach, uint8_t *state, double *ws) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  const int64_t n_wp = T * W;
+  for (int64_t k = 0; k < n_wp; ++k) {                       // k_cont_targets
+    Solve S; double pos[3], goal; int sto;
+    int c = cont_target(A, *par, M + 16 * k, S, pos, goal, sto);
+    ws[k] = goal; reach[k] = (uint8_t)c; state[k] = (uint8_t)sto;
+  }
+  for (int64_t t = 0; t < T; ++t) {                          // k_cont_thetas
+    if (st[t].emergency_stop) continue;
+    double theta = st[t].previous_theta;
+    bool has = st[t].has_previous_sol != 0;
+    for (int32_t w = 0; w < W; ++w) {
+      size_t k = (size_t)t * W + w;
+      int c = reach[k];
+      if (c == R2IK_WP_INVALID) continue;
+      if (!has) { theta = cont_initial_theta(A, *par, cur_joints + 7 * t, cur_pose + 16 * t); has = true; }
+      theta = cont_next_theta(*par, c, ws[k], theta);
+      ws[k] = theta;
+    }
+  }
+  for (int64_t k = 0; k < n_wp; ++k) {                       // k_cont_raw_joints
+    int c = reach[k];
+    double j[7];
+    bool serial = false;
+    if (c == R2IK_WP_INVALID) { for (int q = 0; q < 7; ++q) j[q] = NAN; }
+    else {
+      const double *m = M + 16 * k;
+      Solve S; double pos[3] = {m[3], m[7], m[11]};
+      rotation_from_mat4(m, true, S.R);
+      if (c == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S); else is_reachable_R<false>(A, pos, S);
+      double sn, cs_, E[3];
+      sincos_any(ws[k], sn, cs_);
+      serial = !get_joints_impl<false>(A, S, cs_, sn, 0.0, 0.0, j, E);
+      if (!serial) limit_orbita3d_wrist(j, par->orbita3d_max_angle);
+    }
+    if (serial) { reach[k] = (uint8_t)(c | R2IK_WP_SERIAL); continue; }
+    for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
+  }
+  for (int64_t t = 0; t < T; ++t) {                          // k_cont_finish
+    R2ikTrajState cs = st[t];
+    for (int32_t w = 0; w < W; ++w) {
+      size_t k = (size_t)t * W + w;
+      double j[7];
+      if (cs.emergency_stop) {
+        for (int q = 0; q < 7; ++q) joints[7 * k + q] = cs.previous_sol[q];
+        reach[k] = 0; state[k] = R2IK_STATE_EMERGENCY;
+        continue;
+      }
+      int c = reach[k], kind = c & 0x7f;
+      if (kind == R2IK_WP_INVALID) { reach[k] = 0; continue; }
+      if (!cs.has_previous_sol) {
+        for (int q = 0; q < 7; ++q) cs.previous_sol[q] = cur_joints[7 * t + q];
+        cs.has_previous_sol = 1; cs.init = 1;
+      }
+      cs.previous_theta = ws[k];
+      if (c & R2IK_WP_SERIAL) {
+        const double *m = M + 16 * k;
+        Solve S; double pos[3] = {m[3], m[7], m[11]};
+        rotation_from_mat4(m, true, S.R);
+        if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
+        cont_raw_joints(A, *par, kind, pos, S, cs.previous_theta, cs.previous_sol[0], cs.previous_sol[2], j);
+      } else {
+        for (int q = 0; q < 7; ++q) j[q] = joints[7 * k + q];
+      }
+      cont_finish(cs, j);
+      for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
+      reach[k] = kind == R2IK_WP_TARGET ? 1 : 0;
+    }
+    st[t] = cs;
+  }
+}
+
 }  // extern "C"

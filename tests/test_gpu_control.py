@@ -214,3 +214,30 @@ def test_host_pipelines_match_device_calls(controls):
     np.testing.assert_array_equal(got[1].numpy().astype(bool), want[1])
     np.testing.assert_array_equal(got[2].numpy(), want[2])
     np.testing.assert_array_equal(got[3].numpy().reshape(-1).view(want[3].dtype), want[3])
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_continuous_phased_equals_serial_kernel(controls, arm):
+    """The phased K3 (per-waypoint kernels + per-trajectory scans) and the one-thread-per-trajectory K3 are the
+    same arithmetic regrouped: every output and the final controller states must agree bit for bit, also when a
+    trajectory latches an emergency stop, hits invalid rotations or is resumed from a previous state."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    ctl = controls[False]
+    M = fk.sinusoidal_trajectories(300, 120, arm, seed=41)[0].copy()
+    flip = np.diag([-1.0, -1.0, 1.0])          # half a turn about the tool axis from waypoint 40 on: the wrist
+    M[3, 40:, :3, :3] = M[3, 40:, :3, :3] @ flip  # jumps by pi -> continuity violation -> emergency latch on trajectory 3
+    M[5, 7, :3, :3] = np.diag([-1.0, 1.0, 1.0])    # det < 0 in the middle of trajectory 5
+    M[6, 0, :3, :3] = np.diag([1.0, -1.0, 1.0])    # ... and at the first waypoint of trajectory 6
+    a = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=True)
+    b = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=False)
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    assert a[3].tobytes() == b[3].tobytes()
+    assert a[3]["emergency_stop"][3] == 1 and (a[2][3, -10:] == 8).all()
+    # resume from the returned states
+    a2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:, ::-1].copy(), "continuous", states=a[3], phased=True)
+    b2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:, ::-1].copy(), "continuous", states=b[3], phased=False)
+    for x, y in zip(a2[:3], b2[:3]):
+        np.testing.assert_array_equal(x, y)
+    assert a2[3].tobytes() == b2[3].tobytes()

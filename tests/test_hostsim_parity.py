@@ -179,6 +179,16 @@ def test_ctl_continuous(hs, oracle, arm, variant):
         rep.check()
     np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
     np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+    # the phased form (per-waypoint phases + per-trajectory scans) is the same arithmetic regrouped: bit-identical
+    st2 = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
+    st2["init"] = 1
+    j2 = np.empty((T, W, 7)); r2 = np.zeros((T, W), np.uint8); s2 = np.zeros((T, W), np.uint8); ws = np.empty((T, W))
+    hs.hs_ctl_continuous_phased_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
+                                      st2.ctypes.data_as(C.c_void_p), dp(j2), u8(r2), u8(s2), dp(ws))
+    np.testing.assert_array_equal(j2, joints)
+    np.testing.assert_array_equal(r2, reach)
+    np.testing.assert_array_equal(s2, state)
+    assert st2.tobytes() == st.tobytes()
 
 
 def test_limit_orbita3d_wrist_fast_route(hs):
