@@ -7,13 +7,14 @@ out=gpurun_out
 mkdir -p $out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $out/${tag}_pytest.log
 tail -3 $out/${tag}_pytest.log
-declare -A KRE=( [symik]=k_symik_solve [discrete]=k_ctl_discrete [continuous]=k_ctl_continuous [reachmap]=k_reach_map )
+declare -A KRE=( [symik]=k_symik_solve [discrete]=k_ctl_discrete [continuous]=k_cont_ [reachmap]=k_reach_map )
+declare -A NCAP=( [continuous]=4 )
 for w in $wls; do
   python bench.py --workload $w > $out/${tag}_bench_${w}.json 2> $out/${tag}_bench_${w}.err
   cut -c1-400 $out/${tag}_bench_${w}.json
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/${tag}_launches_${w}.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_${w}.csv \
       python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KRE[$w]} -s 3 -c 1 -f -o $out/${tag}_${w} \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KRE[$w]} -s 4 -c ${NCAP[$w]:-1} -f -o $out/${tag}_${w} \
       python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 done
 ls -la $out | tail -20
