@@ -260,6 +260,89 @@ class Symik:
         return python_reference_baseline("symik", "r_arm", self.poses["r_arm"][:m], m)
 
 
+class SymikF32(Symik):
+    """configs[1] on the FP32 fast path (north_star: optional, 1e-4 rad): float32 poses in, float32 results out."""
+    name = "symik_f32"
+    BYTES_IN, BYTES_OUT = 64, 1 + 1 + 8 + 28 + 12
+    # executed FP32 + FP64 flops per pose are taken from the committed ncu capture when there is one (profiles/symik_f32_ncu.json);
+    # this figure is the static estimate: ~520 FP32 flops (FMA = 2) + ~60 FP64 flops of the mixed-precision front end
+    FLOP_EQ = 640.0
+    FLOP_EQ_SURVEY = 2100.0
+    kernel = "k_symik_solve_f32<MAT4>"
+    fp32 = True
+
+    def config(self, world):
+        c = super().config(world)
+        c["workload"] = c["workload"].replace("FP64", "FP32 fast path (FP64 front end + FP64 re-solve of undecidable poses)")
+        c["pose_layout"] = "mat4_rowmajor_f32"
+        c["l2_policy"] = "inputs+outputs per step (228 MB) exceed the 126 MB L2; the two arms' batches alternate"
+        return c
+
+    def host_poses(self, rank):
+        return {arm: v.astype(np.float32) for arm, v in super().host_poses(rank).items()}
+
+    def setup(self, torch, dev, rank, world):
+        from reachy2_symbolic_ik_b200 import SymbolicIK, _abi
+
+        n = self.POSES_PER_ARM
+        self.poses = self.host_poses(rank)
+        self.solvers = {arm: SymbolicIK(arm=arm, device=dev.index) for arm in ARMS}
+        self.dpose = {arm: torch.from_numpy(self.poses[arm]).reshape(n, 16).to(dev) for arm in ARMS}
+        f32 = torch.float32
+        self.outs = {arm: dict(reach=torch.empty(n, dtype=torch.uint8, device=dev), state=torch.empty(n, dtype=torch.uint8, device=dev),
+                               interval=torch.empty((n, 2), dtype=f32, device=dev), joints=torch.empty((n, 7), dtype=f32, device=dev),
+                               elbow=torch.empty((n, 3), dtype=f32, device=dev)) for arm in ARMS}
+        self.n_esc = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.kind = _abi.POSE_MAT4
+        self.units_per_step = 2 * n
+        self.units_per_launch = n
+
+    def step(self):
+        for arm in ARMS:
+            o = self.outs[arm]
+            self.solvers[arm].solve_into_f32(self.dpose[arm], self.kind, None, None, o["reach"], o["state"], o["interval"], o["joints"],
+                                             o["elbow"], self.n_esc)
+        return 2
+
+    def e2e_setup(self, torch):
+        n = self.POSES_PER_ARM
+        self.host_in = {arm: torch.from_numpy(self.poses[arm]).reshape(n, 16).pin_memory() for arm in ARMS}
+        self.host_out = {arm: self.solvers[arm].alloc_host_outputs(n, "fp32") for arm in ARMS}
+        return {"h2d_bytes_per_step": 2 * n * self.BYTES_IN, "d2h_bytes_per_step": 2 * n * self.BYTES_OUT,
+                "path": "SymbolicIK.is_reachable_batch_host(precision='fp32'): pinned host -> chunked H2D / K1-f32 / D2H on 3 streams"}
+
+    def e2e_step(self, torch):
+        for arm in ARMS:
+            self.solvers[arm].is_reachable_batch_host(self.host_in[arm], self.host_out[arm], precision="fp32")
+
+    def parity(self, torch):
+        from oracle import oracle as O
+
+        m = 100_000
+        self.n_esc.zero_()
+        o = self.outs["r_arm"]
+        self.solvers["r_arm"].solve_into_f32(self.dpose["r_arm"], self.kind, None, None, o["reach"], o["state"], o["interval"],
+                                             o["joints"], o["elbow"], self.n_esc)
+        esc = int(self.n_esc.item())
+        want = O.symik_batch(O.arm_config("r_arm"), self.poses["r_arm"][:m].astype(np.float64))
+        got_j, got_i, got_s = (o[k][:m].cpu().numpy() for k in ("joints", "interval", "state"))
+        ej, ei = np.nan_to_num(np.abs(got_j - want[3])).max(axis=1), np.nan_to_num(np.abs(got_i - want[1])).max(axis=1)
+        ok = want[2] == 0
+        return {"checked_poses": m, "state_mismatches": int((got_s != want[2]).sum()), "tolerance_rad": 1e-4,
+                "max_abs_err_joints_rad": float(ej.max()), "p50_abs_err_joints_rad": float(np.median(ej[ok])),
+                "p99.9_abs_err_joints_rad": float(np.quantile(ej[ok], 0.999)), "max_abs_err_interval_rad": float(ei.max()),
+                "over_1e-4": int((ej > 1e-4).sum()), "escalated_to_fp64_fraction": esc / self.POSES_PER_ARM,
+                "vs": "FP64 CPU oracle on the same float32 inputs widened to double"}
+
+    def cpu_port(self, poses=None, repeats=3):
+        if poses is not None:
+            poses = {a: v.astype(np.float64) for a, v in poses.items()}
+        return super().cpu_port(poses, repeats)
+
+    def pyref(self):
+        return None
+
+
 class Discrete:
     """configs[2]"""
     name = "discrete"
@@ -527,7 +610,7 @@ class ReachMap:
         return None
 
 
-WORKLOADS = {w.name: w for w in (Symik, Discrete, Continuous, ReachMap)}
+WORKLOADS = {w.name: w for w in (Symik, SymikF32, Discrete, Continuous, ReachMap)}
 
 
 def run_reference(args, wl):
@@ -572,8 +655,8 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
-    default_steps = {"symik": 2000, "discrete": 50, "continuous": 5, "reachmap": 5}[wl.name]
-    default_warm = {"symik": 20, "discrete": 5, "continuous": 3, "reachmap": 3}[wl.name]
+    default_steps = {"symik": 2000, "symik_f32": 2000, "discrete": 50, "continuous": 5, "reachmap": 5}[wl.name]
+    default_warm = {"symik": 20, "symik_f32": 20, "discrete": 5, "continuous": 3, "reachmap": 3}[wl.name]
     if args.impl == "reference":
         # one reference step is a fraction of a second to a few seconds of all host cores: bound the run
         args.steps = min(args.steps or 10, 20)
@@ -671,6 +754,10 @@ def main() -> int:
     pms, pfl = C.c_double(), C.c_double()
     _native.check(_native.load().r2ik_dfma_probe(local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_dfma_probe")
     fp64_peak = pfl.value / (pms.value * 1e-3) / 1e12
+    fp32_peak = None
+    if getattr(wl, "fp32", False):
+        _native.check(_native.load().r2ik_ffma_probe(local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_ffma_probe")
+        fp32_peak = pfl.value / (pms.value * 1e-3) / 1e12
     fp64_ach = wl.FLOP_EQ * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
     # dram__bytes_read + dram__bytes_write of one launch and the FP64 pipe activity, from the committed ncu --set full
     # capture of this kernel (scripts/ncu_to_json.py -> profiles/<workload>_ncu.json); null when no capture is committed
@@ -685,7 +772,7 @@ def main() -> int:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"),
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.config(world),
+            "vs_baseline": None, "dtype": "f32" if getattr(wl, "fp32", False) else "f64", "data": "synthetic", "config": wl.config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, **e2e_info, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
@@ -705,6 +792,11 @@ def main() -> int:
                                   "warp_instructions", "source")}},
             "clocks": clocks.summary(), "parity": parity,
         }
+        if fp32_peak is not None:
+            # K1-f32 mixes pipes: report the measured FFMA peak beside the DFMA one; `achieved` counts both kinds of flops
+            line["roofline_fp32"] = {"bound": "fp32", "achieved": fp64_ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                     "frac": fp64_ach / fp32_peak, "flop_per_pose": wl.FLOP_EQ,
+                                     "peak_source": "r2ik_ffma_probe measured in this run (FFMA chains, full grid)"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -12,6 +12,8 @@
  *   r2ik_symik_solve_f64
  *        SymbolicIK.is_reachable                   symbolic_ik.py:121-282
  *        + theta_to_joints_func = get_joints       symbolic_ik.py:697-863
+ *   r2ik_symik_solve_f32
+ *        the same, FP32 fast path (float poses in, float results out)
  *   r2ik_symik_no_limits_f64
  *        SymbolicIK.is_reachable_no_limits         symbolic_ik.py:85-119  (+ get_joints)
  *   r2ik_elbow_positions_f64
@@ -164,6 +166,17 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
                          const double *prev_joints, int64_t n, uint8_t *reachable, uint8_t *state,
                          double *interval, double *joints, double *elbow, void *stream);
 
+/* FP32 fast path of r2ik_symik_solve_f64 (BASELINE.json north_star: "FP32 path within a stated 1e-4 rad"):
+ * float poses (n x 16 row-major 4x4, 16-byte aligned, or n x 6, 8-byte aligned), float outputs.  The solve runs
+ * in FP32 with an FP64 front end for the cancelling differences; a pose within FP32 rounding of one of the
+ * reference's decisions (state codes, branch cuts, elbow projection) or with an ill-conditioned angle is
+ * re-solved by the FP64 solver on the same inputs, so states / flags are those of the FP64 path on the
+ * widened inputs.  n_escalated: nullable device counter, incremented once per re-solved pose (zero it first).
+ * theta / prev_joints as in r2ik_symik_solve_f64 (float). */
+int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const float *theta,
+                         const float *prev_joints, int64_t n, uint8_t *reachable, uint8_t *state,
+                         float *interval, float *joints, float *elbow, uint32_t *n_escalated, void *stream);
+
 /* is_reachable_no_limits + get_joints(theta[i]). */
 int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta,
                              int64_t n, double *joints, double *elbow, void *stream);
@@ -217,6 +230,10 @@ int r2ik_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_p
 /* FP64 FMA peak probe used by bench.py for the compute roofline: runs `iters` dependent
  * DFMA chains (8 per thread) on a full grid and returns elapsed ms / flop count. */
 int r2ik_dfma_probe(int device, int32_t iters, double *out_ms /* host */, double *out_flop /* host */,
+                    void *stream);
+
+/* The same with FFMA chains: FP32 FMA peak for the roofline of r2ik_symik_solve_f32. */
+int r2ik_ffma_probe(int device, int32_t iters, double *out_ms /* host */, double *out_flop /* host */,
                     void *stream);
 
 #ifdef __cplusplus

@@ -16,6 +16,7 @@
 #include <new>
 
 #include "r2ik_control.cuh"
+#include "r2ik_device_f32.cuh"
 #include "r2ik_host.h"
 
 using namespace r2ik;
@@ -103,6 +104,62 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
     for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
   }
   if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1-f32: the FP32 fast path of K1 (r2ik_device_f32.cuh).  One thread / pose; float4 / float2 pose loads
+// (64 B per 4x4 pose, 48 B read); the FP32 solve, and for the few poses whose decisions or conditioning
+// FP32 cannot settle the FP64 solver on the same inputs (out of line, whole warp waits for its flagged
+// lanes).  n_escalated (nullable) counts those poses.
+// ---------------------------------------------------------------------------------------
+#ifndef R2IK_K1F_MINBLOCKS
+#define R2IK_K1F_MINBLOCKS 6
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1F_MINBLOCKS)
+k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ f32::ArmConstF A,
+                  const float *__restrict__ poses, const float *__restrict__ theta, const float *__restrict__ prev_joints,
+                  int64_t n, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state, float *__restrict__ interval,
+                  float *__restrict__ joints, float *__restrict__ elbow, unsigned *__restrict__ n_escalated) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float in[12];
+  if (KIND == R2IK_POSE_EULER6) {
+    const float2 *p = reinterpret_cast<const float2 *>(poses + 6 * i);
+    float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    in[0] = a.x; in[1] = a.y; in[2] = b.x; in[3] = b.y; in[4] = c.x; in[5] = c.y;
+  } else {
+    const float4 *p = reinterpret_cast<const float4 *>(poses + 16 * i);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float4 v = __ldg(p + r);
+      in[4 * r] = v.x; in[4 * r + 1] = v.y; in[4 * r + 2] = v.z; in[4 * r + 3] = v.w;
+    }
+  }
+  const bool has_theta = theta != nullptr;
+  const float th = has_theta ? theta[i] : 0.0f;
+  float out[12];
+  int st;
+  const bool esc = f32::symik_pose_fast<KIND>(A64, A, in, has_theta, th, st, out);
+  if (esc) {
+    float prev0 = 0.0f, prev2 = 0.0f;
+    if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
+    float o2[12];
+    int st2;
+    f32::symik_pose_escalated<KIND>(A64, in, has_theta, th, prev0, prev2, &st2, o2);
+    st = st2;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) out[k] = o2[k];
+    if (n_escalated) atomicAdd(n_escalated, 1u);
+  }
+  reachable[i] = st == R2IK_STATE_REACHABLE ? 1 : 0;
+  state[i] = (uint8_t)st;
+  if (interval) reinterpret_cast<float2 *>(interval)[i] = make_float2(out[0], out[1]);
+  if (joints) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) joints[7 * i + k] = out[2 + k];
+  }
+  if (elbow) { elbow[3 * i] = out[9]; elbow[3 * i + 1] = out[10]; elbow[3 * i + 2] = out[11]; }
 }
 
 template <int KIND>
@@ -524,6 +581,18 @@ __global__ void __launch_bounds__(256) k_dfma_probe(int iters, double seed, doub
   if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
 }
 
+// FP32 counterpart (roofline denominator of K1-f32)
+__global__ void __launch_bounds__(256) k_ffma_probe(int iters, float seed, float *sink) {
+  float a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const float m = 0.999999f, c = 1e-9f;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+  }
+  float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456f) sink[0] = s;
+}
+
 // ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
@@ -531,6 +600,7 @@ struct r2ik_context {
   int device;
   R2ikArmConfig cfg;
   ArmConst A;
+  f32::ArmConstF AF;   // A narrowed to float for K1-f32
   R2ikArmConstants pub;
 };
 
@@ -570,6 +640,7 @@ int r2ik_create(const R2ikArmConfig *cfg, int device, r2ik_handle *out) {
   h->device = device;
   h->cfg = *cfg;
   derive_constants(*cfg, h->A, h->pub);
+  f32::narrow_constants(h->A, h->AF);
   *out = h;
   return 0;
 }
@@ -618,6 +689,26 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
   else
     k_symik_solve<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
   R2IK_CUDA(cudaGetLastError(), "k_symik_solve launch");
+  return 0;
+}
+
+int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const float *theta, const float *prev_joints,
+                         int64_t n, uint8_t *reachable, uint8_t *state, float *interval, float *joints, float *elbow,
+                         uint32_t *n_escalated, void *stream) {
+  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: bad n or pose_kind");
+  if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null handle");
+  if (n == 0) return 0;
+  if (!poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null argument");
+  if (((uintptr_t)poses & (pose_kind == R2IK_POSE_MAT4 ? 15 : 7)) != 0 || ((uintptr_t)interval & 7) != 0)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: poses must be 16-byte (MAT4) / 8-byte (EULER6) aligned, interval 8-byte aligned");
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pose_kind == R2IK_POSE_MAT4)
+    k_symik_solve_f32<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow, n_escalated);
+  else
+    k_symik_solve_f32<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow, n_escalated);
+  R2IK_CUDA(cudaGetLastError(), "k_symik_solve_f32 launch");
   return 0;
 }
 
@@ -771,6 +862,32 @@ int r2ik_dfma_probe(int device, int32_t iters, double *out_ms, double *out_flop,
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(sink);
   if (e != cudaSuccess) return fail_cuda(e, "k_dfma_probe");
+  *out_ms = (double)ms;
+  *out_flop = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  return 0;
+}
+
+int r2ik_ffma_probe(int device, int32_t iters, double *out_ms, double *out_flop, void *stream) {
+  if (!out_ms || !out_flop) return fail_arg(R2IK_ERR_NULL, "r2ik_ffma_probe: null argument");
+  R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  R2IK_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  cudaStream_t s = (cudaStream_t)stream;
+  float *sink = nullptr;
+  R2IK_CUDA(cudaMalloc(&sink, sizeof(float)), "cudaMalloc");
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_ffma_probe<<<blocks, threads, 0, s>>>(iters / 8 + 1, 1.0f, sink);  // warm-up
+  cudaEventRecord(e0, s);
+  k_ffma_probe<<<blocks, threads, 0, s>>>(iters, 1.0f, sink);
+  cudaEventRecord(e1, s);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) return fail_cuda(e, "k_ffma_probe");
   *out_ms = (double)ms;
   *out_flop = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
   return 0;

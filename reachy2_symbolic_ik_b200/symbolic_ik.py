@@ -35,6 +35,7 @@ class BatchResult:
     state: Any            # (N,) uint8, see states.STATE_STRINGS
     joints: Any           # (N, 7) float64, NaN when unreachable
     elbow: Any            # (N, 3) float64
+    n_escalated: Any = None   # precision="fp32" only: poses re-solved by the FP64 solver (int, or a CUDA int32 tensor)
 
     def state_strings(self):
         s = self.state
@@ -47,14 +48,24 @@ def _ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
 
 
-def normalise_poses(torch, poses, device):
+def _precision_dtype(torch, precision: str):
+    if precision == "fp64":
+        return torch.float64
+    if precision == "fp32":
+        return torch.float32
+    raise ValueError(f"precision must be 'fp64' or 'fp32', got {precision!r}")
+
+
+def normalise_poses(torch, poses, device, dtype=None):
     """Accept (N,4,4) / (N,16) homogeneous matrices or (N,2,3) / (N,6) reference goal poses, as
-    NumPy, CPU tensor or CUDA tensor.  Returns (device tensor (N,k) float64, kind, was_cuda)."""
+    NumPy, CPU tensor or CUDA tensor.  Returns (device tensor (N,k) of ``dtype`` (default float64), kind,
+    was_cuda)."""
+    dtype = torch.float64 if dtype is None else dtype
     was_cuda = hasattr(poses, "is_cuda") and poses.is_cuda
     if not hasattr(poses, "is_cuda"):
-        poses = torch.from_numpy(np.ascontiguousarray(poses, dtype=np.float64))
-    if poses.dtype != torch.float64:
-        poses = poses.to(torch.float64)
+        poses = torch.from_numpy(np.ascontiguousarray(poses))
+    if poses.dtype != dtype:
+        poses = poses.to(dtype)
     shp = tuple(poses.shape)
     if len(shp) == 3 and shp[1:] == (4, 4) or len(shp) == 2 and shp[1] == 16:
         kind, k = _abi.POSE_MAT4, 16
@@ -123,34 +134,45 @@ class SymbolicIK:
         self._no_limits = False
 
     # ------------------------------------------------------------------ batched API
-    def is_reachable_batch(self, poses, theta=None, previous_joints=None, want_joints: bool = True) -> BatchResult:
+    def is_reachable_batch(self, poses, theta=None, previous_joints=None, want_joints: bool = True,
+                           precision: str = "fp64") -> BatchResult:
         """``is_reachable`` + ``theta_to_joints_func(theta)`` for N poses in one launch.
 
         poses: (N,4,4) homogeneous matrices (converted like the reference's ControlIK front
         end, ``R.from_matrix(M[:3,:3]).as_euler("xyz")``) or (N,2,3)/(N,6) reference goal poses
         ``[[x,y,z],[roll,pitch,yaw]]``.  theta: None -> ``theta_interval[0]``; else (N,).
+        precision: "fp64" (the correctness reference, 1e-9 rad) or "fp32" (the fast path: float32 poses in,
+        float32 results out, within 1e-4 rad on well-conditioned poses; states are the FP64 path's because poses
+        FP32 cannot decide are re-solved in FP64 -- their count is ``n_escalated``).
         """
         torch = self._torch
+        dt = _precision_dtype(torch, precision)
         with torch.cuda.device(self._device):
-            P, kind, was_cuda = normalise_poses(torch, poses, self._device)
+            P, kind, was_cuda = normalise_poses(torch, poses, self._device, dt)
             n = P.shape[0]
             th = None
             if theta is not None:
-                th = torch.as_tensor(theta, dtype=torch.float64).to(self._device).reshape(n).contiguous()
+                th = torch.as_tensor(theta).to(self._device, dt).reshape(n).contiguous()
             pj = None
             if previous_joints is not None:
-                pj = torch.as_tensor(previous_joints, dtype=torch.float64).to(self._device).reshape(7).contiguous()
+                pj = torch.as_tensor(previous_joints).to(self._device, dt).reshape(7).contiguous()
             reach = torch.empty(n, dtype=torch.uint8, device=self._device)
             state = torch.empty(n, dtype=torch.uint8, device=self._device)
-            interval = torch.empty((n, 2), dtype=torch.float64, device=self._device)
-            joints = torch.empty((n, 7), dtype=torch.float64, device=self._device) if want_joints else None
-            elbow = torch.empty((n, 3), dtype=torch.float64, device=self._device) if want_joints else None
-            self.solve_into(P, kind, th, pj, reach, state, interval, joints, elbow)
-            res = BatchResult(reach.bool(), interval, state, joints, elbow)
+            interval = torch.empty((n, 2), dtype=dt, device=self._device)
+            joints = torch.empty((n, 7), dtype=dt, device=self._device) if want_joints else None
+            elbow = torch.empty((n, 3), dtype=dt, device=self._device) if want_joints else None
+            n_esc = None
+            if precision == "fp32":
+                n_esc = torch.zeros(1, dtype=torch.int32, device=self._device)
+                self.solve_into_f32(P, kind, th, pj, reach, state, interval, joints, elbow, n_esc)
+            else:
+                self.solve_into(P, kind, th, pj, reach, state, interval, joints, elbow)
+            res = BatchResult(reach.bool(), interval, state, joints, elbow, n_esc)
             if was_cuda:
                 return res
-            return BatchResult(*[None if x is None else x.cpu().numpy() for x in
-                                 (res.reachable, res.theta_interval, res.state, res.joints, res.elbow)])
+            out = [None if x is None else x.cpu().numpy() for x in
+                   (res.reachable, res.theta_interval, res.state, res.joints, res.elbow)]
+            return BatchResult(*out, None if n_esc is None else int(n_esc.item()))
 
     def solve_into(self, poses_dev, kind, theta_dev, prev_dev, reach, state, interval, joints, elbow, stream=None):
         """Raw launch on device tensors (no allocation, asynchronous): the C-ABI call itself."""
@@ -161,26 +183,42 @@ class SymbolicIK:
             _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), C.c_void_p(s))
         _native.check(rc, "r2ik_symik_solve_f64")
 
+    def solve_into_f32(self, poses_dev, kind, theta_dev, prev_dev, reach, state, interval, joints, elbow, n_escalated=None,
+                       stream=None):
+        """Raw launch of the FP32 fast path on float32 device tensors (``r2ik_symik_solve_f32``); ``n_escalated`` is an
+        optional int32 device counter the kernel adds to."""
+        torch = self._torch
+        s = torch.cuda.current_stream(self._device).cuda_stream if stream is None else stream
+        rc = self._handle.lib.r2ik_symik_solve_f32(
+            self._handle.h, kind, _ptr(poses_dev), _ptr(theta_dev), _ptr(prev_dev), C.c_int64(poses_dev.shape[0]),
+            _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), _ptr(n_escalated), C.c_void_p(s))
+        _native.check(rc, "r2ik_symik_solve_f32")
+
     # ------------------------------------------------------------------ host-buffer pipeline
-    def alloc_host_outputs(self, n: int) -> BatchResult:
+    def alloc_host_outputs(self, n: int, precision: str = "fp64") -> BatchResult:
         """Pinned host output buffers for ``is_reachable_batch_host`` (reusable across calls)."""
         torch = self._torch
+        dt = _precision_dtype(torch, precision)
         return BatchResult(
             reachable=torch.empty(n, dtype=torch.uint8).pin_memory(),
-            theta_interval=torch.empty((n, 2), dtype=torch.float64).pin_memory(),
+            theta_interval=torch.empty((n, 2), dtype=dt).pin_memory(),
             state=torch.empty(n, dtype=torch.uint8).pin_memory(),
-            joints=torch.empty((n, 7), dtype=torch.float64).pin_memory(),
-            elbow=torch.empty((n, 3), dtype=torch.float64).pin_memory())
+            joints=torch.empty((n, 7), dtype=dt).pin_memory(),
+            elbow=torch.empty((n, 3), dtype=dt).pin_memory())
 
     def is_reachable_batch_host(self, poses_host, out: Optional[BatchResult] = None, chunk: int = 1 << 17,
-                                n_streams: int = 3) -> BatchResult:
+                                n_streams: int = 3, precision: str = "fp64") -> BatchResult:
         """Host-to-host batched solve: ``poses_host`` is a CPU tensor (N,16)/(N,4,4)/(N,6)/(N,2,3),
         ideally pinned; results land in ``out`` (pinned CPU tensors; ``reachable`` is uint8 0/1).
         The batch is cut into chunks that flow H2D -> K1 -> D2H on ``n_streams`` CUDA streams so the
-        PCIe copies in both directions overlap the kernel.  Synchronous on return."""
+        PCIe copies in both directions overlap the kernel.  Synchronous on return.  precision="fp32": float32
+        poses and outputs (half the PCIe bytes), the FP32 fast path of K1."""
         torch = self._torch
+        dt = _precision_dtype(torch, precision)
         if not hasattr(poses_host, "is_cuda"):
-            poses_host = torch.from_numpy(np.ascontiguousarray(poses_host, dtype=np.float64))
+            poses_host = torch.from_numpy(np.ascontiguousarray(poses_host))
+        if poses_host.dtype != dt:
+            poses_host = poses_host.to(dt)
         shp = tuple(poses_host.shape)
         k = 16 if (shp[1:] == (4, 4) or shp[1:] == (16,)) else 6
         if k == 6 and shp[1:] not in ((2, 3), (6,)):
@@ -189,9 +227,12 @@ class SymbolicIK:
         P = poses_host.reshape(shp[0], k)
         n = shp[0]
         if out is None:
-            out = self.alloc_host_outputs(n)
+            out = self.alloc_host_outputs(n, precision)
+        solve = self.solve_into if precision == "fp64" else (
+            lambda P_, kind_, th_, pj_, r_, s_, i_, j_, e_, stream=None: self.solve_into_f32(P_, kind_, th_, pj_, r_, s_, i_, j_,
+                                                                                           e_, None, stream=stream))
         with torch.cuda.device(self._device):
-            pipe = self._pipeline(chunk, n_streams, k)
+            pipe = self._pipeline(chunk, n_streams, k, dt)
             cur = torch.cuda.current_stream(self._device)
             for s in pipe["streams"]:
                 s.wait_stream(cur)
@@ -203,8 +244,8 @@ class SymbolicIK:
                 b = pipe["bufs"][slot]
                 with torch.cuda.stream(s):
                     b["poses"][:m].copy_(P[lo:hi], non_blocking=True)
-                    self.solve_into(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
-                                    b["elbow"], stream=s.cuda_stream)
+                    solve(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
+                          b["elbow"], stream=s.cuda_stream)
                     out.reachable[lo:hi].copy_(b["reach"][:m], non_blocking=True)
                     out.state[lo:hi].copy_(b["state"][:m], non_blocking=True)
                     out.theta_interval[lo:hi].copy_(b["interval"][:m], non_blocking=True)
@@ -214,8 +255,9 @@ class SymbolicIK:
                 s.synchronize()
         return out
 
-    def _pipeline(self, chunk: int, n_streams: int, k: int):
-        key = (chunk, n_streams, k)
+    def _pipeline(self, chunk: int, n_streams: int, k: int, dt=None):
+        dt = self._torch.float64 if dt is None else dt
+        key = (chunk, n_streams, k, dt)
         cache = getattr(self, "_pipe_cache", None)
         if cache is None:
             cache = self._pipe_cache = {}
@@ -224,12 +266,12 @@ class SymbolicIK:
             d = self._device
             cache[key] = {
                 "streams": [torch.cuda.Stream(device=d) for _ in range(n_streams)],
-                "bufs": [dict(poses=torch.empty((chunk, k), dtype=torch.float64, device=d),
+                "bufs": [dict(poses=torch.empty((chunk, k), dtype=dt, device=d),
                               reach=torch.empty(chunk, dtype=torch.uint8, device=d),
                               state=torch.empty(chunk, dtype=torch.uint8, device=d),
-                              interval=torch.empty((chunk, 2), dtype=torch.float64, device=d),
-                              joints=torch.empty((chunk, 7), dtype=torch.float64, device=d),
-                              elbow=torch.empty((chunk, 3), dtype=torch.float64, device=d)) for _ in range(n_streams)],
+                              interval=torch.empty((chunk, 2), dtype=dt, device=d),
+                              joints=torch.empty((chunk, 7), dtype=dt, device=d),
+                              elbow=torch.empty((chunk, 3), dtype=dt, device=d)) for _ in range(n_streams)],
             }
         return cache[key]
 

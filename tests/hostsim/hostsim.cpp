@@ -6,6 +6,8 @@
 #include <cstdint>
 
 #include "../../reachy2_symbolic_ik_b200/csrc/r2ik_control.cuh"
+#define R2IK_F32_DEBUG 1
+#include "../../reachy2_symbolic_ik_b200/csrc/r2ik_device_f32.cuh"
 #include "../../reachy2_symbolic_ik_b200/csrc/r2ik_host.h"
 
 using namespace r2ik;
@@ -209,6 +211,40 @@ void hs_ctl_continuous_phased_batch(const R2ikArmConfig *cfg, const R2ikCtlParam
       reach[k] = kind == R2IK_WP_TARGET ? 1 : 0;
     }
     st[t] = cs;
+  }
+}
+
+// K1-f32 (r2ik_device_f32.cuh): the FP32 fast solve with FP64 escalation, mirroring k_symik_solve_f32.
+// mode: 0 = as the kernel (escalate flagged poses), 1 = never escalate (raw FP32 results, to measure them).
+void hs_symik_batch_f32(const R2ikArmConfig *cfg, int kind, const float *poses, const float *theta, int64_t n, int mode,
+                        uint8_t *reach, uint8_t *state, float *interval, float *joints, float *elbow, uint8_t *escalated) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  f32::ArmConstF F;
+  f32::narrow_constants(A, F);
+  const int stride = kind == R2IK_POSE_EULER6 ? 6 : 16;
+  for (int64_t i = 0; i < n; ++i) {
+    const float *in = poses + i * stride;
+    float out[12];
+    int st;
+    const bool has_theta = theta != nullptr;
+    g_dbg_n = 0;
+    const float th = has_theta ? theta[i] : 0.0f;
+    bool esc = kind == R2IK_POSE_EULER6 ? f32::symik_pose_fast<R2IK_POSE_EULER6>(A, F, in, has_theta, th, st, out)
+                                        : f32::symik_pose_fast<R2IK_POSE_MAT4>(A, F, in, has_theta, th, st, out);
+    escalated[i] = esc;
+    if (mode == 2) { for (int k = 0; k < 12; ++k) out[k] = k < g_dbg_n ? g_dbg[k] : NAN; }
+    if (mode == 3) { out[0] = (float)g_dbg_cause; }
+    g_dbg_n = 0; g_dbg_cause = 0;
+    if (esc && mode == 0) {
+      if (kind == R2IK_POSE_EULER6) f32::symik_pose_escalated<R2IK_POSE_EULER6>(A, in, has_theta, th, 0.0f, 0.0f, &st, out);
+      else f32::symik_pose_escalated<R2IK_POSE_MAT4>(A, in, has_theta, th, 0.0f, 0.0f, &st, out);
+    }
+    state[i] = (uint8_t)st;
+    reach[i] = st == R2IK_STATE_REACHABLE;
+    interval[2 * i] = out[0]; interval[2 * i + 1] = out[1];
+    for (int k = 0; k < 7; ++k) joints[7 * i + k] = out[2 + k];
+    for (int k = 0; k < 3; ++k) elbow[3 * i + k] = out[9 + k];
   }
 }
 

@@ -28,23 +28,36 @@ COND_TOL = 1e-10    # oracle self-movement under perturbation that marks a pose 
 PERTURB = 3e-13
 MAX_ILL_FRACTION = 0.01
 
+# FP32 fast path (north_star: "FP32 path within a stated 1e-4 rad").  The checker is the FP64 oracle on the
+# SAME float32 inputs widened to double.  States / flags must be identical (the kernel re-solves in FP64 the
+# poses FP32 cannot decide); joints / intervals within TOL_F32 on poses that are well-conditioned at FP32 input
+# resolution: a pose whose oracle outputs move by more than COND_TOL_F32 when its inputs move by PERTURB_F32
+# (one float32 ulp of an O(1) coordinate) is classed ill-conditioned, counted and capped.
+TOL_F32 = 1e-4
+PERTURB_F32 = 1.2e-7
+COND_TOL_F32 = 5e-5
+MAX_ILL_FRACTION_F32 = 0.02
+MAX_ESCALATED_FRACTION_F32 = 0.01
+
 
 def load(name: str):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-def perturbed(poses: np.ndarray, seed: int) -> np.ndarray:
+def perturbed(poses: np.ndarray, seed: int, amplitude: float = PERTURB) -> np.ndarray:
     rng = np.random.default_rng(seed)
-    return poses + rng.uniform(-PERTURB, PERTURB, size=poses.shape)
+    return poses + rng.uniform(-amplitude, amplitude, size=poses.shape)
 
 
-def ill_conditioned_mask(run, poses: np.ndarray, n_trials: int = 3) -> np.ndarray:
+def ill_conditioned_mask(run, poses: np.ndarray, n_trials: int = 3, amplitude: float = PERTURB,
+                         cond_tol: float = COND_TOL) -> np.ndarray:
     """run(poses) -> tuple of arrays whose first axis is the pose axis (bool/uint8 arrays are
-    compared exactly, float arrays with COND_TOL; NaN patterns must agree)."""
+    compared exactly, float arrays with cond_tol; NaN patterns must agree)."""
+    COND_TOL = cond_tol  # noqa: N806 (shadows the module default for the FP32 variant)
     base = run(poses)
     ill = np.zeros(len(poses), bool)
     for t in range(n_trials):
-        alt = run(perturbed(poses, 1000 + t))
+        alt = run(perturbed(poses, 1000 + t, amplitude))
         for a, b in zip(base, alt):
             a = np.asarray(a); b = np.asarray(b)
             a2 = a.reshape(len(poses), -1); b2 = b.reshape(len(poses), -1)
@@ -105,3 +118,27 @@ class Report:
         print(msg)
         assert not self.bad.any(), f"genuine parity failures at indices {np.nonzero(self.bad)[0][:10]}\n{msg}"
         assert self.ill.mean() <= max_ill_fraction, f"too many ill-conditioned poses ({self.ill.mean():.4f})\n{msg}"
+
+
+def check_f32(name, oracle, arm, P32, got, theta=None, max_ill=None):
+    """got = (reach, itv, state, joints, elbow, escalated) of an FP32 solve of the float32 poses P32."""
+    ocfg = oracle.arm_config(arm)
+    P64 = P32.astype(np.float64)
+    th64 = None if theta is None else np.asarray(theta, dtype=np.float32).astype(np.float64)
+    run = lambda p: oracle.symik_batch(ocfg, p.reshape(P64.shape), th64)[:4]  # noqa: E731
+    want = run(P64)
+    ill = ill_conditioned_mask(run, P64.reshape(len(P64), -1), amplitude=PERTURB_F32, cond_tol=COND_TOL_F32)
+    reach, itv, state, joints, elbow, esc = got
+    rep = Report(name, len(P32), ill)
+    # states are exact even on ill-conditioned poses: the kernel escalates what FP32 cannot decide
+    rep.exact("reachable", reach, want[0])
+    rep.exact("state", state, want[2])
+    rep.close("interval", itv, want[1], tol=TOL_F32)
+    err = rep.close("joints", joints, want[3], tol=TOL_F32)
+    okm = ~ill & (want[2] == 0)
+    if okm.any():
+        rep.lines.append(f"joints well-conditioned: p50 {np.median(err[okm]):.2e} p99 {np.quantile(err[okm], 0.99):.2e} "
+                         f"p99.9 {np.quantile(err[okm], 0.999):.2e}; escalated to FP64: {int(esc.sum())} ({esc.mean():.4%})")
+    rep.check(max_ill_fraction=MAX_ILL_FRACTION_F32 if max_ill is None else max_ill)
+    assert esc.mean() <= MAX_ESCALATED_FRACTION_F32, f"too many poses escalated to FP64: {esc.mean():.4f}"
+    return rep

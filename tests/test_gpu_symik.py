@@ -3,7 +3,7 @@ against the reference's golden outputs and against the CPU oracle on larger seed
 import numpy as np
 import pytest
 
-from parity import Report, ill_conditioned_mask, load
+from parity import Report, check_f32, ill_conditioned_mask, load
 
 pytestmark = pytest.mark.gpu
 ARMS = ("r_arm", "l_arm")
@@ -270,3 +270,75 @@ def test_misaligned_pose_pointer_is_an_argument_error(solvers):
     # the facade re-aligns such a view instead of failing
     res = ik.is_reachable_batch(P.reshape(4, 16))
     assert res.state.shape == (4,)
+
+
+# ---------------------------------------------------------------------------------------------------
+# FP32 fast path (r2ik_symik_solve_f32): float32 poses in, float32 results out; checked against the FP64
+# oracle on the same inputs widened to double.  Tolerance 1e-4 rad (tests/parity.py TOL_F32), states exact.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arm", ARMS)
+def test_fp32_vs_oracle_100k(solvers, oracle, arm):
+    from reachy2_symbolic_ik_b200 import fk
+
+    seed = 31 if arm == "r_arm" else 32
+    P32 = np.concatenate([fk.sample_fk_poses(70000, arm, seed=seed), fk.sample_task_space_poses(30000, arm, seed=seed + 100)]
+                         ).astype(np.float32)
+    res = solvers[arm].is_reachable_batch(P32, precision="fp32")
+    assert res.joints.dtype == np.float32 and res.theta_interval.dtype == np.float32
+    n_esc = res.n_escalated
+    esc = np.zeros(len(P32), bool)
+    esc[:n_esc] = True   # only the count is known on the GPU path; check_f32 uses its mean
+    check_f32(f"gpu f32 vs oracle 100k {arm}", oracle, arm, P32, (res.reachable, res.theta_interval, res.state, res.joints,
+                                                                    res.elbow, esc))
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_fp32_golden_layouts_and_theta(solvers, oracle, arm):
+    g = load(f"symik_random_{arm}.npz")
+    th = g["theta2"].astype(np.float32)
+    for P in (g["goal_pose"], g["M"]):
+        P32 = P.astype(np.float32)
+        for theta in (None, th):
+            res = solvers[arm].is_reachable_batch(P32, theta=theta, precision="fp32")
+            esc = np.zeros(len(P32), bool); esc[:res.n_escalated] = True
+            check_f32(f"gpu f32 golden {arm} {P.shape[1:]} theta={'given' if theta is not None else 'i0'}", oracle, arm, P32,
+                      (res.reachable, res.theta_interval, res.state, res.joints, res.elbow, esc), theta=theta)
+
+
+def test_fp32_named_degenerate_and_plumbing(solvers, oracle):
+    import torch
+
+    from reachy2_symbolic_ik_b200 import fk
+
+    g = load("symik_named.npz")
+    for arm in ARMS:
+        P32 = g[f"{arm}_poses"].astype(np.float32)
+        res = solvers[arm].is_reachable_batch(P32, precision="fp32")
+        want = oracle.symik_batch(oracle.arm_config(arm), P32.astype(np.float64))
+        assert np.array_equal(res.state, want[2]) and np.array_equal(res.reachable, want[0])
+    ik = solvers["r_arm"]
+    # scaled / left-handed / null rotations are handed to the FP64 solver
+    M = np.tile(np.eye(4, dtype=np.float32), (4, 1, 1))
+    M[:, :3, 3] = [0.3, -0.2, -0.3]
+    M[1, :3, :3] *= 1.5
+    M[2, 0, 0] = -1.0
+    M[3, :3, :3] = 0.0
+    res = ik.is_reachable_batch(M, precision="fp32")
+    want = oracle.symik_batch(oracle.arm_config("r_arm"), M.astype(np.float64))
+    assert np.array_equal(res.state, want[2]) and res.n_escalated >= 3
+    assert np.nanmax(np.abs(res.joints - want[3])) < 1e-5
+    # empty and ragged batches; CUDA tensors in -> CUDA tensors out; float64 input is narrowed
+    assert ik.is_reachable_batch(np.zeros((0, 4, 4), np.float32), precision="fp32").joints.shape == (0, 7)
+    M = fk.sample_fk_poses(1001, "r_arm", seed=12)
+    a = ik.is_reachable_batch(torch.from_numpy(M).cuda(), precision="fp32")
+    assert a.joints.is_cuda and a.joints.dtype == torch.float32
+    b = ik.is_reachable_batch(M.astype(np.float32), precision="fp32")
+    np.testing.assert_array_equal(a.joints.cpu().numpy(), b.joints)
+    # host pipeline (pinned float32 buffers) gives the device call's results
+    P = fk.sample_fk_poses(300_001, "r_arm", seed=13).astype(np.float32)
+    out = ik.is_reachable_batch_host(torch.from_numpy(P).pin_memory(), precision="fp32", chunk=1 << 16)
+    d = ik.is_reachable_batch(P, precision="fp32")
+    np.testing.assert_array_equal(out.joints.numpy(), d.joints)
+    np.testing.assert_array_equal(out.state.numpy(), d.state)
+    with pytest.raises(ValueError):
+        ik.is_reachable_batch(P[:4], precision="fp16")

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from parity import REPO, Report, ill_conditioned_mask, load
+from parity import REPO, Report, check_f32, ill_conditioned_mask, load
 from reachy2_symbolic_ik_b200 import _abi
 
 HS_DIR = os.path.join(REPO, "tests", "hostsim")
@@ -229,3 +229,62 @@ def test_limit_orbita3d_wrist_fast_route(hs):
     assert d.max() < 1e-11, d.max()
     exact = np.abs(got - want) < 1e-11
     assert exact.mean() > 0.999      # the rest sit at the +-pi wrap of an output angle
+
+
+# ---------------------------------------------------------------------------------------------------
+# FP32 fast path (csrc/r2ik_device_f32.cuh) on the host: states identical to the FP64 oracle on the widened
+# inputs, joints / intervals within 1e-4 rad on poses that are well-conditioned at FP32 resolution.
+# ---------------------------------------------------------------------------------------------------
+def fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def hs_symik_f32(hs, cfg, P32, theta=None, mode=0):
+    P32 = np.ascontiguousarray(P32, dtype=np.float32)
+    n = len(P32)
+    kind = _abi.POSE_MAT4 if P32.shape[1:] == (4, 4) else _abi.POSE_EULER6
+    reach = np.zeros(n, np.uint8); state = np.zeros(n, np.uint8); esc = np.zeros(n, np.uint8)
+    itv = np.empty((n, 2), np.float32); j = np.empty((n, 7), np.float32); e = np.empty((n, 3), np.float32)
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float32)
+    hs.hs_symik_batch_f32(C.byref(cfg), kind, fp(P32), fp(th) if th is not None else None, C.c_int64(n), C.c_int(mode), u8(reach),
+                          u8(state), fp(itv), fp(j), fp(e), u8(esc))
+    return reach.astype(bool), itv, state, j, e, esc.astype(bool)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("layout", ["euler", "mat4"])
+def test_symik_f32_random(hs, oracle, arm, layout):
+    g = load(f"symik_random_{arm}.npz")
+    P32 = (g["goal_pose"] if layout == "euler" else g["M"]).astype(np.float32)
+    check_f32(f"hostsim f32 random {arm} {layout}", oracle, arm, P32, hs_symik_f32(hs, cfg_for(arm), P32))
+    th = g["theta2"].astype(np.float32)
+    check_f32(f"hostsim f32 random {arm} {layout} @theta2", oracle, arm, P32, hs_symik_f32(hs, cfg_for(arm), P32, th), theta=th)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_symik_f32_fk_20k(hs, oracle, arm):
+    from reachy2_symbolic_ik_b200 import fk
+
+    P32 = np.concatenate([fk.sample_fk_poses(15000, arm, seed=21), fk.sample_task_space_poses(5000, arm, seed=22)]).astype(np.float32)
+    check_f32(f"hostsim f32 fk+task {arm}", oracle, arm, P32, hs_symik_f32(hs, cfg_for(arm), P32))
+
+
+def test_symik_f32_named_and_degenerate(hs, oracle):
+    g = load("symik_named.npz")
+    for arm in ARMS:
+        P32 = g[f"{arm}_poses"].astype(np.float32)
+        got = hs_symik_f32(hs, cfg_for(arm), P32)
+        # every named pose keeps the reference's state (float32 inputs widened), however close to a boundary
+        want = oracle.symik_batch(oracle.arm_config(arm), P32.astype(np.float64))
+        assert np.array_equal(got[2], want[2])
+        assert np.array_equal(got[0], want[0])
+    # exact-zero / scaled / left-handed rotations are handed to the FP64 solver
+    M = np.tile(np.eye(4, dtype=np.float32), (4, 1, 1))
+    M[:, :3, 3] = [0.3, -0.2, -0.3]
+    M[1, :3, :3] *= 1.5
+    M[2, 0, 0] = -1.0
+    M[3, :3, :3] = 0.0
+    r, itv, st, j, e, esc = hs_symik_f32(hs, cfg_for("r_arm"), M)
+    want = oracle.symik_batch(oracle.arm_config("r_arm"), M.astype(np.float64))
+    assert np.array_equal(st, want[2]) and esc[1:].all()
+    assert np.nanmax(np.abs(j - want[3])) < 1e-5
