@@ -293,6 +293,7 @@ class SymikF32(Symik):
                                interval=torch.empty((n, 2), dtype=f32, device=dev), joints=torch.empty((n, 7), dtype=f32, device=dev),
                                elbow=torch.empty((n, 3), dtype=f32, device=dev)) for arm in ARMS}
         self.n_esc = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.esc = torch.empty(n, dtype=torch.int32, device=dev)
         self.kind = _abi.POSE_MAT4
         self.units_per_step = 2 * n
         self.units_per_launch = n
@@ -301,8 +302,8 @@ class SymikF32(Symik):
         for arm in ARMS:
             o = self.outs[arm]
             self.solvers[arm].solve_into_f32(self.dpose[arm], self.kind, None, None, o["reach"], o["state"], o["interval"], o["joints"],
-                                             o["elbow"], self.n_esc)
-        return 2
+                                             o["elbow"], self.n_esc, scratch=self.esc)
+        return 4
 
     def e2e_setup(self, torch):
         n = self.POSES_PER_ARM
@@ -319,10 +320,9 @@ class SymikF32(Symik):
         from oracle import oracle as O
 
         m = 100_000
-        self.n_esc.zero_()
         o = self.outs["r_arm"]
         self.solvers["r_arm"].solve_into_f32(self.dpose["r_arm"], self.kind, None, None, o["reach"], o["state"], o["interval"],
-                                             o["joints"], o["elbow"], self.n_esc)
+                                             o["joints"], o["elbow"], self.n_esc, scratch=self.esc)
         esc = int(self.n_esc.item())
         want = O.symik_batch(O.arm_config("r_arm"), self.poses["r_arm"][:m].astype(np.float64))
         got_j, got_i, got_s = (o[k][:m].cpu().numpy() for k in ("joints", "interval", "state"))

@@ -170,12 +170,14 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
  * float poses (n x 16 row-major 4x4, 16-byte aligned, or n x 6, 8-byte aligned), float outputs.  The solve runs
  * in FP32 with an FP64 front end for the cancelling differences; a pose within FP32 rounding of one of the
  * reference's decisions (state codes, branch cuts, elbow projection) or with an ill-conditioned angle is
- * re-solved by the FP64 solver on the same inputs, so states / flags are those of the FP64 path on the
- * widened inputs.  n_escalated: nullable device counter, incremented once per re-solved pose (zero it first).
- * theta / prev_joints as in r2ik_symik_solve_f64 (float). */
+ * appended to escalated_idx and re-solved by the FP64 solver on the same inputs in a second kernel of the same
+ * call, so states / flags are those of the FP64 path on the widened inputs.
+ * escalated_idx: n uint32 of caller-owned device scratch; n_escalated: one uint32 on the device, set by the call
+ * to the number of re-solved poses.  theta / prev_joints as in r2ik_symik_solve_f64 (float).  n < 2^32. */
 int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const float *theta,
                          const float *prev_joints, int64_t n, uint8_t *reachable, uint8_t *state,
-                         float *interval, float *joints, float *elbow, uint32_t *n_escalated, void *stream);
+                         float *interval, float *joints, float *elbow, uint32_t *escalated_idx,
+                         uint32_t *n_escalated, void *stream);
 
 /* is_reachable_no_limits + get_joints(theta[i]). */
 int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta,

@@ -47,7 +47,7 @@ def load() -> C.CDLL:
     L.r2ik_get_constants.argtypes = [vp, C.POINTER(_abi.ArmConstants)]
     L.r2ik_interval_limit.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.r2ik_symik_solve_f64.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
-    L.r2ik_symik_solve_f32.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.r2ik_symik_solve_f32.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.r2ik_symik_no_limits_f64.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp, vp]
     L.r2ik_elbow_positions_f64.argtypes = [vp, C.c_int, vp, vp, i32, i64, vp, vp]
     L.r2ik_ctl_discrete_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, vp, vp, vp, vp, vp, vp, vp]

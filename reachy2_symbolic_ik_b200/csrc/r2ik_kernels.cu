@@ -107,23 +107,20 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
 }
 
 // ---------------------------------------------------------------------------------------
-// K1-f32: the FP32 fast path of K1 (r2ik_device_f32.cuh).  One thread / pose; float4 / float2 pose loads
-// (64 B per 4x4 pose, 48 B read); the FP32 solve, and for the few poses whose decisions or conditioning
-// FP32 cannot settle the FP64 solver on the same inputs (out of line, whole warp waits for its flagged
-// lanes).  n_escalated (nullable) counts those poses.
+// K1-f32: the FP32 fast path of K1 (r2ik_device_f32.cuh), two kernels:
+//   k_symik_solve_f32      one thread / pose: float4 / float2 pose loads (64 B per 4x4 pose, 48 B read), the FP32
+//                          solve; a pose whose decisions or conditioning FP32 cannot settle is not stored but
+//                          appended to a list (one atomicAdd per warp);
+//   k_symik_escalated_f32  the FP64 solver on the listed poses (same float inputs widened), results narrowed.
+// Keeping the FP64 solver out of the first kernel matters more than the few poses suggest: inlined behind a
+// branch it cost a 130 KB kernel whose divergent excursions (7 % of the warps, one lane each) thrashed the
+// instruction cache -- 125 us per 1M poses, slower than the FP64 kernel (profiles/r1_s8_symik_f32_ncu_full.txt).
 // ---------------------------------------------------------------------------------------
 #ifndef R2IK_K1F_MINBLOCKS
 #define R2IK_K1F_MINBLOCKS 6
 #endif
 template <int KIND>
-__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1F_MINBLOCKS)
-k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ f32::ArmConstF A,
-                  const float *__restrict__ poses, const float *__restrict__ theta, const float *__restrict__ prev_joints,
-                  int64_t n, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state, float *__restrict__ interval,
-                  float *__restrict__ joints, float *__restrict__ elbow, unsigned *__restrict__ n_escalated) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float in[12];
+__device__ __forceinline__ void load_pose_f32(const float *__restrict__ poses, int64_t i, float in[12]) {
   if (KIND == R2IK_POSE_EULER6) {
     const float2 *p = reinterpret_cast<const float2 *>(poses + 6 * i);
     float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -136,22 +133,11 @@ k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ 
       in[4 * r] = v.x; in[4 * r + 1] = v.y; in[4 * r + 2] = v.z; in[4 * r + 3] = v.w;
     }
   }
-  const bool has_theta = theta != nullptr;
-  const float th = has_theta ? theta[i] : 0.0f;
-  float out[12];
-  int st;
-  const bool esc = f32::symik_pose_fast<KIND>(A64, A, in, has_theta, th, st, out);
-  if (esc) {
-    float prev0 = 0.0f, prev2 = 0.0f;
-    if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
-    float o2[12];
-    int st2;
-    f32::symik_pose_escalated<KIND>(A64, in, has_theta, th, prev0, prev2, &st2, o2);
-    st = st2;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) out[k] = o2[k];
-    if (n_escalated) atomicAdd(n_escalated, 1u);
-  }
+}
+
+__device__ __forceinline__ void store_pose_f32(int64_t i, int st, const float out[12], uint8_t *__restrict__ reachable,
+                                               uint8_t *__restrict__ state, float *__restrict__ interval,
+                                               float *__restrict__ joints, float *__restrict__ elbow) {
   reachable[i] = st == R2IK_STATE_REACHABLE ? 1 : 0;
   state[i] = (uint8_t)st;
   if (interval) reinterpret_cast<float2 *>(interval)[i] = make_float2(out[0], out[1]);
@@ -160,6 +146,57 @@ k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ 
     for (int k = 0; k < 7; ++k) joints[7 * i + k] = out[2 + k];
   }
   if (elbow) { elbow[3 * i] = out[9]; elbow[3 * i + 1] = out[10]; elbow[3 * i + 2] = out[11]; }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1F_MINBLOCKS)
+k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ f32::ArmConstF A,
+                  const float *__restrict__ poses, const float *__restrict__ theta, int64_t n,
+                  uint8_t *__restrict__ reachable, uint8_t *__restrict__ state, float *__restrict__ interval,
+                  float *__restrict__ joints, float *__restrict__ elbow, uint32_t *__restrict__ esc_list,
+                  unsigned *__restrict__ n_escalated) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  bool esc = false;
+  float out[12];
+  int st = 0;
+  if (active) {
+    float in[12];
+    load_pose_f32<KIND>(poses, i, in);
+    const bool has_theta = theta != nullptr;
+    const float th = has_theta ? theta[i] : 0.0f;
+    esc = f32::symik_pose_fast<KIND>(A64, A, in, has_theta, th, st, out);
+  }
+  // warp-aggregated append of the escalated poses
+  const unsigned m = __ballot_sync(0xffffffffu, esc);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_escalated, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (esc) esc_list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+  }
+  if (active && !esc) store_pose_f32(i, st, out, reachable, state, interval, joints, elbow);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_symik_escalated_f32(const __grid_constant__ ArmConst A64, const float *__restrict__ poses, const float *__restrict__ theta,
+                      const float *__restrict__ prev_joints, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state,
+                      float *__restrict__ interval, float *__restrict__ joints, float *__restrict__ elbow,
+                      const uint32_t *__restrict__ esc_list, const unsigned *__restrict__ n_escalated) {
+  const unsigned count = *n_escalated;
+  float prev0 = 0.0f, prev2 = 0.0f;
+  if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const int64_t i = esc_list[k];
+    float in[12], out[12];
+    load_pose_f32<KIND>(poses, i, in);
+    const bool has_theta = theta != nullptr;
+    int st;
+    f32::symik_pose_escalated<KIND>(A64, in, has_theta, has_theta ? theta[i] : 0.0f, prev0, prev2, &st, out);
+    store_pose_f32(i, st, out, reachable, state, interval, joints, elbow);
+  }
 }
 
 template <int KIND>
@@ -694,20 +731,27 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
 
 int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const float *theta, const float *prev_joints,
                          int64_t n, uint8_t *reachable, uint8_t *state, float *interval, float *joints, float *elbow,
-                         uint32_t *n_escalated, void *stream) {
-  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
-    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: bad n or pose_kind");
+                         uint32_t *escalated_idx, uint32_t *n_escalated, void *stream) {
+  if (n < 0 || n > 0xffffffffLL || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: bad n (0 .. 2^32-1) or pose_kind");
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null handle");
   if (n == 0) return 0;
-  if (!poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null argument");
+  if (!poses || !reachable || !state || !escalated_idx || !n_escalated)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null argument");
   if (((uintptr_t)poses & (pose_kind == R2IK_POSE_MAT4 ? 15 : 7)) != 0 || ((uintptr_t)interval & 7) != 0)
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: poses must be 16-byte (MAT4) / 8-byte (EULER6) aligned, interval 8-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
-  if (pose_kind == R2IK_POSE_MAT4)
-    k_symik_solve_f32<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow, n_escalated);
-  else
-    k_symik_solve_f32<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow, n_escalated);
+  R2IK_CUDA(cudaMemsetAsync(n_escalated, 0, sizeof(uint32_t), s), "cudaMemsetAsync");
+  // second pass: a fixed modest grid striding over the (device-side) count -- a few thousand poses per million
+  const unsigned eb = (unsigned)(blocks_for(n) < 592u ? blocks_for(n) : 592u);
+  if (pose_kind == R2IK_POSE_MAT4) {
+    k_symik_solve_f32<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, n, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
+    k_symik_escalated_f32<R2IK_POSE_MAT4><<<eb, R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
+  } else {
+    k_symik_solve_f32<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, n, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
+    k_symik_escalated_f32<R2IK_POSE_EULER6><<<eb, R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
+  }
   R2IK_CUDA(cudaGetLastError(), "k_symik_solve_f32 launch");
   return 0;
 }

@@ -163,7 +163,7 @@ class SymbolicIK:
             elbow = torch.empty((n, 3), dtype=dt, device=self._device) if want_joints else None
             n_esc = None
             if precision == "fp32":
-                n_esc = torch.zeros(1, dtype=torch.int32, device=self._device)
+                n_esc = torch.empty(1, dtype=torch.int32, device=self._device)
                 self.solve_into_f32(P, kind, th, pj, reach, state, interval, joints, elbow, n_esc)
             else:
                 self.solve_into(P, kind, th, pj, reach, state, interval, joints, elbow)
@@ -184,14 +184,25 @@ class SymbolicIK:
         _native.check(rc, "r2ik_symik_solve_f64")
 
     def solve_into_f32(self, poses_dev, kind, theta_dev, prev_dev, reach, state, interval, joints, elbow, n_escalated=None,
-                       stream=None):
-        """Raw launch of the FP32 fast path on float32 device tensors (``r2ik_symik_solve_f32``); ``n_escalated`` is an
-        optional int32 device counter the kernel adds to."""
+                       stream=None, scratch=None):
+        """Raw launch of the FP32 fast path on float32 device tensors (``r2ik_symik_solve_f32``).  ``n_escalated``: int32
+        device tensor (1,) the call sets to the number of poses re-solved in FP64; ``scratch``: int32 device tensor of
+        at least N entries (the list of those poses); both are allocated / cached here when omitted."""
         torch = self._torch
+        n = poses_dev.shape[0]
+        if scratch is None:
+            scratch = getattr(self, "_esc_scratch", None)
+            if scratch is None or scratch.numel() < n or stream is not None:
+                scratch = torch.empty(max(n, 1), dtype=torch.int32, device=self._device)
+                if stream is None:
+                    self._esc_scratch = scratch
+        if n_escalated is None:
+            n_escalated = torch.empty(1, dtype=torch.int32, device=self._device)
         s = torch.cuda.current_stream(self._device).cuda_stream if stream is None else stream
         rc = self._handle.lib.r2ik_symik_solve_f32(
-            self._handle.h, kind, _ptr(poses_dev), _ptr(theta_dev), _ptr(prev_dev), C.c_int64(poses_dev.shape[0]),
-            _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), _ptr(n_escalated), C.c_void_p(s))
+            self._handle.h, kind, _ptr(poses_dev), _ptr(theta_dev), _ptr(prev_dev), C.c_int64(n),
+            _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), _ptr(scratch), _ptr(n_escalated),
+            C.c_void_p(s))
         _native.check(rc, "r2ik_symik_solve_f32")
 
     # ------------------------------------------------------------------ host-buffer pipeline
@@ -228,9 +239,7 @@ class SymbolicIK:
         n = shp[0]
         if out is None:
             out = self.alloc_host_outputs(n, precision)
-        solve = self.solve_into if precision == "fp64" else (
-            lambda P_, kind_, th_, pj_, r_, s_, i_, j_, e_, stream=None: self.solve_into_f32(P_, kind_, th_, pj_, r_, s_, i_, j_,
-                                                                                           e_, None, stream=stream))
+        fp32 = precision == "fp32"
         with torch.cuda.device(self._device):
             pipe = self._pipeline(chunk, n_streams, k, dt)
             cur = torch.cuda.current_stream(self._device)
@@ -244,8 +253,12 @@ class SymbolicIK:
                 b = pipe["bufs"][slot]
                 with torch.cuda.stream(s):
                     b["poses"][:m].copy_(P[lo:hi], non_blocking=True)
-                    solve(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
-                          b["elbow"], stream=s.cuda_stream)
+                    if fp32:
+                        self.solve_into_f32(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
+                                            b["elbow"], b["n_esc"], stream=s.cuda_stream, scratch=b["esc"])
+                    else:
+                        self.solve_into(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
+                                        b["elbow"], stream=s.cuda_stream)
                     out.reachable[lo:hi].copy_(b["reach"][:m], non_blocking=True)
                     out.state[lo:hi].copy_(b["state"][:m], non_blocking=True)
                     out.theta_interval[lo:hi].copy_(b["interval"][:m], non_blocking=True)
@@ -271,7 +284,9 @@ class SymbolicIK:
                               state=torch.empty(chunk, dtype=torch.uint8, device=d),
                               interval=torch.empty((chunk, 2), dtype=dt, device=d),
                               joints=torch.empty((chunk, 7), dtype=dt, device=d),
-                              elbow=torch.empty((chunk, 3), dtype=dt, device=d)) for _ in range(n_streams)],
+                              elbow=torch.empty((chunk, 3), dtype=dt, device=d),
+                              esc=torch.empty(chunk, dtype=torch.int32, device=d),
+                              n_esc=torch.empty(1, dtype=torch.int32, device=d)) for _ in range(n_streams)],
             }
         return cache[key]
 
