@@ -255,21 +255,26 @@ R2IK_HD double det3(const double m[9]) {
 }
 
 // Orthogonal polar factor of a nonsingular 3x3 (what scipy's SVD projection U @ Vt computes,
-// rxp:78-95), by the Newton iteration X <- (X + X^-T) / 2.
+// rxp:78-95), by the Newton iteration X <- (X + X^-T) / 2.  The iteration converges quadratically: once
+// two iterates agree to 1e-8 the next one is the fixed point to rounding, so one more step is taken and
+// the loop ends (waiting for the step itself to fall below one ulp, as an earlier version did, never
+// happens when the last bits keep flipping -- 60 iterations for every nearly-orthonormal input).
 R2IK_HD void polar_orthogonalize(double m[9]) {
+  bool last = false;
   for (int it = 0; it < 60; ++it) {
-    double d = det3(m);
+    double id = 1.0 / det3(m);
     double c[9];
-    c[0] = (m[4] * m[8] - m[5] * m[7]) / d; c[1] = (m[5] * m[6] - m[3] * m[8]) / d; c[2] = (m[3] * m[7] - m[4] * m[6]) / d;
-    c[3] = (m[2] * m[7] - m[1] * m[8]) / d; c[4] = (m[0] * m[8] - m[2] * m[6]) / d; c[5] = (m[1] * m[6] - m[0] * m[7]) / d;
-    c[6] = (m[1] * m[5] - m[2] * m[4]) / d; c[7] = (m[2] * m[3] - m[0] * m[5]) / d; c[8] = (m[0] * m[4] - m[1] * m[3]) / d;
+    c[0] = (m[4] * m[8] - m[5] * m[7]) * id; c[1] = (m[5] * m[6] - m[3] * m[8]) * id; c[2] = (m[3] * m[7] - m[4] * m[6]) * id;
+    c[3] = (m[2] * m[7] - m[1] * m[8]) * id; c[4] = (m[0] * m[8] - m[2] * m[6]) * id; c[5] = (m[1] * m[6] - m[0] * m[7]) * id;
+    c[6] = (m[1] * m[5] - m[2] * m[4]) * id; c[7] = (m[2] * m[3] - m[0] * m[5]) * id; c[8] = (m[0] * m[4] - m[1] * m[3]) * id;
     double delta = 0.0;
     for (int k = 0; k < 9; ++k) {
       double nx = 0.5 * (m[k] + c[k]);
       delta = fmax(delta, fabs(nx - m[k]));
       m[k] = nx;
     }
-    if (delta < 1e-16) break;
+    if (last) break;
+    if (delta < 1e-8) last = true;
   }
 }
 

@@ -463,15 +463,10 @@ R2IK_HD bool symik_pose_fast(const ArmConst &A64, const ArmConstF &A, const floa
   return esc;
 }
 
-// The escalation target: the FP64 solver on the same inputs widened to double, results narrowed.
-// Out of line: a few poses in 10^4 take it.
+// The escalation target: the FP64 solver on the same inputs widened to double, results narrowed
+// (body of k_symik_escalated_f32; a few poses in 10^3 take it).
 template <int KIND>
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-void symik_pose_escalated(const ArmConst &A, const float *in, bool has_theta, float theta, float prev0, float prev2,
+R2IK_HD void symik_pose_escalated(const ArmConst &A, const float *in, bool has_theta, float theta, float prev0, float prev2,
                           int *state, float *out) {
   double pos[3];
   Solve S;
