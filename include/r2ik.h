@@ -24,6 +24,8 @@
  *        (get_best_discrete_theta utils.py:334-396, limit_theta_to_interval utils.py:93-112,
  *         limit_orbita3d_joints_wrist :508-532, allow_multiturn :493-505,
  *         multiturn_safety_check :535-568)
+ *   r2ik_ctl_discrete_scan_f64
+ *        the same, exhaustive warp-cooperative scan of the K samples (cross-check)
  *   r2ik_ctl_continuous_f64
  *        ControlIK.symbolic_inverse_kinematics(name, M, "continuous") over trajectories
  *                                                  control_ik.py:276-407
@@ -194,6 +196,14 @@ int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, co
                           const double *prev_joints, const double *current_joints, double *joints,
                           uint8_t *reachable, uint8_t *state, uint8_t *emergency, void *stream);
 
+/* The same with the exhaustive form of the elbow search: every one of the nb_search_points samples is visited,
+ * the samples of a pose strided over the lanes of its warp and reduced by a shuffle arg-min (lowest index wins
+ * ties).  r2ik_ctl_discrete_f64 finds the same arg-min from the crossings of the two elbow tests without
+ * visiting the samples; this entry is the cross-check of that search (identical outputs) at K times the cost. */
+int r2ik_ctl_discrete_scan_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t n,
+                               const double *prev_joints, const double *current_joints, double *joints,
+                               uint8_t *reachable, uint8_t *state, uint8_t *emergency, void *stream);
+
 /* ControlIK continuous mode: T trajectories x W waypoints, M is T x W x 16.  current_joints
  * (T x 7) and current_pose (T x 16) feed the (re)initialisation; st: T states, in/out. */
 int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
@@ -201,7 +211,7 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, 
                             R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
                             void *stream);
 
-/* The same computation as r2ik_ctl_continuous_f64 (bit-identical outputs), cut at its data dependences:
+/* The same computation as r2ik_ctl_continuous_f64 (same flags / states, joints equal to rounding), cut at its data dependences:
  * the per-waypoint work (reachability, target theta, joints for a given theta, Orbita3D limit) runs with one
  * thread per waypoint, and only the rate-limited theta and the unwrap / continuity / emergency chain run as
  * per-trajectory scans.  workspace: T*W doubles of device scratch (theta per waypoint), caller-owned. */

@@ -153,7 +153,8 @@ class ControlIK:
     def symbolic_inverse_kinematics_batch(self, name: str, M, control_type: str = "discrete", current_joints=None,
                                           constrained_mode: str = "unconstrained", current_pose=None,
                                           d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
-                                          previous_joints=None, states=None, out=None, phased: bool = True):
+                                          previous_joints=None, states=None, out=None, phased: bool = True,
+                                          exhaustive: bool = False):
         """Batched ``symbolic_inverse_kinematics``.
 
         discrete:   M (N,4,4) -> joints (N,7), reachable (N,), state (N,) uint8, emergency bits (N,).
@@ -164,8 +165,11 @@ class ControlIK:
                     ``states`` may also be a CUDA uint8 tensor (T,80): it is then updated in place and
                     returned as is (no host round trip).
         ``out``: the tuple a previous call returned for CUDA input of the same shape; its tensors are reused.
+        ``exhaustive`` (discrete): False = the elbow search finds the arg-min over the nb_search_points samples from
+        the crossings of the two elbow tests (cost independent of K); True = every sample is visited by the
+        warp-cooperative scan kernel.  Same outputs.
         ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans (needs T*W doubles of device
-        scratch, allocated here); False = the single one-thread-per-trajectory kernel.  Same outputs, bit for bit.
+        scratch, allocated here); False = the single one-thread-per-trajectory kernel.  Same flags / states; joints equal to rounding.
         """
         torch = self._torch
         solver = self.symbolic_ik_solver[name]
@@ -186,9 +190,9 @@ class ControlIK:
                     reach = torch.empty(n, dtype=torch.uint8, device=self._device)
                     state = torch.empty(n, dtype=torch.uint8, device=self._device)
                     emg = torch.empty(n, dtype=torch.uint8, device=self._device)
-                rc = solver._handle.lib.r2ik_ctl_discrete_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(n),
-                                                              _ptr(prev), _ptr(cur), _ptr(joints), _ptr(reach), _ptr(state),
-                                                              _ptr(emg), stream)
+                entry = solver._handle.lib.r2ik_ctl_discrete_scan_f64 if exhaustive else solver._handle.lib.r2ik_ctl_discrete_f64
+                rc = entry(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(n),
+                           _ptr(prev), _ptr(cur), _ptr(joints), _ptr(reach), _ptr(state), _ptr(emg), stream)
                 _native.check(rc, "r2ik_ctl_discrete_f64")
                 res = (joints, reach.view(torch.bool), state, emg)
                 return res if was_cuda else tuple(x.cpu().numpy() for x in res)

@@ -69,6 +69,65 @@ R2IK_HD void search_strided(const SearchPlan &P, int nb, int k0, int stride, dou
   }
 }
 
+// The same arg-min WITHOUT visiting the K samples.  On the sampled range (an interval of theta of length
+// <= 2 pi) the cost |angle_diff(theta, preferred)| falls linearly to 0 at the point congruent to the
+// preferred theta and rises to pi at its antipode, and each half-plane test C + A cos + B sin < 0 holds on
+// one arc of the circle (phi + acos(g), phi + 2 pi - acos(g)), g = -C / hypot(A, B), phi = atan2(B, A).
+// The valid samples therefore form a few runs of consecutive indices, and on a run the cheapest sample is
+// either next to the preferred point or at an end of the run -- i.e. next to a crossing of one of the two
+// tests or at an end of the range.  Candidates: the 3 samples around each of the <= 4 crossings, the 3
+// around the preferred point, the first and the last sample; each is evaluated exactly like a visited
+// sample (theta_k from linspace, sincos, the two tests, the wrapped cost) and the minimum is taken in
+// (cost, index) order = the reference's strict-< scan.  17 evaluations instead of K, no cooperation
+// between lanes.  Returns false when an atan2 argument is outside the fast routine's range (the caller
+// scans instead).
+R2IK_HD void search_eval(const SearchPlan &P, int nb, int k, double &best, int &best_k) {
+  if (k < 0 || k >= nb) return;
+  const double th = linspace_value(P.L, k);
+  double s, c;
+  sincos_any(th, s, c);
+  if (!elbow_ok_cs(P.T, c, s)) return;
+  const double cost = fabs(angle_diff(th, P.preferred_theta));
+  if (cost < best || (cost == best && k < best_k)) { best = cost; best_k = k; }
+}
+R2IK_HD void search_around(const SearchPlan &P, int nb, double theta, double inv_step, double &best, int &best_k) {
+  // sample position of the angle congruent to theta in [start, start + 2 pi)
+  const double u = pymod_2pi(theta - P.L.start);
+  const double x = u * inv_step;
+  if (!(x <= (double)nb)) return;                      // beyond the last sample (ranges shorter than 2 pi)
+  const int k = (int)rint(x);
+  search_eval(P, nb, k - 1, best, best_k);
+  search_eval(P, nb, k, best, best_k);
+  search_eval(P, nb, k + 1, best, best_k);
+}
+R2IK_HD bool search_analytic(const SearchPlan &P, int nb, double &best, int &best_k) {
+  best = INFINITY;
+  best_k = 0x7fffffff;
+  if (!(P.L.step > 0.0) || nb < 8) {                     // degenerate range or a handful of samples: just scan
+    double b; int bk;
+    search_strided(P, nb, 0, 1, b, bk);
+    best = b; best_k = bk;
+    return true;
+  }
+  const double inv_step = 1.0 / P.L.step;
+  bool ok = true;
+  const double A_[2] = {P.T.A1, P.T.A2}, B_[2] = {P.T.B1, P.T.B2}, C_[2] = {P.T.C1, P.T.C2};
+  for (int t = 0; t < 2; ++t) {
+    const double R2 = A_[t] * A_[t] + B_[t] * B_[t];
+    const double s2 = R2 - C_[t] * C_[t];                // R^2 sin^2(alpha): < 0 => the test never changes sign
+    if (!(s2 >= 0.0)) continue;
+    ok = ok && atan2_core_ok(B_[t], A_[t]) && (R2 > 1e-280);
+    const double phi = atan2_core(B_[t], A_[t]);
+    const double alpha = atan2_core(sqrt_nonneg(s2), -C_[t]);   // acos(-C / R)
+    search_around(P, nb, phi + alpha, inv_step, best, best_k);
+    search_around(P, nb, phi - alpha, inv_step, best, best_k);
+  }
+  search_around(P, nb, P.preferred_theta, inv_step, best, best_k);
+  search_eval(P, nb, 0, best, best_k);
+  search_eval(P, nb, nb - 1, best, best_k);
+  return ok;
+}
+
 // utl:357-364: preferred_theta is tried first
 R2IK_HD bool preferred_theta_works(const ArmConst &A, const Solve &S, double i0, double i1, double preferred_theta) {
   if (!is_valid_angle(preferred_theta, i0, i1)) return false;
@@ -179,7 +238,7 @@ R2IK_HD int discrete_finish(const ArmConst &A, const R2ikCtlParams &par, Solve &
 // limit -- is a function of the waypoint alone.  The four pieces below are exactly the statements of
 // the reference's function, regrouped; continuous_step composes them for one waypoint (serial kernel,
 // host harness) and the phased kernels run (1) and (3) over all waypoints in parallel and (2), (4) as
-// short per-trajectory scans, with bit-identical results.
+// short per-trajectory scans, with the same flags / states and joints equal to rounding.
 // ---------------------------------------------------------------------------------------
 #define R2IK_WP_INVALID 0        // rotation block with det <= 0
 #define R2IK_WP_TARGET 1         // reachable, a target theta was found                       (ctl:350-361)

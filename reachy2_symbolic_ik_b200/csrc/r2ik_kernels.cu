@@ -238,15 +238,23 @@ k_elbow_positions(const __grid_constant__ ArmConst A, const double *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------
-// K2: ControlIK discrete mode.  Each lane solves its own pose (is_reachable, preferred-theta
+// K2: ControlIK discrete mode, two forms with identical results.
+//
+// k_ctl_discrete (default): one lane / pose end to end.  The K-sample search of get_best_discrete_theta
+// (utl:366-390) is replaced by search_analytic (r2ik_control.cuh): the arg-min over the K samples is found
+// among 17 candidate samples located from the crossings of the two elbow half-plane tests, each evaluated
+// exactly like a visited sample -- the cost of a pose no longer depends on K.
+//
+// k_ctl_discrete_scan: the exhaustive form.  Each lane solves its own pose (is_reachable, preferred-theta
 // shortcut); poses that need the K-sample search are then served one at a time by the whole
 // warp: the circle is broadcast with shuffles, lane l evaluates samples l, l+32, ..., and a
 // shuffle arg-min with lowest-index tie-break reproduces the reference's strict-< scan
-// (utl:381-390).  Each lane finally runs get_joints + safety_checks for its own pose.
+// (utl:381-390).  Each lane finally runs get_joints + safety_checks for its own pose.  Kept as the
+// cross-check of the analytic search (tests compare the two on every sampled pose) and for K < 8.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// K2 spends most of its time in the warp-serial K-sample search, a short dependent chain per lane that
+// The scan form spends most of its time in the warp-serial K-sample search, a short dependent chain per lane that
 // only more resident warps can overlap: holding the kernel to 64 registers (8 blocks / SM; the solve
 // phases spill ~1.1 KB to L1-resident local memory) measured 0.89 ms per 1M poses x 360 samples against
 // 1.18 ms at 128 registers and 1.77 ms unconstrained (176 registers), profiles/r1_experiments.md.
@@ -254,7 +262,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 #define R2IK_K2_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K2_MINBLOCKS)
-k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
+k_ctl_discrete_scan(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
                const double *__restrict__ M, int64_t n, const double *__restrict__ prev_joints,
                const double *__restrict__ current_joints, double *__restrict__ joints, uint8_t *__restrict__ reachable,
                uint8_t *__restrict__ state, uint8_t *__restrict__ emergency) {
@@ -321,6 +329,58 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
   double j[7];
   int bits = 0;
   if (valid_pose) {
+    bits = discrete_finish(A, par, S, found, theta, prev, cur, j);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) j[k] = NAN;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+  reachable[i] = found ? 1 : 0;
+  state[i] = (uint8_t)st;
+  if (emergency) emergency[i] = (uint8_t)bits;
+}
+
+#ifndef R2IK_K2A_MINBLOCKS
+#define R2IK_K2A_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K2A_MINBLOCKS)
+k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
+               const double *__restrict__ M, int64_t n, const double *__restrict__ prev_joints,
+               const double *__restrict__ current_joints, double *__restrict__ joints, uint8_t *__restrict__ reachable,
+               uint8_t *__restrict__ state, uint8_t *__restrict__ emergency) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double prev[7], cur[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { prev[k] = prev_joints[k]; cur[k] = current_joints[k]; }
+  Solve S;
+  int st = R2IK_STATE_INVALID_ROTATION;
+  bool found = false;
+  double theta = 0.0, j[7], pos[3];
+  int bits = 0;
+  if (load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R)) {
+    Reach rc = is_reachable_R<false>(A, pos, S);
+    st = rc.state;
+    if (st == R2IK_STATE_REACHABLE) {
+      if (preferred_theta_works(A, S, rc.i0, rc.i1, par.preferred_theta)) {
+        theta = par.preferred_theta; found = true;
+      } else {
+        SearchPlan plan;
+        plan.preferred_theta = par.preferred_theta;
+        double start, stop;
+        search_range(rc.i0, rc.i1, start, stop);
+        plan.L = make_linspace(start, stop, par.nb_search_points);
+        plan.T = make_elbow_test(A, S);
+        double best;
+        int best_k;
+        if (!search_analytic(plan, par.nb_search_points, best, best_k))
+          search_strided(plan, par.nb_search_points, 0, 1, best, best_k);     // out-of-range magnitudes: scan
+        found = best < INFINITY;
+        if (found) theta = linspace_value(plan.L, best_k);
+        else st = R2IK_STATE_LIMITED_BY_SHOULDER;
+      }
+    }
     bits = discrete_finish(A, par, S, found, theta, prev, cur, j);
   } else {
 #pragma unroll
@@ -792,9 +852,9 @@ int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, 
   return 0;
 }
 
-int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n, const double *prev_joints,
-                          const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
-                          uint8_t *emergency, void *stream) {
+static int ctl_discrete_launch(bool scan, r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n,
+                               const double *prev_joints, const double *current_joints, double *joints, uint8_t *reachable,
+                               uint8_t *state, uint8_t *emergency, void *stream) {
   if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null handle or parameters");
   if (n < 0 || par->nb_search_points < 2) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_f64: bad n or nb_search_points");
   if (n == 0) return 0;
@@ -802,10 +862,26 @@ int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double 
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null argument");
   if (misaligned16(M)) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_f64: M must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
-  k_ctl_discrete<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints, joints,
-                                                                        reachable, state, emergency);
+  if (scan)
+    k_ctl_discrete_scan<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints,
+                                                                               joints, reachable, state, emergency);
+  else
+    k_ctl_discrete<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints, joints,
+                                                                          reachable, state, emergency);
   R2IK_CUDA(cudaGetLastError(), "k_ctl_discrete launch");
   return 0;
+}
+
+int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n, const double *prev_joints,
+                          const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
+                          uint8_t *emergency, void *stream) {
+  return ctl_discrete_launch(false, h, par, M, n, prev_joints, current_joints, joints, reachable, state, emergency, stream);
+}
+
+int r2ik_ctl_discrete_scan_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n, const double *prev_joints,
+                               const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
+                               uint8_t *emergency, void *stream) {
+  return ctl_discrete_launch(true, h, par, M, n, prev_joints, current_joints, joints, reachable, state, emergency, stream);
 }
 
 int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,

@@ -52,6 +52,21 @@ def cmd_time():
     mism = int((o["state"][:m].cpu().numpy() != want[2]).sum())
     print(f"{os.environ.get('R2IK_LIB', 'in-tree'):60s} K1 {ms * 1e3:8.1f} us/1M  {n / ms * 1e3:.3e} poses/s  "
           f"state_mismatch={mism} max_dj={np.nanmax(ej):.2e} max_di={np.nanmax(ei):.2e}", flush=True)
+    # K2 (ControlIK discrete, K = 360) and K1-f32 of the same library
+    from reachy2_symbolic_ik_b200 import ControlIK, fk
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    ctl.nb_search_points = 360
+    M3 = torch.from_numpy(fk.sample_fk_poses(n, "r_arm", seed=3)).cuda().reshape(n, 16)
+    out = [None]
+    def k2():
+        out[0] = ctl.symbolic_inverse_kinematics_batch("r_arm", M3, "discrete", out=out[0])
+    ms2 = time_launch(torch, k2, reps=10, warm=3)
+    P32 = Md.float()
+    o32 = dict(itv=torch.empty((n, 2), device="cuda"), j=torch.empty((n, 7), device="cuda"), e=torch.empty((n, 3), device="cuda"),
+               ne=torch.empty(1, dtype=torch.int32, device="cuda"), sc=torch.empty(n, dtype=torch.int32, device="cuda"))
+    ms3 = time_launch(torch, lambda: ik.solve_into_f32(P32, 1, None, None, o["reach"], o["state"], o32["itv"], o32["j"], o32["e"],
+                                                       o32["ne"], scratch=o32["sc"]))
+    print(f"{'':60s} K2 {ms2 * 1e3:8.1f} us/1M (K=360)   K1-f32 {ms3 * 1e3:8.1f} us/1M", flush=True)
 
 
 def cmd_sweep():

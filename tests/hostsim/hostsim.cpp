@@ -248,4 +248,21 @@ void hs_symik_batch_f32(const R2ikArmConfig *cfg, int kind, const float *poses, 
   }
 }
 
+// search_analytic vs the exhaustive scan (search_strided, stride 1) on n random search plans:
+// plans[i] = start, stop, A1, B1, C1, A2, B2, C2, preferred (9 doubles).
+void hs_search_compare(const double *plans, int64_t n, int nb, double *best_scan, int32_t *k_scan, double *best_ana,
+                       int32_t *k_ana, uint8_t *ok) {
+  for (int64_t i = 0; i < n; ++i) {
+    const double *q = plans + 9 * i;
+    SearchPlan P;
+    P.L = make_linspace(q[0], q[1], nb);
+    P.T.A1 = q[2]; P.T.B1 = q[3]; P.T.C1 = q[4]; P.T.A2 = q[5]; P.T.B2 = q[6]; P.T.C2 = q[7];
+    P.preferred_theta = q[8];
+    int ks, ka;
+    search_strided(P, nb, 0, 1, best_scan[i], ks);
+    ok[i] = search_analytic(P, nb, best_ana[i], ka);
+    k_scan[i] = ks; k_ana[i] = ka;
+  }
+}
+
 }  // extern "C"

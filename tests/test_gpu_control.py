@@ -219,8 +219,10 @@ def test_host_pipelines_match_device_calls(controls):
 @pytest.mark.parametrize("arm", ARMS)
 def test_continuous_phased_equals_serial_kernel(controls, arm):
     """The phased K3 (per-waypoint kernels + per-trajectory scans) and the one-thread-per-trajectory K3 are the
-    same arithmetic regrouped: every output and the final controller states must agree bit for bit, also when a
-    trajectory latches an emergency stop, hits invalid rotations or is resumed from a previous state."""
+    same arithmetic regrouped: flags, state codes and the integer controller state must be identical, and the joints
+    / thetas equal to rounding (the two forms are separate compilations, so FMA contraction may differ in the last
+    bit: 1e-12 rad is allowed), also when a trajectory latches an emergency stop, hits invalid rotations or is
+    resumed from a previous state."""
     from reachy2_symbolic_ik_b200 import fk
 
     ctl = controls[False]
@@ -231,13 +233,43 @@ def test_continuous_phased_equals_serial_kernel(controls, arm):
     M[6, 0, :3, :3] = np.diag([1.0, -1.0, 1.0])    # ... and at the first waypoint of trajectory 6
     a = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=True)
     b = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=False)
-    for x, y in zip(a[:3], b[:3]):
-        np.testing.assert_array_equal(x, y)
-    assert a[3].tobytes() == b[3].tobytes()
+    def same(p, q):
+        np.testing.assert_allclose(p[0], q[0], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(p[1], q[1])
+        np.testing.assert_array_equal(p[2], q[2])
+        for f in ("has_previous_sol", "init", "emergency_stop", "emergency_bits"):
+            np.testing.assert_array_equal(p[3][f], q[3][f])
+        np.testing.assert_allclose(p[3]["previous_theta"], q[3]["previous_theta"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(p[3]["previous_sol"], q[3]["previous_sol"], rtol=0, atol=1e-12)
+
+    same(a, b)
     assert a[3]["emergency_stop"][3] == 1 and (a[2][3, -10:] == 8).all()
     # resume from the returned states
     a2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:, ::-1].copy(), "continuous", states=a[3], phased=True)
     b2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:, ::-1].copy(), "continuous", states=b[3], phased=False)
-    for x, y in zip(a2[:3], b2[:3]):
+    same(a2, b2)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("K", [20, 360, 1000])
+def test_discrete_analytic_search_equals_exhaustive_scan(controls, arm, K):
+    """K2's default elbow search locates the arg-min over the K samples from the crossings of the two elbow tests;
+    the scan kernel visits every sample (warp-cooperative, shuffle arg-min).  Same theta, hence identical outputs."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    ctl = controls[False]
+    M = np.concatenate([fk.sample_fk_poses(150_000, arm, seed=51 + K), fk.sample_task_space_poses(50_000, arm, seed=52 + K)])
+    old = ctl.nb_search_points
+    try:
+        ctl.nb_search_points = K
+        a = ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete")
+        b = ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete", exhaustive=True)
+        for mode in ("low_elbow",):
+            a2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:50_000], "discrete", constrained_mode=mode)
+            b2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:50_000], "discrete", constrained_mode=mode, exhaustive=True)
+    finally:
+        ctl.nb_search_points = old
+    searched = int((a[2] == 6).sum() + (a[1] & (a[2] == 0)).sum())
+    assert searched > 10_000
+    for (x, y) in list(zip(a, b)) + list(zip(a2, b2)):
         np.testing.assert_array_equal(x, y)
-    assert a2[3].tobytes() == b2[3].tobytes()

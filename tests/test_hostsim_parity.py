@@ -288,3 +288,35 @@ def test_symik_f32_named_and_degenerate(hs, oracle):
     want = oracle.symik_batch(oracle.arm_config("r_arm"), M.astype(np.float64))
     assert np.array_equal(st, want[2]) and esc[1:].all()
     assert np.nanmax(np.abs(j - want[3])) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2's analytic elbow search (search_analytic) against the exhaustive scan of the K samples
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nb", [8, 10, 20, 360, 3600])
+@pytest.mark.parametrize("mode", ["full", "interval"])
+def test_search_analytic_equals_scan(hs, nb, mode):
+    rng = np.random.default_rng(nb + (0 if mode == "full" else 1))
+    n = 50000
+    plans = np.empty((n, 9))
+    if mode == "full":                                   # utl:366-369 full circle: [pi/2, 5pi/2]
+        plans[:, 0] = np.pi / 2; plans[:, 1] = np.pi / 2 + 2 * np.pi
+    else:                                                # utl:370-375 interval, unrolled past pi when wrapped
+        i0 = rng.uniform(-np.pi, np.pi, n); i1 = rng.uniform(-np.pi, np.pi, n)
+        plans[:, 0] = i0; plans[:, 1] = np.where(i0 < i1, i1, i1 + 2 * np.pi)
+    for c in (2, 3, 5, 6):                               # half-plane tests with the magnitudes of the arm (r <= 0.28 m)
+        plans[:, c] = rng.uniform(-0.28, 0.28, n)
+    for c in (4, 7):
+        plans[:, c] = rng.uniform(-0.35, 0.2, n)
+    plans[:, 8] = rng.choice([-2 * np.pi / 3, -np.pi / 3, 0.3, 2.5], n)
+    # samples exactly on a crossing / on the preferred angle
+    plans[:100, 8] = plans[:100, 0] + (plans[:100, 1] - plans[:100, 0]) * rng.integers(0, nb, 100) / (nb - 1)
+    bs = np.empty(n); ba = np.empty(n); ks = np.empty(n, np.int32); ka = np.empty(n, np.int32); ok = np.empty(n, np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    hs.hs_search_compare(vp(plans), C.c_int64(n), C.c_int(nb), vp(bs), vp(ks), vp(ba), vp(ka), vp(ok))
+    assert ok.all()
+    found = np.isfinite(bs)
+    assert 0.3 < found.mean() < 0.99
+    assert np.array_equal(found, np.isfinite(ba))
+    assert np.array_equal(ks, ka), f"{int((ks != ka).sum())} arg-min differ"
+    assert np.array_equal(bs[found], ba[found])
