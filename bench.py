@@ -351,13 +351,14 @@ class Discrete:
     BYTES_IN, BYTES_OUT = 128, 56 + 3
     kernel = "k_ctl_discrete"
 
-    SEARCH_FRACTION = 0.65   # share of the FK-sampled poses whose preferred theta fails and that run the K-sample search
+    SEARCH_FRACTION = 0.65   # share of the FK-sampled poses whose preferred theta fails and that run the elbow search
 
     @property
     def FLOP_EQ(self):
-        # solve + joints + safety chain ~2400 flops per pose; per sample of the search 24 flops (rotation recurrence 6,
-        # two half-plane tests 8, theta_k 2, wrapped cost 8); 65 % of the poses search (measured with the oracle)
-        return 2400.0 + self.SEARCH_FRACTION * 24.0 * self.K
+        # solve + joints + safety chain ~2400 flops per pose; the analytic search evaluates 17 candidate samples (sincos 35,
+        # two half-plane tests 8, theta_k 2, wrapped cost 10) plus 4 atan2 + 2 roots to locate them (~200): independent of K;
+        # 65 % of the poses search (measured with the oracle)
+        return 2400.0 + self.SEARCH_FRACTION * (17 * 55.0 + 200.0)
 
     @property
     def FLOP_EQ_SURVEY(self):

@@ -90,16 +90,6 @@ R2IK_HD void search_eval(const SearchPlan &P, int nb, int k, double &best, int &
   const double cost = fabs(angle_diff(th, P.preferred_theta));
   if (cost < best || (cost == best && k < best_k)) { best = cost; best_k = k; }
 }
-R2IK_HD void search_around(const SearchPlan &P, int nb, double theta, double inv_step, double &best, int &best_k) {
-  // sample position of the angle congruent to theta in [start, start + 2 pi)
-  const double u = pymod_2pi(theta - P.L.start);
-  const double x = u * inv_step;
-  if (!(x <= (double)nb)) return;                      // beyond the last sample (ranges shorter than 2 pi)
-  const int k = (int)rint(x);
-  search_eval(P, nb, k - 1, best, best_k);
-  search_eval(P, nb, k, best, best_k);
-  search_eval(P, nb, k + 1, best, best_k);
-}
 R2IK_HD bool search_analytic(const SearchPlan &P, int nb, double &best, int &best_k) {
   best = INFINITY;
   best_k = 0x7fffffff;
@@ -111,20 +101,38 @@ R2IK_HD bool search_analytic(const SearchPlan &P, int nb, double &best, int &bes
   }
   const double inv_step = 1.0 / P.L.step;
   bool ok = true;
+  // angles whose neighbouring samples are candidates: the crossings phi +- alpha of each test, the preferred theta
+  // (NaN = no such crossing; its candidates are skipped)
+  double cand[5];
   const double A_[2] = {P.T.A1, P.T.A2}, B_[2] = {P.T.B1, P.T.B2}, C_[2] = {P.T.C1, P.T.C2};
+#pragma unroll
   for (int t = 0; t < 2; ++t) {
     const double R2 = A_[t] * A_[t] + B_[t] * B_[t];
     const double s2 = R2 - C_[t] * C_[t];                // R^2 sin^2(alpha): < 0 => the test never changes sign
-    if (!(s2 >= 0.0)) continue;
-    ok = ok && atan2_core_ok(B_[t], A_[t]) && (R2 > 1e-280);
+    const bool cross = s2 >= 0.0;
+    ok = ok && (!cross || (atan2_core_ok(B_[t], A_[t]) && (R2 > 1e-280)));
     const double phi = atan2_core(B_[t], A_[t]);
-    const double alpha = atan2_core(sqrt_nonneg(s2), -C_[t]);   // acos(-C / R)
-    search_around(P, nb, phi + alpha, inv_step, best, best_k);
-    search_around(P, nb, phi - alpha, inv_step, best, best_k);
+    const double alpha = atan2_core(sqrt_nonneg(cross ? s2 : 0.0), -C_[t]);   // acos(-C / R)
+    cand[2 * t] = cross ? phi + alpha : NAN;
+    cand[2 * t + 1] = cross ? phi - alpha : NAN;
   }
-  search_around(P, nb, P.preferred_theta, inv_step, best, best_k);
-  search_eval(P, nb, 0, best, best_k);
-  search_eval(P, nb, nb - 1, best, best_k);
+  cand[4] = P.preferred_theta;
+  // One copy of the sample evaluation in the instruction stream, visited 17 times (unrolled it is ~2000
+  // instructions and the kernel no longer fits the instruction cache).
+#pragma unroll 1
+  for (int q = 0; q < 17; ++q) {
+    int k;
+    if (q < 15) {
+      const double theta = cand[q / 3];
+      // sample position of the angle congruent to theta in [start, start + 2 pi)
+      const double x = pymod_2pi(theta - P.L.start) * inv_step;
+      if (!(x <= (double)nb)) continue;                  // NaN, or beyond the last sample (ranges shorter than 2 pi)
+      k = (int)rint(x) + (q % 3) - 1;
+    } else {
+      k = q == 15 ? 0 : nb - 1;
+    }
+    search_eval(P, nb, k, best, best_k);
+  }
   return ok;
 }
 

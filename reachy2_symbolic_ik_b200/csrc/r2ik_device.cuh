@@ -386,6 +386,10 @@ R2IK_HD void limit_orbita3d_wrist(double j[7], double max_angle) {
   {
     const double a = j[4], b = j[5], c = j[6];
     if (fabs(a) <= kPi && fabs(c) <= kPi && fabs(b) < kHalfPi - 1e-3 && sincos_small_ok(max_angle)) {
+      // Exactly zero roll and pitch (the wrist of ControlIK's default previous solution, which every unreachable
+      // pose returns): R = Rz(c), beta = 0 sits in scipy's ZYZ gimbal band where the conversions give
+      // alpha = c, gamma = 0 and back (0, 0, c) -- the input, to one rounding of c / 2.
+      if (a == 0.0 && b == 0.0) return;
       double sa, ca, sb, cb, sm, cm;
       sincos_small(a, sa, ca);
       sincos_small(b, sb, cb);

@@ -342,7 +342,7 @@ k_ctl_discrete_scan(const __grid_constant__ ArmConst A, const __grid_constant__ 
 }
 
 #ifndef R2IK_K2A_MINBLOCKS
-#define R2IK_K2A_MINBLOCKS 4
+#define R2IK_K2A_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K2A_MINBLOCKS)
 k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par,
