@@ -168,10 +168,10 @@ class Symik:
     POSES_PER_ARM = 1_000_000
     SEEDS = {"r_arm": 1, "l_arm": 2}
     BYTES_IN, BYTES_OUT = 128, 1 + 1 + 16 + 56 + 24
-    # FP64 flops the kernel executes per pose (FMA = 2): 352 DFMA + 222 DMUL + 175 DADD + 41 DSETP per pose in the
-    # ncu source-level counts of profiles/r1_s6.  SURVEY.md 8(d)'s weighted estimate for the
-    # reference's formulation (library-cost transcendentals) is 2100 flop-equivalents; it is reported beside it.
-    FLOP_EQ = 1142.0
+    # FP64 flops the kernel executes per pose (FMA = 2): 272 DFMA + 176 DMUL + 125 DADD + 30 DSETP per pose, averaged over
+    # the batch, in the ncu source-level counts of profiles/r1_s16.  SURVEY.md 8(d)'s weighted estimate
+    # for the reference's formulation (library-cost transcendentals) is 2100 flop-equivalents; it is reported beside it.
+    FLOP_EQ = 874.0
     FLOP_EQ_SURVEY = 2100.0
     kernel = "k_symik_solve<MAT4>"
 
@@ -264,9 +264,9 @@ class SymikF32(Symik):
     """configs[1] on the FP32 fast path (north_star: optional, 1e-4 rad): float32 poses in, float32 results out."""
     name = "symik_f32"
     BYTES_IN, BYTES_OUT = 64, 1 + 1 + 8 + 28 + 12
-    # executed FP32 + FP64 flops per pose are taken from the committed ncu capture when there is one (profiles/symik_f32_ncu.json);
-    # this figure is the static estimate: ~520 FP32 flops (FMA = 2) + ~60 FP64 flops of the mixed-precision front end
-    FLOP_EQ = 640.0
+    # executed flops per pose (FMA = 2) in the ncu source-level counts of profiles/r1_s16: 573 FP32 (145 FFMA + 134 FMUL +
+    # 78 FADD + 71 FSETP) + 58 FP64 of the mixed-precision front end (11 DFMA + 10 DMUL + 20 DADD + 6 DSETP)
+    FLOP_EQ = 631.0
     FLOP_EQ_SURVEY = 2100.0
     kernel = "k_symik_solve_f32<MAT4>"
     fp32 = True
