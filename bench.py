@@ -642,11 +642,34 @@ def run_reference(args, wl):
                 "its algorithm (oracle/, pinned to the reference's outputs by tests/golden) on all host threads -- a much "
                 "stronger CPU baseline than the reference itself.",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly ONE line (the JSON result): everything else that writes to file descriptor 1 -- the facade's
+    reference-style prints, NCCL's version banner when NCCL_DEBUG is set -- is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> int:
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -800,7 +823,7 @@ def main() -> int:
                                      "peak_source": "r2ik_ffma_probe measured in this run (FFMA chains, full grid)"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
