@@ -439,9 +439,12 @@ k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2i
 // K3, phased form (needs a T x W double workspace).  See r2ik_control.cuh "Continuous mode, cut at its
 // data dependences":
 //   k_cont_targets     1 thread / waypoint    classify + target theta            -> code, state, ws = goal
-//   k_cont_thetas      1 thread / trajectory  rate-limited theta scan            -> ws = theta
+//   k_cont_thetas      1 thread / trajectory  rate-limited theta scan (tiles through shared memory) -> ws = theta
 //   k_cont_raw_joints  1 thread / waypoint    get_joints(theta) + Orbita3D limit -> joints (raw)
-//   k_cont_finish      1 thread / trajectory  unwrap / continuity / emergency scan -> joints, reachable, state, states
+//   k_cont_finish8     8 lanes / trajectory   unwrap / continuity / emergency scan, one lane per joint
+//                                                                                -> joints, reachable, state, states
+//   k_cont_finish_direct<fixup>  1 thread / trajectory: finishes the trajectories k_cont_finish8 had to leave at a
+//                      waypoint that needs the serial get_joints (exact singularities; none on physical data)
 // The two per-waypoint kernels hold ~85 % of the arithmetic and run at full parallelism (T x W threads); the
 // two scans are a few dozen FP64 operations per waypoint.  `reachable` carries the waypoint code and
 // `state` the reference state between the phases, so the only scratch is the theta workspace.
@@ -461,29 +464,59 @@ k_cont_targets(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
   state[k] = (uint8_t)st;
 }
 
+// The theta scan walks each trajectory's row in order, one thread per trajectory: read directly, every warp request
+// touches 32 different sectors (the rows of 32 trajectories are W waypoints apart; ncu on the first form of the
+// scans: 35.7 GB between L1 and L2 for 7.3 GB of payload, long_scoreboard 11 cycles per issue,
+// profiles/r1_s16_continuous_ncu_full.txt).  It therefore moves tiles of (block trajectories) x 8 waypoints
+// through shared memory with cooperative, row-contiguous loads and stores; each thread then walks its own row of the
+// tile.  Row stride 9 doubles: bank-conflict free for the 64-bit accesses of a half warp.  1.33 -> 1.05 ms for cfg 4.
+#define R2IK_TH_TILE 8    // waypoints per tile of the theta scan (64 B of thetas per trajectory)
+
 __global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
 k_cont_thetas(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, int64_t T, int W,
               const double *__restrict__ current_joints, const double *__restrict__ current_pose,
               const R2ikTrajState *__restrict__ states, double *__restrict__ ws, const uint8_t *__restrict__ code) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  if (states[t].emergency_stop) return;   // every waypoint will answer with the latched solution
-  double theta = states[t].previous_theta;
-  bool has = states[t].has_previous_sol != 0;
-  const size_t base = (size_t)t * W;
-  for (int w = 0; w < W; ++w) {
-    const int c = code[base + w];
-    if (c == R2IK_WP_INVALID) continue;
-    if (!has) {                                                // ctl:306-325, at the first valid waypoint
-      double cj[7], cp[16];
-#pragma unroll
-      for (int q = 0; q < 7; ++q) cj[q] = current_joints[7 * t + q];
-      load_mat4(current_pose + 16 * t, cp);
-      theta = cont_initial_theta(A, par, cj, cp);
-      has = true;
+  __shared__ double s_th[R2IK_K3_BLOCK][R2IK_TH_TILE + 1];
+  __shared__ uint8_t s_code[R2IK_K3_BLOCK][R2IK_TH_TILE];
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t t = t0 + threadIdx.x;
+  const bool live = t < T && !states[t].emergency_stop;   // a latched trajectory answers every waypoint with its solution
+  double theta = 0.0;
+  bool has = false;
+  if (live) { theta = states[t].previous_theta; has = states[t].has_previous_sol != 0; }
+  for (int w0 = 0; w0 < W; w0 += R2IK_TH_TILE) {
+    const int nw = min(R2IK_TH_TILE, W - w0);
+    for (int f = threadIdx.x; f < R2IK_K3_BLOCK * R2IK_TH_TILE; f += R2IK_K3_BLOCK) {
+      const int r = f / R2IK_TH_TILE, e = f % R2IK_TH_TILE;
+      if (t0 + r < T && e < nw) {
+        const size_t g = (size_t)(t0 + r) * W + w0 + e;
+        s_th[r][e] = ws[g];
+        s_code[r][e] = code[g];
+      }
     }
-    theta = cont_next_theta(par, c, ws[base + w], theta);
-    ws[base + w] = theta;
+    __syncthreads();
+    if (live) {
+      for (int e = 0; e < nw; ++e) {
+        const int c = s_code[threadIdx.x][e];
+        if (c == R2IK_WP_INVALID) continue;
+        if (!has) {                                                // ctl:306-325, at the first valid waypoint
+          double cj[7], cp[16];
+#pragma unroll
+          for (int q = 0; q < 7; ++q) cj[q] = current_joints[7 * t + q];
+          load_mat4(current_pose + 16 * t, cp);
+          theta = cont_initial_theta(A, par, cj, cp);
+          has = true;
+        }
+        theta = cont_next_theta(par, c, s_th[threadIdx.x][e], theta);
+        s_th[threadIdx.x][e] = theta;
+      }
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < R2IK_K3_BLOCK * R2IK_TH_TILE; f += R2IK_K3_BLOCK) {
+      const int r = f / R2IK_TH_TILE, e = f % R2IK_TH_TILE;
+      if (t0 + r < T && e < nw) ws[(size_t)(t0 + r) * W + w0 + e] = s_th[r][e];
+    }
+    __syncthreads();
   }
 }
 
@@ -517,53 +550,187 @@ k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2
   for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
 }
 
+// One waypoint of the finish scan on the joints j (in / out); returns the flag to store in `reachable`.
+__device__ __forceinline__ uint8_t cont_finish_waypoint(const ArmConst &A, const R2ikCtlParams &par, const double *__restrict__ M,
+                                                        const double *__restrict__ current_joints, int64_t t, size_t k, int c,
+                                                        double theta, R2ikTrajState &cs, double j[7], uint8_t *__restrict__ state) {
+  if (cs.emergency_stop) {                                   // ctl:205-210
+#pragma unroll
+    for (int q = 0; q < 7; ++q) j[q] = cs.previous_sol[q];
+    state[k] = R2IK_STATE_EMERGENCY;
+    return 0;
+  }
+  const int kind = c & 0x7f;
+  if (kind == R2IK_WP_INVALID) return 0;                     // joints are NaN, state is INVALID_ROTATION already
+  if (!cs.has_previous_sol) {                                // ctl:306-313
+#pragma unroll
+    for (int q = 0; q < 7; ++q) cs.previous_sol[q] = current_joints[7 * t + q];
+    cs.has_previous_sol = 1;
+    cs.init = 1;
+  }
+  cs.previous_theta = theta;
+  if (c & R2IK_WP_SERIAL) {                                  // exact singularity of get_joints: redo it with previous_sol
+    double m[16];
+    load_mat4(M + 16 * k, m);
+    Solve S;
+    double pos[3] = {m[3], m[7], m[11]};
+    rotation_from_mat4(m, true, S.R);
+    if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
+    cont_raw_joints(A, par, kind, pos, S, cs.previous_theta, cs.previous_sol[0], cs.previous_sol[2], j);
+  }
+  cont_finish(cs, j);
+  return kind == R2IK_WP_TARGET ? 1 : 0;
+}
+
+// Generic form: every thread reads / writes its trajectory's rows directly.  With fixup = true it only serves the
+// trajectories that k_cont_finish8 left at a waypoint needing the serial get_joints (code bit R2IK_WP_SERIAL still set):
+// it resumes there, from the controller state that kernel stored.
 __global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
-k_cont_finish(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
-              int64_t T, int W, const double *__restrict__ current_joints, R2ikTrajState *__restrict__ states,
-              const double *__restrict__ ws, double *__restrict__ joints, uint8_t *__restrict__ reachable,
-              uint8_t *__restrict__ state) {
+k_cont_finish_direct(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
+                     int64_t T, int W, const double *__restrict__ current_joints, R2ikTrajState *__restrict__ states,
+                     const double *__restrict__ ws, double *__restrict__ joints, uint8_t *__restrict__ reachable,
+                     uint8_t *__restrict__ state, bool fixup) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  R2ikTrajState cs = states[t];
   const size_t base = (size_t)t * W;
-  for (int w = 0; w < W; ++w) {
+  int w_begin = 0;
+  if (fixup) {
+    w_begin = W;
+    if (((base | (size_t)W) & 7) == 0) {      // 8 codes per load
+      const unsigned long long *c8 = reinterpret_cast<const unsigned long long *>(reachable + base);
+      for (int g = 0; g < W / 8; ++g) {
+        const unsigned long long hit = c8[g] & 0x8080808080808080ull;
+        if (hit) { w_begin = 8 * g + ((__ffsll((long long)hit) - 1) >> 3); break; }
+      }
+    } else {
+      for (int w = 0; w < W; ++w)
+        if (reachable[base + w] & R2IK_WP_SERIAL) { w_begin = w; break; }
+    }
+    if (w_begin >= W) return;
+  }
+  R2ikTrajState cs = states[t];
+  for (int w = w_begin; w < W; ++w) {
     const size_t k = base + w;
     double j[7];
-    if (cs.emergency_stop) {                                   // ctl:205-210
 #pragma unroll
-      for (int q = 0; q < 7; ++q) joints[7 * k + q] = cs.previous_sol[q];
-      reachable[k] = 0;
-      state[k] = R2IK_STATE_EMERGENCY;
-      continue;
-    }
-    const int c = reachable[k];
-    const int kind = c & 0x7f;
-    if (kind == R2IK_WP_INVALID) { reachable[k] = 0; continue; }   // joints are NaN, state is INVALID_ROTATION already
-    if (!cs.has_previous_sol) {                                // ctl:306-313
-#pragma unroll
-      for (int q = 0; q < 7; ++q) cs.previous_sol[q] = current_joints[7 * t + q];
-      cs.has_previous_sol = 1;
-      cs.init = 1;
-    }
-    cs.previous_theta = ws[k];
-    if (c & R2IK_WP_SERIAL) {                                  // exact singularity of get_joints: redo it with previous_sol
-      double m[16];
-      load_mat4(M + 16 * k, m);
-      Solve S;
-      double pos[3] = {m[3], m[7], m[11]};
-      rotation_from_mat4(m, true, S.R);
-      if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
-      cont_raw_joints(A, par, kind, pos, S, cs.previous_theta, cs.previous_sol[0], cs.previous_sol[2], j);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 7; ++q) j[q] = joints[7 * k + q];
-    }
-    cont_finish(cs, j);
+    for (int q = 0; q < 7; ++q) j[q] = joints[7 * k + q];
+    const uint8_t flag = cont_finish_waypoint(A, par, M, current_joints, t, k, reachable[k], ws[k], cs, j, state);
 #pragma unroll
     for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
-    reachable[k] = kind == R2IK_WP_TARGET ? 1 : 0;
+    reachable[k] = flag;
   }
   states[t] = cs;
+}
+
+// Lane-parallel form of the finish scan: 8 lanes per trajectory, lane q < 7 owns joint q (its previous_sol[q] stays in
+// a register), the per-joint statements of allow_multiturn / multiturn_safety_check / continuity_check (utl:493-589) run
+// in parallel over the lanes and their "any joint" conditions are ballots within the 8-lane group.  Against one thread
+// per trajectory this is 8x the threads (the scan is a latency chain: 14 warps / SM could not hide it), a 7x shorter
+// chain per waypoint, and one 56-byte row per group and request instead of 7 requests of 32 sectors.  A trajectory
+// that meets a waypoint whose get_joints needs the serial route (R2IK_WP_SERIAL: exact singularities, out-of-range
+// magnitudes) stops there, keeps its state, and is finished by k_cont_finish_direct<fixup>.
+#define R2IK_FIN8_BLOCK 128
+// Constants of the scan as a kernel parameter: constant-bank operands of DADD / DSETP instead of 64-bit immediates
+// that cost a UMOV pair per use (23 of the first version's 206 instructions per waypoint).
+struct ScanConst { double pi, two_pi, four_pi, eight_pi, lim; };
+
+// utl:486-490 angle_diff for the scan: pymod_2pi's exact subtraction ladder on constant-bank operands; arguments
+// outside [-2 pi, 8 pi) (never for joints within +-6 pi) take the generic routine.
+__device__ __forceinline__ double angle_diff_scan(const ScanConst &K, double a, double b) {
+  double x = (a - b) + K.pi;
+  if (!(x >= -K.two_pi && x < K.eight_pi)) return pymod(x, kTwoPi) - kPi;
+  double r = x < 0.0 ? x + K.two_pi : x;
+  r = r >= K.four_pi ? r - K.four_pi : r;
+  r = r >= K.two_pi ? r - K.two_pi : r;
+  return r - K.pi;
+}
+
+__global__ void __launch_bounds__(R2IK_FIN8_BLOCK)
+k_cont_finish8(const __grid_constant__ ScanConst K, int64_t T, int W, const double *__restrict__ current_joints,
+               R2ikTrajState *__restrict__ states, const double *__restrict__ ws, double *__restrict__ joints,
+               uint8_t *__restrict__ reachable, uint8_t *__restrict__ state) {
+  const int lane = threadIdx.x & 31, q = lane & 7;
+  const unsigned gshift = 8u * (unsigned)(lane >> 3);
+  const int64_t t_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool live = t_raw < T;
+  const int64_t t = live ? t_raw : T - 1;               // idle groups of the last warp read a valid trajectory, write nothing
+  const bool jl = q < 7;                                // lane 7 of a group carries no joint
+  const R2ikTrajState *cs = states + t;
+  double prev = jl ? cs->previous_sol[q] : 0.0;
+  double previous_theta = cs->previous_theta;
+  int has_prev = cs->has_previous_sol, init = cs->init, emergency_stop = cs->emergency_stop, emergency_bits = cs->emergency_bits;
+  bool stopped = false;
+  const double max_step = q < 4 ? 0.5 : 1.0;            // utl:571-589 [0.5, 0.5, 0.5, 0.5, 1, 1, 1]
+  const bool clampq = q == 0 || q == 2 || q == 6;       // utl:535-568
+  const size_t base = (size_t)t * W;
+  double *pj = joints + 7 * base + (jl ? q : 0);
+  uint8_t *pc = reachable + base;
+  const double *pth = ws + base;
+  for (int w = 0; w < W; ++w, pj += 7) {
+    const int c = pc[w];
+    const double theta = pth[w];
+    const double j = *pj;
+    const int kind = c & 0x7f;
+    // utl:493-505 allow_multiturn; utl:535-568 clamp of joints 0 / 2 / 6; ctl:395-400 continuity against previous_sol
+    const double jm = prev + angle_diff_scan(K, j, prev);
+    const bool hit = clampq && (jm > K.lim || jm < -K.lim);
+    const bool viol = jl && fabs(angle_diff_scan(K, jm, prev)) > max_step;
+    // The ordinary waypoint -- valid code, no serial route, state initialised and not latched, no clamp, continuous --
+    // is recognised for the whole warp at once; everything else takes the full statement order below.
+    const bool ordinary = live && !stopped && !emergency_stop && has_prev && !init && kind != R2IK_WP_INVALID &&
+                          !(c & R2IK_WP_SERIAL) && !hit && !viol;
+    if (__all_sync(0xffffffffu, ordinary || !live)) {
+      if (live) {
+        previous_theta = theta;
+        prev = jm;
+        if (jl) *pj = jm;
+        else pc[w] = kind == R2IK_WP_TARGET ? 1 : 0;
+      }
+      continue;
+    }
+    stopped = stopped || (!emergency_stop && kind != R2IK_WP_INVALID && (c & R2IK_WP_SERIAL));
+    const bool emg = emergency_stop != 0;
+    const bool work = live && !stopped && !emg && kind != R2IK_WP_INVALID;
+    if (work && !has_prev) {                            // ctl:306-313
+      prev = jl ? current_joints[7 * t + q] : 0.0;
+      has_prev = 1; init = 1;
+    }
+    if (work) previous_theta = theta;
+    double jn = prev + angle_diff_scan(K, j, prev);
+    bool hit2 = false;
+    if (clampq) {
+      if (jn > K.lim) { jn = K.lim; hit2 = true; }
+      if (jn < -K.lim) { jn = -K.lim; hit2 = true; }
+    }
+    const unsigned hits = (__ballot_sync(0xffffffffu, work && hit2) >> gshift) & 0xffu;
+    const int bits = ((hits & 1u) ? R2IK_EMG_SHOULDER_PITCH : 0) | ((hits & 4u) ? R2IK_EMG_ELBOW_YAW : 0) |
+                     ((hits & 64u) ? R2IK_EMG_WRIST_YAW : 0);
+    if (bits) { emergency_stop = 1; emergency_bits |= bits; }
+    const bool viol2 = work && !init && jl && fabs(angle_diff_scan(K, jn, prev)) > max_step;
+    const bool disc = ((__ballot_sync(0xffffffffu, viol2) >> gshift) & 0xffu) != 0;
+    if (disc) { jn = prev; emergency_stop = 1; emergency_bits |= R2IK_EMG_DISCONTINUITY; }
+    if (work) {
+      init = 0;
+      if (!emergency_stop) prev = jn;
+    }
+    if (live && !stopped) {
+      if (emg) {                                        // ctl:205-210: latched, answers with the last solution
+        if (jl) *pj = prev;
+        else { pc[w] = 0; state[base + w] = R2IK_STATE_EMERGENCY; }
+      } else {
+        if (work && jl) *pj = jn;
+        if (!jl) pc[w] = (work && kind == R2IK_WP_TARGET) ? 1 : 0;
+      }
+    }
+  }
+  if (live) {
+    R2ikTrajState *o = states + t;
+    if (jl) o->previous_sol[q] = prev;
+    else {
+      o->previous_theta = previous_theta;
+      o->has_previous_sol = has_prev; o->init = init; o->emergency_stop = emergency_stop; o->emergency_bits = emergency_bits;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -920,7 +1087,11 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
   k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
   k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
   k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints);
-  k_cont_finish<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state);
+  const ScanConst K = {kPi, kTwoPi, 2.0 * kTwoPi, 4.0 * kTwoPi, 6.0 * kPi};
+  k_cont_finish8<<<(unsigned)((T * 8 + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK), R2IK_FIN8_BLOCK, 0, s>>>(
+      K, T, W, current_joints, st, workspace, joints, reachable, state);
+  k_cont_finish_direct<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state,
+                                                    true);
   R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
   return 0;
 }

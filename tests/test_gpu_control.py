@@ -216,8 +216,9 @@ def test_host_pipelines_match_device_calls(controls):
     np.testing.assert_array_equal(got[3].numpy().reshape(-1).view(want[3].dtype), want[3])
 
 
+@pytest.mark.parametrize("W", [120, 30, 33])   # multiple of the scan tile; even with a 2-waypoint tail; odd (direct scan kernel)
 @pytest.mark.parametrize("arm", ARMS)
-def test_continuous_phased_equals_serial_kernel(controls, arm):
+def test_continuous_phased_equals_serial_kernel(controls, arm, W):
     """The phased K3 (per-waypoint kernels + per-trajectory scans) and the one-thread-per-trajectory K3 are the
     same arithmetic regrouped: flags, state codes and the integer controller state must be identical, and the joints
     / thetas equal to rounding (the two forms are separate compilations, so FMA contraction may differ in the last
@@ -226,9 +227,9 @@ def test_continuous_phased_equals_serial_kernel(controls, arm):
     from reachy2_symbolic_ik_b200 import fk
 
     ctl = controls[False]
-    M = fk.sinusoidal_trajectories(300, 120, arm, seed=41)[0].copy()
-    flip = np.diag([-1.0, -1.0, 1.0])          # half a turn about the tool axis from waypoint 40 on: the wrist
-    M[3, 40:, :3, :3] = M[3, 40:, :3, :3] @ flip  # jumps by pi -> continuity violation -> emergency latch on trajectory 3
+    M = fk.sinusoidal_trajectories(300, W, arm, seed=41)[0].copy()
+    flip = np.diag([-1.0, -1.0, 1.0])          # half a turn about the tool axis from waypoint 13 on: the wrist
+    M[3, 13:, :3, :3] = M[3, 13:, :3, :3] @ flip  # jumps by pi -> continuity violation -> emergency latch on trajectory 3
     M[5, 7, :3, :3] = np.diag([-1.0, 1.0, 1.0])    # det < 0 in the middle of trajectory 5
     M[6, 0, :3, :3] = np.diag([1.0, -1.0, 1.0])    # ... and at the first waypoint of trajectory 6
     a = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=True)
