@@ -986,6 +986,29 @@ __host__ __device__ __noinline__
 inline
 #endif
 bool rotation_from_mat3_literal(const double m[9], double R[9]) {
+  if (!(det3(m) > 0.0)) return false;
+  // A block that fails scipy's orthogonality test (rxp:78-95) is replaced there by its polar factor; outside the
+  // gimbal band of as_euler the from_matrix -> as_euler -> from_euler round trip of that factor is the identity
+  // up to rounding, so the factor is the goal rotation (saves the quaternion / three atan2 / three sincos detour
+  // for every non-orthonormal input, e.g. all float32-rounded rotations re-solved by the FP32 path).
+  {
+    bool orthogonal = true;
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) {
+        double g = m[3 * i] * m[3 * j] + m[3 * i + 1] * m[3 * j + 1] + m[3 * i + 2] * m[3 * j + 2];
+        double e = (i == j) ? 1.0 : 0.0;
+        if (!(fabs(g - e) <= 1e-12 + 1e-5 * e)) orthogonal = false;
+      }
+    if (!orthogonal) {
+      double p[9];
+      for (int k = 0; k < 9; ++k) p[k] = m[k];
+      polar_orthogonalize(p);
+      if (p[0] * p[0] + p[3] * p[3] > 1e-10) {
+        for (int k = 0; k < 9; ++k) R[k] = p[k];
+        return true;
+      }
+    }
+  }
   double e[3];
   Quat q;
   if (!quat_from_matrix(m, q)) return false;
