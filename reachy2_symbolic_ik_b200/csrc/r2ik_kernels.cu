@@ -739,7 +739,12 @@ k_cont_finish8(const __grid_constant__ ScanConst K, int64_t T, int W, const doub
 // Voxels outside the reach sphere or behind the torso plane leave before the orientation loop
 // (those two states do not depend on the orientation, sik:284-307).
 // ---------------------------------------------------------------------------------------
-#define R2IK_ORI_CHUNK 64
+// Orientations whose rotation matrices a block stages at once.  With 64 the loop below crossed two block barriers
+// per chunk and `barrier` was the first stall reason of the kernel (4.3 cycles per issue: voxels of a block leave the
+// solve at different depths); 512 = the whole orientation set of cfg 5 in 36 KB of shared memory, two barriers per block.
+#ifndef R2IK_ORI_CHUNK
+#define R2IK_ORI_CHUNK 512
+#endif
 
 __global__ void __launch_bounds__(R2IK_BLOCK)
 k_reach_map(const __grid_constant__ ArmConst A, double ox, double oy, double oz, double sx, double sy, double sz,
@@ -759,9 +764,14 @@ k_reach_map(const __grid_constant__ ArmConst A, double ox, double oy, double oz,
     live = reach_prechecks(A, px, py, pz) < 0;
   }
   uint32_t count = 0;
+  // a block with no voxel inside the reach pre-checks (3/4 of the bounding cube) has nothing to stage
+  if (!__syncthreads_or(live ? 1 : 0)) {
+    if (in_grid) counts[v] = 0;
+    return;
+  }
   for (int base = ori_begin; base < ori_end; base += R2IK_ORI_CHUNK) {
     int m = min(R2IK_ORI_CHUNK, ori_end - base);
-    __syncthreads();
+    if (base != ori_begin) __syncthreads();
     for (int o = threadIdx.x; o < m; o += blockDim.x) {
       const double *e = ori_euler + 3 * (size_t)(base + o);
       double R[9];
