@@ -125,7 +125,8 @@ R2IK_HD bool search_analytic(const SearchPlan &P, int nb, double &best, int &bes
     if (q < 15) {
       const double theta = cand[q / 3];
       // sample position of the angle congruent to theta in [start, start + 2 pi)
-      const double x = pymod_2pi(theta - P.L.start) * inv_step;
+      // (+ 4 pi keeps the argument inside pymod_2pi's exact fast range; the candidate index tolerates the rounding)
+      const double x = pymod_2pi((theta - P.L.start) + 2.0 * kTwoPi) * inv_step;
       if (!(x <= (double)nb)) continue;                  // NaN, or beyond the last sample (ranges shorter than 2 pi)
       k = (int)rint(x) + (q % 3) - 1;
     } else {

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -350,6 +351,7 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
                const double *__restrict__ current_joints, double *__restrict__ joints, uint8_t *__restrict__ reachable,
                uint8_t *__restrict__ state, uint8_t *__restrict__ emergency) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned wmask = __ballot_sync(0xffffffffu, i < n);
   if (i >= n) return;
   double prev[7], cur[7];
 #pragma unroll
@@ -357,30 +359,39 @@ k_ctl_discrete(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikC
   Solve S;
   int st = R2IK_STATE_INVALID_ROTATION;
   bool found = false;
-  double theta = 0.0, j[7], pos[3];
+  double theta = 0.0, j[7], pos[3], i0 = 0.0, i1 = 0.0;
   int bits = 0;
-  if (load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R)) {
+  const bool valid = load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R);
+  if (valid) {
     Reach rc = is_reachable_R<false>(A, pos, S);
-    st = rc.state;
-    if (st == R2IK_STATE_REACHABLE) {
-      if (preferred_theta_works(A, S, rc.i0, rc.i1, par.preferred_theta)) {
-        theta = par.preferred_theta; found = true;
-      } else {
-        SearchPlan plan;
-        plan.preferred_theta = par.preferred_theta;
-        double start, stop;
-        search_range(rc.i0, rc.i1, start, stop);
-        plan.L = make_linspace(start, stop, par.nb_search_points);
-        plan.T = make_elbow_test(A, S);
-        double best;
-        int best_k;
-        if (!search_analytic(plan, par.nb_search_points, best, best_k))
-          search_strided(plan, par.nb_search_points, 0, 1, best, best_k);     // out-of-range magnitudes: scan
-        found = best < INFINITY;
-        if (found) theta = linspace_value(plan.L, best_k);
-        else st = R2IK_STATE_LIMITED_BY_SHOULDER;
-      }
-    }
+    st = rc.state; i0 = rc.i0; i1 = rc.i1;
+  }
+  // The three sections below are kept apart by warp barriers: without them the compiler threads the preferred-theta
+  // and the search paths separately through their own copies of the tail (get_joints + safety chain), and a warp runs
+  // that tail twice at half the lanes (ncu: get_joints at 10 of 32 lanes for 64 % of the poses found).
+  bool need_search = false;
+  if (st == R2IK_STATE_REACHABLE) {
+    if (preferred_theta_works(A, S, i0, i1, par.preferred_theta)) { theta = par.preferred_theta; found = true; }
+    else need_search = true;
+  }
+  __syncwarp(wmask);
+  if (need_search) {
+    SearchPlan plan;
+    plan.preferred_theta = par.preferred_theta;
+    double start, stop;
+    search_range(i0, i1, start, stop);
+    plan.L = make_linspace(start, stop, par.nb_search_points);
+    plan.T = make_elbow_test(A, S);
+    double best;
+    int best_k;
+    if (!search_analytic(plan, par.nb_search_points, best, best_k))
+      search_strided(plan, par.nb_search_points, 0, 1, best, best_k);     // out-of-range magnitudes: scan
+    found = best < INFINITY;
+    if (found) theta = linspace_value(plan.L, best_k);
+    else st = R2IK_STATE_LIMITED_BY_SHOULDER;
+  }
+  __syncwarp(wmask);
+  if (valid) {
     bits = discrete_finish(A, par, S, found, theta, prev, cur, j);
   } else {
 #pragma unroll
