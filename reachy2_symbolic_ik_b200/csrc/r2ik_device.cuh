@@ -132,16 +132,16 @@ R2IK_HD double pymod(double a, double m) {
 // range), so each step is error-free and the value is bit-identical to fmod's.  Negative x in
 // [-2 pi, 0) is Python's `fmod(x) + m`, one rounded add, as here.  Anything else takes pymod().
 R2IK_HD double pymod_2pi(double x) {
-  if (!(x >= -kTwoPi && x < 4.0 * kTwoPi)) return pymod(x, kTwoPi);
-  if (x < 0.0) return x + kTwoPi;
-  double r = x;
-  if (r >= 2.0 * kTwoPi) r -= 2.0 * kTwoPi;
-  if (r >= kTwoPi) r -= kTwoPi;
+  const double two_pi = R2IK_WRAP(1), four_pi = R2IK_WRAP(2);
+  if (!(x >= -two_pi && x < R2IK_WRAP(3))) return pymod(x, kTwoPi);
+  double r = x < 0.0 ? x + two_pi : x;
+  r = r >= four_pi ? r - four_pi : r;
+  r = r >= two_pi ? r - two_pi : r;
   return r;
 }
 
 // utl:486-490
-R2IK_HD double angle_diff(double a, double b) { return pymod_2pi((a - b) + kPi) - kPi; }
+R2IK_HD double angle_diff(double a, double b) { return pymod_2pi((a - b) + R2IK_WRAP(0)) - R2IK_WRAP(0); }
 
 // np.isclose(a, b), rtol 1e-5, atol 1e-8 (asymmetric in b)
 R2IK_HD bool np_isclose(double a, double b) { return fabs(a - b) <= 1e-8 + 1e-5 * fabs(b); }
