@@ -539,7 +539,9 @@ R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &p
 // (true) after the pre-checks: S.p (pre-checked goal position) and S.R (goal rotation) are
 // set by the caller.  FLAG_ONLY skips the interval angles (reach-map kernel): state is exact,
 // i0/i1 are not computed.
-template <bool NO_LIMITS, bool FLAG_ONLY, bool LIT>
+// CIRCLE_ONLY: stop once the elbow circle and its frame are in S (a pose already known to be reachable whose
+// interval is not needed again: the joints pass of the continuous mode).
+template <bool NO_LIMITS, bool FLAG_ONLY, bool LIT, bool CIRCLE_ONLY = false>
 R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
   Reach out;
   out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false;
@@ -581,6 +583,7 @@ R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
     out.state = R2IK_STATE_REACHABLE; out.i0 = -kPi; out.i1 = kPi; out.c0 = -1.0; out.s0 = kSinMinusPi;
     return out;
   }
+  if (CIRCLE_ONLY) { out.state = R2IK_STATE_REACHABLE; return out; }
 
   // --- sik:401-416 wrist-limit circle, relative to the wrist: centre p1 = n1 * hL
   double nLx = S.w[0] - S.p[0], nLy = S.w[1] - S.p[1], nLz = S.w[2] - S.p[2];
@@ -770,6 +773,13 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
     out = lit;
   }
   return out;
+}
+
+// Elbow circle of a pose that is_reachable has already accepted (pre-checks passed, wrist in range): the state
+// is_reachable leaves in S, without the circle linking.
+R2IK_HD void circle_of_reachable(const ArmConst &A, const double pos[3], Solve &S) {
+  S.p[0] = pos[0]; S.p[1] = pos[1]; S.p[2] = pos[2];
+  solve_core_impl<false, false, false, true>(A, S);
 }
 
 template <bool NO_LIMITS>

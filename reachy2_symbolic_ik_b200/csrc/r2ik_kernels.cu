@@ -549,7 +549,7 @@ k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2
     double pos[3] = {m[3], m[7], m[11]};
     rotation_from_mat4(m, true, S.R);
     if (c == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S);
-    else is_reachable_R<false>(A, pos, S);
+    else circle_of_reachable(A, pos, S);   // reachable (phase 1 decided): the elbow circle is all get_joints needs
     double st, ct, E[3];
     sincos_any(ws[k], st, ct);
     // straight-line get_joints only; a degenerate input (exact singularity: needs previous_sol) is left to the scan
