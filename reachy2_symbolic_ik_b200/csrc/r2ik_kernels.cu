@@ -22,7 +22,9 @@
 
 using namespace r2ik;
 
+#ifndef R2IK_BLOCK
 #define R2IK_BLOCK 128
+#endif
 #ifndef R2IK_K1_MINBLOCKS
 #define R2IK_K1_MINBLOCKS 4   // resident blocks / SM the register allocation of K1 is held to
 #endif
