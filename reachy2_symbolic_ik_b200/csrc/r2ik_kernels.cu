@@ -454,9 +454,9 @@ k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2i
 //   k_cont_targets     1 thread / waypoint    classify + target theta            -> code, state, ws = goal
 //   k_cont_thetas      1 thread / trajectory  rate-limited theta scan (tiles through shared memory) -> ws = theta
 //   k_cont_raw_joints  1 thread / waypoint    get_joints(theta) + Orbita3D limit -> joints (raw)
-//   k_cont_finish8     8 lanes / trajectory   unwrap / continuity / emergency scan, one lane per joint
+//   k_cont_finish_lanes<G>  G = 4 lanes / trajectory  unwrap / continuity / emergency scan, joints split over the lanes
 //                                                                                -> joints, reachable, state, states
-//   k_cont_finish_direct<fixup>  1 thread / trajectory: finishes the trajectories k_cont_finish8 had to leave at a
+//   k_cont_finish_direct<fixup>  1 thread / trajectory: finishes the trajectories the lane scan had to leave at a
 //                      waypoint that needs the serial get_joints (exact singularities; none on physical data)
 // The two per-waypoint kernels hold ~85 % of the arithmetic and run at full parallelism (T x W threads); the
 // two scans are a few dozen FP64 operations per waypoint.  `reachable` carries the waypoint code and
@@ -596,7 +596,7 @@ __device__ __forceinline__ uint8_t cont_finish_waypoint(const ArmConst &A, const
 }
 
 // Generic form: every thread reads / writes its trajectory's rows directly.  With fixup = true it only serves the
-// trajectories that k_cont_finish8 left at a waypoint needing the serial get_joints (code bit R2IK_WP_SERIAL still set):
+// trajectories that k_cont_finish_lanes left at a waypoint needing the serial get_joints (code bit R2IK_WP_SERIAL still set):
 // it resumes there, from the controller state that kernel stored.
 __global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
 k_cont_finish_direct(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
@@ -643,6 +643,9 @@ k_cont_finish_direct(const __grid_constant__ ArmConst A, const __grid_constant__
 // that meets a waypoint whose get_joints needs the serial route (R2IK_WP_SERIAL: exact singularities, out-of-range
 // magnitudes) stops there, keeps its state, and is finished by k_cont_finish_direct<fixup>.
 #define R2IK_FIN8_BLOCK 128
+#ifndef R2IK_FIN_LANES
+#define R2IK_FIN_LANES 4   // lanes per trajectory of the finish scan (2, 4 or 8; env R2IK_FIN_LANES overrides for tuning)
+#endif
 // Constants of the scan as a kernel parameter: constant-bank operands of DADD / DSETP instead of 64-bit immediates
 // that cost a UMOV pair per use (23 of the first version's 206 instructions per waypoint).
 struct ScanConst { double pi, two_pi, four_pi, eight_pi, lim; };
@@ -658,36 +661,55 @@ __device__ __forceinline__ double angle_diff_scan(const ScanConst &K, double a, 
   return r - K.pi;
 }
 
+// G lanes per trajectory (G = 2, 4, 8): lane g owns joints g, g + G, ... < 7; the last lane of a group also writes the
+// flags.  Fewer lanes per trajectory share the per-waypoint overhead (loop, code / theta loads, votes, addresses) among
+// more trajectories per warp, more lanes shorten the chain and raise the thread count.
+template <int G>
 __global__ void __launch_bounds__(R2IK_FIN8_BLOCK)
-k_cont_finish8(const __grid_constant__ ScanConst K, int64_t T, int W, const double *__restrict__ current_joints,
-               R2ikTrajState *__restrict__ states, const double *__restrict__ ws, double *__restrict__ joints,
-               uint8_t *__restrict__ reachable, uint8_t *__restrict__ state) {
-  const int lane = threadIdx.x & 31, q = lane & 7;
-  const unsigned gshift = 8u * (unsigned)(lane >> 3);
-  const int64_t t_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+k_cont_finish_lanes(const __grid_constant__ ScanConst K, int64_t T, int W, const double *__restrict__ current_joints,
+                    R2ikTrajState *__restrict__ states, const double *__restrict__ ws, double *__restrict__ joints,
+                    uint8_t *__restrict__ reachable, uint8_t *__restrict__ state) {
+  constexpr int NJ = (7 + G - 1) / G;                   // joints per lane (the last slot may be empty)
+  constexpr unsigned GM = (1u << G) - 1u;
+  const int lane = threadIdx.x & 31, g = lane & (G - 1);
+  const unsigned gshift = (unsigned)(lane & ~(G - 1));
+  const int64_t t_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool live = t_raw < T;
   const int64_t t = live ? t_raw : T - 1;               // idle groups of the last warp read a valid trajectory, write nothing
-  const bool jl = q < 7;                                // lane 7 of a group carries no joint
+  const bool flagger = g == G - 1;
+  bool has[NJ];
+  int qj[NJ];
+  double prev[NJ];
   const R2ikTrajState *cs = states + t;
-  double prev = jl ? cs->previous_sol[q] : 0.0;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    has[i] = g + i * G < 7;
+    qj[i] = has[i] ? g + i * G : 6;
+    prev[i] = has[i] ? cs->previous_sol[qj[i]] : 0.0;
+  }
   double previous_theta = cs->previous_theta;
   int has_prev = cs->has_previous_sol, init = cs->init, emergency_stop = cs->emergency_stop, emergency_bits = cs->emergency_bits;
   bool stopped = false;
-  const double max_step = q < 4 ? 0.5 : 1.0;            // utl:571-589 [0.5, 0.5, 0.5, 0.5, 1, 1, 1]
-  const bool clampq = q == 0 || q == 2 || q == 6;       // utl:535-568
   const size_t base = (size_t)t * W;
-  double *pj = joints + 7 * base + (jl ? q : 0);
+  double *pj = joints + 7 * base;
   uint8_t *pc = reachable + base;
   const double *pth = ws + base;
   for (int w = 0; w < W; ++w, pj += 7) {
     const int c = pc[w];
     const double theta = pth[w];
-    const double j = *pj;
     const int kind = c & 0x7f;
-    // utl:493-505 allow_multiturn; utl:535-568 clamp of joints 0 / 2 / 6; ctl:395-400 continuity against previous_sol
-    const double jm = prev + angle_diff_scan(K, j, prev);
-    const bool hit = clampq && (jm > K.lim || jm < -K.lim);
-    const bool viol = jl && fabs(angle_diff_scan(K, jm, prev)) > max_step;
+    double j[NJ], m[NJ];
+    bool hit = false, viol = false;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      j[i] = has[i] ? pj[qj[i]] : 0.0;
+      // utl:493-505 allow_multiturn; utl:535-568 clamp of joints 0 / 2 / 6; ctl:395-400 continuity against previous_sol
+      // (max step 0.5 rad for joints 0-3, 1 rad for joints 4-6, utl:571-589)
+      m[i] = prev[i] + angle_diff_scan(K, j[i], prev[i]);
+      const bool clampq = has[i] && (qj[i] == 0 || qj[i] == 2 || qj[i] == 6);
+      hit = hit || (clampq && (m[i] > K.lim || m[i] < -K.lim));
+      viol = viol || (has[i] && fabs(angle_diff_scan(K, m[i], prev[i])) > (qj[i] < 4 ? 0.5 : 1.0));
+    }
     // The ordinary waypoint -- valid code, no serial route, state initialised and not latched, no clamp, continuous --
     // is recognised for the whole warp at once; everything else takes the full statement order below.
     const bool ordinary = live && !stopped && !emergency_stop && has_prev && !init && kind != R2IK_WP_INVALID &&
@@ -695,9 +717,10 @@ k_cont_finish8(const __grid_constant__ ScanConst K, int64_t T, int W, const doub
     if (__all_sync(0xffffffffu, ordinary || !live)) {
       if (live) {
         previous_theta = theta;
-        prev = jm;
-        if (jl) *pj = jm;
-        else pc[w] = kind == R2IK_WP_TARGET ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i)
+          if (has[i]) { prev[i] = m[i]; pj[qj[i]] = m[i]; }
+        if (flagger) pc[w] = kind == R2IK_WP_TARGET ? 1 : 0;
       }
       continue;
     }
@@ -705,41 +728,66 @@ k_cont_finish8(const __grid_constant__ ScanConst K, int64_t T, int W, const doub
     const bool emg = emergency_stop != 0;
     const bool work = live && !stopped && !emg && kind != R2IK_WP_INVALID;
     if (work && !has_prev) {                            // ctl:306-313
-      prev = jl ? current_joints[7 * t + q] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) prev[i] = has[i] ? current_joints[7 * t + qj[i]] : 0.0;
       has_prev = 1; init = 1;
     }
     if (work) previous_theta = theta;
-    double jn = prev + angle_diff_scan(K, j, prev);
-    bool hit2 = false;
-    if (clampq) {
-      if (jn > K.lim) { jn = K.lim; hit2 = true; }
-      if (jn < -K.lim) { jn = -K.lim; hit2 = true; }
+    double nj[NJ];
+    int bits = 0;
+    bool viol2 = false;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      nj[i] = prev[i] + angle_diff_scan(K, j[i], prev[i]);
+      bool h = false;
+      if (has[i] && (qj[i] == 0 || qj[i] == 2 || qj[i] == 6)) {
+        if (nj[i] > K.lim) { nj[i] = K.lim; h = true; }
+        if (nj[i] < -K.lim) { nj[i] = -K.lim; h = true; }
+      }
+      const unsigned hits = (__ballot_sync(0xffffffffu, work && h) >> gshift) & GM;   // bit g' <=> joint g' + i G
+      if (0 / G == i && (hits >> (0 % G) & 1u)) bits |= R2IK_EMG_SHOULDER_PITCH;
+      if (2 / G == i && (hits >> (2 % G) & 1u)) bits |= R2IK_EMG_ELBOW_YAW;
+      if (6 / G == i && (hits >> (6 % G) & 1u)) bits |= R2IK_EMG_WRIST_YAW;
     }
-    const unsigned hits = (__ballot_sync(0xffffffffu, work && hit2) >> gshift) & 0xffu;
-    const int bits = ((hits & 1u) ? R2IK_EMG_SHOULDER_PITCH : 0) | ((hits & 4u) ? R2IK_EMG_ELBOW_YAW : 0) |
-                     ((hits & 64u) ? R2IK_EMG_WRIST_YAW : 0);
     if (bits) { emergency_stop = 1; emergency_bits |= bits; }
-    const bool viol2 = work && !init && jl && fabs(angle_diff_scan(K, jn, prev)) > max_step;
-    const bool disc = ((__ballot_sync(0xffffffffu, viol2) >> gshift) & 0xffu) != 0;
-    if (disc) { jn = prev; emergency_stop = 1; emergency_bits |= R2IK_EMG_DISCONTINUITY; }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i)
+      viol2 = viol2 || (has[i] && fabs(angle_diff_scan(K, nj[i], prev[i])) > (qj[i] < 4 ? 0.5 : 1.0));
+    const bool disc = ((__ballot_sync(0xffffffffu, work && !init && viol2) >> gshift) & GM) != 0;
+    if (disc) {
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) nj[i] = prev[i];
+      emergency_stop = 1; emergency_bits |= R2IK_EMG_DISCONTINUITY;
+    }
     if (work) {
       init = 0;
-      if (!emergency_stop) prev = jn;
+      if (!emergency_stop) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) prev[i] = nj[i];
+      }
     }
     if (live && !stopped) {
       if (emg) {                                        // ctl:205-210: latched, answers with the last solution
-        if (jl) *pj = prev;
-        else { pc[w] = 0; state[base + w] = R2IK_STATE_EMERGENCY; }
+#pragma unroll
+        for (int i = 0; i < NJ; ++i)
+          if (has[i]) pj[qj[i]] = prev[i];
+        if (flagger) { pc[w] = 0; state[base + w] = R2IK_STATE_EMERGENCY; }
       } else {
-        if (work && jl) *pj = jn;
-        if (!jl) pc[w] = (work && kind == R2IK_WP_TARGET) ? 1 : 0;
+        if (work) {
+#pragma unroll
+          for (int i = 0; i < NJ; ++i)
+            if (has[i]) pj[qj[i]] = nj[i];
+        }
+        if (flagger) pc[w] = (work && kind == R2IK_WP_TARGET) ? 1 : 0;
       }
     }
   }
   if (live) {
     R2ikTrajState *o = states + t;
-    if (jl) o->previous_sol[q] = prev;
-    else {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i)
+      if (has[i]) o->previous_sol[qj[i]] = prev[i];
+    if (flagger) {
       o->previous_theta = previous_theta;
       o->has_previous_sol = has_prev; o->init = init; o->emergency_stop = emergency_stop; o->emergency_bits = emergency_bits;
     }
@@ -1111,8 +1159,16 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
   k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
   k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints);
   const ScanConst K = {kPi, kTwoPi, 2.0 * kTwoPi, 4.0 * kTwoPi, 6.0 * kPi};
-  k_cont_finish8<<<(unsigned)((T * 8 + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK), R2IK_FIN8_BLOCK, 0, s>>>(
-      K, T, W, current_joints, st, workspace, joints, reachable, state);
+  {
+    static const int lanes = [] { const char *e = getenv("R2IK_FIN_LANES"); return e ? atoi(e) : R2IK_FIN_LANES; }();
+    const auto blocks = [&](int G) { return (unsigned)((T * G + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK); };
+    if (lanes == 2)
+      k_cont_finish_lanes<2><<<blocks(2), R2IK_FIN8_BLOCK, 0, s>>>(K, T, W, current_joints, st, workspace, joints, reachable, state);
+    else if (lanes == 8)
+      k_cont_finish_lanes<8><<<blocks(8), R2IK_FIN8_BLOCK, 0, s>>>(K, T, W, current_joints, st, workspace, joints, reachable, state);
+    else
+      k_cont_finish_lanes<4><<<blocks(4), R2IK_FIN8_BLOCK, 0, s>>>(K, T, W, current_joints, st, workspace, joints, reachable, state);
+  }
   k_cont_finish_direct<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state,
                                                     true);
   R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
