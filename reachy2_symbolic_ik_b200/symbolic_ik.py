@@ -217,7 +217,7 @@ class SymbolicIK:
             joints=torch.empty((n, 7), dtype=dt).pin_memory(),
             elbow=torch.empty((n, 3), dtype=dt).pin_memory())
 
-    def is_reachable_batch_host(self, poses_host, out: Optional[BatchResult] = None, chunk: int = 1 << 17,
+    def is_reachable_batch_host(self, poses_host, out: Optional[BatchResult] = None, chunk: Optional[int] = None,
                                 n_streams: int = 3, precision: str = "fp64") -> BatchResult:
         """Host-to-host batched solve: ``poses_host`` is a CPU tensor (N,16)/(N,4,4)/(N,6)/(N,2,3),
         ideally pinned; results land in ``out`` (pinned CPU tensors; ``reachable`` is uint8 0/1).
@@ -226,6 +226,8 @@ class SymbolicIK:
         poses and outputs (half the PCIe bytes), the FP32 fast path of K1."""
         torch = self._torch
         dt = _precision_dtype(torch, precision)
+        if chunk is None:   # measured optimum on B200 / PCIe 5 (scripts/exp_e2e.py): 128 k poses (FP64), 256 k (FP32)
+            chunk = 1 << 17 if precision == "fp64" else 1 << 18
         if not hasattr(poses_host, "is_cuda"):
             poses_host = torch.from_numpy(np.ascontiguousarray(poses_host))
         if poses_host.dtype != dt:
