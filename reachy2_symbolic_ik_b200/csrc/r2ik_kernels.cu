@@ -535,7 +535,8 @@ k_cont_thetas(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCt
 
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
 k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
-                  int64_t n_wp, const double *__restrict__ ws, uint8_t *__restrict__ code, double *__restrict__ joints) {
+                  int64_t n_wp, const double *__restrict__ ws, uint8_t *__restrict__ code, double *__restrict__ joints,
+                  int force_serial_mod) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_wp) return;
   const int c = code[k];
@@ -556,6 +557,9 @@ k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2
     sincos_any(ws[k], st, ct);
     // straight-line get_joints only; a degenerate input (exact singularity: needs previous_sol) is left to the scan
     serial = !get_joints_impl<false>(A, S, ct, st, 0.0, 0.0, j, E);
+    // test hook (R2IK_DEBUG_FORCE_SERIAL=m): every m-th waypoint is sent down the serial route although it does not
+    // need it, so that the stop / fixup machinery of the finish scan is exercised on ordinary data
+    if (force_serial_mod > 0 && k % force_serial_mod == 0) serial = true;
     if (!serial) limit_orbita3d_wrist(j, par.orbita3d_max_angle);
   }
   if (serial) { code[k] = (uint8_t)(c | R2IK_WP_SERIAL); return; }
@@ -1157,7 +1161,8 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
   const unsigned tb = (unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK);
   k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
   k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
-  k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints);
+  const char *dbg = getenv("R2IK_DEBUG_FORCE_SERIAL");
+  k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints, dbg ? atoi(dbg) : 0);
   const ScanConst K = {kPi, kTwoPi, 2.0 * kTwoPi, 4.0 * kTwoPi, 6.0 * kPi};
   {
     static const int lanes = [] { const char *e = getenv("R2IK_FIN_LANES"); return e ? atoi(e) : R2IK_FIN_LANES; }();

@@ -274,3 +274,28 @@ def test_discrete_analytic_search_equals_exhaustive_scan(controls, arm, K):
     assert searched > 10_000
     for (x, y) in list(zip(a, b)) + list(zip(a2, b2)):
         np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_continuous_serial_route_and_fixup(controls, arm, monkeypatch):
+    """A waypoint whose get_joints needs the previous solution (exact singularities) stops the lane-parallel finish
+    scan of its trajectory; a fixup kernel resumes it serially.  No physical pose triggers that, so the library's test
+    hook sends every m-th waypoint down that route: outputs and final states must not change."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    ctl = controls[False]
+    M = fk.sinusoidal_trajectories(257, 90, arm, seed=43)[0].copy()
+    flip = np.diag([-1.0, -1.0, 1.0])
+    M[3, 13:, :3, :3] = M[3, 13:, :3, :3] @ flip       # emergency latch on trajectory 3
+    M[5, 7, :3, :3] = np.diag([-1.0, 1.0, 1.0])        # invalid rotation in trajectory 5
+    want = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous")
+    for m in (1, 7, 97):
+        monkeypatch.setenv("R2IK_DEBUG_FORCE_SERIAL", str(m))
+        got = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous")
+        monkeypatch.delenv("R2IK_DEBUG_FORCE_SERIAL")
+        np.testing.assert_allclose(got[0], want[0], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(got[1], want[1])
+        np.testing.assert_array_equal(got[2], want[2])
+        for f in ("has_previous_sol", "init", "emergency_stop", "emergency_bits"):
+            np.testing.assert_array_equal(got[3][f], want[3][f])
+        np.testing.assert_allclose(got[3]["previous_sol"], want[3]["previous_sol"], rtol=0, atol=1e-12)
