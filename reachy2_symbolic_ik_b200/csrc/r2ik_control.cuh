@@ -168,7 +168,8 @@ R2IK_HD bool best_discrete_theta(const ArmConst &A, const Solve &S, double i0, d
 R2IK_HD double step_toward(double target, double previous_theta, double d_theta_max) {
   double ad = angle_diff(target, previous_theta);
   if (fabs(ad) < d_theta_max) return target;
-  double sign = ad / fabs(ad);
+  // ad / fabs(ad) of the reference is exactly +-1 (0 / 0 = nan when d_theta_max <= 0 lets ad = 0 through): no division
+  const double sign = ad == 0.0 ? NAN : copysign(1.0, ad);
   return previous_theta + sign * d_theta_max;
 }
 
