@@ -190,15 +190,14 @@ class SymbolicIK:
         at least N entries (the list of those poses); both are allocated / cached here when omitted."""
         torch = self._torch
         n = poses_dev.shape[0]
-        if scratch is None:
-            scratch = getattr(self, "_esc_scratch", None)
-            if scratch is None or scratch.numel() < n or stream is not None:
-                scratch = torch.empty(max(n, 1), dtype=torch.int32, device=self._device)
-                if stream is None:
-                    self._esc_scratch = scratch
+        s = torch.cuda.current_stream(self._device).cuda_stream if stream is None else stream
+        if scratch is None:   # one cached list per stream: calls on one stream are ordered, calls on two may overlap
+            cache = self.__dict__.setdefault("_esc_scratch", {})
+            scratch = cache.get(s)
+            if scratch is None or scratch.numel() < n:
+                scratch = cache[s] = torch.empty(max(n, 1), dtype=torch.int32, device=self._device)
         if n_escalated is None:
             n_escalated = torch.empty(1, dtype=torch.int32, device=self._device)
-        s = torch.cuda.current_stream(self._device).cuda_stream if stream is None else stream
         rc = self._handle.lib.r2ik_symik_solve_f32(
             self._handle.h, kind, _ptr(poses_dev), _ptr(theta_dev), _ptr(prev_dev), C.c_int64(n),
             _ptr(reach), _ptr(state), _ptr(interval), _ptr(joints), _ptr(elbow), _ptr(scratch), _ptr(n_escalated),
