@@ -33,6 +33,8 @@
  *         get_best_theta_to_current_joints :267-331, continuity_check :571-589)
  *   r2ik_reach_map_u32
  *        grid sweep of is_reachable (shape of src/benchmark/ik_comparison.py:137-181)
+ *   r2ik_reach_map_f64_u32
+ *        the same volume, every pair by the all-FP64 flag solve (cross-check)
  *   r2ik_interval_limit
  *        interval_limit + l_arm mirroring          control_ik.py:225-252
  *   r2ik_fk_f64
@@ -227,6 +229,13 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par /* ho
 int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
                        const double *orientations_euler /* device, n_ori x 3 */, int32_t ori_begin,
                        int32_t ori_end, uint32_t *counts, void *stream);
+
+/* The same volume with every (voxel, orientation) pair decided by the all-FP64 flag solve.  r2ik_reach_map_u32 decides
+ * a pair with an FP64 front end + FP32 linking test and hands the pairs within the FP32 error bands of a decision to
+ * that solve, so the two entries return identical counts; this one is the cross-check (and ~2-3x slower). */
+int r2ik_reach_map_f64_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                           const double *orientations_euler /* device, n_ori x 3 */, int32_t ori_begin,
+                           int32_t ori_end, uint32_t *counts, void *stream);
 
 /* Forward kinematics: M[i] (row-major 4x4) = tip pose in the torso frame for joints[i] (7).
  * chain: host pointer.  device: CUDA ordinal to launch on. */

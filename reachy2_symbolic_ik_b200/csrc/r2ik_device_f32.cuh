@@ -429,6 +429,71 @@ R2IK_HD void get_joints_f(const ArmConstF &A, SolveF &S, float ct, float st, flo
 }
 
 // ---------------------------------------------------------------------------------------
+// Flag-only solve for the workspace reachability map (K4): is (voxel centre p, orientation o) reachable?
+//
+// What depends on the orientation alone is hoisted into OriConst: wv = R wo (so that the wrist is p + wv: 3 adds instead
+// of a 3x3 product per pair) and the limit-plane normal n1 = (w - p) / |w - p| = wv / |wo| (no normalisation per pair).
+// Per pair, the cancelling front end (wrist, distance, radicand) runs in FP64 -- ~15 operations -- and the in-plane
+// linking test sign(r^2 rho^2 - Xc^2) in FP32, with the same error bands as the K1 fast path; a pair that is too
+// close to call is decided by the FP64 solver (solve_core<false, true>), so the COUNTS are those of the FP64 path.
+// ---------------------------------------------------------------------------------------
+struct OriConst {
+  double wv[3];   // R wo
+  float n1[3];    // wv / |wv|
+  int special;    // rotation_matrix_from_vector(n1) would take one of its isclose special cases: always escalate
+};
+
+R2IK_HD OriConst make_ori_const(const ArmConst &A, const double R[9]) {
+  OriConst O;
+  for (int k = 0; k < 3; ++k) O.wv[k] = R[3 * k] * A.wo[0] + R[3 * k + 1] * A.wo[1] + R[3 * k + 2] * A.wo[2];
+  const double n = sqrt(O.wv[0] * O.wv[0] + O.wv[1] * O.wv[1] + O.wv[2] * O.wv[2]);
+  for (int k = 0; k < 3; ++k) O.n1[k] = (float)(O.wv[k] / n);
+  O.special = !(n > 1e-6) || (fabsf(O.n1[1]) < 3e-5f && fabsf(O.n1[2]) < 3e-5f);
+  return O;
+}
+
+// ps = p - s (FP64, p already through the reach pre-checks), px = p.x.  Returns the state; esc: decide in FP64 instead.
+R2IK_HD int reach_flag_mixed(const ArmConst &A64, const ArmConstF &A, const double ps[3], double px, const OriConst &O, bool &esc) {
+  esc = O.special != 0;
+  double P[3] = {ps[0] + O.wv[0], ps[1] + O.wv[1], ps[2] + O.wv[2]};
+  const double wx = px + O.wv[0];
+  if (wx < A64.backward_limit) P[0] += A64.backward_limit - wx;          // sik:146-153: p and w move together
+  double d2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+  if (d2 > A64.L12 * A64.L12) return R2IK_STATE_WRIST_OUT_OF_RANGE;
+  if (d2 < A64.d_min * A64.d_min) {
+    // sik:166-171, 337-349: the wrist is pushed out radially to d_min d / (d + margin), the goal follows and the wrist is
+    // recomputed from it: P scales by sc (the recomputed wrist is the pushed one up to rounding)
+    double invd64;
+    const double d = sqrt_rsqrt_nonneg(d2, invd64);
+    esc = esc || !(d2 > 1e-12);
+    const double sc = div_fast(A64.d_min, d + A64.proj_margin);
+    P[0] *= sc; P[1] *= sc; P[2] *= sc;
+    d2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+  }
+  const double kk = d2 - A64.L2sq + A64.L1sq;
+  const double rad = 4.0 * d2 * A64.L1sq - kk * kk;
+  const float invd = rsqrt_f((float)d2);
+  const float inv2d = 0.5f * invd;
+  const float r2 = (float)rad * inv2d * inv2d;
+  R2IK_ESC(18, !(r2 > kMinRadius2));
+  const float n2[3] = {(float)P[0] * invd, (float)P[1] * invd, (float)P[2] * invd};
+  const float Ca = O.n1[0] * n2[0] + O.n1[1] * n2[1] + O.n1[2] * n2[2];
+  const float rho2 = fmaf(-Ca, Ca, 1.0f);
+  R2IK_ESC(19, !(rho2 > 1e-4f));                                   // (nearly) parallel planes, and the cancellation in 1 - Ca^2
+  const float cdw = (float)(kk - 2.0 * d2) * inv2d;                // |c - w| with sign: c - w = n2 cdw
+  const float Xc = cdw * Ca - A.hL, nb = cdw - A.hL * Ca;
+  R2IK_ESC(20, fabsf(Xc - nb) <= 4.0f * (1e-8f + 1e-5f * fabsf(nb)) + kBandLen);   // np.isclose(u, t), sik:581
+  const float rr = r2 * rho2, xx = Xc * Xc;
+  const float dl = rr - xx;
+  R2IK_ESC(21, fabsf(dl) <= 1e-5f * (rr + xx));
+  if (dl < 0.0f) {
+    R2IK_ESC(22, fabsf(Xc) < kBandLen);
+    return Xc > 0.0f ? R2IK_STATE_REACHABLE : R2IK_STATE_LIMITED_BY_WRIST;
+  }
+  return R2IK_STATE_REACHABLE;
+}
+
+// ---------------------------------------------------------------------------------------
 // per-pose bodies of K1-f32
 // ---------------------------------------------------------------------------------------
 // out[12] = theta interval (2), joints (7), elbow (3); NaN when unreachable.

@@ -799,41 +799,92 @@ k_cont_finish_lanes(const __grid_constant__ ScanConst K, int64_t T, int W, const
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: workspace reachability map.  One thread per voxel; the rotation-dependent data of the
-// orientation slice (goal rotation matrix) is computed once per block into shared memory.
-// Voxels outside the reach sphere or behind the torso plane leave before the orientation loop
-// (those two states do not depend on the orientation, sik:284-307).
+// K4: workspace reachability map.  One thread per voxel.  Voxels outside the reach sphere or behind the torso plane
+// leave before the orientation loop (those two states do not depend on the orientation, sik:284-307), and a block
+// without a live voxel (3/4 of the bounding cube) leaves before staging anything.
+//
+// Per (voxel, orientation) pair only a flag is needed.  k_reach_map decides it with reach_flag_mixed
+// (r2ik_device_f32.cuh): what depends on the orientation alone (R wo and the limit-plane normal) is staged once per
+// block in shared memory, the cancelling front end of a pair runs in FP64 (~15 operations) and the in-plane linking
+// test in FP32; a pair within the FP32 error bands of a decision (3e-4 of them) is decided by the FP64 flag solve,
+// so the counts are those of the all-FP64 kernel k_reach_map_f64 (kept: tests compare the two volumes).
 // ---------------------------------------------------------------------------------------
-// Orientations whose rotation matrices a block stages at once.  With 64 the loop below crossed two block barriers
-// per chunk and `barrier` was the first stall reason of the kernel (4.3 cycles per issue: voxels of a block leave the
-// solve at different depths); 512 = the whole orientation set of cfg 5 in 36 KB of shared memory, two barriers per block.
+// Orientations staged at once.  In the FP64 kernel, 64 meant two block barriers per chunk and `barrier` as the first
+// stall reason (4.3 cycles per issue: voxels of a block leave the solve at different depths); 512 = the whole
+// orientation set of cfg 5 (36 KB of rotation matrices / 20 KB of OriConst), two barriers per block.
 #ifndef R2IK_ORI_CHUNK
 #define R2IK_ORI_CHUNK 512
 #endif
 
+__device__ __forceinline__ bool voxel_live(const ArmConst &A, int64_t v, int64_t nv, double ox, double oy, double oz, double sx,
+                                           double sy, double sz, int d1, int d2, double &px, double &py, double &pz) {
+  px = 0; py = 0; pz = 0;
+  if (v >= nv) return false;
+  int iz = (int)(v % d2);
+  int iy = (int)((v / d2) % d1);
+  int ix = (int)(v / ((int64_t)d2 * d1));
+  px = ox + ix * sx; py = oy + iy * sy; pz = oz + iz * sz;
+  return reach_prechecks(A, px, py, pz) < 0;
+}
+
 __global__ void __launch_bounds__(R2IK_BLOCK)
-k_reach_map(const __grid_constant__ ArmConst A, double ox, double oy, double oz, double sx, double sy, double sz,
-            int d0, int d1, int d2, const double *__restrict__ ori_euler, int ori_begin, int ori_end,
-            uint32_t *__restrict__ counts) {
+k_reach_map(const __grid_constant__ ArmConst A, const __grid_constant__ f32::ArmConstF AF, double ox, double oy, double oz,
+            double sx, double sy, double sz, int d0, int d1, int d2, const double *__restrict__ ori_euler, int ori_begin,
+            int ori_end, uint32_t *__restrict__ counts) {
+  __shared__ f32::OriConst sO[R2IK_ORI_CHUNK];
+  const int64_t nv = (int64_t)d0 * d1 * d2;
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double px, py, pz;
+  const bool live = voxel_live(A, v, nv, ox, oy, oz, sx, sy, sz, d1, d2, px, py, pz);
+  if (!__syncthreads_or(live ? 1 : 0)) {
+    if (v < nv) counts[v] = 0;
+    return;
+  }
+  const double ps[3] = {px - A.s[0], py - A.s[1], pz - A.s[2]};
+  uint32_t count = 0;
+  for (int base = ori_begin; base < ori_end; base += R2IK_ORI_CHUNK) {
+    const int m = min(R2IK_ORI_CHUNK, ori_end - base);
+    if (base != ori_begin) __syncthreads();
+    for (int o = threadIdx.x; o < m; o += blockDim.x) {
+      const double *e = ori_euler + 3 * (size_t)(base + o);
+      double R[9];
+      rot_from_euler_xyz(e[0], e[1], e[2], R);
+      sO[o] = f32::make_ori_const(A, R);
+    }
+    __syncthreads();
+    if (live) {
+      for (int o = 0; o < m; ++o) {
+        bool esc;
+        int st = f32::reach_flag_mixed(A, AF, ps, px, sO[o], esc);
+        if (esc) {   // too close to call in FP32 (3e-4 of the pairs): the FP64 flag solve decides
+          const double *e = ori_euler + 3 * (size_t)(base + o);
+          Solve S;
+          S.p[0] = px; S.p[1] = py; S.p[2] = pz;
+          rot_from_euler_xyz(e[0], e[1], e[2], S.R);
+          st = solve_core<false, true>(A, S).state;
+        }
+        count += (st == R2IK_STATE_REACHABLE) ? 1u : 0u;
+      }
+    }
+  }
+  if (v < nv) counts[v] = count;
+}
+
+// The all-FP64 form (every pair through solve_core<false, true>): the cross-check of k_reach_map.
+__global__ void __launch_bounds__(R2IK_BLOCK)
+k_reach_map_f64(const __grid_constant__ ArmConst A, double ox, double oy, double oz, double sx, double sy, double sz,
+                int d0, int d1, int d2, const double *__restrict__ ori_euler, int ori_begin, int ori_end,
+                uint32_t *__restrict__ counts) {
   __shared__ double sR[R2IK_ORI_CHUNK][9];
   const int64_t nv = (int64_t)d0 * d1 * d2;
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_grid = v < nv;
-  double px = 0, py = 0, pz = 0;
-  bool live = false;
-  if (in_grid) {
-    int iz = (int)(v % d2);
-    int iy = (int)((v / d2) % d1);
-    int ix = (int)(v / ((int64_t)d2 * d1));
-    px = ox + ix * sx; py = oy + iy * sy; pz = oz + iz * sz;
-    live = reach_prechecks(A, px, py, pz) < 0;
-  }
-  uint32_t count = 0;
-  // a block with no voxel inside the reach pre-checks (3/4 of the bounding cube) has nothing to stage
+  double px, py, pz;
+  const bool live = voxel_live(A, v, nv, ox, oy, oz, sx, sy, sz, d1, d2, px, py, pz);
   if (!__syncthreads_or(live ? 1 : 0)) {
-    if (in_grid) counts[v] = 0;
+    if (v < nv) counts[v] = 0;
     return;
   }
+  uint32_t count = 0;
   for (int base = ori_begin; base < ori_end; base += R2IK_ORI_CHUNK) {
     int m = min(R2IK_ORI_CHUNK, ori_end - base);
     if (base != ori_begin) __syncthreads();
@@ -856,12 +907,9 @@ k_reach_map(const __grid_constant__ ArmConst A, double ox, double oy, double oz,
       }
     }
   }
-  if (in_grid) counts[v] = count;
+  if (v < nv) counts[v] = count;
 }
 
-// ---------------------------------------------------------------------------------------
-// FK: tip pose of the 7-joint arm chain (synthetic FK-sampled workloads, round-trip checks).
-// A = A * [R|t] on 3x4 affine transforms held in registers; joint rotations by Rodrigues.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void affine_mul(double A[12], const double B[12]) {
   double o[12];
@@ -1180,19 +1228,36 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
   return 0;
 }
 
-int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
-                       const double *orientations_euler, int32_t ori_begin, int32_t ori_end, uint32_t *counts, void *stream) {
+static int reach_map_launch(bool all_f64, r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                            const double *orientations_euler, int32_t ori_begin, int32_t ori_end, uint32_t *counts,
+                            void *stream) {
   if (!h || !origin || !step || !dims || !orientations_euler || !counts)
     return fail_arg(R2IK_ERR_NULL, "r2ik_reach_map_u32: null argument");
   if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || ori_begin < 0 || ori_end < ori_begin)
     return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_u32: bad dims or orientation range");
   int64_t nv = (int64_t)dims[0] * dims[1] * dims[2];
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
-  k_reach_map<<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, origin[0], origin[1], origin[2], step[0], step[1],
-                                                                      step[2], dims[0], dims[1], dims[2], orientations_euler,
-                                                                      ori_begin, ori_end, counts);
+  if (all_f64)
+    k_reach_map_f64<<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, origin[0], origin[1], origin[2], step[0],
+                                                                            step[1], step[2], dims[0], dims[1], dims[2],
+                                                                            orientations_euler, ori_begin, ori_end, counts);
+  else
+    k_reach_map<<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, h->AF, origin[0], origin[1], origin[2], step[0],
+                                                                        step[1], step[2], dims[0], dims[1], dims[2],
+                                                                        orientations_euler, ori_begin, ori_end, counts);
   R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
   return 0;
+}
+
+int r2ik_reach_map_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                       const double *orientations_euler, int32_t ori_begin, int32_t ori_end, uint32_t *counts, void *stream) {
+  return reach_map_launch(false, h, origin, step, dims, orientations_euler, ori_begin, ori_end, counts, stream);
+}
+
+int r2ik_reach_map_f64_u32(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                           const double *orientations_euler, int32_t ori_begin, int32_t ori_end, uint32_t *counts,
+                           void *stream) {
+  return reach_map_launch(true, h, origin, step, dims, orientations_euler, ori_begin, ori_end, counts, stream);
 }
 
 int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int64_t n, double *M, void *stream) {

@@ -52,12 +52,14 @@ def sharded_sum(launch: Callable[[int, int], "object"], n_orientations: int, dis
 
 
 def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int = 512, origin=None, step=None,
-              dims=None, dist=None, group=None, out=None):
+              dims=None, dist=None, group=None, out=None, all_fp64: bool = False):
     """Reachability count volume of ``solver`` (a ``SymbolicIK``): int32 CUDA tensor (d0, d1, d2).
 
     orientations_euler: (n_ori, 3) xyz Euler angles (default: ``fibonacci_orientations(n_orientations)``).
     With an initialised ``torch.distributed`` passed as ``dist`` the orientation set is sharded over the
-    ranks and the volume is all-reduced; every rank returns the full map."""
+    ranks and the volume is all-reduced; every rank returns the full map.
+    all_fp64: decide every (voxel, orientation) pair with the FP64 flag solve instead of the mixed-precision test with
+    FP64 escalation (identical counts, slower: the cross-check)."""
     torch = solver._torch
     if orientations_euler is None:
         orientations_euler = fibonacci_orientations(n_orientations)
@@ -78,7 +80,8 @@ def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int
 
         def launch(b: int, e: int):
             s = torch.cuda.current_stream(dev).cuda_stream
-            rc = solver._handle.lib.r2ik_reach_map_u32(
+            entry = solver._handle.lib.r2ik_reach_map_f64_u32 if all_fp64 else solver._handle.lib.r2ik_reach_map_u32
+            rc = entry(
                 solver._handle.h, origin.ctypes.data_as(C.POINTER(C.c_double)), step.ctypes.data_as(C.POINTER(C.c_double)),
                 dims.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(ori.data_ptr()), C.c_int32(b), C.c_int32(e),
                 C.c_void_p(out.data_ptr()), C.c_void_p(s))

@@ -265,4 +265,48 @@ void hs_search_compare(const double *plans, int64_t n, int nb, double *best_scan
   }
 }
 
+// K4 with the mixed-precision flag (reach_flag_mixed) and FP64 escalation, mirroring k_reach_map.
+// mode 0: as the kernel; mode 1: never escalate (to measure what the bands catch).  n_esc: escalated pairs.
+void hs_reach_map_mixed(const R2ikArmConfig *cfg, const double *origin, const double *step, const int32_t *dims,
+                        const double *ori_euler, int32_t ori_begin, int32_t ori_end, int mode, uint32_t *counts,
+                        uint64_t *n_esc, uint64_t *n_live_pairs) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  f32::ArmConstF F;
+  f32::narrow_constants(A, F);
+  const int no = ori_end - ori_begin;
+  f32::OriConst *O = new f32::OriConst[no];
+  double *Rs = new double[9 * (size_t)no];
+  for (int o = 0; o < no; ++o) {
+    const double *e = ori_euler + 3 * (size_t)(ori_begin + o);
+    rot_from_euler_xyz(e[0], e[1], e[2], Rs + 9 * o);
+    O[o] = f32::make_ori_const(A, Rs + 9 * o);
+  }
+  *n_esc = 0; *n_live_pairs = 0;
+  for (int ix = 0; ix < dims[0]; ++ix)
+    for (int iy = 0; iy < dims[1]; ++iy)
+      for (int iz = 0; iz < dims[2]; ++iz) {
+        double px = origin[0] + ix * step[0], py = origin[1] + iy * step[1], pz = origin[2] + iz * step[2];
+        uint32_t count = 0;
+        if (reach_prechecks(A, px, py, pz) < 0) {
+          const double ps[3] = {px - A.s[0], py - A.s[1], pz - A.s[2]};
+          for (int o = 0; o < no; ++o) {
+            bool esc = false;
+            int st = f32::reach_flag_mixed(A, F, ps, px, O[o], esc);
+            ++*n_live_pairs;
+            if (esc) ++*n_esc;
+            if (esc && mode == 0) {
+              Solve S;
+              S.p[0] = px; S.p[1] = py; S.p[2] = pz;
+              for (int k = 0; k < 9; ++k) S.R[k] = Rs[9 * o + k];
+              st = solve_core<false, true>(A, S).state;
+            }
+            count += st == R2IK_STATE_REACHABLE;
+          }
+        }
+        counts[((size_t)ix * dims[1] + iy) * dims[2] + iz] = count;
+      }
+  delete[] O; delete[] Rs;
+}
+
 }  // extern "C"

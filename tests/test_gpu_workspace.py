@@ -87,3 +87,23 @@ def test_fk_round_trip_full_size(arm):
     pos_err = (M2[:, :3, 3] - M[ok][:, :3, 3]).norm(dim=1)
     assert pos_err.median().item() < 1e-5
     assert (pos_err < 1e-4).double().mean().item() > 0.9
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_reach_map_mixed_equals_all_fp64(arm):
+    """K4 decides a (voxel, orientation) pair with an FP64 front end + FP32 linking test and hands the pairs it cannot
+    call to the FP64 flag solve: the volume must equal the all-FP64 kernel's, voxel by voxel."""
+    from reachy2_symbolic_ik_b200 import SymbolicIK, fk
+
+    ik = SymbolicIK(arm=arm)
+    ori = fk.fibonacci_orientations(96)
+    a = ik.reach_map(n=112, orientations_euler=ori).cpu().numpy()
+    b = ik.reach_map(n=112, orientations_euler=ori, all_fp64=True).cpu().numpy()
+    assert a.sum() > 1_000_000
+    np.testing.assert_array_equal(a, b)
+    # an orientation slice, as a rank of the sharded map computes it
+    from reachy2_symbolic_ik_b200 import workspace
+    origin, step, dims = workspace.reach_grid(ik.shoulder_position, ik.max_arm_length, 64)
+    c = ik.reach_map(orientations_euler=ori, origin=origin + 1e-3, step=step, dims=dims).cpu().numpy()
+    d = ik.reach_map(orientations_euler=ori, origin=origin + 1e-3, step=step, dims=dims, all_fp64=True).cpu().numpy()
+    np.testing.assert_array_equal(c, d)

@@ -320,3 +320,31 @@ def test_search_analytic_equals_scan(hs, nb, mode):
     assert np.array_equal(found, np.isfinite(ba))
     assert np.array_equal(ks, ka), f"{int((ks != ka).sum())} arg-min differ"
     assert np.array_equal(bs[found], ba[found])
+
+
+# ---------------------------------------------------------------------------------------------------
+# K4's mixed-precision flag (reach_flag_mixed + FP64 escalation) against the oracle's reach map: identical counts
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arm", ARMS)
+def test_reach_map_mixed_flag_counts(hs, oracle, arm):
+    from reachy2_symbolic_ik_b200 import fk, workspace
+
+    n, no = 36, 40
+    shoulder = np.array([0.0, -0.2 if arm == "r_arm" else 0.2, 0.0])
+    origin, step, dims = workspace.reach_grid(shoulder, 0.66, n)
+    origin = origin + 3e-4                      # off the symmetric grid
+    ori = fk.fibonacci_orientations(no)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    want = oracle.reach_map(oracle.arm_config(arm), origin, step, dims, ori).reshape(-1)
+    cfg = cfg_for(arm)
+    res = {}
+    for mode in (0, 1):
+        counts = np.zeros(n ** 3, np.uint32)
+        n_esc, n_live = C.c_uint64(), C.c_uint64()
+        hs.hs_reach_map_mixed(C.byref(cfg), vp(origin), vp(step), vp(dims), vp(ori), C.c_int32(0), C.c_int32(no), C.c_int(mode),
+                              vp(counts), C.byref(n_esc), C.byref(n_live))
+        res[mode] = (counts, n_esc.value / max(n_live.value, 1))
+    assert np.array_equal(res[0][0], want), "mixed-precision reach map differs from the oracle"
+    assert res[0][1] < 2e-3, f"too many pairs escalated to FP64: {res[0][1]:.2e}"
+    # without the escalation only a handful of pairs differ: the bands are what makes the counts exact
+    assert np.abs(res[1][0].astype(np.int64) - want.astype(np.int64)).sum() < 1e-4 * want.sum()
