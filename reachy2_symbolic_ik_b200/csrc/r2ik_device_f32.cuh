@@ -485,7 +485,9 @@ R2IK_HD int reach_flag_mixed(const ArmConst &A64, const ArmConstF &A, const doub
   R2IK_ESC(20, fabsf(Xc - nb) <= 4.0f * (1e-8f + 1e-5f * fabsf(nb)) + kBandLen);   // np.isclose(u, t), sik:581
   const float rr = r2 * rho2, xx = Xc * Xc;
   const float dl = rr - xx;
-  R2IK_ESC(21, fabsf(dl) <= 1e-5f * (rr + xx));
+  // error of dl: rho2 = 1 - Ca^2 carries the absolute rounding of Ca (~2e-7, relative 1e-4 at 3 degrees between the
+  // planes), Xc that of cdw Ca (~5e-8): r2 d(rho2) + 2 |Xc| d(Xc), plus the relative rounding of the products
+  R2IK_ESC(21, fabsf(dl) <= 1e-5f * (rr + xx) + 1.5e-6f * r2 + 4e-7f * fabsf(Xc));
   if (dl < 0.0f) {
     R2IK_ESC(22, fabsf(Xc) < kBandLen);
     return Xc > 0.0f ? R2IK_STATE_REACHABLE : R2IK_STATE_LIMITED_BY_WRIST;

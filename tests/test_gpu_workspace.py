@@ -107,3 +107,17 @@ def test_reach_map_mixed_equals_all_fp64(arm):
     c = ik.reach_map(orientations_euler=ori, origin=origin + 1e-3, step=step, dims=dims).cpu().numpy()
     d = ik.reach_map(orientations_euler=ori, origin=origin + 1e-3, step=step, dims=dims, all_fp64=True).cpu().numpy()
     np.testing.assert_array_equal(c, d)
+
+
+def test_reach_map_full_size_mixed_equals_all_fp64():
+    """BASELINE configs[4] at full size (256^3 voxels x 512 orientations, 2.1e9 live pairs): the mixed-precision volume
+    equals the all-FP64 one voxel by voxel.  (Two pairs of this very map sit 3e-9 from the discriminant's zero with the
+    planes 3 degrees from parallel; they fixed the width of the FP32 error band of the test.)"""
+    from reachy2_symbolic_ik_b200 import SymbolicIK, fk
+
+    ik = SymbolicIK(arm="r_arm")
+    ori = fk.fibonacci_orientations(512)
+    a = ik.reach_map(n=256, orientations_euler=ori).clone()
+    b = ik.reach_map(n=256, orientations_euler=ori, all_fp64=True)
+    assert int((a != b).sum().item()) == 0
+    assert int(a.sum().item()) == 856520774

@@ -348,3 +348,24 @@ def test_reach_map_mixed_flag_counts(hs, oracle, arm):
     assert res[0][1] < 2e-3, f"too many pairs escalated to FP64: {res[0][1]:.2e}"
     # without the escalation only a handful of pairs differ: the bands are what makes the counts exact
     assert np.abs(res[1][0].astype(np.int64) - want.astype(np.int64)).sum() < 1e-4 * want.sum()
+
+
+def test_reach_map_mixed_flag_regression_pairs(hs, oracle):
+    """Two (voxel, orientation) pairs of the full 256^3 x 512 map whose discriminant is 3e-9 from zero while the planes
+    are 3 degrees from parallel (the cancellation in 1 - Ca^2 is then the largest FP32 error): they must be escalated."""
+    from reachy2_symbolic_ik_b200 import fk, workspace
+
+    origin, step, dims = workspace.reach_grid(np.array([0.0, -0.2, 0.0]), 0.66, 256)
+    ori = fk.fibonacci_orientations(512)
+    one = np.array([1, 1, 1], np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    cfg = cfg_for("r_arm")
+    for vox, o in (([196, 191, 113], 17), ([223, 115, 124], 118)):
+        p = origin + np.array(vox) * step
+        oo = np.ascontiguousarray(ori[o:o + 1])
+        want = oracle.reach_map(oracle.arm_config("r_arm"), p, step, one, oo).reshape(-1)[0]
+        counts = np.zeros(1, np.uint32)
+        n_esc, n_live = C.c_uint64(), C.c_uint64()
+        hs.hs_reach_map_mixed(C.byref(cfg), vp(p), vp(step), vp(one), vp(oo), C.c_int32(0), C.c_int32(1), C.c_int(0), vp(counts),
+                              C.byref(n_esc), C.byref(n_live))
+        assert counts[0] == want == 0 and n_esc.value == 1
