@@ -266,7 +266,8 @@ class SymikF32(Symik):
     BYTES_IN, BYTES_OUT = 64, 1 + 1 + 8 + 28 + 12
     # executed flops per pose (FMA = 2) in the ncu source-level counts of profiles/r1_s16: 573 FP32 (145 FFMA + 134 FMUL +
     # 78 FADD + 71 FSETP) + 58 FP64 of the mixed-precision front end (11 DFMA + 10 DMUL + 20 DADD + 6 DSETP)
-    FLOP_EQ = 631.0
+    FLOP_EQ = 58.0       # FP64 part (roofline_fp64)
+    FLOP_FP32 = 573.0    # FP32 part (roofline_fp32)
     FLOP_EQ_SURVEY = 2100.0
     kernel = "k_symik_solve_f32<MAT4>"
     fp32 = True
@@ -544,9 +545,12 @@ class ReachMap:
     N, N_ORI = 256, 512
     BYTES_IN, BYTES_OUT = 0, 4.0 / 512
     # per (voxel, orientation): ~25 % of the voxels pass the orientation-independent early-outs; a live pair costs the
-    # wrist point + range test (~33 flops) and, for the ~60 % inside the arm's range, the two circles and the
-    # plane/line/discriminant chain of the flag-only solve (~330 flops): 0.25 * (33 + 0.6 * 330) = 58
-    FLOP_EQ = 58.0
+    # FP64 front end of reach_flag_mixed (wrist, distance, radicand: ~17 flops) and its FP32 in-plane test (~35 flops);
+    # 3e-4 of the live pairs are re-decided by the all-FP64 flag solve (~230 flops, negligible on average)
+    FLOP_EQ = 0.25 * 17.0
+    FLOP_FP32 = 0.25 * 35.0
+    fp32 = True
+    dtype = "f64+f32"   # FP64 front end and escalation, FP32 linking test; integer counts identical to the all-FP64 kernel
     FLOP_EQ_SURVEY = 900.0 * 0.25
     kernel = "k_reach_map"
 
@@ -806,7 +810,7 @@ def main() -> int:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"),
-            "vs_baseline": None, "dtype": "f32" if getattr(wl, "fp32", False) else "f64", "data": "synthetic", "config": wl.config(world),
+            "vs_baseline": None, "dtype": getattr(wl, "dtype", "f32" if getattr(wl, "fp32", False) else "f64"), "data": "synthetic", "config": wl.config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, **e2e_info, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
@@ -827,10 +831,13 @@ def main() -> int:
             "clocks": clocks.summary(), "parity": parity,
         }
         if fp32_peak is not None:
-            # K1-f32 mixes pipes: report the measured FFMA peak beside the DFMA one; `achieved` counts both kinds of flops
-            line["roofline_fp32"] = {"bound": "fp32", "achieved": fp64_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                                     "frac": fp64_ach / fp32_peak, "flop_per_pose": wl.FLOP_EQ,
-                                     "peak_source": "r2ik_ffma_probe measured in this run (FFMA chains, full grid)"}
+            # mixed-precision kernels (K1-f32, K4): the measured FFMA peak beside the DFMA one
+            fp32_ach = wl.FLOP_FP32 * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
+            line["roofline_fp32"] = {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                     "frac": fp32_ach / fp32_peak, "fp32_flop_per_pose": wl.FLOP_FP32,
+                                     "peak_source": "r2ik_ffma_probe measured in this run (FFMA chains, full grid)",
+                                     "note": "mixed-precision kernel: the FP32 flops are counted here, the FP64 flops in "
+                                             "roofline_fp64; the two pipes issue from the same slots"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
