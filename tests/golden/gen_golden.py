@@ -340,6 +340,46 @@ def gen_ctl_continuous(T_sin=6, W=300):
     ref_control.time = time
 
 
+def example_matrices():
+    """4x4 goal matrices that appear verbatim in the reference's examples (truncated decimals: not orthonormal)."""
+    M_r = np.array([[-0.34159004, -0.90910326, -0.23842717, 0.15009035], [0.92063745, -0.3746924, 0.10969179, -0.36832501],
+                    [-0.18905801, -0.18203536, 0.9649457, 0.05864802], [0.0, 0.0, 0.0, 1.0]])   # test_continuous_ik.py:345-357
+    M_l = np.array([[-0.34159004, 0.90910326, -0.23842717, 0.15009035], [-0.92063745, -0.3746924, -0.10969179, 0.36832501],
+                    [-0.18905801, 0.18203536, 0.9649457, 0.05864802], [0.0, 0.0, 0.0, 1.0]])    # test_continuous_ik.py:358-370
+    M_g = np.array([[0.36861, 0.089736, -0.92524, 0.37213], [-0.068392, 0.99525, 0.069279, -0.028012],
+                    [0.92706, 0.037742, 0.373, -0.38572], [0, 0, 0, 1.0]])                       # test_go_to.py:250-257
+    M_g_r = M_g.copy()
+    M_g_r[1, 3] *= -1; M_g_r[0, 1] *= -1; M_g_r[1, 0] *= -1; M_g_r[1, 2] *= -1; M_g_r[2, 1] *= -1   # its y-mirror for the r_arm
+    return {"r_arm": np.array([M_r, M_g_r]), "l_arm": np.array([M_l, M_g])}
+
+
+def gen_ctl_examples(W=40):
+    """The debug matrices of src/example through SymbolicIK, ControlIK discrete and ControlIK continuous (the matrix held
+    for W calls: the rate-limited theta walks from the initial theta toward its target)."""
+    out = dict(META)
+    for arm, Ms in example_matrices().items():
+        gp = np.array([euler_pose_from_matrix(m) for m in Ms])
+        with _Quiet():
+            ik = SymbolicIK(arm=arm)
+        flag, state, interval, joints, elbow = run_symik(ik, gp)
+        out.update({f"{arm}_M": Ms, f"{arm}_goal_pose": gp, f"{arm}_sym_reachable": flag, f"{arm}_sym_state": state,
+                    f"{arm}_sym_interval": interval, f"{arm}_sym_joints": joints, f"{arm}_sym_elbow": elbow})
+        dj, df, ds = [], [], []
+        for m in Ms:
+            with _Quiet():
+                j, f, st = run_discrete(new_control(), arm, m[None])
+            dj.append(j[0]); df.append(f[0]); ds.append(st[0])
+        out.update({f"{arm}_dis_joints": np.array(dj), f"{arm}_dis_reachable": np.array(df), f"{arm}_dis_state": np.array(ds)})
+        cj, cf, cs, ce = [], [], [], []
+        for m in Ms:
+            j, f, st, emg, _ = run_continuous(arm, np.repeat(m[None], W, axis=0))
+            cj.append(j); cf.append(f); cs.append(st); ce.append(emg)
+        out.update({f"{arm}_con_joints": np.array(cj), f"{arm}_con_reachable": np.array(cf), f"{arm}_con_state": np.array(cs),
+                    f"{arm}_con_emergency": np.array(ce)})
+        print(arm, "examples: sym", state, "dis", ds, "con states", [np.unique(x).tolist() for x in cs], "emergency", ce)
+    np.savez_compressed(os.path.join(HERE, "ctl_examples.npz"), **out)
+
+
 def gen_helpers(n=2000):
     """Pins of the scipy / utils helpers the kernels restate."""
     from reachy2_symbolic_ik.utils import (angle_diff, limit_orbita3d_joints, limit_theta_to_interval,
@@ -378,7 +418,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -391,4 +431,6 @@ if __name__ == "__main__":
         gen_ctl_discrete()
     if "continuous" in which:
         gen_ctl_continuous()
+    if "examples" in which:
+        gen_ctl_examples()
     print(f"done in {time.time() - t0:.1f}s")

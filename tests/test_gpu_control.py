@@ -299,3 +299,34 @@ def test_continuous_serial_route_and_fixup(controls, arm, monkeypatch):
         for f in ("has_previous_sol", "init", "emergency_stop", "emergency_bits"):
             np.testing.assert_array_equal(got[3][f], want[3][f])
         np.testing.assert_allclose(got[3]["previous_sol"], want[3]["previous_sol"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_reference_example_matrices(arm):
+    """The goal matrices printed in the reference's examples (src/example/test_continuous_ik.py:345-370,
+    test_go_to.py:250-257; tests/golden/ctl_examples.npz) through the library: SymbolicIK, ControlIK discrete (scalar
+    and batched), ControlIK continuous."""
+    from reachy2_symbolic_ik_b200 import ControlIK, SymbolicIK
+
+    g = load("ctl_examples.npz")
+    M = np.ascontiguousarray(g[f"{arm}_M"])
+    res = SymbolicIK(arm=arm).is_reachable_batch(M)
+    assert np.array_equal(res.state, g[f"{arm}_sym_state"]) and np.array_equal(res.reachable, g[f"{arm}_sym_reachable"])
+    np.testing.assert_allclose(res.theta_interval, g[f"{arm}_sym_interval"], atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(res.joints, g[f"{arm}_sym_joints"], atol=1e-9, equal_nan=True)
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    j, r, s, e = ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete")
+    assert np.array_equal(s, g[f"{arm}_dis_state"]) and np.array_equal(r, g[f"{arm}_dis_reachable"])
+    np.testing.assert_allclose(j, g[f"{arm}_dis_joints"], atol=1e-9)
+    for i in range(len(M)):   # the scalar API, a fresh controller per call like the fixture
+        js, ok, st = ControlIK(urdf_path="../config_files/reachy2.urdf").symbolic_inverse_kinematics(arm, M[i], "discrete")
+        np.testing.assert_allclose(js, g[f"{arm}_dis_joints"][i], atol=1e-9)
+        assert ok == bool(g[f"{arm}_dis_reachable"][i])
+    W = g[f"{arm}_con_joints"].shape[1]
+    MT = np.ascontiguousarray(np.repeat(M[:, None], W, axis=1))
+    for phased in (True, False):
+        cj, cr, cs, st = ControlIK(urdf_path="../config_files/reachy2.urdf").symbolic_inverse_kinematics_batch(
+            arm, MT, "continuous", phased=phased)
+        assert np.array_equal(cs, g[f"{arm}_con_state"]) and np.array_equal(cr, g[f"{arm}_con_reachable"])
+        np.testing.assert_allclose(cj, g[f"{arm}_con_joints"], atol=1e-9)
+        assert np.array_equal(st["emergency_stop"].astype(bool), g[f"{arm}_con_emergency"])

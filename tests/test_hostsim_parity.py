@@ -369,3 +369,39 @@ def test_reach_map_mixed_flag_regression_pairs(hs, oracle):
         hs.hs_reach_map_mixed(C.byref(cfg), vp(p), vp(step), vp(one), vp(oo), C.c_int32(0), C.c_int32(1), C.c_int(0), vp(counts),
                               C.byref(n_esc), C.byref(n_live))
         assert counts[0] == want == 0 and n_esc.value == 1
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_reference_example_matrices(hs, oracle, arm):
+    """The goal matrices printed in the reference's examples (tests/golden/ctl_examples.npz) through the kernel source:
+    SymbolicIK (4x4 input), ControlIK discrete, ControlIK continuous (serial and phased forms)."""
+    g = load("ctl_examples.npz")
+    params = urdf_params()
+    M = np.ascontiguousarray(g[f"{arm}_M"])
+    n = len(M)
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg_for(arm), M)
+    assert np.array_equal(state, g[f"{arm}_sym_state"]) and np.array_equal(reach, g[f"{arm}_sym_reachable"])
+    np.testing.assert_allclose(itv, g[f"{arm}_sym_interval"], atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(joints, g[f"{arm}_sym_joints"], atol=1e-9, equal_nan=True)
+    cfg = cfg_for(arm, params, -1.01)
+    par = ctl_params(oracle, arm)
+    prev = np.array(oracle.DEFAULT_PREV_JOINTS[arm])
+    dj = np.empty((n, 7)); dr = np.zeros(n, np.uint8); ds = np.zeros(n, np.uint8); de = np.zeros(n, np.uint8)
+    hs.hs_ctl_discrete_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(n), dp(prev), dp(prev), dp(dj), u8(dr), u8(ds), u8(de))
+    assert np.array_equal(ds, g[f"{arm}_dis_state"]) and np.array_equal(dr.astype(bool), g[f"{arm}_dis_reachable"])
+    np.testing.assert_allclose(dj, g[f"{arm}_dis_joints"], atol=1e-9)
+    W = g[f"{arm}_con_joints"].shape[1]
+    MT = np.ascontiguousarray(np.repeat(M[:, None], W, axis=1))
+    cj = np.empty((n, 7)); cp = np.empty((n, 4, 4))
+    cj[:] = oracle.DEFAULT_PREV_JOINTS[arm]; cp[:] = oracle.DEFAULT_CURRENT_POSE[arm]
+    for entry in ("hs_ctl_continuous_batch", "hs_ctl_continuous_phased_batch"):
+        st = np.zeros(n, dtype=_abi.TRAJ_STATE_DTYPE); st["init"] = 1
+        j = np.empty((n, W, 7)); r = np.zeros((n, W), np.uint8); s_ = np.zeros((n, W), np.uint8)
+        args = [C.byref(cfg), C.byref(par), dp(MT), C.c_int64(n), C.c_int32(W), dp(cj), dp(cp), st.ctypes.data_as(C.c_void_p),
+                dp(j), u8(r), u8(s_)]
+        if entry.endswith("phased_batch"):
+            ws = np.empty((n, W)); args.append(dp(ws))
+        getattr(hs, entry)(*args)
+        assert np.array_equal(s_, g[f"{arm}_con_state"]) and np.array_equal(r.astype(bool), g[f"{arm}_con_reachable"]), entry
+        np.testing.assert_allclose(j, g[f"{arm}_con_joints"], atol=1e-9)
+        assert np.array_equal(st["emergency_stop"].astype(bool), g[f"{arm}_con_emergency"])

@@ -173,3 +173,27 @@ def test_invalid_rotation_is_flagged(oracle):
     assert not reach[0] and state[0] == 9 and np.isnan(joints).all()
     with pytest.raises(ValueError):
         oracle.euler_xyz_from_matrix(M[0, :3, :3])
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_reference_example_matrices(oracle, arm):
+    """The goal matrices printed in the reference's examples (src/example/test_continuous_ik.py:345-370,
+    test_go_to.py:250-257; truncated decimals, so scipy projects them) through SymbolicIK, ControlIK discrete and
+    ControlIK continuous: tests/golden/ctl_examples.npz."""
+    g = load("ctl_examples.npz")
+    u = load("symik_urdf.npz")
+    M = g[f"{arm}_M"]
+    reach, itv, state, joints, elbow = oracle.symik_batch(oracle.arm_config(arm), g[f"{arm}_goal_pose"])
+    assert np.array_equal(state, g[f"{arm}_sym_state"]) and np.array_equal(reach, g[f"{arm}_sym_reachable"])
+    np.testing.assert_allclose(itv, g[f"{arm}_sym_interval"], atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(joints, g[f"{arm}_sym_joints"], atol=1e-9, equal_nan=True)
+    cfg = _urdf_cfg(oracle, u, arm)
+    par = oracle.ControlParams(arm=arm)
+    j, r, s, e = oracle.ctl_discrete_batch(cfg, par, M)
+    assert np.array_equal(s, g[f"{arm}_dis_state"]) and np.array_equal(r, g[f"{arm}_dis_reachable"])
+    np.testing.assert_allclose(j, g[f"{arm}_dis_joints"], atol=1e-9)
+    W = g[f"{arm}_con_joints"].shape[1]
+    cj, cr, cs, st = oracle.ctl_continuous_batch(cfg, par, np.repeat(M[:, None], W, axis=1))
+    assert np.array_equal(cs, g[f"{arm}_con_state"]) and np.array_equal(cr, g[f"{arm}_con_reachable"])
+    np.testing.assert_allclose(cj, g[f"{arm}_con_joints"], atol=1e-9)
+    assert np.array_equal(st["emergency_stop"].astype(bool), g[f"{arm}_con_emergency"])
