@@ -4,19 +4,25 @@
 // optional ... FP32 path within a stated 1e-4 rad".  This header restates the K1 part of
 // r2ik_device.cuh (sik:121-282 is_reachable, sik:697-863 get_joints and what they call) in single
 // precision: float4 pose loads, MUFU.RSQ / MUFU.RCP seeds used as they are (no Newton steps), 5-term
-// polynomials, 32-bit registers -- twice the arithmetic rate of the FP64 pipe and half the bytes.
+// polynomials, 32-bit registers -- twice the arithmetic rate of the FP64 pipe and half the bytes.  The few
+// differences that cancel catastrophically for a nearly straight arm (wrist centre, its distance to the
+// shoulder, the radicand of the elbow-circle radius) stay in FP64 on the exactly-widened inputs, and the
+// circle linking uses the in-plane form of r2ik_device.cuh, which divides one well-conditioned scalar by
+// r rho instead of locating points of a small circle from FP32 coordinates.
 //
 // What FP32 cannot do is take the reference's DECISIONS (state codes, interval order, branch cuts of
 // atan2, the elbow-projection predicate) when a pose sits within rounding distance of one of them, and
 // it cannot resolve the exact-zero special cases.  The fast / literal duality of the FP64 solver is
 // therefore extended by one level: every decision of the FP32 solve tests its margin against an error
 // band of a few FP32 ulps of the quantities involved and ORs "too close to call" into an `esc` flag;
-// a flagged pose is solved again by the FP64 solver (out of line, from the same FP32 inputs widened to
-// double) and its results are narrowed to float.  States and flags of the FP32 path are thereby the
-// FP64 path's states on the same inputs; joints and intervals carry FP32 rounding (a few 1e-6 rad
-// typically), amplified where the geometry itself is ill-conditioned (elbow circle of vanishing radius,
-// a point on a joint axis) -- those poses are also escalated when the conditioning number is visible
-// in the fast solve (the squared length under an atan2, the circle radius).
+// a flagged pose is solved again by the FP64 solver (a second kernel over the compacted list of flagged
+// poses, from the same FP32 inputs widened to double) and its results are narrowed to float.  States and
+// flags of the FP32 path are thereby the FP64 path's states on the same inputs; joints and intervals
+// carry FP32 rounding (5e-7 rad median, 1.6e-5 at the 99.9th percentile), amplified where the geometry
+// itself is ill-conditioned (a point on a joint axis, interval ends of a tiny elbow circle) -- those poses
+// are also escalated when the lever is visible in the fast solve (the squared length under an atan2,
+// (r rho sin alpha)^2 for the interval ends).  The same machinery decides the (voxel, orientation) pairs of
+// the workspace reachability map (reach_flag_mixed, K4).
 //
 // "sik" = src/reachy2_symbolic_ik/symbolic_ik.py, "utl" = .../utils.py (reference checkout).
 #pragma once
@@ -105,7 +111,6 @@ constexpr float kTwoPiF = 6.28318530717958647692f;
 // cover the accumulated FP32 rounding of the straight-line solve (a few 1e-7 on O(1) quantities) with a
 // margin of ~10x; the measured share of escalated poses is reported by the tests / bench.
 constexpr float kBandLen = 4e-6f;      // lengths and coordinates [m]
-constexpr float kBandAng = 2e-5f;      // angle comparisons [rad]
 constexpr float kBandSin = 1e-5f;      // |sin| below which an angle sits on the +-pi / 0 branch cut
 constexpr float kMinH2 = 4e-6f;        // squared length under an atan2 below which the angle is ill-conditioned (2 mm)
 constexpr float kMinRadius2 = 1e-9f;   // elbow-circle radius^2 below which 1 / r is not trusted (0.03 mm)
