@@ -1,12 +1,17 @@
 // r2ik_kernels.cu -- sm_100a kernels and the C ABI of libr2ik.so (include/r2ik.h).
 //
-//   K1 k_symik_solve     one thread / pose   : is_reachable + get_joints
-//   K1b k_symik_no_limits, k_elbow_positions : is_reachable_no_limits, get_elbow_position
-//   K2 k_ctl_discrete    one lane / pose, warp-cooperative K-sample elbow search
-//   K3 k_ctl_continuous  one thread / trajectory, sequential over waypoints
-//   K4 k_reach_map       one thread / voxel, orientation table staged in shared memory
+//   K1     k_symik_solve                        one thread / pose: is_reachable + get_joints (FP64)
+//   K1-f32 k_symik_solve_f32 + k_symik_escalated_f32   the FP32 fast path; undecidable poses re-solved in FP64
+//   K1b    k_symik_no_limits, k_elbow_positions    is_reachable_no_limits, get_elbow_position
+//   K2     k_ctl_discrete                       one lane / pose, analytic arg-min over the K elbow samples
+//          k_ctl_discrete_scan                  the exhaustive warp-cooperative scan of the K samples (cross-check)
+//   K3     k_cont_targets / k_cont_thetas / k_cont_raw_joints / k_cont_finish_lanes (+ k_cont_finish_direct)
+//                                               continuous mode cut at its data dependences: per-waypoint kernels
+//                                               and per-trajectory scans;  k_ctl_continuous = the one-kernel form
+//   K4     k_reach_map                          one thread / voxel, mixed-precision flag with FP64 escalation
+//          k_reach_map_f64                      every pair by the FP64 flag solve (cross-check)
 //
-// The work is scalar FP64 (sincos / atan2 / sqrt / FMA chains): it runs on the FP64 pipe, not on
+// The work is scalar FP64 / FP32 (sincos / atan2 / sqrt / FMA chains): it runs on the FP64 and FP32 pipes, not on
 // tensor cores; HBM traffic is a few hundred bytes per pose.  There is no host implementation
 // of any entry point in this library.
 #include <cuda_runtime.h>

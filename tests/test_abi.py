@@ -75,3 +75,21 @@ def test_sass_is_sm100a_fp64():
     assert "arch = sm_100a" in out
     k1 = out.split("k_symik_solveILi1E")[1].split("Function :")[0]
     assert k1.count("DFMA") > 500
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's contract: stdout carries exactly one JSON line.  The reference arm (C oracle on the host cores)
+    needs no GPU, so it is checked here."""
+    import json
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ik_poses_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
