@@ -330,6 +330,13 @@ class SymbolicIK:
 
         return workspace.reach_map(self, n=n, orientations_euler=orientations_euler, n_orientations=n_orientations, **kw)
 
+    def task_space_test(self, arm_length: float = 0.5, precision: str = "fp64", **steps):
+        """Batched form of the reference's ``task_space_test`` sweep (``src/benchmark/ik_comparison.py:137-181``):
+        returns (goal_poses, BatchResult) for the position x Euler-angle grid (see ``workspace.task_space_grid``)."""
+        from . import workspace
+
+        return workspace.task_space_test(self, arm_length=arm_length, precision=precision, **steps)
+
     # ------------------------------------------------------------------ scalar API (reference signatures)
     @staticmethod
     def _pose6(goal_pose) -> np.ndarray:

@@ -89,3 +89,50 @@ def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int
             return out
 
         return sharded_sum(launch, n_ori, dist, group)
+
+
+def task_space_grid(shoulder_position, arm_length: float = 0.5, x_step: float = 0.15, y_step: float = 0.15,
+                    z_step: float = 0.15, roll_step: int = 45, pitch_step: int = 45, yaw_step: int = 45) -> np.ndarray:
+    """The goal poses of the reference's ``task_space_test`` (``src/benchmark/ik_comparison.py:137-170``): a position
+    grid over the cube shoulder +- arm_length, kept where it lies inside the sphere of that radius and in front of the
+    robot (x >= 0), crossed with an Euler-angle grid in degrees.  Returns (N, 2, 3) ``[[x, y, z], [roll, pitch, yaw]]``
+    in the reference's loop order."""
+    s = np.asarray(shoulder_position, dtype=np.float64)
+    xs = np.arange(s[0] - arm_length, s[0] + arm_length + x_step, x_step)
+    ys = np.arange(s[1] - arm_length, s[1] + arm_length + y_step, y_step)
+    zs = np.arange(s[2] - arm_length, s[2] + arm_length + z_step, z_step)
+    P = np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), axis=-1).reshape(-1, 3)
+    keep = ~((np.linalg.norm(P - s, axis=1) > arm_length) | (P[:, 0] < 0))
+    P = P[keep]
+    ang = [np.radians(np.arange(0, 360, st)) for st in (roll_step, pitch_step, yaw_step)]
+    E = np.stack(np.meshgrid(*ang, indexing="ij"), axis=-1).reshape(-1, 3)
+    out = np.empty((len(P), len(E), 2, 3))
+    out[:, :, 0, :] = P[:, None, :]
+    out[:, :, 1, :] = E[None, :, :]
+    return out.reshape(-1, 2, 3)
+
+
+def task_space_test(solver, arm_length: float = 0.5, precision: str = "fp64", **steps):
+    """Batched ``task_space_test`` (``ik_comparison.py:137-181``): ``is_reachable`` on every pose of ``task_space_grid``
+    in one launch.  Returns (goal_poses (N,2,3), BatchResult); ``int(result.reachable.sum())`` is the reference's
+    "reachable poses" count."""
+    poses = task_space_grid(solver.shoulder_position, arm_length, **steps)
+    return poses, solver.is_reachable_batch(poses, want_joints=False, precision=precision)
+
+
+def save_reach_map(path: str, counts, origin, step, orientations_euler, arm: str = "") -> None:
+    """Write a reachability count volume with its grid (cell centres = origin + index * step) and orientation set to a
+    compressed ``.npz``."""
+    c = counts.cpu().numpy() if hasattr(counts, "cpu") else np.asarray(counts)
+    np.savez_compressed(path, counts=c.astype(np.uint32), origin=np.asarray(origin, dtype=np.float64),
+                        step=np.asarray(step, dtype=np.float64), orientations_euler=np.asarray(orientations_euler, dtype=np.float64),
+                        arm=np.array(arm))
+
+
+def load_reach_map(path: str) -> dict:
+    """Read a volume written by ``save_reach_map``; adds ``fraction`` = counts / number of orientations."""
+    with np.load(path, allow_pickle=False) as z:
+        d = {k: z[k] for k in z.files}
+    d["arm"] = str(d["arm"])
+    d["fraction"] = d["counts"].astype(np.float64) / max(len(d["orientations_euler"]), 1)
+    return d

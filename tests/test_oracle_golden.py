@@ -197,3 +197,26 @@ def test_reference_example_matrices(oracle, arm):
     assert np.array_equal(cs, g[f"{arm}_con_state"]) and np.array_equal(cr, g[f"{arm}_con_reachable"])
     np.testing.assert_allclose(cj, g[f"{arm}_con_joints"], atol=1e-9)
     assert np.array_equal(st["emergency_stop"].astype(bool), g[f"{arm}_con_emergency"])
+
+
+def test_task_space_sweep(oracle, tmp_path):
+    """The reference's task_space_test sweep (src/benchmark/ik_comparison.py:137-181): the grid builder reproduces its
+    37 376 goal poses, and the oracle reproduces the reference's flags / states on them (tests/golden/task_space.npz)."""
+    from reachy2_symbolic_ik_b200 import workspace
+
+    g = load("task_space.npz")
+    poses = workspace.task_space_grid([0.0, -0.2, 0.0])
+    assert len(poses) == int(g["n_poses"]) == 37376
+    # spot-check the loop order of the reference: position-major, then roll, pitch, yaw
+    np.testing.assert_allclose(poses[0, 1], [0, 0, 0]); np.testing.assert_allclose(poses[1, 1], [0, 0, np.radians(45)])
+    np.testing.assert_allclose(poses[8, 1], [0, np.radians(45), 0]); assert np.array_equal(poses[0, 0], poses[511, 0])
+    want = np.unpackbits(g["reachable_packed"])[: len(poses)].astype(bool)
+    reach, itv, state, joints, elbow = oracle.symik_batch(oracle.arm_config("r_arm"), poses)
+    assert np.array_equal(state, g["state"]) and np.array_equal(reach, want)
+    assert int(reach.sum()) == int(g["reachable_count"]) == 13492
+    # export / import of a count volume
+    counts = np.arange(24, dtype=np.uint32).reshape(2, 3, 4)
+    f = str(tmp_path / "map.npz")
+    workspace.save_reach_map(f, counts, [0.1, 0.2, 0.3], [0.01] * 3, np.zeros((8, 3)), arm="r_arm")
+    d = workspace.load_reach_map(f)
+    assert np.array_equal(d["counts"], counts) and d["arm"] == "r_arm" and d["fraction"].max() == 23 / 8
