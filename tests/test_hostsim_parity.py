@@ -420,3 +420,23 @@ def test_task_space_sweep(hs):
     r32, i32, s32, j32, e32, esc = hs_symik_f32(hs, cfg_for("r_arm"), poses.astype(np.float32))
     assert int((s32 != g["state"]).sum()) <= 40       # the FP32 path sees the float32-rounded grid
     assert 0.02 < esc.mean() < 0.3                    # axis-aligned orientations sit on the special cases: many re-solves
+
+
+@pytest.mark.parametrize("kind", ["float32_rounded", "five_digits"])
+def test_non_orthonormal_rotation_blocks(hs, oracle, kind):
+    """4x4 goals whose rotation block is not orthonormal (float32-rounded, or printed with 5 digits like the matrices in
+    the reference's examples): scipy replaces the block by its polar factor; the kernel source uses that factor directly
+    outside the gimbal band (no quaternion / as_euler / from_euler detour).  FP64 path against the oracle, 1e-9 rad."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    M = fk.sample_fk_poses(20000, "r_arm", seed=5)
+    X = M.astype(np.float32).astype(np.float64) if kind == "float32_rounded" else np.round(M, 5)
+    ocfg = oracle.arm_config("r_arm")
+    ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(X.shape))[:4], X.reshape(len(X), -1), n_trials=2)
+    want = oracle.symik_batch(ocfg, X)
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg_for("r_arm"), X)
+    rep = Report(f"hostsim non-orthonormal {kind}", len(X), ill)
+    rep.exact("state", state, want[2])
+    rep.close("interval", itv, want[1])
+    rep.close("joints", joints, want[3])
+    rep.check(max_ill_fraction=0.03)   # FK-sampled poses reach down to a straight arm: ~1.7 % move by > 1e-10 under 3e-13
