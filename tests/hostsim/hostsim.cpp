@@ -116,8 +116,24 @@ void hs_ctl_discrete_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, c
     bool ok = st == R2IK_STATE_REACHABLE;
     double theta = 0.0;
     if (ok) {
-      ok = best_discrete_theta(A, S, rc.i0, rc.i1, par->nb_search_points, par->preferred_theta, theta);
-      if (!ok) st = R2IK_STATE_LIMITED_BY_SHOULDER;
+      // mirrors k_ctl_discrete: preferred-theta shortcut, else the analytic arg-min over the K samples (scan fallback)
+      if (preferred_theta_works(A, S, rc.i0, rc.i1, par->preferred_theta)) {
+        theta = par->preferred_theta;
+      } else {
+        SearchPlan plan;
+        plan.preferred_theta = par->preferred_theta;
+        double start, stop;
+        search_range(rc.i0, rc.i1, start, stop);
+        plan.L = make_linspace(start, stop, par->nb_search_points);
+        plan.T = make_elbow_test(A, S);
+        double best;
+        int best_k;
+        if (!search_analytic(plan, par->nb_search_points, best, best_k))
+          search_strided(plan, par->nb_search_points, 0, 1, best, best_k);
+        ok = best < INFINITY;
+        if (ok) theta = linspace_value(plan.L, best_k);
+        else st = R2IK_STATE_LIMITED_BY_SHOULDER;
+      }
     }
     emg[i] = (uint8_t)discrete_finish(A, *par, S, ok, theta, prev, cur, joints + 7 * i);
     reach[i] = ok; state[i] = (uint8_t)st;
