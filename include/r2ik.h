@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define R2IK_ABI_VERSION 1
+#define R2IK_ABI_VERSION 2 /* 2: + symik_solve_f32, ctl_discrete_scan, reach_map_f64, ffma_probe */
 
 /* argument errors */
 #define R2IK_ERR_NULL 1
