@@ -123,7 +123,7 @@ def _pyref_worker(args):
         if kind == "symik":
             ik = SymbolicIK(arm=arm)
             for M in poses:
-                goal = [M[:3, 3], get_euler_from_homogeneous_matrix(M)]
+                goal = np.array(get_euler_from_homogeneous_matrix(M))  # (position, euler xyz), the reference's goal_pose
                 ok, itv, f, _ = ik.is_reachable(goal)
                 if ok:
                     f(itv[0])
@@ -656,6 +656,18 @@ def run_reference(args, wl):
                 "its algorithm (oracle/, pinned to the reference's outputs by tests/golden) on all host threads -- a much "
                 "stronger CPU baseline than the reference itself.",
     }
+    # the unmodified Python reference itself (baseline/_ref), on a bounded sample, beside the port
+    pr = None
+    try:
+        if isinstance(wl, Symik):
+            from reachy2_symbolic_ik_b200 import fk
+
+            m = 400 * (os.cpu_count() or 1)
+            pr = python_reference_baseline("symik", "r_arm", fk.sample_fk_poses(m, "r_arm", seed=wl.SEEDS["r_arm"]), m)
+    except Exception as e:  # the installed reference is optional
+        pr = {"unavailable": repr(e)}
+    if pr is not None:
+        line["cpu_baseline"]["python_reference"] = pr
     emit(line)
     return 0
 
