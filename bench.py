@@ -652,7 +652,7 @@ def run_reference(args, wl):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"per step: {sample}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python (NumPy/SciPy, single-threaded, ~590 poses/s/core); this arm times the C port of "
+        "note": "the reference is pure Python (NumPy/SciPy, single-threaded, ~1e3 poses/s/core, reported as cpu_baseline.python_reference); this arm times the C port of "
                 "its algorithm (oracle/, pinned to the reference's outputs by tests/golden) on all host threads -- a much "
                 "stronger CPU baseline than the reference itself.",
     }
