@@ -340,6 +340,78 @@ def gen_ctl_continuous(T_sin=6, W=300):
     ref_control.time = time
 
 
+OVERRIDE_VARIANTS = {                      # per-call keyword overrides of symbolic_inverse_kinematics (control_ik.py:162-172)
+    "dth_big": dict(d_theta_max=0.05),
+    "dth_small": dict(d_theta_max=0.002),
+    "pref": dict(preferred_theta=-np.pi / 2),
+    "low": dict(constrained_mode="low_elbow"),
+    "low_pref_dth": dict(constrained_mode="low_elbow", preferred_theta=-5 * np.pi / 6, d_theta_max=0.03),
+}
+UNFREEZE_AT = (120, 125)                   # waypoints at which the "unfreeze" control type is sent
+
+
+def gen_ctl_overrides(T=3, W=160, n_dis=600):
+    """Per-call overrides (d_theta_max, preferred_theta, constrained_mode) in continuous and discrete mode, and the
+    "unfreeze" control type after an emergency latch (control_ik.py:198-212, :262)."""
+    ref_control.time = FakeTime()
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        side = 1.0 if arm == "r_arm" else -1.0
+        Ms, q = fk.sinusoidal_trajectories(T, W, arm, seed=90 + seed)
+        # a trajectory that leaves the workspace and comes back: the unreachable branch uses the per-call preferred
+        # theta (control_ik.py:373-379), the reachable branch the constructor's (:348)
+        s = np.linspace(0, 1, W)
+        Mo = np.tile(np.eye(4), (W, 1, 1))
+        Mo[:, :3, :3] = R.from_euler("xyz", [0.2 * side, -np.pi / 2 + 0.1, 0.3 * side]).as_matrix()
+        Mo[:, 0, 3] = 0.35 + 0.45 * np.sin(np.pi * s) ** 2
+        Mo[:, 1, 3] = -0.25 * side + 0.1 * side * np.sin(2 * np.pi * s)
+        Mo[:, 2, 3] = -0.25 + 0.15 * np.cos(2 * np.pi * s)
+        trajs = np.concatenate([Ms, Mo[None]])
+        Tn = len(trajs)
+        out = dict(META, M=trajs, variants=np.array(list(OVERRIDE_VARIANTS)))
+        for name, kw in OVERRIDE_VARIANTS.items():
+            J = np.zeros((Tn, W, 7)); F = np.zeros((Tn, W), bool); S = np.zeros((Tn, W), np.uint8)
+            E = np.zeros(Tn, bool); TH = np.zeros(Tn)
+            for t in range(Tn):
+                ctl = new_control()
+                with _Quiet():
+                    for w in range(W):
+                        j, ok, st = ctl.symbolic_inverse_kinematics(arm, trajs[t, w], "continuous", **kw)
+                        J[t, w], F[t, w], S[t, w] = j, ok, state_code(st)
+                E[t], TH[t] = ctl.emergency_stop, ctl.previous_theta[arm]
+            out.update({f"con_{name}_joints": J, f"con_{name}_reachable": F, f"con_{name}_state": S,
+                        f"con_{name}_emergency": E, f"con_{name}_final_theta": TH})
+            print(arm, "overrides continuous", name, "reachable", F.mean(axis=1), "emergency", E)
+        # discrete mode with a per-call preferred theta
+        Md = np.concatenate([fk.sample_fk_poses(n_dis - 200, arm, seed=94 + seed, min_x=0.0),
+                             fk.sample_task_space_poses(200, arm, seed=96 + seed)])
+        for name, kw in (("pref", dict(preferred_theta=-np.pi / 3)),
+                         ("low_pref", dict(preferred_theta=-np.pi / 4, constrained_mode="low_elbow"))):
+            ctl = new_control()
+            J = np.zeros((n_dis, 7)); F = np.zeros(n_dis, bool); S = np.zeros(n_dis, np.uint8)
+            with _Quiet():
+                for i in range(n_dis):
+                    j, ok, st = ctl.symbolic_inverse_kinematics(arm, Md[i], "discrete", **kw)
+                    J[i], F[i], S[i] = j, ok, state_code(st)
+            assert not ctl.emergency_stop
+            out.update({f"dis_{name}_joints": J, f"dis_{name}_reachable": F, f"dis_{name}_state": S})
+            print(arm, "overrides discrete", name, "reachable", F.mean())
+        out["dis_M"] = Md
+        # emergency latch, then "unfreeze" (twice: the second one while not latched)
+        Mj = Ms[0].copy()
+        Mj[W // 2:, :3, :3] = Mj[W // 2:, :3, :3] @ np.diag([-1.0, -1.0, 1.0])   # half a turn about the tool axis
+        ctl = new_control()
+        J = np.zeros((W, 7)); F = np.zeros(W, bool); S = np.zeros(W, np.uint8); EM = np.zeros(W, bool)
+        with _Quiet():
+            for w in range(W):
+                j, ok, st = ctl.symbolic_inverse_kinematics(arm, Mj[w], "unfreeze" if w in UNFREEZE_AT else "continuous")
+                J[w], F[w], S[w], EM[w] = j, ok, state_code(st), ctl.emergency_stop
+        out.update(unf_M=Mj, unf_joints=J, unf_reachable=F, unf_state=S, unf_emergency_after=EM,
+                   unf_at=np.array(UNFREEZE_AT), unf_final_theta=ctl.previous_theta[arm])
+        print(arm, "unfreeze: latched waypoints", int(EM.sum()), "first", int(np.argmax(EM)), "states", np.bincount(S, minlength=9))
+        np.savez_compressed(os.path.join(HERE, f"ctl_overrides_{arm}.npz"), **out)
+    ref_control.time = time
+
+
 def example_matrices():
     """4x4 goal matrices that appear verbatim in the reference's examples (truncated decimals: not orthonormal)."""
     M_r = np.array([[-0.34159004, -0.90910326, -0.23842717, 0.15009035], [0.92063745, -0.3746924, 0.10969179, -0.36832501],
@@ -437,7 +509,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -452,6 +524,8 @@ if __name__ == "__main__":
         gen_ctl_continuous()
     if "examples" in which:
         gen_ctl_examples()
+    if "overrides" in which:
+        gen_ctl_overrides()
     if "task_space" in which:
         gen_task_space()
     print(f"done in {time.time() - t0:.1f}s")

@@ -142,3 +142,38 @@ def check_f32(name, oracle, arm, P32, got, theta=None, max_ill=None):
     rep.check(max_ill_fraction=MAX_ILL_FRACTION_F32 if max_ill is None else max_ill)
     assert esc.mean() <= MAX_ESCALATED_FRACTION_F32, f"too many poses escalated to FP64: {esc.mean():.4f}"
     return rep
+
+
+# Per-call overrides of ControlIK.symbolic_inverse_kinematics pinned by tests/golden/ctl_overrides_*.npz
+# (gen_golden.py: OVERRIDE_VARIANTS); the names are the fixture's key infixes.
+OVERRIDE_VARIANTS = {
+    "dth_big": dict(d_theta_max=0.05),
+    "dth_small": dict(d_theta_max=0.002),
+    "pref": dict(preferred_theta=-np.pi / 2),
+    "low": dict(constrained_mode="low_elbow"),
+    "low_pref_dth": dict(constrained_mode="low_elbow", preferred_theta=-5 * np.pi / 6, d_theta_max=0.03),
+}
+OVERRIDE_DISCRETE = {
+    "pref": dict(preferred_theta=-np.pi / 3),
+    "low_pref": dict(preferred_theta=-np.pi / 4, constrained_mode="low_elbow"),
+}
+
+
+def run_with_unfreeze(run_segment, M: np.ndarray, unfreeze_at, states):
+    """The "unfreeze" control type (control_ik.py:198-205) in terms of the batched continuous entry: the trajectory
+    M (W,4,4) is cut at the waypoints that carry "unfreeze"; before each of those segments the controller state is
+    reset the way the reference resets it (emergency_stop = False, emergency_state = "", init = True) and the call
+    then proceeds like "continuous" (:262).  run_segment(M (1,w,4,4), states (1,)) -> joints, reachable, state, states."""
+    cuts = [0, *sorted(int(u) for u in unfreeze_at), len(M)]
+    J, F, S = [], [], []
+    for k, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+        if hi <= lo:
+            continue
+        if k > 0:
+            states = states.copy()
+            states["emergency_stop"] = 0
+            states["emergency_bits"] = 0
+            states["init"] = 1
+        j, f, s, states = run_segment(np.ascontiguousarray(M[None, lo:hi]), states)
+        J.append(np.asarray(j)[0]); F.append(np.asarray(f)[0]); S.append(np.asarray(s)[0])
+    return np.concatenate(J), np.concatenate(F).astype(bool), np.concatenate(S), states

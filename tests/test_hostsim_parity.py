@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from parity import REPO, Report, check_f32, ill_conditioned_mask, load
+from parity import (OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, REPO, Report, check_f32, ill_conditioned_mask, load,
+                    run_with_unfreeze)
 from reachy2_symbolic_ik_b200 import _abi
 
 HS_DIR = os.path.join(REPO, "tests", "hostsim")
@@ -189,6 +190,97 @@ def test_ctl_continuous(hs, oracle, arm, variant):
     np.testing.assert_array_equal(r2, reach)
     np.testing.assert_array_equal(s2, state)
     assert st2.tobytes() == st.tobytes()
+
+
+def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False):
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    T, W = M.shape[:2]
+    cj = np.empty((T, 7)); cp = np.empty((T, 4, 4))
+    cj[:] = oracle.DEFAULT_PREV_JOINTS[arm]
+    cp[:] = oracle.DEFAULT_CURRENT_POSE[arm]
+    if states is None:
+        states = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
+        states["init"] = 1
+    st = np.ascontiguousarray(states).copy()
+    joints = np.empty((T, W, 7)); reach = np.zeros((T, W), np.uint8); state = np.zeros((T, W), np.uint8)
+    if phased:
+        ws = np.empty((T, W))
+        hs.hs_ctl_continuous_phased_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
+                                          st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws))
+    else:
+        hs.hs_ctl_continuous_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
+                                   st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state))
+    return joints, reach.astype(bool), state, st
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(OVERRIDE_VARIANTS))
+def test_ctl_continuous_overrides(hs, oracle, arm, variant):
+    """Per-call d_theta_max / preferred_theta / constrained_mode (control_ik.py:162-172), serial and phased forms."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = cfg_for(arm, urdf_params(), -1.01)
+    par = ctl_params(oracle, arm, **OVERRIDE_VARIANTS[variant])
+    pre = f"con_{variant}_"
+    M = g["M"]
+    T, W = M.shape[:2]
+    joints, reach, state, st = hs_continuous(hs, oracle, cfg, par, arm, M)
+    for t in range(T):
+        rep = Report(f"hostsim ctl continuous override {variant} {arm} traj {t}", W)
+        rep.exact("reachable", reach[t], g[pre + "reachable"][t])
+        rep.exact("state", state[t], g[pre + "state"][t])
+        rep.close("joints", joints[t], g[pre + "joints"][t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+    j2, r2, s2, st2 = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
+    np.testing.assert_array_equal(j2, joints)
+    np.testing.assert_array_equal(r2, reach)
+    np.testing.assert_array_equal(s2, state)
+    assert st2.tobytes() == st.tobytes()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(OVERRIDE_DISCRETE))
+def test_ctl_discrete_overrides(hs, oracle, arm, variant):
+    g = load(f"ctl_overrides_{arm}.npz")
+    params = urdf_params()
+    M = np.ascontiguousarray(g["dis_M"])
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=-1.01)
+    opar = oracle.ControlParams(arm=arm, **OVERRIDE_DISCRETE[variant])
+    ill = ill_conditioned_mask(lambda p: oracle.ctl_discrete_batch(ocfg, opar, p.reshape(M.shape))[:3], M.reshape(len(M), -1))
+    cfg = cfg_for(arm, params, -1.01)
+    par = ctl_params(oracle, arm, **OVERRIDE_DISCRETE[variant])
+    n = len(M)
+    prev = np.array(oracle.DEFAULT_PREV_JOINTS[arm])
+    joints = np.empty((n, 7)); reach = np.zeros(n, np.uint8); state = np.zeros(n, np.uint8); emg = np.zeros(n, np.uint8)
+    hs.hs_ctl_discrete_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(n), dp(prev), dp(prev), dp(joints), u8(reach),
+                             u8(state), u8(emg))
+    rep = Report(f"hostsim ctl discrete override {variant} {arm}", n, ill)
+    rep.exact("reachable", reach.astype(bool), g[f"dis_{variant}_reachable"])
+    rep.exact("state", state, g[f"dis_{variant}_state"])
+    rep.close("joints", joints, g[f"dis_{variant}_joints"])
+    rep.check(max_ill_fraction=0.02)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("phased", [False, True])
+def test_ctl_unfreeze(hs, oracle, arm, phased):
+    """Emergency latch, frozen returns, then control_type="unfreeze" (control_ik.py:198-212) on the kernel source."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = cfg_for(arm, urdf_params(), -1.01)
+    par = ctl_params(oracle, arm)
+    M = g["unf_M"]
+    st0 = np.zeros(1, dtype=_abi.TRAJ_STATE_DTYPE)
+    st0["init"] = 1
+    seg = lambda m, st: hs_continuous(hs, oracle, cfg, par, arm, m, states=st, phased=phased)  # noqa: E731
+    joints, reach, state, st = run_with_unfreeze(seg, M, g["unf_at"], st0)
+    rep = Report(f"hostsim ctl unfreeze {arm} phased={phased}", len(M))
+    rep.exact("reachable", reach, g["unf_reachable"])
+    rep.exact("state", state, g["unf_state"])
+    rep.close("joints", joints, g["unf_joints"])
+    rep.check()
+    assert bool(st["emergency_stop"][0]) == bool(g["unf_emergency_after"][-1])
+    np.testing.assert_allclose(st["previous_theta"][0], g["unf_final_theta"], atol=1e-9)
 
 
 def test_limit_orbita3d_wrist_fast_route(hs):

@@ -8,7 +8,7 @@ reference's own CI test (tests/test_ik.py:12-79) only pins flags and shapes on 6
 import numpy as np
 import pytest
 
-from parity import Report, ill_conditioned_mask, load
+from parity import OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, Report, ill_conditioned_mask, load, run_with_unfreeze
 
 ARMS = ("r_arm", "l_arm")
 
@@ -144,6 +144,64 @@ def test_ctl_continuous(oracle, arm, variant):
         rep.check()
     np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
     np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(OVERRIDE_VARIANTS))
+def test_ctl_continuous_overrides(oracle, arm, variant):
+    """Per-call d_theta_max / preferred_theta / constrained_mode (control_ik.py:162-172) in continuous mode."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = _urdf_cfg(oracle, load("symik_urdf.npz"), arm, singularity_offset=-1.01)
+    par = oracle.ControlParams(arm=arm, **OVERRIDE_VARIANTS[variant])
+    pre = f"con_{variant}_"
+    M = g["M"]
+    T, W = M.shape[:2]
+    joints, reach, state, st = oracle.ctl_continuous_batch(cfg, par, M)
+    for t in range(T):
+        rep = Report(f"oracle ctl continuous override {variant} {arm} traj {t}", W)
+        rep.exact("reachable", reach[t], g[pre + "reachable"][t])
+        rep.exact("state", state[t], g[pre + "state"][t])
+        rep.close("joints", joints[t], g[pre + "joints"][t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(OVERRIDE_DISCRETE))
+def test_ctl_discrete_overrides(oracle, arm, variant):
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = _urdf_cfg(oracle, load("symik_urdf.npz"), arm, singularity_offset=-1.01)
+    par = oracle.ControlParams(arm=arm, **OVERRIDE_DISCRETE[variant])
+    M = g["dis_M"]
+    run = lambda p: oracle.ctl_discrete_batch(cfg, par, p.reshape(M.shape))[:3]  # noqa: E731
+    ill = ill_conditioned_mask(run, M.reshape(len(M), -1))
+    joints, reach, state, emg = oracle.ctl_discrete_batch(cfg, par, M)
+    rep = Report(f"oracle ctl discrete override {variant} {arm}", len(M), ill)
+    rep.exact("reachable", reach, g[f"dis_{variant}_reachable"])
+    rep.exact("state", state, g[f"dis_{variant}_state"])
+    rep.close("joints", joints, g[f"dis_{variant}_joints"])
+    assert not emg.any()
+    rep.check(max_ill_fraction=0.02)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_ctl_unfreeze(oracle, arm):
+    """Emergency latch (continuity violation), the frozen returns, then control_type="unfreeze" (control_ik.py:198-212)."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = _urdf_cfg(oracle, load("symik_urdf.npz"), arm, singularity_offset=-1.01)
+    par = oracle.ControlParams(arm=arm)
+    M = g["unf_M"]
+    seg = lambda m, st: oracle.ctl_continuous_batch(cfg, par, m, states=st)  # noqa: E731
+    joints, reach, state, st = run_with_unfreeze(seg, M, g["unf_at"], oracle.new_ctl_states(1))
+    assert g["unf_emergency_after"].sum() > 10 and (g["unf_state"] == 8).sum() > 10
+    rep = Report(f"oracle ctl unfreeze {arm}", len(M))
+    rep.exact("reachable", reach, g["unf_reachable"])
+    rep.exact("state", state, g["unf_state"])
+    rep.close("joints", joints, g["unf_joints"])
+    rep.check()
+    assert bool(st["emergency_stop"][0]) == bool(g["unf_emergency_after"][-1])
+    np.testing.assert_allclose(st["previous_theta"][0], g["unf_final_theta"], atol=1e-9)
 
 
 def test_helpers(oracle):
