@@ -256,8 +256,11 @@ R2IK_HD ReachF is_reachable_f(const ArmConst &A64, const ArmConstF &A, float pxf
       R2IK_ESC(6, fabsf(pxp - A.backward_limit) < kBandLen);
       pre = R2IK_STATE_POSE_OUT_OF_REACH;
       if (pxp < A.backward_limit) pre = R2IK_STATE_BACKWARD_POSE;
+    } else if (p[0] < A64.backward_limit) {
+      // inside the sphere the goal itself is tested (sik:303); outside, only its projection is (a backward_limit
+      // behind the shoulder can admit the projection of a goal that lies behind it)
+      pre = R2IK_STATE_BACKWARD_POSE;
     }
-    if (p[0] < A64.backward_limit) pre = R2IK_STATE_BACKWARD_POSE;
     if (pre >= 0) { out.state = pre; return out; }
   }
   // --- sik:418-425 wrist centre, sik:146-153 kept in front of the torso plane

@@ -175,6 +175,42 @@ def gen_symik_random(n_fk=3000, n_task=3000):
         print(arm, "symik_random: reachable", flag.mean(), "states", np.bincount(state, minlength=8))
 
 
+CTOR_VARIANTS = {                          # non-default SymbolicIK constructor arguments (symbolic_ik.py:26-37)
+    "limits": dict(elbow_limit=110, wrist_limit=np.float64(30.0)),
+    "margins": dict(backward_limit=0.10, projection_margin=1e-6, normal_vector_margin=1e-3),
+    "singularity": dict(singularity_offset=0.08, singularity_limit_coeff=0.7),
+    "wide": dict(elbow_limit=140, wrist_limit=np.float64(55.0), backward_limit=-0.05, singularity_offset=-0.02,
+                 singularity_limit_coeff=1.4),
+}
+
+
+def gen_symik_ctor(n_fk=900, n_task=900):
+    """SymbolicIK with non-default limits / margins / singularity plane: flags, states, intervals, joints at
+    theta_interval[0] and at a second theta inside the interval."""
+    out = dict(META, variants=np.array(list(CTOR_VARIANTS)))
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        M = np.concatenate([fk.sample_fk_poses(n_fk, arm, seed=110 + seed, min_x=0.0),
+                            fk.sample_task_space_poses(n_task, arm, seed=120 + seed)])
+        gp = np.array([euler_pose_from_matrix(m) for m in M])
+        out.update({f"{arm}_M": M, f"{arm}_goal_pose": gp})
+        for name, kw in CTOR_VARIANTS.items():
+            with _Quiet():
+                ik = SymbolicIK(arm=arm, **kw)
+            flag, state, interval, joints, elbow = run_symik(ik, gp)
+            rng = np.random.default_rng(130 + seed)
+            u = rng.uniform(0, 1, len(M))
+            width = np.where(interval[:, 0] <= interval[:, 1], interval[:, 1] - interval[:, 0],
+                             interval[:, 1] + 2 * np.pi - interval[:, 0])
+            theta2 = np.where(flag, interval[:, 0] + u * width, 0.0)
+            _, _, _, joints2, elbow2 = run_symik(ik, gp, theta2)
+            pre = f"{arm}_{name}_"
+            out.update({pre + "reachable": flag, pre + "state": state, pre + "interval": interval, pre + "joints": joints,
+                        pre + "elbow": elbow, pre + "theta2": theta2, pre + "joints_theta2": joints2,
+                        pre + "elbow_theta2": elbow2})
+            print(arm, "symik_ctor", name, "reachable", flag.mean(), "states", np.bincount(state, minlength=8))
+    np.savez_compressed(os.path.join(HERE, "symik_ctor.npz"), **out)
+
+
 def urdf_params():
     with open(URDF_PATH) as f:
         urdf = f.read()
@@ -509,7 +545,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -526,6 +562,8 @@ if __name__ == "__main__":
         gen_ctl_examples()
     if "overrides" in which:
         gen_ctl_overrides()
+    if "ctor" in which:
+        gen_symik_ctor()
     if "task_space" in which:
         gen_task_space()
     print(f"done in {time.time() - t0:.1f}s")

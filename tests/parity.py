@@ -120,9 +120,9 @@ class Report:
         assert self.ill.mean() <= max_ill_fraction, f"too many ill-conditioned poses ({self.ill.mean():.4f})\n{msg}"
 
 
-def check_f32(name, oracle, arm, P32, got, theta=None, max_ill=None):
+def check_f32(name, oracle, arm, P32, got, theta=None, max_ill=None, ocfg=None):
     """got = (reach, itv, state, joints, elbow, escalated) of an FP32 solve of the float32 poses P32."""
-    ocfg = oracle.arm_config(arm)
+    ocfg = oracle.arm_config(arm) if ocfg is None else ocfg
     P64 = P32.astype(np.float64)
     th64 = None if theta is None else np.asarray(theta, dtype=np.float32).astype(np.float64)
     run = lambda p: oracle.symik_batch(ocfg, p.reshape(P64.shape), th64)[:4]  # noqa: E731
@@ -177,3 +177,13 @@ def run_with_unfreeze(run_segment, M: np.ndarray, unfreeze_at, states):
         j, f, s, states = run_segment(np.ascontiguousarray(M[None, lo:hi]), states)
         J.append(np.asarray(j)[0]); F.append(np.asarray(f)[0]); S.append(np.asarray(s)[0])
     return np.concatenate(J), np.concatenate(F).astype(bool), np.concatenate(S), states
+
+
+# Non-default SymbolicIK constructor arguments pinned by tests/golden/symik_ctor.npz (gen_golden.py: CTOR_VARIANTS)
+CTOR_VARIANTS = {
+    "limits": dict(elbow_limit=110, wrist_limit=30.0),
+    "margins": dict(backward_limit=0.10, projection_margin=1e-6, normal_vector_margin=1e-3),
+    "singularity": dict(singularity_offset=0.08, singularity_limit_coeff=0.7),
+    "wide": dict(elbow_limit=140, wrist_limit=55.0, backward_limit=-0.05, singularity_offset=-0.02,
+                 singularity_limit_coeff=1.4),
+}

@@ -5,7 +5,7 @@ The same fixtures pin the oracle (test_oracle_golden.py) and the kernel source o
 import numpy as np
 import pytest
 
-from parity import OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, Report, ill_conditioned_mask, load, run_with_unfreeze
+from parity import CTOR_VARIANTS, OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, Report, ill_conditioned_mask, load, run_with_unfreeze
 from reachy2_symbolic_ik_b200 import _abi
 
 pytestmark = pytest.mark.gpu
@@ -115,3 +115,30 @@ def test_unfreeze_scalar_api(arm, monkeypatch):
         assert c.emergency_stop == bool(g["unf_emergency_after"][w]), w
         np.testing.assert_allclose(np.asarray(j, dtype=np.float64), g["unf_joints"][w], rtol=0, atol=1e-9, err_msg=f"waypoint {w}")
     np.testing.assert_allclose(c.previous_theta[arm], g["unf_final_theta"], atol=1e-9)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
+def test_constructor_variants(oracle, arm, variant):
+    """SymbolicIK with non-default elbow / wrist limits, margins and singularity plane (symbolic_ik.py:26-37):
+    tests/golden/symik_ctor.npz through the facade."""
+    from reachy2_symbolic_ik_b200 import SymbolicIK
+
+    g = load("symik_ctor.npz")
+    ik = SymbolicIK(arm=arm, **CTOR_VARIANTS[variant])
+    ocfg = oracle.arm_config(arm, **CTOR_VARIANTS[variant])
+    pre = f"{arm}_{variant}_"
+    for layout in ("euler", "mat4"):
+        P = g[f"{arm}_goal_pose"] if layout == "euler" else g[f"{arm}_M"]
+        ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+        res = ik.is_reachable_batch(P)
+        rep = Report(f"gpu ctor {variant} {arm} {layout}", len(P), ill)
+        rep.exact("reachable", res.reachable, g[pre + "reachable"])
+        rep.exact("state", res.state, g[pre + "state"])
+        rep.close("interval", res.theta_interval, g[pre + "interval"])
+        rep.close("joints@interval[0]", res.joints, g[pre + "joints"])
+        rep.close("elbow", res.elbow, g[pre + "elbow"])
+        res2 = ik.is_reachable_batch(P, theta=g[pre + "theta2"])
+        rep.close("joints@theta2", res2.joints, g[pre + "joints_theta2"])
+        rep.close("elbow@theta2", res2.elbow, g[pre + "elbow_theta2"])
+        rep.check(max_ill_fraction=0.03)

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from parity import (OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, REPO, Report, check_f32, ill_conditioned_mask, load,
+from parity import (CTOR_VARIANTS, OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, REPO, Report, check_f32, ill_conditioned_mask, load,
                     run_with_unfreeze)
 from reachy2_symbolic_ik_b200 import _abi
 
@@ -74,6 +74,35 @@ def test_symik_random(hs, oracle, arm, layout):
     rep.close("joints@theta2", j2, g["joints_theta2"])
     rep.close("elbow@theta2", e2, g["elbow_theta2"])
     rep.check()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
+def test_constructor_variants(hs, oracle, arm, variant):
+    """Non-default elbow / wrist limits, margins and singularity plane (symbolic_ik.py:26-37) on the kernel source."""
+    g = load("symik_ctor.npz")
+    kw = dict(elbow_limit=127, wrist_limit=42.5, projection_margin=1e-8, backward_limit=0.02, normal_vector_margin=1e-7,
+              singularity_offset=0.03, singularity_limit_coeff=1.0)
+    kw.update(CTOR_VARIANTS[variant])
+    cfg = _abi.make_arm_config(arm, _abi.DEFAULT_IK_PARAMETERS, kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
+                               kw["backward_limit"], kw["normal_vector_margin"], kw["singularity_offset"],
+                               kw["singularity_limit_coeff"])
+    ocfg = oracle.arm_config(arm, **CTOR_VARIANTS[variant])
+    pre = f"{arm}_{variant}_"
+    for layout in ("euler", "mat4"):
+        P = g[f"{arm}_goal_pose"] if layout == "euler" else g[f"{arm}_M"]
+        ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+        reach, itv, state, joints, elbow = hs_symik(hs, cfg, P)
+        rep = Report(f"hostsim ctor {variant} {arm} {layout}", len(P), ill)
+        rep.exact("reachable", reach, g[pre + "reachable"])
+        rep.exact("state", state, g[pre + "state"])
+        rep.close("interval", itv, g[pre + "interval"])
+        rep.close("joints", joints, g[pre + "joints"])
+        rep.close("elbow", elbow, g[pre + "elbow"])
+        _, _, _, j2, e2 = hs_symik(hs, cfg, P, g[pre + "theta2"])
+        rep.close("joints@theta2", j2, g[pre + "joints_theta2"])
+        rep.close("elbow@theta2", e2, g[pre + "elbow_theta2"])
+        rep.check(max_ill_fraction=0.03)
 
 
 @pytest.mark.parametrize("arm", ARMS)
@@ -351,6 +380,23 @@ def test_symik_f32_random(hs, oracle, arm, layout):
     check_f32(f"hostsim f32 random {arm} {layout}", oracle, arm, P32, hs_symik_f32(hs, cfg_for(arm), P32))
     th = g["theta2"].astype(np.float32)
     check_f32(f"hostsim f32 random {arm} {layout} @theta2", oracle, arm, P32, hs_symik_f32(hs, cfg_for(arm), P32, th), theta=th)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
+def test_symik_f32_constructor_variants(hs, oracle, arm, variant):
+    """The FP32 fast path under non-default limits / margins / singularity plane: its error bands and escalation
+    tests are written against the constants of the handle, not the default ones."""
+    g = load("symik_ctor.npz")
+    kw = dict(elbow_limit=127, wrist_limit=42.5, projection_margin=1e-8, backward_limit=0.02, normal_vector_margin=1e-7,
+              singularity_offset=0.03, singularity_limit_coeff=1.0)
+    kw.update(CTOR_VARIANTS[variant])
+    cfg = _abi.make_arm_config(arm, _abi.DEFAULT_IK_PARAMETERS, kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
+                               kw["backward_limit"], kw["normal_vector_margin"], kw["singularity_offset"],
+                               kw["singularity_limit_coeff"])
+    ocfg = oracle.arm_config(arm, **CTOR_VARIANTS[variant])
+    P32 = g[f"{arm}_M"].astype(np.float32)
+    check_f32(f"hostsim f32 ctor {variant} {arm}", oracle, arm, P32, hs_symik_f32(hs, cfg, P32), ocfg=ocfg, max_ill=0.04)
 
 
 @pytest.mark.parametrize("arm", ARMS)

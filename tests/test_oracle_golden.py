@@ -8,7 +8,7 @@ reference's own CI test (tests/test_ik.py:12-79) only pins flags and shapes on 6
 import numpy as np
 import pytest
 
-from parity import OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, Report, ill_conditioned_mask, load, run_with_unfreeze
+from parity import CTOR_VARIANTS, OVERRIDE_DISCRETE, OVERRIDE_VARIANTS, Report, ill_conditioned_mask, load, run_with_unfreeze
 
 ARMS = ("r_arm", "l_arm")
 
@@ -71,6 +71,30 @@ def test_random_poses(oracle, arm, layout):
     rep.close("joints@theta2", j2, g["joints_theta2"])
     rep.close("elbow@theta2", e2, g["elbow_theta2"])
     rep.check()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
+def test_constructor_variants(oracle, arm, variant):
+    """Non-default elbow / wrist limits, margins and singularity plane (symbolic_ik.py:26-37)."""
+    g = load("symik_ctor.npz")
+    cfg = oracle.arm_config(arm, **CTOR_VARIANTS[variant])
+    pre = f"{arm}_{variant}_"
+    for layout in ("euler", "mat4"):
+        P = g[f"{arm}_goal_pose"] if layout == "euler" else g[f"{arm}_M"]
+        run = lambda p: oracle.symik_batch(cfg, p.reshape(P.shape))[:4]  # noqa: E731
+        ill = ill_conditioned_mask(run, P.reshape(len(P), -1))
+        reach, itv, state, joints, elbow = oracle.symik_batch(cfg, P)
+        rep = Report(f"oracle ctor {variant} {arm} {layout}", len(P), ill)
+        rep.exact("reachable", reach, g[pre + "reachable"])
+        rep.exact("state", state, g[pre + "state"])
+        rep.close("interval", itv, g[pre + "interval"])
+        rep.close("joints@interval[0]", joints, g[pre + "joints"])
+        rep.close("elbow", elbow, g[pre + "elbow"])
+        _, _, _, j2, e2 = oracle.symik_batch(cfg, P, g[pre + "theta2"])
+        rep.close("joints@theta2", j2, g[pre + "joints_theta2"])
+        rep.close("elbow@theta2", e2, g[pre + "elbow_theta2"])
+        rep.check(max_ill_fraction=0.03)
 
 
 def _urdf_cfg(oracle, g, arm, singularity_offset=-1.01):
