@@ -175,7 +175,14 @@ def gen_symik_random(n_fk=3000, n_task=3000):
         print(arm, "symik_random: reachable", flag.mean(), "states", np.bincount(state, minlength=8))
 
 
+GEOMETRY_PARAMETERS = {                    # an arm that is not Reachy's: unequal links, offset tip, tilted shoulder
+    "r_shoulder_position": np.array([0.02, -0.22, 0.05]), "r_shoulder_orientation": [-12, 3, 8],
+    "r_upper_arm_size": np.float64(0.30), "r_forearm_size": np.float64(0.25), "r_tip_position": np.array([0.01, -0.005, 0.12]),
+    "l_shoulder_position": np.array([0.02, 0.22, 0.05]), "l_shoulder_orientation": [12, 3, -8],
+    "l_upper_arm_size": np.float64(0.30), "l_forearm_size": np.float64(0.25), "l_tip_position": np.array([0.01, 0.005, 0.12]),
+}
 CTOR_VARIANTS = {                          # non-default SymbolicIK constructor arguments (symbolic_ik.py:26-37)
+    "geometry": dict(ik_parameters=GEOMETRY_PARAMETERS),
     "limits": dict(elbow_limit=110, wrist_limit=np.float64(30.0)),
     "margins": dict(backward_limit=0.10, projection_margin=1e-6, normal_vector_margin=1e-3),
     "singularity": dict(singularity_offset=0.08, singularity_limit_coeff=0.7),

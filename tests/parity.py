@@ -180,7 +180,14 @@ def run_with_unfreeze(run_segment, M: np.ndarray, unfreeze_at, states):
 
 
 # Non-default SymbolicIK constructor arguments pinned by tests/golden/symik_ctor.npz (gen_golden.py: CTOR_VARIANTS)
+GEOMETRY_PARAMETERS = {                    # an arm that is not Reachy's: unequal links, offset tip, tilted shoulder
+    "r_shoulder_position": np.array([0.02, -0.22, 0.05]), "r_shoulder_orientation": [-12, 3, 8],
+    "r_upper_arm_size": np.float64(0.30), "r_forearm_size": np.float64(0.25), "r_tip_position": np.array([0.01, -0.005, 0.12]),
+    "l_shoulder_position": np.array([0.02, 0.22, 0.05]), "l_shoulder_orientation": [12, 3, -8],
+    "l_upper_arm_size": np.float64(0.30), "l_forearm_size": np.float64(0.25), "l_tip_position": np.array([0.01, 0.005, 0.12]),
+}
 CTOR_VARIANTS = {
+    "geometry": dict(ik_parameters=GEOMETRY_PARAMETERS),
     "limits": dict(elbow_limit=110, wrist_limit=30.0),
     "margins": dict(backward_limit=0.10, projection_margin=1e-6, normal_vector_margin=1e-3),
     "singularity": dict(singularity_offset=0.08, singularity_limit_coeff=0.7),

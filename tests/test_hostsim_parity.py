@@ -84,7 +84,7 @@ def test_constructor_variants(hs, oracle, arm, variant):
     kw = dict(elbow_limit=127, wrist_limit=42.5, projection_margin=1e-8, backward_limit=0.02, normal_vector_margin=1e-7,
               singularity_offset=0.03, singularity_limit_coeff=1.0)
     kw.update(CTOR_VARIANTS[variant])
-    cfg = _abi.make_arm_config(arm, _abi.DEFAULT_IK_PARAMETERS, kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
+    cfg = _abi.make_arm_config(arm, kw.get("ik_parameters", _abi.DEFAULT_IK_PARAMETERS), kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
                                kw["backward_limit"], kw["normal_vector_margin"], kw["singularity_offset"],
                                kw["singularity_limit_coeff"])
     ocfg = oracle.arm_config(arm, **CTOR_VARIANTS[variant])
@@ -391,7 +391,7 @@ def test_symik_f32_constructor_variants(hs, oracle, arm, variant):
     kw = dict(elbow_limit=127, wrist_limit=42.5, projection_margin=1e-8, backward_limit=0.02, normal_vector_margin=1e-7,
               singularity_offset=0.03, singularity_limit_coeff=1.0)
     kw.update(CTOR_VARIANTS[variant])
-    cfg = _abi.make_arm_config(arm, _abi.DEFAULT_IK_PARAMETERS, kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
+    cfg = _abi.make_arm_config(arm, kw.get("ik_parameters", _abi.DEFAULT_IK_PARAMETERS), kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
                                kw["backward_limit"], kw["normal_vector_margin"], kw["singularity_offset"],
                                kw["singularity_limit_coeff"])
     ocfg = oracle.arm_config(arm, **CTOR_VARIANTS[variant])
