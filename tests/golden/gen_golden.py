@@ -439,6 +439,27 @@ def gen_ctl_overrides(T=3, W=160, n_dis=600):
             out.update({f"dis_{name}_joints": J, f"dis_{name}_reachable": F, f"dis_{name}_state": S})
             print(arm, "overrides discrete", name, "reachable", F.mean())
         out["dis_M"] = Md
+        # discrete mode from a multi-turn previous solution (allow_multiturn + the +-6 pi clamp / emergency of
+        # multiturn_safety_check, utils.py:493-568) and explicit current_joints (returned for unreachable poses)
+        prevs = np.array([[4 * np.pi + 0.3, 0.2 * side, -5.9 * np.pi, -1.0, 0.1, 0.1, 5.95 * np.pi],
+                          [-5.97 * np.pi, -0.1 * side, 5.99 * np.pi, -0.5, -0.2, 0.3, -5.98 * np.pi]])
+        cur = np.array([0.4, 0.3 * side, -0.2, -1.2, 0.05, -0.05, 7.0])
+        nm = 300
+        J = np.zeros((2, nm, 7)); F = np.zeros((2, nm), bool); S = np.zeros((2, nm), np.uint8); B = np.zeros((2, nm), np.uint8)
+        for k in range(2):
+            ctl = new_control()
+            with _Quiet():
+                for i in range(nm):
+                    ctl.previous_sol[arm] = prevs[k].copy()
+                    ctl.emergency_stop, ctl.emergency_state = False, ""
+                    j, ok, st = ctl.symbolic_inverse_kinematics(arm, Md[i], "discrete", current_joints=cur.tolist())
+                    J[k, i], F[k, i], S[k, i] = j, ok, state_code(st)
+                    es = ctl.emergency_state
+                    B[k, i] = (1 * ("shoulder pitch" in es)) | (2 * ("elbow yaw" in es)) | (4 * ("wrist yaw" in es))
+                    assert ctl.emergency_stop == bool(B[k, i])
+        out.update(dis_mt_prev=prevs, dis_mt_current=cur, dis_mt_joints=J, dis_mt_reachable=F, dis_mt_state=S, dis_mt_bits=B)
+        print(arm, "overrides discrete multiturn: emergency bits", np.bincount(B.ravel(), minlength=8), "max |j|/pi",
+              np.abs(J).max() / np.pi)
         # emergency latch, then "unfreeze" (twice: the second one while not latched)
         Mj = Ms[0].copy()
         Mj[W // 2:, :3, :3] = Mj[W // 2:, :3, :3] @ np.diag([-1.0, -1.0, 1.0])   # half a turn about the tool axis

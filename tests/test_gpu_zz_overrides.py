@@ -118,6 +118,31 @@ def test_unfreeze_scalar_api(arm, monkeypatch):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_discrete_multiturn_previous_solution(ctl, oracle, arm):
+    """Discrete mode from a multi-turn previous solution (allow_multiturn, the +-6 pi clamp and the emergency bits of
+    multiturn_safety_check, utils.py:493-568) with explicit current_joints."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    ocfg = oracle.arm_config(arm, ik_parameters=urdf_params(), singularity_offset=-1.01)
+    opar = oracle.ControlParams(arm=arm)
+    n = g["dis_mt_joints"].shape[1]
+    M = np.ascontiguousarray(g["dis_M"][:n])
+    cur = g["dis_mt_current"]
+    for k in range(len(g["dis_mt_prev"])):
+        prev = g["dis_mt_prev"][k]
+        ill = ill_conditioned_mask(lambda p: oracle.ctl_discrete_batch(ocfg, opar, p.reshape(M.shape), prev_joints=prev,
+                                                                       current_joints=cur)[:3], M.reshape(len(M), -1))
+        for exhaustive in (False, True):
+            joints, reach, state, emg = ctl.symbolic_inverse_kinematics_batch(
+                arm, M, "discrete", previous_joints=prev, current_joints=cur, exhaustive=exhaustive)
+            rep = Report(f"gpu ctl discrete multiturn {arm} prev {k} exhaustive={exhaustive}", n, ill)
+            rep.exact("reachable", reach, g["dis_mt_reachable"][k])
+            rep.exact("state", state, g["dis_mt_state"][k])
+            rep.exact("emergency bits", emg, g["dis_mt_bits"][k])
+            rep.close("joints", joints, g["dis_mt_joints"][k])
+            rep.check(max_ill_fraction=0.03)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
 def test_constructor_variants(oracle, arm, variant):
     """SymbolicIK with non-default elbow / wrist limits, margins and singularity plane (symbolic_ik.py:26-37):

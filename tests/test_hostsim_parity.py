@@ -292,6 +292,34 @@ def test_ctl_discrete_overrides(hs, oracle, arm, variant):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_ctl_discrete_multiturn_previous_solution(hs, oracle, arm):
+    """Discrete mode from a multi-turn previous solution (allow_multiturn, +-6 pi clamp, emergency bits;
+    utils.py:493-568) and explicit current_joints, on the kernel source."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    params = urdf_params()
+    ocfg = oracle.arm_config(arm, ik_parameters=params, singularity_offset=-1.01)
+    opar = oracle.ControlParams(arm=arm)
+    cfg = cfg_for(arm, params, -1.01)
+    par = ctl_params(oracle, arm)
+    n = g["dis_mt_joints"].shape[1]
+    M = np.ascontiguousarray(g["dis_M"][:n])
+    cur = np.ascontiguousarray(g["dis_mt_current"])
+    for k in range(len(g["dis_mt_prev"])):
+        prev = np.ascontiguousarray(g["dis_mt_prev"][k])
+        ill = ill_conditioned_mask(lambda p: oracle.ctl_discrete_batch(ocfg, opar, p.reshape(M.shape), prev_joints=prev,
+                                                                       current_joints=cur)[:3], M.reshape(len(M), -1))
+        joints = np.empty((n, 7)); reach = np.zeros(n, np.uint8); state = np.zeros(n, np.uint8); emg = np.zeros(n, np.uint8)
+        hs.hs_ctl_discrete_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(n), dp(prev), dp(cur), dp(joints), u8(reach),
+                                 u8(state), u8(emg))
+        rep = Report(f"hostsim ctl discrete multiturn {arm} prev {k}", n, ill)
+        rep.exact("reachable", reach.astype(bool), g["dis_mt_reachable"][k])
+        rep.exact("state", state, g["dis_mt_state"][k])
+        rep.exact("emergency bits", emg, g["dis_mt_bits"][k])
+        rep.close("joints", joints, g["dis_mt_joints"][k])
+        rep.check(max_ill_fraction=0.03)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("phased", [False, True])
 def test_ctl_unfreeze(hs, oracle, arm, phased):
     """Emergency latch, frozen returns, then control_type="unfreeze" (control_ik.py:198-212) on the kernel source."""

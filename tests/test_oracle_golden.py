@@ -210,6 +210,29 @@ def test_ctl_discrete_overrides(oracle, arm, variant):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_ctl_discrete_multiturn_previous_solution(oracle, arm):
+    """Discrete mode from a multi-turn previous solution: allow_multiturn, the +-6 pi clamp and the emergency bits of
+    multiturn_safety_check (utils.py:493-568); explicit current_joints come back for unreachable poses."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = _urdf_cfg(oracle, load("symik_urdf.npz"), arm, singularity_offset=-1.01)
+    par = oracle.ControlParams(arm=arm)
+    n = g["dis_mt_joints"].shape[1]
+    M = g["dis_M"][:n]
+    assert (g["dis_mt_bits"] != 0).mean() > 0.3
+    for k in range(len(g["dis_mt_prev"])):
+        kw = dict(prev_joints=g["dis_mt_prev"][k], current_joints=g["dis_mt_current"])
+        run = lambda p: oracle.ctl_discrete_batch(cfg, par, p.reshape(M.shape), **kw)[:3]  # noqa: E731
+        ill = ill_conditioned_mask(run, M.reshape(len(M), -1))
+        joints, reach, state, emg = oracle.ctl_discrete_batch(cfg, par, M, **kw)
+        rep = Report(f"oracle ctl discrete multiturn {arm} prev {k}", n, ill)
+        rep.exact("reachable", reach, g["dis_mt_reachable"][k])
+        rep.exact("state", state, g["dis_mt_state"][k])
+        rep.exact("emergency bits", emg, g["dis_mt_bits"][k])
+        rep.close("joints", joints, g["dis_mt_joints"][k])
+        rep.check(max_ill_fraction=0.03)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_ctl_unfreeze(oracle, arm):
     """Emergency latch (continuity violation), the frozen returns, then control_type="unfreeze" (control_ik.py:198-212)."""
     g = load(f"ctl_overrides_{arm}.npz")
