@@ -460,6 +460,33 @@ def gen_ctl_overrides(T=3, W=160, n_dis=600):
         out.update(dis_mt_prev=prevs, dis_mt_current=cur, dis_mt_joints=J, dis_mt_reachable=F, dis_mt_state=S, dis_mt_bits=B)
         print(arm, "overrides discrete multiturn: emergency bits", np.bincount(B.ravel(), minlength=8), "max |j|/pi",
               np.abs(J).max() / np.pi)
+        # multi-turn trajectories: joint-space ramps of wrist yaw / elbow yaw / shoulder pitch through several turns
+        # (allow_multiturn unwrapping; the +-6 pi clamp of multiturn_safety_check latches the emergency at the end)
+        Wm = 260
+        u = np.linspace(0.0, 1.0, Wm)[:, None]
+        q0 = np.radians([-25.0, -40.0 * side, 0.0, -70.0, 0.0, 0.0, 0.0])
+        ramps = np.array([[0, 0, 0, 0, 0, 0, 6.4 * np.pi],                        # wrist yaw up: clamp at +6 pi
+                          [0, 0, -3.0 * np.pi * side, 0, 0, 0, -4.5 * np.pi],     # elbow yaw and wrist yaw, opposite senses
+                          [2.5 * np.pi, 0, 0, 0, 0, 0, 3.0 * np.pi],              # shoulder pitch circles
+                          [0, 0, 6.3 * np.pi * side, 0, 0, 0, 0]])                # elbow yaw to its clamp
+        qm = q0[None, None, :] + u[None, :, :] * ramps[:, None, :]
+        qm[..., 4] += 0.2 * np.sin(9 * u[None, :, 0]); qm[..., 5] += 0.15 * np.cos(7 * u[None, :, 0])
+        Mm = fk.forward_kinematics(qm.reshape(-1, 7), arm).reshape(len(ramps), Wm, 4, 4)
+        J = np.zeros((len(ramps), Wm, 7)); F = np.zeros((len(ramps), Wm), bool); S = np.zeros((len(ramps), Wm), np.uint8)
+        E = np.zeros(len(ramps), bool); TH = np.zeros(len(ramps)); EW = np.full(len(ramps), -1)
+        for t in range(len(ramps)):
+            ctl = new_control()
+            with _Quiet():
+                for w in range(Wm):
+                    j, ok, st = ctl.symbolic_inverse_kinematics(arm, Mm[t, w], "continuous")
+                    J[t, w], F[t, w], S[t, w] = j, ok, state_code(st)
+                    if ctl.emergency_stop and EW[t] < 0:
+                        EW[t] = w
+            E[t], TH[t] = ctl.emergency_stop, ctl.previous_theta[arm]
+        out.update(mt_M=Mm, mt_q=qm, mt_joints=J, mt_reachable=F, mt_state=S, mt_emergency=E, mt_final_theta=TH,
+                   mt_emergency_waypoint=EW)
+        print(arm, "multi-turn continuous: max |j|/pi per joint", np.round(np.abs(J).max(axis=(0, 1)) / np.pi, 2),
+              "emergency", E, "at", EW, "reachable", F.mean(axis=1))
         # emergency latch, then "unfreeze" (twice: the second one while not latched)
         Mj = Ms[0].copy()
         Mj[W // 2:, :3, :3] = Mj[W // 2:, :3, :3] @ np.diag([-1.0, -1.0, 1.0])   # half a turn about the tool axis

@@ -118,6 +118,25 @@ def test_unfreeze_scalar_api(arm, monkeypatch):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("phased", [True, False])
+def test_continuous_multiturn(ctl, arm, phased):
+    """Joint-space ramps through several turns: wrist yaw unwraps up to the +-6 pi clamp of multiturn_safety_check, which
+    latches the emergency (utils.py:493-568)."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    M = np.ascontiguousarray(g["mt_M"])
+    T, W = M.shape[:2]
+    joints, reach, state, st = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=phased)
+    for t in range(T):
+        rep = Report(f"gpu ctl continuous multi-turn {arm} phased={phased} traj {t}", W)
+        rep.exact("reachable", reach[t], g["mt_reachable"][t])
+        rep.exact("state", state[t], g["mt_state"][t])
+        rep.close("joints", joints[t], g["mt_joints"][t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g["mt_emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g["mt_final_theta"], atol=1e-9)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_discrete_multiturn_previous_solution(ctl, oracle, arm):
     """Discrete mode from a multi-turn previous solution (allow_multiturn, the +-6 pi clamp and the emergency bits of
     multiturn_safety_check, utils.py:493-568) with explicit current_joints."""

@@ -320,6 +320,30 @@ def test_ctl_discrete_multiturn_previous_solution(hs, oracle, arm):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_ctl_continuous_multiturn(hs, oracle, arm):
+    """Multi-turn wrist yaw up to the +-6 pi clamp and its emergency latch, serial and phased forms of the kernel source."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = cfg_for(arm, urdf_params(), -1.01)
+    par = ctl_params(oracle, arm)
+    M = g["mt_M"]
+    T, W = M.shape[:2]
+    joints, reach, state, st = hs_continuous(hs, oracle, cfg, par, arm, M)
+    for t in range(T):
+        rep = Report(f"hostsim ctl continuous multi-turn {arm} traj {t}", W)
+        rep.exact("reachable", reach[t], g["mt_reachable"][t])
+        rep.exact("state", state[t], g["mt_state"][t])
+        rep.close("joints", joints[t], g["mt_joints"][t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g["mt_emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g["mt_final_theta"], atol=1e-9)
+    j2, r2, s2, st2 = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
+    np.testing.assert_array_equal(j2, joints)
+    np.testing.assert_array_equal(r2, reach)
+    np.testing.assert_array_equal(s2, state)
+    assert st2.tobytes() == st.tobytes()
+
+
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("phased", [False, True])
 def test_ctl_unfreeze(hs, oracle, arm, phased):
     """Emergency latch, frozen returns, then control_type="unfreeze" (control_ik.py:198-212) on the kernel source."""

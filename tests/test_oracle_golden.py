@@ -233,6 +233,27 @@ def test_ctl_discrete_multiturn_previous_solution(oracle, arm):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_ctl_continuous_multiturn(oracle, arm):
+    """Joint-space ramps through several turns: allow_multiturn unwraps wrist yaw up to the +-6 pi clamp of
+    multiturn_safety_check, which latches the emergency (utils.py:493-568)."""
+    g = load(f"ctl_overrides_{arm}.npz")
+    cfg = _urdf_cfg(oracle, load("symik_urdf.npz"), arm, singularity_offset=-1.01)
+    par = oracle.ControlParams(arm=arm)
+    M = g["mt_M"]
+    T, W = M.shape[:2]
+    assert np.abs(g["mt_joints"][..., 6]).max() > 5.9 * np.pi and g["mt_emergency"].any()
+    joints, reach, state, st = oracle.ctl_continuous_batch(cfg, par, M)
+    for t in range(T):
+        rep = Report(f"oracle ctl continuous multi-turn {arm} traj {t}", W)
+        rep.exact("reachable", reach[t], g["mt_reachable"][t])
+        rep.exact("state", state[t], g["mt_state"][t])
+        rep.close("joints", joints[t], g["mt_joints"][t])
+        rep.check()
+    np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g["mt_emergency"])
+    np.testing.assert_allclose(st["previous_theta"], g["mt_final_theta"], atol=1e-9)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_ctl_unfreeze(oracle, arm):
     """Emergency latch (continuity violation), the frozen returns, then control_type="unfreeze" (control_ik.py:198-212)."""
     g = load(f"ctl_overrides_{arm}.npz")
