@@ -540,6 +540,35 @@ def test_reach_map_mixed_flag_counts(hs, oracle, arm):
     assert np.abs(res[1][0].astype(np.int64) - want.astype(np.int64)).sum() < 1e-4 * want.sum()
 
 
+@pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
+def test_reach_map_mixed_flag_constructor_variants(hs, oracle, variant):
+    """K4's mixed-precision flag under non-default limits / margins / geometry: its FP32 error bands are written against
+    the constants of the handle; the counts must still be the oracle's."""
+    from reachy2_symbolic_ik_b200 import fk, workspace
+
+    arm = "l_arm"
+    kw = dict(elbow_limit=127, wrist_limit=42.5, projection_margin=1e-8, backward_limit=0.02, normal_vector_margin=1e-7,
+              singularity_offset=0.03, singularity_limit_coeff=1.0)
+    kw.update(CTOR_VARIANTS[variant])
+    params = kw.get("ik_parameters", _abi.DEFAULT_IK_PARAMETERS)
+    cfg = _abi.make_arm_config(arm, params, kw["elbow_limit"], kw["wrist_limit"], kw["projection_margin"],
+                               kw["backward_limit"], kw["normal_vector_margin"], kw["singularity_offset"],
+                               kw["singularity_limit_coeff"])
+    n, no = 30, 32
+    origin, step, dims = workspace.reach_grid(np.asarray(params["l_shoulder_position"], dtype=np.float64), 0.66, n)
+    origin = origin + 3e-4
+    ori = fk.fibonacci_orientations(no)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    want = oracle.reach_map(oracle.arm_config(arm, **CTOR_VARIANTS[variant]), origin, step, dims, ori).reshape(-1)
+    counts = np.zeros(n ** 3, np.uint32)
+    n_esc, n_live = C.c_uint64(), C.c_uint64()
+    hs.hs_reach_map_mixed(C.byref(cfg), vp(origin), vp(step), vp(dims), vp(ori), C.c_int32(0), C.c_int32(no), C.c_int(0),
+                          vp(counts), C.byref(n_esc), C.byref(n_live))
+    assert want.sum() > 10_000
+    assert np.array_equal(counts, want), f"{int((counts != want).sum())} voxels differ from the oracle"
+    assert n_esc.value < 2e-3 * n_live.value
+
+
 def test_reach_map_mixed_flag_regression_pairs(hs, oracle):
     """Two (voxel, orientation) pairs of the full 256^3 x 512 map whose discriminant is 3e-9 from zero while the planes
     are 3 degrees from parallel (the cancellation in 1 - Ca^2 is then the largest FP32 error): they must be escalated."""
