@@ -106,10 +106,12 @@ for ai, arm in enumerate(("r_arm", "l_arm")):
                                hst.ctypes.data_as(C.c_void_p), dp(hj), u8(hr), u8(hss))
     for who, (jj, rr, ss, stt) in (("oracle", (oj, orr, os_, ost)), ("hostsim", (hj, hr.astype(bool), hss, hst))):
         for t in range(T):
-            rep = Report(f"soak {who} continuous {arm} seed {seed} traj {t}", W)
+            # a nearly straight arm (|elbow pitch| < 1e-3 rad) is a kinematic singularity: the reference's own elbow / wrist
+            # yaw there moves by ~1e-6 rad under a 3e-13 perturbation of the pose; such waypoints are counted, not compared
+            rep = Report(f"soak {who} continuous {arm} seed {seed} traj {t}", W, np.abs(J[t, :, 3]) < 1e-3)
             rep.exact("reachable", rr[t], F[t]); rep.exact("state", ss[t], S[t]); rep.close("joints", jj[t], J[t])
-            if rep.bad.any():
-                close(rep)
+            if rep.bad.any() or rep.ill.any():
+                close(rep, max_ill=0.1)
         ok = np.array_equal(stt["emergency_stop"].astype(bool), E) and np.allclose(stt["previous_theta"], TH, atol=1e-9)
         print(f"soak {who} continuous {arm}: {T} trajectories x {W}, final states {'ok' if ok else 'DIFFER'}")
         fails += not ok

@@ -218,6 +218,25 @@ def gen_symik_ctor(n_fk=900, n_task=900):
     np.savez_compressed(os.path.join(HERE, "symik_ctor.npz"), **out)
 
 
+def gen_symik_big_euler(n=800):
+    """Goal orientations given as large euler angles (the same rotations shifted by multiples of 2 pi, and angles drawn
+    in +-15 rad): the reference goes through scipy's from_euler, the kernels through their argument reduction."""
+    out = dict(META)
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        rng = np.random.default_rng(140 + seed)
+        M = fk.sample_fk_poses(n, arm, seed=142 + seed, min_x=0.05)
+        gp = np.array([euler_pose_from_matrix(m) for m in M])
+        gp[:, 1, :] += 2 * np.pi * rng.integers(-3, 4, (n, 3))
+        gp[n // 2:, 1, :] = rng.uniform(-15, 15, (n - n // 2, 3))
+        with _Quiet():
+            ik = SymbolicIK(arm=arm)
+        flag, state, interval, joints, elbow = run_symik(ik, gp)
+        out.update({f"{arm}_goal_pose": gp, f"{arm}_reachable": flag, f"{arm}_state": state, f"{arm}_interval": interval,
+                    f"{arm}_joints": joints, f"{arm}_elbow": elbow})
+        print(arm, "symik_big_euler: reachable", flag.mean(), "states", np.bincount(state, minlength=8))
+    np.savez_compressed(os.path.join(HERE, "symik_big_euler.npz"), **out)
+
+
 def urdf_params():
     with open(URDF_PATH) as f:
         urdf = f.read()
@@ -600,7 +619,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -619,6 +638,8 @@ if __name__ == "__main__":
         gen_ctl_overrides()
     if "ctor" in which:
         gen_symik_ctor()
+    if "big_euler" in which:
+        gen_symik_big_euler()
     if "task_space" in which:
         gen_task_space()
     print(f"done in {time.time() - t0:.1f}s")

@@ -106,6 +106,26 @@ def test_constructor_variants(hs, oracle, arm, variant):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_big_euler_angles(hs, oracle, arm):
+    """Goal orientations as euler angles far outside [-pi, pi]: the argument reduction of the kernels' sincos (fast
+    route for ordinary magnitudes, literal route beyond) against scipy's from_euler in the reference."""
+    g = load("symik_big_euler.npz")
+    P = g[f"{arm}_goal_pose"]
+    ocfg = oracle.arm_config(arm)
+    ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg_for(arm), P)
+    rep = Report(f"hostsim big euler {arm}", len(P), ill)
+    rep.exact("reachable", reach, g[f"{arm}_reachable"])
+    rep.exact("state", state, g[f"{arm}_state"])
+    rep.close("interval", itv, g[f"{arm}_interval"])
+    rep.close("joints", joints, g[f"{arm}_joints"])
+    rep.close("elbow", elbow, g[f"{arm}_elbow"])
+    rep.check(max_ill_fraction=0.03)
+    P32 = P.astype(np.float32)
+    check_f32(f"hostsim f32 big euler {arm}", oracle, arm, P32, hs_symik_f32(hs, cfg_for(arm), P32), max_ill=0.04)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_named(hs, oracle, arm):
     g = load("symik_named.npz")
     P = g[f"{arm}_poses"]

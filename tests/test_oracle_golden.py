@@ -97,6 +97,23 @@ def test_constructor_variants(oracle, arm, variant):
         rep.check(max_ill_fraction=0.03)
 
 
+@pytest.mark.parametrize("arm", ARMS)
+def test_big_euler_angles(oracle, arm):
+    """Goal orientations as euler angles far outside [-pi, pi] (tests/golden/symik_big_euler.npz)."""
+    g = load("symik_big_euler.npz")
+    cfg = oracle.arm_config(arm)
+    P = g[f"{arm}_goal_pose"]
+    ill = ill_conditioned_mask(lambda p: oracle.symik_batch(cfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+    reach, itv, state, joints, elbow = oracle.symik_batch(cfg, P)
+    rep = Report(f"oracle big euler {arm}", len(P), ill)
+    rep.exact("reachable", reach, g[f"{arm}_reachable"])
+    rep.exact("state", state, g[f"{arm}_state"])
+    rep.close("interval", itv, g[f"{arm}_interval"])
+    rep.close("joints@interval[0]", joints, g[f"{arm}_joints"])
+    rep.close("elbow", elbow, g[f"{arm}_elbow"])
+    rep.check(max_ill_fraction=0.03)
+
+
 def _urdf_cfg(oracle, g, arm, singularity_offset=-1.01):
     params = {k[len("param_"):]: g[k] for k in g.files if k.startswith("param_")}
     return oracle.arm_config(arm, ik_parameters=params, singularity_offset=singularity_offset)
