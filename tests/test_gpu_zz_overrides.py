@@ -162,6 +162,25 @@ def test_discrete_multiturn_previous_solution(ctl, oracle, arm):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_big_euler_angles(oracle, arm):
+    """Goal orientations as euler angles far outside [-pi, pi] (tests/golden/symik_big_euler.npz)."""
+    from reachy2_symbolic_ik_b200 import SymbolicIK
+
+    g = load("symik_big_euler.npz")
+    P = g[f"{arm}_goal_pose"]
+    ocfg = oracle.arm_config(arm)
+    ill = ill_conditioned_mask(lambda p: oracle.symik_batch(ocfg, p.reshape(P.shape))[:4], P.reshape(len(P), -1))
+    res = SymbolicIK(arm=arm).is_reachable_batch(P)
+    rep = Report(f"gpu big euler {arm}", len(P), ill)
+    rep.exact("reachable", res.reachable, g[f"{arm}_reachable"])
+    rep.exact("state", res.state, g[f"{arm}_state"])
+    rep.close("interval", res.theta_interval, g[f"{arm}_interval"])
+    rep.close("joints@interval[0]", res.joints, g[f"{arm}_joints"])
+    rep.close("elbow", res.elbow, g[f"{arm}_elbow"])
+    rep.check(max_ill_fraction=0.03)
+
+
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("variant", sorted(CTOR_VARIANTS))
 def test_constructor_variants(oracle, arm, variant):
     """SymbolicIK with non-default elbow / wrist limits, margins and singularity plane (symbolic_ik.py:26-37):
