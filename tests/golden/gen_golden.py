@@ -237,6 +237,33 @@ def gen_symik_big_euler(n=800):
     np.savez_compressed(os.path.join(HERE, "symik_big_euler.npz"), **out)
 
 
+def gen_api_surface():
+    """Names, parameter names and defaults of the public methods of the reference's two classes (the drop-in boundary,
+    SURVEY.md 8(b)) -> api_surface.json."""
+    import inspect
+    import json
+
+    def describe(cls):
+        out = {}
+        for name, fn in inspect.getmembers(cls, predicate=inspect.isfunction):
+            if name.startswith("_") and name != "__init__":
+                continue
+            sig = inspect.signature(fn)
+            out[name] = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                         for p in sig.parameters.values()]
+        return out
+
+    with _Quiet():
+        ik = SymbolicIK()
+        ctl = new_control()
+    surface = {"SymbolicIK": describe(SymbolicIK), "ControlIK": describe(ControlIK),
+               "SymbolicIK_attributes": sorted(k for k in vars(ik) if not k.startswith("_")),
+               "ControlIK_attributes": sorted(k for k in vars(ctl) if not k.startswith("_"))}
+    with open(os.path.join(HERE, "api_surface.json"), "w") as f:
+        json.dump(surface, f, indent=1, sort_keys=True)
+    print("api_surface:", {k: len(v) for k, v in surface.items()})
+
+
 def urdf_params():
     with open(URDF_PATH) as f:
         urdf = f.read()
@@ -619,7 +646,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler", "api"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -640,6 +667,8 @@ if __name__ == "__main__":
         gen_symik_ctor()
     if "big_euler" in which:
         gen_symik_big_euler()
+    if "api" in which:
+        gen_api_surface()
     if "task_space" in which:
         gen_task_space()
     print(f"done in {time.time() - t0:.1f}s")

@@ -93,3 +93,29 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "ik_poses_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+BOUNDARY_METHODS = {   # what a user of the reference calls
+    "SymbolicIK": ["__init__", "is_reachable", "is_reachable_no_limits", "get_joints", "get_elbow_position"],
+    "ControlIK": ["__init__", "symbolic_inverse_kinematics"],
+}
+
+
+def test_facade_signatures_match_the_reference():
+    """Parameter names, order and defaults of the drop-in classes against those of the reference's classes
+    (tests/golden/api_surface.json, written by gen_golden.py from the unmodified reference).  The facade may append
+    parameters of its own (device=...) after the reference's."""
+    import inspect
+    import json
+
+    from reachy2_symbolic_ik_b200 import ControlIK, SymbolicIK
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(repo, "tests", "golden", "api_surface.json")))
+    for cname, cls in (("SymbolicIK", SymbolicIK), ("ControlIK", ControlIK)):
+        for m in BOUNDARY_METHODS[cname]:
+            want = ref[cname][m]
+            sig = inspect.signature(getattr(cls, m))
+            mine = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)] for p in sig.parameters.values()]
+            assert mine[: len(want)] == want, f"{cname}.{m}: {mine} != {want}"
+            assert all(d is not None for _, d in mine[len(want):]), f"{cname}.{m}: extra parameters must have defaults"

@@ -205,3 +205,21 @@ def test_constructor_variants(oracle, arm, variant):
         rep.close("joints@theta2", res2.joints, g[pre + "joints_theta2"])
         rep.close("elbow@theta2", res2.elbow, g[pre + "elbow_theta2"])
         rep.check(max_ill_fraction=0.03)
+
+
+def test_facade_attributes_match_the_reference():
+    """Every public attribute an instance of the reference's classes carries (tests/golden/api_surface.json) exists on
+    the drop-in classes (examples read them: src/example/test_continuous_ik.py:60, 235-238)."""
+    import json
+    import os
+
+    from parity import GOLDEN
+    from reachy2_symbolic_ik_b200 import ControlIK, SymbolicIK
+
+    ref = json.load(open(os.path.join(GOLDEN, "api_surface.json")))
+    ik = SymbolicIK()
+    missing = [a for a in ref["SymbolicIK_attributes"] if not hasattr(ik, a)]
+    assert not missing, f"SymbolicIK lacks {missing}"
+    c = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    missing = [a for a in ref["ControlIK_attributes"] if not hasattr(c, a)]
+    assert not missing, f"ControlIK lacks {missing}"
