@@ -223,6 +223,37 @@ class Symik:
     def e2e_check(self, torch):
         assert torch.equal(self.host_out["r_arm"].joints[:1000].nan_to_num(), self.outs["r_arm"]["joints"][:1000].cpu().nan_to_num())
 
+    def e2e_goal_pose(self, torch, steps):
+        """Optional extra leg (single GPU, run last, never fatal): the same solves fed in the reference's OWN input format,
+        goal_pose = (position, xyz euler) = 48 B / pose instead of the 128 B of a 4x4 matrix; outputs unchanged."""
+        from scipy.spatial.transform import Rotation as R
+
+        n = self.POSES_PER_ARM
+        host_in = {}
+        for arm in ARMS:
+            M = self.poses[arm]
+            gp = np.concatenate([M[:, :3, 3], R.from_matrix(M[:, :3, :3]).as_euler("xyz")], axis=1)
+            host_in[arm] = torch.from_numpy(np.ascontiguousarray(gp)).pin_memory()
+        for _ in range(2):
+            for arm in ARMS:
+                self.solvers[arm].is_reachable_batch_host(host_in[arm], self.host_out[arm])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for arm in ARMS:
+                self.solvers[arm].is_reachable_batch_host(host_in[arm], self.host_out[arm])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        got = self.host_out["r_arm"].joints[:100_000].numpy()
+        ref = self.outs["r_arm"]["joints"][:100_000].cpu().numpy()
+        both = np.isfinite(got).all(axis=1) & np.isfinite(ref).all(axis=1)
+        dj = np.abs(got[both] - ref[both]).max(axis=1)
+        return {"value": 2 * n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 48, "d2h_bytes_per_step": 2 * n * self.BYTES_OUT,
+                "steps": steps, "path": "SymbolicIK.is_reachable_batch_host on (N,6) goal poses (the reference's input format)",
+                "median_abs_joint_difference_vs_mat4_input_rad": float(np.median(dj)),
+                "state_agreement_vs_mat4_input": float((self.host_out["r_arm"].state[:100_000].numpy() ==
+                                                        self.outs["r_arm"]["state"][:100_000].cpu().numpy()).mean())}
+
     def parity(self, torch):
         from oracle import oracle as O
 
@@ -852,6 +883,11 @@ def main() -> int:
                                              "roofline_fp64; the two pipes issue from the same slots"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and type(wl) is Symik:
+            try:     # optional, last, never fatal: the line above is complete without it
+                line["e2e"]["goal_pose_input"] = wl.e2e_goal_pose(torch, e2e_steps)
+            except Exception as e:
+                line["e2e"]["goal_pose_input"] = {"unavailable": repr(e)}
         emit(line)
     if dist is not None:
         dist.barrier()
