@@ -241,7 +241,7 @@ def test_ctl_continuous(hs, oracle, arm, variant):
     assert st2.tobytes() == st.tobytes()
 
 
-def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False):
+def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, lanes=0, force_serial=0):
     M = np.ascontiguousarray(M, dtype=np.float64)
     T, W = M.shape[:2]
     cj = np.empty((T, 7)); cp = np.empty((T, 4, 4))
@@ -252,7 +252,12 @@ def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False):
         states["init"] = 1
     st = np.ascontiguousarray(states).copy()
     joints = np.empty((T, W, 7)); reach = np.zeros((T, W), np.uint8); state = np.zeros((T, W), np.uint8)
-    if phased:
+    if lanes:   # phases 1-3, the lane-parallel finish kernel body under the warp emulation, the fixup pass
+        ws = np.empty((T, W))
+        hs.hs_ctl_continuous_phased_lanes_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
+                                                st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws),
+                                                C.c_int(lanes), C.c_int(force_serial))
+    elif phased:
         ws = np.empty((T, W))
         hs.hs_ctl_continuous_phased_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
                                           st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws))
@@ -361,6 +366,38 @@ def test_ctl_continuous_multiturn(hs, oracle, arm):
     np.testing.assert_array_equal(r2, reach)
     np.testing.assert_array_equal(s2, state)
     assert st2.tobytes() == st.tobytes()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+def test_ctl_continuous_lane_parallel_finish_kernel(hs, oracle, arm, lanes):
+    """k_cont_finish_lanes<G> -- the kernel body of csrc/r2ik_scan_lanes.cuh itself, run on the host by one thread per CUDA
+    thread with emulated warp votes -- against the serial finish scan: identical joints, flags, states and controller
+    states on the golden trajectories (continuity latch, unreachable stretches), on the multi-turn ramps (the +-6 pi clamp
+    and its emergency bits), when resumed from returned states, and when the test hook sends every m-th waypoint down the
+    serial get_joints route (stop + fixup pass)."""
+    cfg = cfg_for(arm, urdf_params(), -1.01)
+    par = ctl_params(oracle, arm)
+    g, go = load(f"ctl_continuous_{arm}.npz"), load(f"ctl_overrides_{arm}.npz")
+    hit_clamp = False
+    for name, M in (("golden", g["M"]), ("multi-turn", go["mt_M"]), ("unfreeze", go["unf_M"][None])):
+        M = np.ascontiguousarray(M)
+        want = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
+        for force in (0, 1, 7, 97):
+            got = hs_continuous(hs, oracle, cfg, par, arm, M, lanes=lanes, force_serial=force)
+            np.testing.assert_array_equal(got[0], want[0], err_msg=f"{name} joints, force={force}")
+            np.testing.assert_array_equal(got[1], want[1], err_msg=f"{name} flags, force={force}")
+            np.testing.assert_array_equal(got[2], want[2], err_msg=f"{name} states, force={force}")
+            assert got[3].tobytes() == want[3].tobytes(), f"{name} controller states, force={force}"
+        hit_clamp = hit_clamp or bool((want[3]["emergency_bits"] & 7).any())
+        # resume the reversed trajectories from the returned states (latched and unlatched alike)
+        Mr = np.ascontiguousarray(M[:, ::-1])
+        want2 = hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], phased=True)
+        got2 = hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], lanes=lanes)
+        np.testing.assert_array_equal(got2[0], want2[0])
+        np.testing.assert_array_equal(got2[2], want2[2])
+        assert got2[3].tobytes() == want2[3].tobytes()
+    assert hit_clamp, "no trajectory reached the +-6 pi clamp"
 
 
 @pytest.mark.parametrize("arm", ARMS)
