@@ -126,6 +126,33 @@ def test_big_euler_angles(hs, oracle, arm):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_fk_round_trip(hs, arm):
+    """Reference-independent property: forward kinematics of the returned joints reproduces the goal pose whenever no
+    goal-shifting branch fired (singularity_offset = -1.01 disables the elbow projection).  Host twin of
+    tests/test_gpu_workspace.py::test_fk_round_trip_full_size; the URDF's truncated rpy literals bound the agreement
+    at ~1e-6."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    q = fk.sample_fk_joints(40_000, np.random.default_rng(21))
+    M = fk.forward_kinematics(q, arm)
+    reach, itv, state, joints, elbow = hs_symik(hs, cfg_for(arm, None, -1.01), M)
+    assert 0.3 < reach.mean() < 0.7
+    M2 = fk.forward_kinematics(joints[reach], arm)
+    rot_err = np.abs(M2[:, :3, :3] - M[reach][:, :3, :3]).max(axis=(1, 2))
+    pos_err = np.linalg.norm(M2[:, :3, 3] - M[reach][:, :3, 3], axis=1)
+    assert np.quantile(rot_err, 0.999) < 1e-5
+    assert np.median(pos_err) < 1e-6 and (pos_err < 1e-5).mean() > 0.9
+    # every theta of the interval is a solution of the same pose: the round trip holds at a second theta too
+    width = np.where(itv[:, 0] <= itv[:, 1], itv[:, 1] - itv[:, 0], itv[:, 1] + 2 * np.pi - itv[:, 0])
+    theta2 = np.where(reach, itv[:, 0] + 0.37 * width, 0.0)
+    _, _, _, j2, _ = hs_symik(hs, cfg_for(arm, None, -1.01), M, theta2)
+    M3 = fk.forward_kinematics(j2[reach], arm)
+    assert np.quantile(np.abs(M3[:, :3, :3] - M[reach][:, :3, :3]).max(axis=(1, 2)), 0.999) < 1e-5
+    p3 = np.linalg.norm(M3[:, :3, 3] - M[reach][:, :3, 3], axis=1)
+    assert np.median(p3) < 1e-6 and (p3 < 1e-5).mean() > 0.9
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_named(hs, oracle, arm):
     g = load("symik_named.npz")
     P = g[f"{arm}_poses"]
