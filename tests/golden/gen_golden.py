@@ -211,6 +211,18 @@ def gen_symik_ctor(n_fk=900, n_task=900):
             theta2 = np.where(flag, interval[:, 0] + u * width, 0.0)
             _, _, _, joints2, elbow2 = run_symik(ik, gp, theta2)
             pre = f"{arm}_{name}_"
+            # is_reachable_no_limits + get_joints(theta) on the first n_nl poses (symbolic_ik.py:85-119)
+            n_nl = 500
+            nl_th = np.random.default_rng(135 + seed).uniform(-np.pi, np.pi, n_nl)
+            nl_j = np.full((n_nl, 7), np.nan); nl_e = np.full((n_nl, 3), np.nan)
+            with _Quiet():
+                for i in list(range(n_nl // 2)) + list(range(len(M) - n_nl // 2, len(M))):
+                    k = i if i < n_nl // 2 else i - (len(M) - n_nl)
+                    ok, _, fn = ik.is_reachable_no_limits(np.array(gp[i]))
+                    assert ok
+                    j, e = fn(nl_th[k])
+                    nl_j[k], nl_e[k] = j, np.asarray(e)[:3]
+            out.update({pre + "nl_theta": nl_th, pre + "nl_joints": nl_j, pre + "nl_elbow": nl_e})
             out.update({pre + "reachable": flag, pre + "state": state, pre + "interval": interval, pre + "joints": joints,
                         pre + "elbow": elbow, pre + "theta2": theta2, pre + "joints_theta2": joints2,
                         pre + "elbow_theta2": elbow2})

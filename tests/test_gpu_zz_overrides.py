@@ -205,6 +205,16 @@ def test_constructor_variants(oracle, arm, variant):
         rep.close("joints@theta2", res2.joints, g[pre + "joints_theta2"])
         rep.close("elbow@theta2", res2.elbow, g[pre + "elbow_theta2"])
         rep.check(max_ill_fraction=0.03)
+    # is_reachable_no_limits (symbolic_ik.py:85-119) on the first / last 250 poses
+    M = g[f"{arm}_M"]
+    sel = np.r_[0:250, len(M) - 250:len(M)]
+    Mc, th = np.ascontiguousarray(M[sel]), g[pre + "nl_theta"]
+    ill = ill_conditioned_mask(lambda p: oracle.symik_no_limits_batch(ocfg, p.reshape(Mc.shape), th), Mc.reshape(len(sel), -1))
+    nj, ne = ik.is_reachable_no_limits_batch(Mc, th)
+    rep = Report(f"gpu ctor {variant} {arm} no_limits", len(sel), ill)
+    rep.close("no_limits joints", nj, g[pre + "nl_joints"])
+    rep.close("no_limits elbow", ne, g[pre + "nl_elbow"])
+    rep.check(max_ill_fraction=0.03)
 
 
 def test_facade_attributes_match_the_reference():

@@ -103,6 +103,18 @@ def test_constructor_variants(hs, oracle, arm, variant):
         rep.close("joints@theta2", j2, g[pre + "joints_theta2"])
         rep.close("elbow@theta2", e2, g[pre + "elbow_theta2"])
         rep.check(max_ill_fraction=0.03)
+    # is_reachable_no_limits (symbolic_ik.py:85-119) on the first / last 250 poses (FK-sampled / task space)
+    Mn = g[f"{arm}_M"]
+    sel = np.r_[0:250, len(Mn) - 250:len(Mn)]
+    Mc = np.ascontiguousarray(Mn[sel])
+    th = np.ascontiguousarray(g[pre + "nl_theta"])
+    nj = np.empty((len(sel), 7)); ne = np.empty((len(sel), 3))
+    hs.hs_no_limits_batch(C.byref(cfg), _abi.POSE_MAT4, dp(Mc), dp(th), C.c_int64(len(sel)), dp(nj), dp(ne))
+    ill_nl = ill_conditioned_mask(lambda p: oracle.symik_no_limits_batch(ocfg, p.reshape(Mc.shape), th), Mc.reshape(len(sel), -1))
+    rep = Report(f"hostsim ctor {variant} {arm} no_limits", len(sel), ill_nl)
+    rep.close("no_limits joints", nj, g[pre + "nl_joints"])
+    rep.close("no_limits elbow", ne, g[pre + "nl_elbow"])
+    rep.check(max_ill_fraction=0.03)
 
 
 @pytest.mark.parametrize("arm", ARMS)

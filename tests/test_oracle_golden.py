@@ -95,6 +95,15 @@ def test_constructor_variants(oracle, arm, variant):
         rep.close("joints@theta2", j2, g[pre + "joints_theta2"])
         rep.close("elbow@theta2", e2, g[pre + "elbow_theta2"])
         rep.check(max_ill_fraction=0.03)
+        # is_reachable_no_limits (symbolic_ik.py:85-119) on the first / last 250 poses (FK-sampled / task space)
+        sel = np.r_[0:250, len(P) - 250:len(P)]
+        nj, ne = oracle.symik_no_limits_batch(cfg, P[sel], g[pre + "nl_theta"])
+        ill_nl = ill_conditioned_mask(lambda p: oracle.symik_no_limits_batch(cfg, p.reshape(P[sel].shape), g[pre + "nl_theta"]),
+                                      P[sel].reshape(len(sel), -1))
+        rep = Report(f"oracle ctor {variant} {arm} {layout} no_limits", len(sel), ill_nl)
+        rep.close("no_limits joints", nj, g[pre + "nl_joints"])
+        rep.close("no_limits elbow", ne, g[pre + "nl_elbow"])
+        rep.check(max_ill_fraction=0.03)
 
 
 @pytest.mark.parametrize("arm", ARMS)
