@@ -112,6 +112,7 @@ constexpr float kTwoPiF = 6.28318530717958647692f;
 // margin of ~10x; the measured share of escalated poses is reported by the tests / bench.
 constexpr float kBandLen = 4e-6f;      // lengths and coordinates [m]
 constexpr float kBandSin = 1e-5f;      // |sin| below which an angle sits on the +-pi / 0 branch cut
+constexpr double kBandD2 = 4e-8;       // squared wrist distance [m^2] around the range / minimum-distance spheres
 constexpr float kMinH2 = 4e-6f;        // squared length under an atan2 below which the angle is ill-conditioned (2 mm)
 constexpr float kMinRadius2 = 1e-9f;   // elbow-circle radius^2 below which 1 / r is not trusted (0.03 mm)
 constexpr float kMinLever2 = 1e-6f;    // (r rho sin alpha)^2 below which the interval ends are ill-conditioned (1 mm)
@@ -274,6 +275,11 @@ R2IK_HD ReachF is_reachable_f(const ArmConst &A64, const ArmConstF &A, float pxf
   }
   double P[3] = {w[0] - A64.s[0], w[1] - A64.s[1], w[2] - A64.s[2]};
   double d2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+  // The FP64 arithmetic above is exact on its inputs, but the rotation is the FP32 one: it differs from the FP64 solver's
+  // (polar factor of the same float matrix / euler angles in double) by ~6e-8 per element, i.e. ~1e-8 m in the wrist
+  // centre and ~2e-8 in d^2.  A wrist within that of the range sphere or of the minimum-distance sphere (a fully
+  // stretched or fully folded arm: FK samples with elbow pitch < 1e-3 rad) is decided by the FP64 solver.
+  R2IK_ESC(23, fabs(d2 - A64.L12 * A64.L12) < kBandD2 || fabs(d2 - A64.d_min * A64.d_min) < kBandD2);
   if (d2 > A64.L12 * A64.L12) { out.state = R2IK_STATE_WRIST_OUT_OF_RANGE; return out; }
   if (d2 < A64.d_min * A64.d_min) {
     // sik:166-171, 337-349: wrist pushed out radially to d_min, the goal follows, the wrist is recomputed

@@ -548,6 +548,28 @@ def test_symik_f32_constructor_variants(hs, oracle, arm, variant):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_symik_f32_stretched_arm_boundary(hs, oracle, arm):
+    """FK samples with an elbow pitch of 1e-6 .. 2e-3 rad put the wrist within ~1e-7 m of the range sphere d = L1 + L2.
+    The FP32 path's wrist centre carries the ~1e-8 m error of its FP32 rotation, so "wrist out of range" against "reachable"
+    must be settled by the FP64 solver there (2 of 1 000 000 plain FK samples differed before the band on d^2 existed:
+    profiles/r1_experiments.md).  States identical to the FP64 oracle; the raw FP32 decision alone is not."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    rng = np.random.default_rng(5)
+    q = fk.sample_fk_joints(150_000, rng)
+    q[:, 3] = -10.0 ** rng.uniform(-6, -2.7, len(q))
+    M = fk.forward_kinematics(q, arm)
+    M = M[M[:, 0, 3] > 0.1]
+    P32 = M.astype(np.float32)
+    want = oracle.symik_batch(oracle.arm_config(arm), P32.astype(np.float64))
+    assert 0.05 < (want[2] == 3).mean() < 0.95            # the sample straddles the sphere
+    got = hs_symik_f32(hs, cfg_for(arm), P32)
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0])
+    raw = hs_symik_f32(hs, cfg_for(arm), P32, mode=1)
+    assert (raw[2] != want[2]).sum() > 0
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_symik_f32_fk_20k(hs, oracle, arm):
     from reachy2_symbolic_ik_b200 import fk
 
