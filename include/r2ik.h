@@ -18,6 +18,11 @@
  *        SymbolicIK.is_reachable_no_limits         symbolic_ik.py:85-119  (+ get_joints)
  *   r2ik_elbow_positions_f64
  *        SymbolicIK.get_elbow_position             symbolic_ik.py:684-695
+ *        (on the circle stored by is_reachable :197 or by is_reachable_no_limits :114-116)
+ *   r2ik_symik_scalar_f64
+ *        the scalar call sequence is_reachable / is_reachable_no_limits -> get_elbow_position
+ *        -> get_joints of ONE pose in one launch   symbolic_ik.py:121-282, 85-119, 684-695, 697-863
+ *        (the reference's consumer calls it once per control tick, src/example/example_control.py:9-27)
  *   r2ik_ctl_discrete_f64
  *        ControlIK.symbolic_inverse_kinematics(name, M, "discrete")
  *                                                  control_ik.py:162-274, 409-462, 464-497
@@ -37,6 +42,8 @@
  *        the same volume, every pair by the all-FP64 flag solve (cross-check)
  *   r2ik_interval_limit
  *        interval_limit + l_arm mirroring          control_ik.py:225-252
+ *   r2ik_ctl_ctor_theta_f64
+ *        ControlIK.__init__'s previous_theta seed  control_ik.py:142-159 (utils.py:267-331)
  *   r2ik_fk_f64
  *        forward kinematics of the arm chain of config_files/reachy2.urdf (torso -> arm tip).
  *        The reference has no FK of its own: its examples call the Reachy SDK's
@@ -62,7 +69,8 @@
 extern "C" {
 #endif
 
-#define R2IK_ABI_VERSION 2 /* 2: + symik_solve_f32, ctl_discrete_scan, reach_map_f64, ffma_probe */
+#define R2IK_ABI_VERSION 3 /* 3: + symik_scalar, stream_synchronize; no_limits / projected in elbow_positions, prev_joints in
+                              no_limits, nullable `reachable`, test hook of the phased continuous entry as a parameter */
 
 /* argument errors */
 #define R2IK_ERR_NULL 1
@@ -149,6 +157,32 @@ typedef struct R2ikFkChain {
   double axis[7][3];
 } R2ikFkChain;
 
+/* One scalar call sequence of SymbolicIK (r2ik_symik_scalar_f64). */
+typedef struct R2ikScalarQuery {
+  double goal_pose[6];        /* x y z roll pitch yaw: the reference's goal_pose [[x,y,z],[r,p,y]]  */
+  double theta;               /* elbow angle for get_elbow_position / get_joints (has_theta != 0)   */
+  double previous_joints[7];  /* get_joints(theta, previous_joints); zeros = the reference default  */
+  int32_t no_limits;          /* 0: is_reachable, 1: is_reachable_no_limits                         */
+  int32_t has_theta;          /* 0: theta = theta_interval[0]                                       */
+} R2ikScalarQuery;
+
+typedef struct R2ikScalarResult {
+  double interval[2];              /* theta_interval; NaN when the call failed                          */
+  double joints[7];                /* get_joints(theta, previous_joints); NaN when unreachable          */
+  double elbow[3];                 /* elbow get_joints returns (after make_elbow_projection, if fired)  */
+  double elbow_on_circle[3];       /* get_elbow_position(theta): defined once the circle is stored,     */
+                                   /*   i.e. also for "limited by wrist" (symbolic_ik.py:197)           */
+  double goal_position_solved[3];  /* self.goal_pose[0] / self.wrist_position after is_reachable or     */
+  double wrist_position_solved[3]; /*   is_reachable_no_limits (symbolic_ik.py:143-171, 91-112)         */
+  double goal_position[3];         /* ... after get_joints (symbolic_ik.py:711-716)                     */
+  double wrist_position[3];
+  int32_t reachable;               /* 0 / 1                                                             */
+  int32_t state;                   /* R2IK_STATE_*                                                      */
+  int32_t projected;               /* 1: make_elbow_projection fired => the reference returns a         */
+                                   /*   3-vector elbow instead of [x, y, z, 1] (symbolic_ik.py:714,863) */
+  int32_t reserved;
+} R2ikScalarResult;
+
 typedef struct r2ik_context *r2ik_handle;
 
 int r2ik_abi_version(void);
@@ -165,7 +199,8 @@ int r2ik_interval_limit(int side, int low_elbow, double *out);
 /* is_reachable + get_joints(theta) for n independent poses (fresh solver state per pose).
  * theta: nullable; NULL => theta_interval[0].  prev_joints: nullable 7 doubles (device),
  * broadcast; NULL => zeros (the reference default).  Unreachable poses get NaN interval /
- * joints / elbow.  Any output pointer except reachable/state may be NULL. */
+ * joints / elbow.  Any output pointer except `state` may be NULL (state == R2IK_STATE_REACHABLE <=> reachable, so a
+ * lean host record is state + joints = 57 bytes per pose). */
 int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta,
                          const double *prev_joints, int64_t n, uint8_t *reachable, uint8_t *state,
                          double *interval, double *joints, double *elbow, void *stream);
@@ -183,13 +218,33 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
                          float *interval, float *joints, float *elbow, uint32_t *escalated_idx,
                          uint32_t *n_escalated, void *stream);
 
-/* is_reachable_no_limits + get_joints(theta[i]). */
+/* is_reachable_no_limits + get_joints(theta[i], previous_joints).  prev_joints: nullable (zeros); prev_stride 0 = one
+ * vector of 7 broadcast, 7 = one per pose.  projected: nullable, 1 where make_elbow_projection fired. */
 int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta,
-                             int64_t n, double *joints, double *elbow, void *stream);
+                             const double *prev_joints, int32_t prev_stride, int64_t n, double *joints,
+                             double *elbow, uint8_t *projected, void *stream);
 
-/* get_elbow_position(thetas[i][k]) after is_reachable(poses[i]); NaN when unreachable. */
+/* get_elbow_position(thetas[i][k]) after is_reachable(poses[i]) (no_limits = 0) or is_reachable_no_limits (1); NaN
+ * when no circle was stored.  projected: nullable n*K, 1 where get_joints(theta) would project the elbow. */
 int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, const double *thetas,
-                             int32_t K, int64_t n, double *elbows /* n*K*3 */, void *stream);
+                             int32_t K, int64_t n, int32_t no_limits, double *elbows /* n*K*3 */,
+                             uint8_t *projected, void *stream);
+
+/* The scalar call sequence of SymbolicIK for one pose in one launch.  query: HOST pointer (passed to the kernel by
+ * value).  out: any device-accessible address -- device memory, or pinned host memory (cudaHostAlloc / torch
+ * pin_memory: mapped under unified addressing), in which case the call needs no copy at all. */
+int r2ik_symik_scalar_f64(r2ik_handle h, const R2ikScalarQuery *query, R2ikScalarResult *out, void *stream);
+
+/* ControlIK.__init__'s seed of previous_theta[arm] (control_ik.py:142-159): is_reachable_no_limits on current_pose,
+ * then get_best_theta_to_current_joints as the constructor calls it -- with the list of BOTH arms' joints, so its
+ * cost runs over n_rows rows of 7 (utils.py:267-331).  current_joints_rows (n_rows x 7, n_rows <= 7) and
+ * current_pose (row-major 4x4): HOST pointers, passed to the kernel by value.  out_theta: one double at any
+ * device-accessible address (NaN when the current pose has no valid rotation). */
+int r2ik_ctl_ctor_theta_f64(r2ik_handle h, double preferred_theta, const double *current_joints_rows,
+                            int32_t n_rows, const double *current_pose, double *out_theta, void *stream);
+
+/* cudaStreamSynchronize(stream): lets a binding without a CUDA runtime of its own wait for a scalar call. */
+int r2ik_stream_synchronize(void *stream);
 
 /* ControlIK discrete mode for n poses M (n x 16).  prev_joints / current_joints: 7 doubles
  * each (device), broadcast: ControlIK.previous_sol[arm] and the per-call current_joints.
@@ -216,11 +271,13 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, 
 /* The same computation as r2ik_ctl_continuous_f64 (same flags / states, joints equal to rounding), cut at its data dependences:
  * the per-waypoint work (reachability, target theta, joints for a given theta, Orbita3D limit) runs with one
  * thread per waypoint, and only the rate-limited theta and the unwrap / continuity / emergency chain run as
- * per-trajectory scans.  workspace: T*W doubles of device scratch (theta per waypoint), caller-owned. */
+ * per-trajectory scans.  workspace: T*W doubles of device scratch (theta per waypoint), caller-owned.
+ * test_force_serial_mod: 0 in production; m > 0 sends every m-th waypoint down the serial get_joints route (which no
+ * physical pose takes) so that tests can hold that route to the ordinary result. */
 int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
                                    int32_t W, const double *current_joints, const double *current_pose,
                                    R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
-                                   double *workspace, void *stream);
+                                   double *workspace, int32_t test_force_serial_mod, void *stream);
 
 /* Workspace reachability map: counts[v] += #orientations o in [ori_begin, ori_end) with
  * is_reachable(voxel centre, orientations_euler[o]) true.  Voxel (ix,iy,iz) centre =

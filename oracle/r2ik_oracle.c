@@ -1041,8 +1041,17 @@ void orc_symik_batch(const orc_arm_config *cfg, int pose_kind, const double *pos
                     interval + 2 * i, joints + 7 * i, elbow + 3 * i);
 }
 
+/* sik:697-718: does get_joints(theta) take the make_elbow_projection branch on the solved pose?  (The reference then
+ * returns the elbow as a 3-vector instead of get_elbow_position's homogeneous [x, y, z, 1], sik:714 / :863.) */
+static int elbow_projection_fires(const orc_solver *s, double theta) {
+  double e[3];
+  get_elbow_position(s, theta, e);
+  return e[2] > (e[0] - s->elbow_singularity_position[0]) * s->cfg.singularity_limit_coeff +
+                    s->elbow_singularity_position[2] - s->cfg.singularity_offset;
+}
+
 void orc_symik_no_limits_batch(const orc_arm_config *cfg, int pose_kind, const double *poses, const double *theta,
-                               int64_t n, double *joints, double *elbow) {
+                               const double *prev_joints, int64_t n, double *joints, double *elbow, uint8_t *projected) {
   static const double zero7[7] = {0, 0, 0, 0, 0, 0, 0};
   int stride = pose_kind == ORC_POSE_EULER6 ? 6 : 16;
 #pragma omp parallel for schedule(static)
@@ -1050,16 +1059,18 @@ void orc_symik_no_limits_batch(const orc_arm_config *cfg, int pose_kind, const d
     orc_solver s;
     solver_init(&s, cfg);
     double pos[3], eul[3];
+    if (projected) projected[i] = 0;
     if (load_pose(pose_kind, poses + i * stride, pos, eul) || !solver_is_reachable_no_limits(&s, pos, eul)) {
       fill_nan(joints + 7 * i, 7); fill_nan(elbow + 3 * i, 3);
       continue;
     }
-    solver_get_joints(&s, theta[i], zero7, joints + 7 * i, elbow + 3 * i);
+    if (projected) projected[i] = (uint8_t)elbow_projection_fires(&s, theta[i]);
+    solver_get_joints(&s, theta[i], prev_joints ? prev_joints + 7 * i : zero7, joints + 7 * i, elbow + 3 * i);
   }
 }
 
 void orc_elbow_positions_batch(const orc_arm_config *cfg, int pose_kind, const double *poses, const double *thetas,
-                               int K, int64_t n, double *elbows) {
+                               int K, int64_t n, int no_limits, double *elbows, uint8_t *projected) {
   int stride = pose_kind == ORC_POSE_EULER6 ? 6 : 16;
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; i++) {
@@ -1067,11 +1078,61 @@ void orc_elbow_positions_batch(const orc_arm_config *cfg, int pose_kind, const d
     solver_init(&s, cfg);
     double pos[3], eul[3], itv[2];
     int st;
-    if (load_pose(pose_kind, poses + i * stride, pos, eul) || !solver_is_reachable(&s, pos, eul, itv, &st)) {
+    int bad = load_pose(pose_kind, poses + i * stride, pos, eul);
+    /* the intersection circle is stored as soon as it exists (sik:197), also when the wrist limit then rejects the pose */
+    if (!bad) bad = no_limits ? !solver_is_reachable_no_limits(&s, pos, eul)
+                              : !(solver_is_reachable(&s, pos, eul, itv, &st) || st == ORC_STATE_LIMITED_BY_WRIST);
+    if (bad) {
       fill_nan(elbows + (size_t)i * K * 3, K * 3);
+      if (projected) memset(projected + (size_t)i * K, 0, (size_t)K);
       continue;
     }
-    for (int k = 0; k < K; k++) get_elbow_position(&s, thetas[(size_t)i * K + k], elbows + ((size_t)i * K + k) * 3);
+    for (int k = 0; k < K; k++) {
+      get_elbow_position(&s, thetas[(size_t)i * K + k], elbows + ((size_t)i * K + k) * 3);
+      if (projected) projected[(size_t)i * K + k] = (uint8_t)elbow_projection_fires(&s, thetas[(size_t)i * K + k]);
+    }
+  }
+}
+
+/* One scalar call sequence of the reference's SymbolicIK on goal_pose6 = (x, y, z, roll, pitch, yaw):
+ *   is_reachable (no_limits = 0, sik:121-282) or is_reachable_no_limits (1, sik:85-119), then -- when the call
+ *   succeeded -- get_elbow_position(theta) (sik:684-695) and get_joints(theta, previous_joints) (sik:697-863) with
+ *   theta = *theta_opt or theta_interval[0].  The record also holds the solver attributes the two calls leave behind. */
+void orc_symik_scalar(const orc_arm_config *cfg, const double *goal_pose6, int no_limits, const double *theta_opt,
+                      const double *prev_joints, orc_scalar_result *out) {
+  static const double zero7[7] = {0, 0, 0, 0, 0, 0, 0};
+  orc_solver s;
+  solver_init(&s, cfg);
+  memset(out, 0, sizeof *out);
+  fill_nan(out->interval, 2); fill_nan(out->joints, 7); fill_nan(out->elbow, 3); fill_nan(out->elbow_on_circle, 3);
+  fill_nan(out->goal_position_solved, 3); fill_nan(out->wrist_position_solved, 3);
+  fill_nan(out->goal_position, 3); fill_nan(out->wrist_position, 3);
+  int st = ORC_STATE_REACHABLE, ok;
+  if (no_limits) {
+    ok = solver_is_reachable_no_limits(&s, goal_pose6, goal_pose6 + 3);
+    if (ok) { out->interval[0] = -ORC_PI; out->interval[1] = ORC_PI; } else st = ORC_STATE_SHOULD_NOT_HAPPEN;
+  } else {
+    ok = solver_is_reachable(&s, goal_pose6, goal_pose6 + 3, out->interval, &st);
+  }
+  out->reachable = ok;
+  out->state = st;
+  /* attributes exist once the pre-checks passed (sik:143-144); the circle once it was found (sik:197) */
+  int attrs = no_limits || st == ORC_STATE_REACHABLE || st == ORC_STATE_LIMITED_BY_WRIST || st == ORC_STATE_WRIST_OUT_OF_RANGE ||
+              st == ORC_STATE_SHOULD_NOT_HAPPEN;
+  if (attrs) {
+    memcpy(out->goal_position_solved, s.goal_position, 3 * sizeof(double));
+    memcpy(out->wrist_position_solved, s.wrist_position, 3 * sizeof(double));
+  }
+  int circle = ok || st == ORC_STATE_LIMITED_BY_WRIST;
+  if (circle && (theta_opt || ok)) {
+    double th = theta_opt ? *theta_opt : out->interval[0];
+    get_elbow_position(&s, th, out->elbow_on_circle);
+    if (ok) {
+      out->projected = elbow_projection_fires(&s, th);
+      solver_get_joints(&s, th, prev_joints ? prev_joints : zero7, out->joints, out->elbow);
+      memcpy(out->goal_position, s.goal_position, 3 * sizeof(double));
+      memcpy(out->wrist_position, s.wrist_position, 3 * sizeof(double));
+    }
   }
 }
 

@@ -103,15 +103,36 @@ void orc_symik_batch(const orc_arm_config *cfg, int pose_kind, const double *pos
                      uint8_t *reachable, uint8_t *state, double *interval /* n*2 */,
                      double *joints /* n*7 */, double *elbow /* n*3 */);
 
-/* is_reachable_no_limits + get_joints(theta) (symbolic_ik.py:85-119) */
+/* is_reachable_no_limits + get_joints(theta, previous_joints) (symbolic_ik.py:85-119, 697-863).
+ * prev_joints: nullable n*7 (zeros = the reference default); projected: nullable n, 1 where
+ * make_elbow_projection fired (the reference then returns a 3-vector elbow, :714 / :863). */
 void orc_symik_no_limits_batch(const orc_arm_config *cfg, int pose_kind, const double *poses,
-                               const double *theta /* n */, int64_t n,
-                               double *joints, double *elbow);
+                               const double *theta /* n */, const double *prev_joints, int64_t n,
+                               double *joints, double *elbow, uint8_t *projected);
 
-/* get_elbow_position for K thetas per pose after is_reachable (symbolic_ik.py:684-695) */
+/* get_elbow_position for K thetas per pose after is_reachable (no_limits = 0) or after
+ * is_reachable_no_limits (no_limits = 1) (symbolic_ik.py:684-695; circle stored at :114-116 / :197).
+ * projected: nullable n*K, 1 where get_joints(theta) would take the elbow-projection branch. */
 void orc_elbow_positions_batch(const orc_arm_config *cfg, int pose_kind, const double *poses,
-                               const double *thetas /* n*K */, int K, int64_t n,
-                               double *elbows /* n*K*3 */);
+                               const double *thetas /* n*K */, int K, int64_t n, int no_limits,
+                               double *elbows /* n*K*3 */, uint8_t *projected);
+
+/* Result of one scalar call sequence (orc_symik_scalar); same layout as R2ikScalarResult of include/r2ik.h. */
+typedef struct orc_scalar_result {
+  double interval[2];               /* theta_interval; NaN when the call failed                           */
+  double joints[7];                 /* get_joints(theta, previous_joints)                                 */
+  double elbow[3];                  /* elbow returned by get_joints (after the projection, if it fired)   */
+  double elbow_on_circle[3];        /* get_elbow_position(theta)                                          */
+  double goal_position_solved[3];   /* self.goal_pose[0] / self.wrist_position after is_reachable[_no_limits] */
+  double wrist_position_solved[3];
+  double goal_position[3];          /* ... after get_joints                                               */
+  double wrist_position[3];
+  int32_t reachable, state, projected, reserved;
+} orc_scalar_result;
+
+void orc_symik_scalar(const orc_arm_config *cfg, const double *goal_pose6, int no_limits,
+                      const double *theta_opt /* nullable: theta_interval[0] */,
+                      const double *prev_joints /* nullable 7 */, orc_scalar_result *out);
 
 /* ControlIK.symbolic_inverse_kinematics(name, M, "discrete") (control_ik.py:162-274,409-462).
  * prev_joints: ControlIK.previous_sol[arm]; current_joints: per-call current_joints

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 POSE_EULER6 = 0
 POSE_MAT4 = 1
@@ -69,6 +69,30 @@ class TrajState(C.Structure):
         ("emergency_stop", C.c_int32),
         ("emergency_bits", C.c_int32),
     ]
+
+
+class ScalarQuery(C.Structure):
+    """R2ikScalarQuery: one scalar call sequence of SymbolicIK."""
+
+    _fields_ = [("goal_pose", C.c_double * 6), ("theta", C.c_double), ("previous_joints", C.c_double * 7),
+                ("no_limits", C.c_int32), ("has_theta", C.c_int32)]
+
+
+class ScalarResult(C.Structure):
+    """R2ikScalarResult."""
+
+    _fields_ = [("interval", C.c_double * 2), ("joints", C.c_double * 7), ("elbow", C.c_double * 3),
+                ("elbow_on_circle", C.c_double * 3), ("goal_position_solved", C.c_double * 3),
+                ("wrist_position_solved", C.c_double * 3), ("goal_position", C.c_double * 3),
+                ("wrist_position", C.c_double * 3), ("reachable", C.c_int32), ("state", C.c_int32),
+                ("projected", C.c_int32), ("reserved", C.c_int32)]
+
+
+SCALAR_RESULT_DTYPE = np.dtype([
+    ("interval", "f8", (2,)), ("joints", "f8", (7,)), ("elbow", "f8", (3,)), ("elbow_on_circle", "f8", (3,)),
+    ("goal_position_solved", "f8", (3,)), ("wrist_position_solved", "f8", (3,)), ("goal_position", "f8", (3,)),
+    ("wrist_position", "f8", (3,)), ("reachable", "i4"), ("state", "i4"), ("projected", "i4"), ("reserved", "i4")])
+assert SCALAR_RESULT_DTYPE.itemsize == C.sizeof(ScalarResult) == 232
 
 
 class FkChain(C.Structure):

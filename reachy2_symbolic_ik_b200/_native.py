@@ -9,13 +9,24 @@ import os
 
 from . import _abi
 
-# R2IK_LIB: development aid (kernel tuning variants built by scripts/build_variants.py); same C ABI, same CUDA code base.
-_LIB_PATH = os.environ.get("R2IK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr2ik.so")
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr2ik.so")
 _lib = None
+
+
+def use_library(path: str) -> None:
+    """Bind another build of the same C ABI (the tuning variants of scripts/build_variants.py) instead of the in-tree
+    ``lib/libr2ik.so``.  An explicit call of the experiment scripts, before the first ``load()``; nothing in the
+    package reads the environment for it."""
+    global _LIB_PATH
+    if _lib is not None:
+        raise R2ikError("use_library() must be called before the library is loaded")
+    _LIB_PATH = os.path.abspath(path)
+
 
 EXPORTS = (
     "r2ik_abi_version", "r2ik_last_error", "r2ik_create", "r2ik_destroy", "r2ik_get_constants",
     "r2ik_interval_limit", "r2ik_symik_solve_f64", "r2ik_symik_solve_f32", "r2ik_symik_no_limits_f64", "r2ik_elbow_positions_f64",
+    "r2ik_symik_scalar_f64", "r2ik_stream_synchronize", "r2ik_ctl_ctor_theta_f64",
     "r2ik_ctl_discrete_f64", "r2ik_ctl_discrete_scan_f64", "r2ik_ctl_continuous_f64", "r2ik_ctl_continuous_phased_f64", "r2ik_reach_map_u32", "r2ik_reach_map_f64_u32", "r2ik_fk_f64", "r2ik_copy2d_async",
     "r2ik_dfma_probe", "r2ik_ffma_probe",
 )
@@ -48,12 +59,15 @@ def load() -> C.CDLL:
     L.r2ik_interval_limit.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.r2ik_symik_solve_f64.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.r2ik_symik_solve_f32.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
-    L.r2ik_symik_no_limits_f64.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp, vp]
-    L.r2ik_elbow_positions_f64.argtypes = [vp, C.c_int, vp, vp, i32, i64, vp, vp]
+    L.r2ik_symik_no_limits_f64.argtypes = [vp, C.c_int, vp, vp, vp, i32, i64, vp, vp, vp, vp]
+    L.r2ik_elbow_positions_f64.argtypes = [vp, C.c_int, vp, vp, i32, i64, i32, vp, vp, vp]
+    L.r2ik_symik_scalar_f64.argtypes = [vp, C.POINTER(_abi.ScalarQuery), vp, vp]
+    L.r2ik_stream_synchronize.argtypes = [vp]
+    L.r2ik_ctl_ctor_theta_f64.argtypes = [vp, C.c_double, C.POINTER(C.c_double), i32, C.POINTER(C.c_double), vp, vp]
     L.r2ik_ctl_discrete_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.r2ik_ctl_discrete_scan_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.r2ik_ctl_continuous_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
-    L.r2ik_ctl_continuous_phased_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.r2ik_ctl_continuous_phased_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     L.r2ik_reach_map_u32.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), vp, i32, i32, vp, vp]
     L.r2ik_reach_map_f64_u32.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), vp, i32, i32, vp, vp]
     L.r2ik_fk_f64.argtypes = [C.POINTER(_abi.FkChain), C.c_int, vp, i64, vp, vp]

@@ -115,11 +115,33 @@ class ControlIK:
             self.preferred_theta[arm] = preferred_theta if prefix == "r" else -np.pi - preferred_theta
             self.previous_sol[arm] = np.array(current_joints[k], dtype=np.float64)
             self.previous_pose[arm] = np.array(current_pose[k], dtype=np.float64)
-            # The reference seeds previous_theta here from a call that receives the two-arm joint
-            # list by mistake (control_ik.py:152-158); the value never reaches an
-            # output (discrete mode ignores it, continuous mode re-initialises on its first call).
-            self.previous_theta[arm] = self.preferred_theta[arm]
+            self.previous_theta[arm] = self._initial_previous_theta(arm, current_joints)
             self.last_call_t[arm] = 0.0
+        self._scalar_bufs: Dict[str, Any] = {}
+
+    def _initial_previous_theta(self, arm: str, current_joints) -> float:
+        """``previous_theta`` as the reference's constructor seeds it (control_ik.py:142-159): is_reachable_no_limits on
+        the current pose, then the ternary search of ``get_best_theta_to_current_joints`` (utils.py:267-331) -- which
+        receives the list of BOTH arms' joints there, so its cost runs over ``len(current_joints)`` rows, each
+        broadcast against one joint.  The value never reaches an output (discrete mode ignores
+        it, continuous mode re-initialises on its first call); it is reproduced because it is a visible attribute.
+        One launch of a one-thread kernel (``r2ik_ctl_ctor_theta_f64``), result in mapped pinned memory."""
+        torch = self._torch
+        solver = self.symbolic_ik_solver[arm]
+        rows = np.ascontiguousarray([np.asarray(c, dtype=np.float64) for c in current_joints], dtype=np.float64).reshape(-1, 7)
+        pose = np.ascontiguousarray(self.previous_pose[arm], dtype=np.float64).reshape(16)
+        out = torch.zeros(1, dtype=torch.float64).pin_memory()
+        dp = C.POINTER(C.c_double)
+        lib = solver._handle.lib
+        stream = C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        rc = lib.r2ik_ctl_ctor_theta_f64(solver._handle.h, C.c_double(self.preferred_theta[arm]), rows.ctypes.data_as(dp),
+                                         C.c_int32(len(rows)), pose.ctypes.data_as(dp), C.c_void_p(out.data_ptr()), stream)
+        _native.check(rc, "r2ik_ctl_ctor_theta_f64")
+        _native.check(lib.r2ik_stream_synchronize(stream), "r2ik_stream_synchronize")
+        theta = float(out[0])
+        if np.isnan(theta):
+            raise ValueError("Non-positive determinant (left-handed or null coordinate frame) in rotation matrix")
+        return theta
 
     # ------------------------------------------------------------------ parameters
     def _ctl_params(self, name: str, constrained_mode: str, preferred_theta: float, d_theta_max: float) -> _abi.CtlParams:
@@ -154,7 +176,7 @@ class ControlIK:
                                           constrained_mode: str = "unconstrained", current_pose=None,
                                           d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
                                           previous_joints=None, states=None, out=None, phased: bool = True,
-                                          exhaustive: bool = False):
+                                          exhaustive: bool = False, devices=None, _test_force_serial_mod: int = 0):
         """Batched ``symbolic_inverse_kinematics``.
 
         discrete:   M (N,4,4) -> joints (N,7), reachable (N,), state (N,) uint8, emergency bits (N,).
@@ -170,7 +192,13 @@ class ControlIK:
         warp-cooperative scan kernel.  Same outputs.
         ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans (needs T*W doubles of device
         scratch, allocated here); False = the single one-thread-per-trajectory kernel.  Same flags / states; joints equal to rounding.
+        ``devices``: CUDA ordinals of this node to spread a HOST batch over (contiguous slices of the poses / of the
+        trajectories, one pipeline per device, no inter-GPU traffic); results are NumPy arrays.
         """
+        if devices is not None:
+            return self._batch_on_devices(name, M, control_type, devices, current_joints=current_joints,
+                                          constrained_mode=constrained_mode, current_pose=current_pose, d_theta_max=d_theta_max,
+                                          preferred_theta=preferred_theta, previous_joints=previous_joints, states=states)
         torch = self._torch
         solver = self.symbolic_ik_solver[name]
         par = self._ctl_params(name, constrained_mode, preferred_theta, d_theta_max)
@@ -218,10 +246,10 @@ class ControlIK:
                     reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                     state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                 if phased:
-                    ws = self._scratch(T * W)
+                    ws = self._scratch(T * W, stream.value)
                     rc = solver._handle.lib.r2ik_ctl_continuous_phased_f64(
                         solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
-                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), stream)
+                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
                     _native.check(rc, "r2ik_ctl_continuous_phased_f64")
                 else:
                     rc = solver._handle.lib.r2ik_ctl_continuous_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T),
@@ -234,13 +262,89 @@ class ControlIK:
                 return (*res, st_out)
             raise ValueError(f"Unknown type {control_type}")
 
-    def _scratch(self, n: int):
-        """Device scratch of n doubles for the phased continuous kernels (grown on demand, reused across calls)."""
+    def _scratch(self, n: int, stream_key=0):
+        """Device scratch of n doubles for the phased continuous kernels, one buffer per CUDA stream (launches on one
+        stream are ordered; two streams, or two threads on two streams, must not share it), grown on demand."""
         torch = self._torch
-        buf = getattr(self, "_scratch_buf", None)
+        cache = self.__dict__.setdefault("_scratch_bufs", {})
+        buf = cache.get(stream_key)
         if buf is None or buf.numel() < n or buf.device != self._device:
-            buf = self._scratch_buf = torch.empty(n, dtype=torch.float64, device=self._device)
+            buf = cache[stream_key] = torch.empty(n, dtype=torch.float64, device=self._device)
         return buf
+
+    def clear_caches(self) -> None:
+        """Drop the cached scratch and host-pipeline device buffers."""
+        self.__dict__.pop("_scratch_bufs", None)
+        self.__dict__.pop("_pipe_cache", None)
+
+    def _replica(self, device: int) -> "ControlIK":
+        """This controller's solvers bound to another CUDA device of the process (same parameters, same controller
+        dictionaries): the per-device worker of ``devices=[...]``."""
+        device = int(device)
+        reps = self.__dict__.setdefault("_replicas", {})
+        if self._device is not None and device == self._device.index:
+            return self
+        if device not in reps:
+            import copy
+
+            r = copy.copy(self)
+            r.symbolic_ik_solver = {arm: sv.replica(device) for arm, sv in self.symbolic_ik_solver.items()}
+            r._device = self._torch.device("cuda", device)
+            r.__dict__.pop("_scratch_bufs", None)
+            r.__dict__.pop("_pipe_cache", None)
+            r._scalar_bufs = {}
+            reps[device] = r
+        r = reps[device]
+        r.nb_search_points = self.nb_search_points
+        r.previous_sol, r.previous_pose, r.preferred_theta = self.previous_sol, self.previous_pose, self.preferred_theta
+        return r
+
+    def _batch_on_devices(self, name, M, control_type, devices, **kw):
+        from .workspace import shard_range
+
+        torch = self._torch
+        if hasattr(M, "is_cuda") and M.is_cuda:
+            raise ValueError("devices=[...] spreads a host batch; a CUDA tensor already lives on one device")
+        Mh = M if hasattr(M, "is_cuda") else torch.from_numpy(np.ascontiguousarray(M, dtype=np.float64))
+        Mh = Mh.to(torch.float64).contiguous()
+        n = Mh.shape[0]
+        if control_type == "discrete":
+            out = self.alloc_host_outputs("discrete", n)
+        elif control_type == "continuous":
+            out = self.alloc_host_outputs("continuous", (n, Mh.shape[1]))
+        else:
+            raise ValueError(f"Unknown type {control_type}")
+        devices = [int(d) for d in devices]
+        per_traj = {}
+        if control_type == "continuous":          # per-trajectory arguments follow their trajectories
+            for key, single_ndim in (("current_joints", 1), ("current_pose", 2), ("states", 0)):
+                v = kw.get(key)
+                if v is not None and np.ndim(v) == single_ndim + 1 and len(v) == n and np.shape(v) != (4, 4):
+                    per_traj[key] = v
+        workers = []
+        for r, d in enumerate(devices):
+            lo, hi = shard_range(n, r, len(devices))
+            if hi == lo:
+                continue
+            kws = dict(kw)
+            for key, v in per_traj.items():
+                kws[key] = v[lo:hi]
+            sub = tuple(o[lo:hi] for o in out)
+            rep = self._replica(d)
+            rep.symbolic_inverse_kinematics_batch_host(name, Mh[lo:hi], control_type, out=sub, _wait=False, **kws)
+            workers.append(rep)
+        for rep in workers:
+            rep._wait_pipelines()
+        res = [o.numpy() for o in out]
+        res[1] = res[1].astype(bool)
+        if control_type == "continuous":
+            res[3] = res[3].reshape(-1).view(_abi.TRAJ_STATE_DTYPE).copy()
+        return tuple(res)
+
+    def _wait_pipelines(self):
+        for pipe in getattr(self, "_pipe_cache", {}).values():
+            for s in pipe["streams"]:
+                s.synchronize()
 
     # ------------------------------------------------------------------ host-buffer pipelines
     def alloc_host_outputs(self, control_type: str, shape) -> tuple:
@@ -261,7 +365,7 @@ class ControlIK:
                                                chunk: int | None = None, n_streams: int = 3, current_joints=None,
                                                constrained_mode: str = "unconstrained", current_pose=None,
                                                d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
-                                               previous_joints=None, states=None):
+                                               previous_joints=None, states=None, _wait: bool = True):
         """Host-to-host ``symbolic_inverse_kinematics_batch``: ``M_host`` is a CPU tensor (ideally pinned),
         (N,4,4)/(N,16) for discrete mode or (T,W,4,4)/(T,W,16) for continuous mode; the results land in
         ``out`` (pinned CPU tensors from ``alloc_host_outputs``).  The batch is cut into chunks -- ``chunk``
@@ -274,6 +378,12 @@ class ControlIK:
         lib, h = solver._handle.lib, solver._handle.h
         if not hasattr(M_host, "is_cuda"):
             M_host = torch.from_numpy(np.ascontiguousarray(M_host, dtype=np.float64))
+        if M_host.is_cuda:
+            raise ValueError("symbolic_inverse_kinematics_batch_host takes host matrices; use symbolic_inverse_kinematics_batch "
+                             "for CUDA tensors")
+        # the copies below address raw rows of the host buffers: dense float64 only (a float32 tensor or a strided view
+        # such as big[:, :W] would be read with the wrong pitch)
+        M_host = M_host.to(torch.float64).contiguous()
         dev = self._device
         f64, u8 = torch.float64, torch.uint8
         with torch.cuda.device(dev):
@@ -317,6 +427,13 @@ class ControlIK:
                 wc = chunk or max(1, min(W, (1 << 18) // max(T, 1)))          # waypoints per chunk
                 if out is None:
                     out = self.alloc_host_outputs("continuous", (T, W))
+                want = (((T, W, 7), f64), ((T, W), u8), ((T, W), u8), ((T, _abi.TRAJ_STATE_DTYPE.itemsize), u8))
+                for i, (shape, dtype) in enumerate(want):
+                    o = out[i]
+                    if (not hasattr(o, "is_cuda") or o.is_cuda or o.dtype != dtype or tuple(o.shape) != shape
+                            or not o.is_contiguous()):
+                        raise ValueError(f"out[{i}] must be a contiguous CPU tensor of shape {shape} and dtype {dtype} "
+                                         "(see alloc_host_outputs)")
                 cj = torch.empty((T, 7), dtype=f64, device=dev)
                 cj[:] = self._dev(self.previous_sol[name] if current_joints is None else current_joints)
                 cp = torch.empty((T, 16), dtype=f64, device=dev)
@@ -354,7 +471,8 @@ class ControlIK:
                         s_k.wait_event(e["d2h"])                  # this slot's previous results have left
                     rc = lib.r2ik_ctl_continuous_phased_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
                                                             _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]),
-                                                            _ptr(b["state"]), _ptr(b["ws"]), C.c_void_p(s_k.cuda_stream))
+                                                            _ptr(b["state"]), _ptr(b["ws"]), C.c_int32(0),
+                                                            C.c_void_p(s_k.cuda_stream))
                     _native.check(rc, "r2ik_ctl_continuous_phased_f64")
                     e["k"] = torch.cuda.Event()
                     e["k"].record(s_k)
@@ -369,9 +487,12 @@ class ControlIK:
                     out[3].copy_(st, non_blocking=True)
             else:
                 raise ValueError(f"Unknown type {control_type}")
-            for s in pipe["streams"]:
-                s.synchronize()
+            if _wait:
+                for s in pipe["streams"]:
+                    s.synchronize()
         return out
+
+    _PIPE_CACHE_MAX = 4   # distinct pipeline shapes kept per controller (device buffers)
 
     def _pipeline(self, key, make_bufs, n_streams: int):
         cache = getattr(self, "_pipe_cache", None)
@@ -379,6 +500,8 @@ class ControlIK:
             cache = self._pipe_cache = {}
         if key not in cache:
             torch = self._torch
+            while len(cache) >= self._PIPE_CACHE_MAX:      # bounded: the oldest pipeline's buffers go back to the allocator
+                cache.pop(next(iter(cache)))
             cache[key] = {"streams": [torch.cuda.Stream(device=self._device) for _ in range(n_streams)],
                           "bufs": [make_bufs() for _ in range(n_streams)]}
         return cache[key]
@@ -419,40 +542,86 @@ class ControlIK:
             ik_joints, is_reachable, state = self._continuous_one(name, M, current_joints, current_pose, constrained_mode,
                                                                   preferred_theta, d_theta_max)
         elif control_type == "discrete":
-            j, r, s, e = self.symbolic_inverse_kinematics_batch(
-                name, M[None], "discrete", current_joints=current_joints, constrained_mode=constrained_mode,
-                preferred_theta=preferred_theta)
-            if int(s[0]) == STATE_INVALID_ROTATION:
-                raise ValueError("Non-positive determinant (left-handed or null coordinate frame) in rotation matrix")
-            ik_joints, is_reachable, state = j[0], bool(r[0]), STATE_STRINGS[int(s[0])]
-            if int(e[0]):
-                self.emergency_state += emergency_text(int(e[0]))
-                self.emergency_stop = True
+            ik_joints, is_reachable, state = self._discrete_one(name, M, current_joints, constrained_mode, preferred_theta)
         else:
             raise ValueError(f"Unknown type {control_type}")
         self.previous_pose[name] = M
         return ik_joints, is_reachable, state
 
-    def _continuous_one(self, name, M, current_joints, current_pose, constrained_mode, preferred_theta, d_theta_max):
-        t = time.time()
-        if abs(t - self.last_call_t[name]) > self.call_timeout:  # control_ik.py:296-304
-            self.previous_sol[name] = np.array([])
-            self.init = True
-        self.last_call_t[name] = t
-        st = np.zeros(1, dtype=_abi.TRAJ_STATE_DTYPE)
-        st["init"] = int(self.init)
-        st["previous_theta"] = self.previous_theta[name]
-        if len(self.previous_sol[name]) != 0:
-            st["has_previous_sol"] = 1
-            st["previous_sol"][0] = self.previous_sol[name]
-        # previous_sol must be defined for the parameter builder when it was just reset
-        j, r, s, st = self.symbolic_inverse_kinematics_batch(
-            name, M[None, None], "continuous", current_joints=np.asarray(current_joints, dtype=np.float64),
-            constrained_mode=constrained_mode, current_pose=np.asarray(current_pose, dtype=np.float64),
-            d_theta_max=d_theta_max, preferred_theta=preferred_theta, states=st)
-        code = int(s[0, 0])
+    # One control tick = ONE kernel launch + one stream synchronisation: the inputs and the results of the N = 1 call live
+    # in a page of mapped pinned host memory that the kernel reads and writes directly (no allocation, no cudaMemcpy).
+    _SC_M, _SC_PREV, _SC_CUR, _SC_CP, _SC_ST, _SC_J, _SC_FLAGS = 0, 16, 23, 30, 46, 56, 63   # offsets in doubles
+
+    def _scalar_page(self, name: str):
+        b = self._scalar_bufs.get(name)
+        if b is None:
+            torch = self._torch
+            page = torch.zeros(64, dtype=torch.float64).pin_memory()
+            b = self._scalar_bufs[name] = dict(page=page, f=page.numpy(), u8=page.numpy().view(np.uint8), base=page.data_ptr())
+        return b
+
+    def _discrete_one(self, name, M, current_joints, constrained_mode, preferred_theta):
+        torch = self._torch
+        solver = self.symbolic_ik_solver[name]
+        par = self._ctl_params(name, constrained_mode, preferred_theta, 0.01)
+        b = self._scalar_page(name)
+        f, u8, base = b["f"], b["u8"], b["base"]
+        f[self._SC_M:self._SC_M + 16] = M.reshape(16)
+        f[self._SC_PREV:self._SC_PREV + 7] = self.previous_sol[name]
+        f[self._SC_CUR:self._SC_CUR + 7] = current_joints
+        at = lambda off: C.c_void_p(base + 8 * off)   # noqa: E731
+        fl = 8 * self._SC_FLAGS
+        lib = solver._handle.lib
+        stream = C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        rc = lib.r2ik_ctl_discrete_f64(solver._handle.h, C.byref(par), at(self._SC_M), C.c_int64(1), at(self._SC_PREV),
+                                       at(self._SC_CUR), at(self._SC_J), C.c_void_p(base + fl), C.c_void_p(base + fl + 1),
+                                       C.c_void_p(base + fl + 2), stream)
+        _native.check(rc, "r2ik_ctl_discrete_f64")
+        _native.check(lib.r2ik_stream_synchronize(stream), "r2ik_stream_synchronize")
+        reach, code, bits = int(u8[fl]), int(u8[fl + 1]), int(u8[fl + 2])
         if code == STATE_INVALID_ROTATION:
             raise ValueError("Non-positive determinant (left-handed or null coordinate frame) in rotation matrix")
+        if bits:
+            self.emergency_state += emergency_text(bits)
+            self.emergency_stop = True
+        return f[self._SC_J:self._SC_J + 7].copy(), bool(reach), STATE_STRINGS[code]
+
+    def _continuous_one(self, name, M, current_joints, current_pose, constrained_mode, preferred_theta, d_theta_max):
+        torch = self._torch
+        solver = self.symbolic_ik_solver[name]
+        par = self._ctl_params(name, constrained_mode, preferred_theta, d_theta_max)
+        t = time.time()
+        timed_out = abs(t - self.last_call_t[name]) > self.call_timeout            # control_ik.py:296-304
+        st = np.zeros(1, dtype=_abi.TRAJ_STATE_DTYPE)
+        st["init"] = 1 if timed_out else int(self.init)
+        st["previous_theta"] = self.previous_theta[name]
+        if not timed_out and len(self.previous_sol[name]) != 0:
+            st["has_previous_sol"] = 1
+            st["previous_sol"][0] = self.previous_sol[name]
+        b = self._scalar_page(name)
+        f, u8, base = b["f"], b["u8"], b["base"]
+        f[self._SC_M:self._SC_M + 16] = M.reshape(16)
+        f[self._SC_CUR:self._SC_CUR + 7] = np.asarray(current_joints, dtype=np.float64)
+        f[self._SC_CP:self._SC_CP + 16] = np.asarray(current_pose, dtype=np.float64).reshape(16)
+        u8[8 * self._SC_ST:8 * self._SC_ST + 80] = st.view(np.uint8)
+        at = lambda off: C.c_void_p(base + 8 * off)   # noqa: E731
+        fl = 8 * self._SC_FLAGS
+        lib = solver._handle.lib
+        stream = C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        rc = lib.r2ik_ctl_continuous_f64(solver._handle.h, C.byref(par), at(self._SC_M), C.c_int64(1), C.c_int32(1),
+                                         at(self._SC_CUR), at(self._SC_CP), at(self._SC_ST), at(self._SC_J),
+                                         C.c_void_p(base + fl), C.c_void_p(base + fl + 1), stream)
+        _native.check(rc, "r2ik_ctl_continuous_f64")
+        _native.check(lib.r2ik_stream_synchronize(stream), "r2ik_stream_synchronize")
+        reach, code = int(u8[fl]), int(u8[fl + 1])
+        if code == STATE_INVALID_ROTATION:
+            # scipy raises inside get_euler_from_homogeneous_matrix (control_ik.py:216), before the reference touches
+            # any controller state: nothing of this call is kept
+            raise ValueError("Non-positive determinant (left-handed or null coordinate frame) in rotation matrix")
+        if timed_out:
+            self.init = True
+        self.last_call_t[name] = t
+        st = u8[8 * self._SC_ST:8 * self._SC_ST + 80].copy().view(_abi.TRAJ_STATE_DTYPE)
         self.previous_theta[name] = float(st["previous_theta"][0])
         self.previous_sol[name] = np.array(st["previous_sol"][0])
         self.init = bool(st["init"][0])
@@ -464,4 +633,4 @@ class ControlIK:
                 self.emergency_state += (f"\n EMERGENCY STOP: joints are not continuous \n previous_joints: "
                                          f"{self.previous_sol[name]} \n joints: (see device log)")
         state = self.emergency_state if code == STATE_EMERGENCY else STATE_STRINGS[code]
-        return np.array(j[0, 0]), bool(r[0, 0]), state
+        return f[self._SC_J:self._SC_J + 7].copy(), bool(reach), state

@@ -226,6 +226,33 @@ R2IK_HD double best_theta_to_current_joints(const ArmConst &A, Solve &S, const d
   return best;
 }
 
+// The same search as ControlIK's CONSTRUCTOR runs it (ctl:142-159): there `current_joints` is the list of BOTH arms' joint
+// lists, so the reference's cost loops over i < len(current_joints) = n_rows and broadcasts joints[i] against the whole
+// row i:  cost^2 = sum_{i < n_rows} sum_{k < 7} angle_diff(joints[i], rows[i][k])^2  (SURVEY.md A.6.11).  The value
+// seeds ControlIK.previous_theta, a visible attribute that no output depends on.
+R2IK_HD double ctor_rows_distance(const double j[7], const double *rows, int n_rows) {
+  double s = 0.0;
+  for (int i = 0; i < n_rows; ++i)
+    for (int k = 0; k < 7; ++k) { double d = angle_diff(j[i], rows[7 * i + k]); s += d * d; }
+  return sqrt(s);
+}
+R2IK_HD double ctor_previous_theta(const ArmConst &A, Solve &S, const double *rows, int n_rows, double preferred_theta) {
+  double low = -kPi, high = kPi;
+  if (A.side < 0) { low = 0.0; high = kTwoPi; }
+  const double tolerance = 0.01;
+  double j1[7], j2[7], E[3];
+  get_joints(A, S, preferred_theta, 0.0, 0.0, j1, E);
+  if (ctor_rows_distance(j1, rows, n_rows) < tolerance) return preferred_theta;
+  while ((high - low) > tolerance) {
+    double mid1 = low + (high - low) / 3;
+    double mid2 = high - (high - low) / 3;
+    get_joints(A, S, mid1, 0.0, 0.0, j1, E);
+    get_joints(A, S, mid2, 0.0, 0.0, j2, E);
+    if (ctor_rows_distance(j1, rows, n_rows) < ctor_rows_distance(j2, rows, n_rows)) high = mid2; else low = mid1;
+  }
+  return (low + high) / 2;
+}
+
 // Selection + joints + safety for one pose whose is_reachable result is already known.
 // Shared tail of the discrete path (ctl:454-462).
 R2IK_HD int discrete_finish(const ArmConst &A, const R2ikCtlParams &par, Solve &S, bool found, double theta,

@@ -93,7 +93,7 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
     rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
   }
   bool ok = rc.state == R2IK_STATE_REACHABLE;
-  reachable[i] = ok ? 1 : 0;
+  if (reachable) reachable[i] = ok ? 1 : 0;   // nullable: state == R2IK_STATE_REACHABLE says the same (lean host record)
   state[i] = (uint8_t)rc.state;
   if (interval) { interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1; }
   if (!joints && !elbow) return;
@@ -207,42 +207,133 @@ k_symik_escalated_f32(const __grid_constant__ ArmConst A64, const float *__restr
   }
 }
 
+// sik:697-718: does get_joints(cos theta, sin theta) take the make_elbow_projection branch on the solved pose?  (The
+// reference then returns the elbow as a 3-vector instead of get_elbow_position's homogeneous [x, y, z, 1], sik:714, :863.)
+__device__ __forceinline__ bool elbow_projection_fires(const ArmConst &A, const Solve &S, double ct, double st) {
+  double E[3];
+  elbow_position_cs(S, ct, st, E);
+  return E[2] > (E[0] - A.es[0]) * A.sing_coeff + A.es[2] - A.sing_offset;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(R2IK_BLOCK)
 k_symik_no_limits(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ theta,
-                  int64_t n, double *__restrict__ joints, double *__restrict__ elbow) {
+                  const double *__restrict__ prev_joints, int prev_stride, int64_t n, double *__restrict__ joints,
+                  double *__restrict__ elbow, uint8_t *__restrict__ projected) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double pos[3], j[7], E[3];
   Solve S;
   bool ok = load_pose<KIND>(poses, i, false, pos, S.R);
   if (ok) ok = is_reachable_R<true>(A, pos, S).state == R2IK_STATE_REACHABLE;
+  bool proj = false;
   if (ok) {
-    get_joints(A, S, theta[i], 0.0, 0.0, j, E);
+    double prev0 = 0.0, prev2 = 0.0;   // previous_joints only matter at the exact singularities (sik:751, 782)
+    if (prev_joints) { prev0 = prev_joints[(size_t)prev_stride * i]; prev2 = prev_joints[(size_t)prev_stride * i + 2]; }
+    double st, ct;
+    sincos_any(theta[i], st, ct);
+    proj = elbow_projection_fires(A, S, ct, st);
+    get_joints_cs(A, S, ct, st, prev0, prev2, j, E);
   } else {
     for (int k = 0; k < 7; ++k) j[k] = NAN;
     E[0] = NAN; E[1] = NAN; E[2] = NAN;
   }
   for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
   if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+  if (projected) projected[i] = proj ? 1 : 0;
 }
 
-template <int KIND>
+// get_elbow_position(thetas[i][k]) on the circle is_reachable (NO_LIMITS = false) or is_reachable_no_limits (true) stores.
+// The reference stores the circle as soon as it exists (sik:197), i.e. also when the wrist limit then rejects the pose.
+template <int KIND, bool NO_LIMITS>
 __global__ void __launch_bounds__(R2IK_BLOCK)
 k_elbow_positions(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ thetas,
-                  int K, int64_t n, double *__restrict__ elbows) {
+                  int K, int64_t n, double *__restrict__ elbows, uint8_t *__restrict__ projected) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double pos[3];
   Solve S;
   bool ok = load_pose<KIND>(poses, i, false, pos, S.R);
-  if (ok) ok = is_reachable_R<false>(A, pos, S).state == R2IK_STATE_REACHABLE;
+  if (ok) {
+    const int st = is_reachable_R<NO_LIMITS>(A, pos, S).state;
+    ok = st == R2IK_STATE_REACHABLE || (!NO_LIMITS && st == R2IK_STATE_LIMITED_BY_WRIST);
+  }
   for (int k = 0; k < K; ++k) {
     double E[3] = {NAN, NAN, NAN};
-    if (ok) elbow_position(S, thetas[(size_t)i * K + k], E);
+    bool proj = false;
+    if (ok) {
+      double st, ct;
+      sincos_any(thetas[(size_t)i * K + k], st, ct);
+      elbow_position_cs(S, ct, st, E);
+      proj = E[2] > (E[0] - A.es[0]) * A.sing_coeff + A.es[2] - A.sing_offset;
+    }
     double *o = elbows + ((size_t)i * K + k) * 3;
     o[0] = E[0]; o[1] = E[1]; o[2] = E[2];
+    if (projected) projected[(size_t)i * K + k] = proj ? 1 : 0;
   }
+}
+
+// The reference's scalar call sequence in ONE launch of one thread: is_reachable (or is_reachable_no_limits), then
+// get_elbow_position(theta) and get_joints(theta, previous_joints).  The query travels as a kernel parameter (no
+// input buffer) and the record may live in mapped pinned host memory, so a scalar facade call is one launch + one
+// stream synchronisation (the consumer of the reference calls it once per control tick, src/example/example_control.py:9-27).
+template <bool NO_LIMITS>
+__device__ __forceinline__ void scalar_body(const ArmConst &A, const R2ikScalarQuery &q, R2ikScalarResult &r) {
+  const double pos[3] = {q.goal_pose[0], q.goal_pose[1], q.goal_pose[2]};
+  Solve S;
+  rot_from_euler_xyz(q.goal_pose[3], q.goal_pose[4], q.goal_pose[5], S.R);
+  // the pre-checked position is what the reference stores in self.goal_pose (sik:143); is_reachable_R recomputes it
+  const Reach rc = is_reachable_R<NO_LIMITS>(A, pos, S);
+  r.state = rc.state;
+  r.reachable = rc.state == R2IK_STATE_REACHABLE ? 1 : 0;
+  const bool attrs = NO_LIMITS || rc.state == R2IK_STATE_REACHABLE || rc.state == R2IK_STATE_LIMITED_BY_WRIST ||
+                     rc.state == R2IK_STATE_WRIST_OUT_OF_RANGE || rc.state == R2IK_STATE_SHOULD_NOT_HAPPEN;
+  if (attrs) {
+    for (int k = 0; k < 3; ++k) { r.goal_position_solved[k] = S.p[k]; r.wrist_position_solved[k] = S.w[k]; }
+  }
+  if (r.reachable) { r.interval[0] = rc.i0; r.interval[1] = rc.i1; }
+  const bool circle = r.reachable || (!NO_LIMITS && rc.state == R2IK_STATE_LIMITED_BY_WRIST);
+  if (circle && (q.has_theta || r.reachable)) {
+    double st = rc.s0, ct = rc.c0;
+    if (q.has_theta) sincos_any(q.theta, st, ct);
+    elbow_position_cs(S, ct, st, r.elbow_on_circle);
+    if (r.reachable) {
+      r.projected = elbow_projection_fires(A, S, ct, st) ? 1 : 0;
+      get_joints_cs(A, S, ct, st, q.previous_joints[0], q.previous_joints[2], r.joints, r.elbow);
+      for (int k = 0; k < 3; ++k) { r.goal_position[k] = S.p[k]; r.wrist_position[k] = S.w[k]; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_symik_scalar(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikScalarQuery q, R2ikScalarResult *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  R2ikScalarResult r;
+  r.interval[0] = NAN; r.interval[1] = NAN;
+  for (int k = 0; k < 7; ++k) r.joints[k] = NAN;
+  for (int k = 0; k < 3; ++k) {
+    r.elbow[k] = NAN; r.elbow_on_circle[k] = NAN; r.goal_position_solved[k] = NAN; r.wrist_position_solved[k] = NAN;
+    r.goal_position[k] = NAN; r.wrist_position[k] = NAN;
+  }
+  r.reachable = 0; r.state = 0; r.projected = 0; r.reserved = 0;
+  if (q.no_limits) scalar_body<true>(A, q, r);
+  else scalar_body<false>(A, q, r);
+  *out = r;
+}
+
+// ControlIK.__init__'s seed of previous_theta (ctl:142-159): is_reachable_no_limits on the current pose (identity snap of
+// ctl:142), then the constructor's form of the ternary search.  One thread; arguments by value; result to any
+// device-accessible address.
+struct CtorThetaArgs { double rows[49]; double current_pose[16]; double preferred_theta; int n_rows; int pad; };
+__global__ void __launch_bounds__(32)
+k_ctl_ctor_theta(const __grid_constant__ ArmConst A, const __grid_constant__ CtorThetaArgs a, double *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Solve S;
+  const double cpos[3] = {a.current_pose[3], a.current_pose[7], a.current_pose[11]};
+  double theta = NAN;
+  if (rotation_from_mat4(a.current_pose, true, S.R) && is_reachable_R<true>(A, cpos, S).state == R2IK_STATE_REACHABLE)
+    theta = ctor_previous_theta(A, S, a.rows, a.n_rows, a.preferred_theta);
+  out[0] = theta;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -562,7 +653,7 @@ k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2
     sincos_any(ws[k], st, ct);
     // straight-line get_joints only; a degenerate input (exact singularity: needs previous_sol) is left to the scan
     serial = !get_joints_impl<false>(A, S, ct, st, 0.0, 0.0, j, E);
-    // test hook (R2IK_DEBUG_FORCE_SERIAL=m): every m-th waypoint is sent down the serial route although it does not
+    // test hook (ABI parameter test_force_serial_mod = m > 0): every m-th waypoint is sent down the serial route although it does not
     // need it, so that the stop / fixup machinery of the finish scan is exercised on ordinary data
     if (force_serial_mod > 0 && k % force_serial_mod == 0) serial = true;
     if (!serial) limit_orbita3d_wrist(j, par.orbita3d_max_angle);
@@ -915,7 +1006,7 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: bad n or pose_kind");
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null handle");
   if (n == 0) return 0;  // empty batch: nothing to read or write
-  if (!poses || !reachable || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
+  if (!poses || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
@@ -933,7 +1024,13 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
   if (n < 0 || n > 0xffffffffLL || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: bad n (0 .. 2^32-1) or pose_kind");
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null handle");
-  if (n == 0) return 0;
+  if (n == 0) {   // the contract "the call sets n_escalated" holds for an empty batch too
+    if (n_escalated) {
+      R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+      R2IK_CUDA(cudaMemsetAsync(n_escalated, 0, sizeof(uint32_t), (cudaStream_t)stream), "cudaMemsetAsync");
+    }
+    return 0;
+  }
   if (!poses || !reachable || !state || !escalated_idx || !n_escalated)
     return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null argument");
   if (((uintptr_t)poses & (pose_kind == R2IK_POSE_MAT4 ? 15 : 7)) != 0 || ((uintptr_t)interval & 7) != 0)
@@ -954,10 +1051,10 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
   return 0;
 }
 
-int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, int64_t n,
-                             double *joints, double *elbow, void *stream) {
-  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
-    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_no_limits_f64: bad n or pose_kind");
+int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, const double *prev_joints,
+                             int32_t prev_stride, int64_t n, double *joints, double *elbow, uint8_t *projected, void *stream) {
+  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4) || (prev_stride != 0 && prev_stride != 7))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_symik_no_limits_f64: bad n, pose_kind or prev_stride (0 = broadcast, 7 = per pose)");
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null handle");
   if (n == 0) return 0;
   if (!poses || !theta || !joints) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null argument");
@@ -965,15 +1062,15 @@ int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, 
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
-    k_symik_no_limits<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, n, joints, elbow);
+    k_symik_no_limits<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, prev_stride, n, joints, elbow, projected);
   else
-    k_symik_no_limits<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, n, joints, elbow);
+    k_symik_no_limits<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, prev_stride, n, joints, elbow, projected);
   R2IK_CUDA(cudaGetLastError(), "k_symik_no_limits launch");
   return 0;
 }
 
 int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, const double *thetas, int32_t K, int64_t n,
-                             double *elbows, void *stream) {
+                             int32_t no_limits, double *elbows, uint8_t *projected, void *stream) {
   if (n < 0 || K < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
     return fail_arg(R2IK_ERR_ARG, "r2ik_elbow_positions_f64: bad n, K or pose_kind");
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null handle");
@@ -982,11 +1079,44 @@ int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, 
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_elbow_positions_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
-  if (pose_kind == R2IK_POSE_MAT4)
-    k_elbow_positions<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows);
-  else
-    k_elbow_positions<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows);
+  const unsigned g = blocks_for(n);
+  if (pose_kind == R2IK_POSE_MAT4) {
+    if (no_limits) k_elbow_positions<R2IK_POSE_MAT4, true><<<g, R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows, projected);
+    else k_elbow_positions<R2IK_POSE_MAT4, false><<<g, R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows, projected);
+  } else {
+    if (no_limits) k_elbow_positions<R2IK_POSE_EULER6, true><<<g, R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows, projected);
+    else k_elbow_positions<R2IK_POSE_EULER6, false><<<g, R2IK_BLOCK, 0, s>>>(h->A, poses, thetas, K, n, elbows, projected);
+  }
   R2IK_CUDA(cudaGetLastError(), "k_elbow_positions launch");
+  return 0;
+}
+
+int r2ik_symik_scalar_f64(r2ik_handle h, const R2ikScalarQuery *query, R2ikScalarResult *out, void *stream) {
+  if (!h || !query || !out) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_scalar_f64: null argument");
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  k_symik_scalar<<<1, 32, 0, (cudaStream_t)stream>>>(h->A, *query, out);
+  R2IK_CUDA(cudaGetLastError(), "k_symik_scalar launch");
+  return 0;
+}
+
+int r2ik_ctl_ctor_theta_f64(r2ik_handle h, double preferred_theta, const double *current_joints_rows, int32_t n_rows,
+                            const double *current_pose, double *out_theta, void *stream) {
+  if (!h || !current_joints_rows || !current_pose || !out_theta) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_ctor_theta_f64: null argument");
+  if (n_rows < 0 || n_rows > 7) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_ctor_theta_f64: n_rows must be 0 .. 7 (the reference indexes joints[i] by the row)");
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  CtorThetaArgs a;
+  memset(&a, 0, sizeof a);
+  memcpy(a.rows, current_joints_rows, sizeof(double) * 7 * (size_t)n_rows);
+  memcpy(a.current_pose, current_pose, sizeof(double) * 16);
+  a.preferred_theta = preferred_theta;
+  a.n_rows = n_rows;
+  k_ctl_ctor_theta<<<1, 32, 0, (cudaStream_t)stream>>>(h->A, a, out_theta);
+  R2IK_CUDA(cudaGetLastError(), "k_ctl_ctor_theta launch");
+  return 0;
+}
+
+int r2ik_stream_synchronize(void *stream) {
+  R2IK_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
   return 0;
 }
 
@@ -1042,7 +1172,8 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const doubl
 
 int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
                                    const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
-                                   uint8_t *reachable, uint8_t *state, double *workspace, void *stream) {
+                                   uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
+                                   void *stream) {
   if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_phased_f64: null handle or parameters");
   if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: bad T, W or nb_search_points_continuous");
@@ -1057,19 +1188,10 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
   const unsigned tb = (unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK);
   k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
   k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
-  const char *dbg = getenv("R2IK_DEBUG_FORCE_SERIAL");
-  k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints, dbg ? atoi(dbg) : 0);
+  k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints, test_force_serial_mod);
   const ScanConst K = {kPi, kTwoPi, 2.0 * kTwoPi, 4.0 * kTwoPi, 6.0 * kPi};
-  {
-    static const int lanes = [] { const char *e = getenv("R2IK_FIN_LANES"); return e ? atoi(e) : R2IK_FIN_LANES; }();
-    const auto blocks = [&](int G) { return (unsigned)((T * G + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK); };
-    if (lanes == 2)
-      k_cont_finish_lanes<2><<<blocks(2), R2IK_FIN8_BLOCK, 0, s>>>(K, T, W, current_joints, st, workspace, joints, reachable, state);
-    else if (lanes == 8)
-      k_cont_finish_lanes<8><<<blocks(8), R2IK_FIN8_BLOCK, 0, s>>>(K, T, W, current_joints, st, workspace, joints, reachable, state);
-    else
-      k_cont_finish_lanes<4><<<blocks(4), R2IK_FIN8_BLOCK, 0, s>>>(K, T, W, current_joints, st, workspace, joints, reachable, state);
-  }
+  k_cont_finish_lanes<R2IK_FIN_LANES><<<(unsigned)((T * R2IK_FIN_LANES + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK), R2IK_FIN8_BLOCK, 0, s>>>(
+      K, T, W, current_joints, st, workspace, joints, reachable, state);
   k_cont_finish_direct<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state,
                                                     true);
   R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");

@@ -12,7 +12,7 @@
 // magnitudes) stops there, keeps its state, and is finished by k_cont_finish_direct<fixup>.
 #define R2IK_FIN8_BLOCK 128
 #ifndef R2IK_FIN_LANES
-#define R2IK_FIN_LANES 4   // lanes per trajectory of the finish scan (2, 4 or 8; env R2IK_FIN_LANES overrides for tuning)
+#define R2IK_FIN_LANES 4   // lanes per trajectory of the finish scan (2, 4 or 8; a build-time choice)
 #endif
 // Constants of the scan as a kernel parameter: constant-bank operands of DADD / DSETP instead of 64-bit immediates
 // that cost a UMOV pair per use (23 of the first version's 206 instructions per waypoint).

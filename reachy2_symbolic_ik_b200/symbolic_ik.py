@@ -3,8 +3,9 @@ runs in the sm_100a CUDA library (``libr2ik.so``), plus batched entry points.
 
 Reference interface mirrored here: constructor ``symbolic_ik.py:26-83``; ``is_reachable``
 ``:121-282``; ``is_reachable_no_limits`` ``:85-119``; ``get_joints`` ``:697-863``;
-``get_elbow_position`` ``:684-695``.  The scalar calls are N = 1 launches of the same kernels
-as the batched calls; there is no CPU code path.
+``get_elbow_position`` ``:684-695``.  A scalar call is ONE launch of a one-thread kernel
+(``r2ik_symik_scalar_f64``: the query travels as a kernel parameter, the result record lands in mapped pinned
+host memory) plus one stream synchronisation; there is no CPU code path.
 
 Semantics that differ from the reference on purpose: ``get_joints`` of the
 reference mutates the solver when the elbow projection fires, so a second call on the same
@@ -128,14 +129,38 @@ class SymbolicIK:
         self.elbow_singularity_position = np.array(k.elbow_singularity_position[:])
         self.wrist_singularity_position = np.array(k.wrist_singularity_position[:])
 
-        # state of the scalar API: the last pose handed to is_reachable / is_reachable_no_limits
+        self._ctor = dict(arm=arm, ik_parameters=ik_parameters, elbow_limit=elbow_limit, wrist_limit=wrist_limit,
+                          projection_margin=projection_margin, backward_limit=backward_limit,
+                          normal_vector_margin=normal_vector_margin, singularity_offset=singularity_offset,
+                          singularity_limit_coeff=singularity_limit_coeff)
+        self._replicas: dict = {self._handle.device: self}
+
+        # state of the scalar API: the last pose handed to is_reachable / is_reachable_no_limits (the reference
+        # keeps the solved pose on the instance; here every later call re-solves from the pose as it was given)
         self.goal_pose: Optional[np.ndarray] = None
+        self.wrist_position: Optional[np.ndarray] = None
         self.elbow_position: Optional[np.ndarray] = None
+        self._pose_in: Optional[np.ndarray] = None
         self._no_limits = False
+        self._scalar_query = _abi.ScalarQuery()
+        self._scalar_pinned = None   # pinned (mapped) host record the scalar kernel writes, allocated on first use
+
+    def replica(self, device: int) -> "SymbolicIK":
+        """The same solver (same constructor arguments) bound to another CUDA device of this process; cached."""
+        device = int(device)
+        if device not in self._replicas:
+            import contextlib
+            import io
+
+            with contextlib.redirect_stdout(io.StringIO()):   # the constructor prints like the reference's
+                r = SymbolicIK(device=device, **self._ctor)
+            r._replicas = self._replicas
+            self._replicas[device] = r
+        return self._replicas[device]
 
     # ------------------------------------------------------------------ batched API
     def is_reachable_batch(self, poses, theta=None, previous_joints=None, want_joints: bool = True,
-                           precision: str = "fp64") -> BatchResult:
+                           precision: str = "fp64", devices=None) -> BatchResult:
         """``is_reachable`` + ``theta_to_joints_func(theta)`` for N poses in one launch.
 
         poses: (N,4,4) homogeneous matrices (converted like the reference's ControlIK front
@@ -144,9 +169,20 @@ class SymbolicIK:
         precision: "fp64" (the correctness reference, 1e-9 rad) or "fp32" (the fast path: float32 poses in,
         float32 results out, within 1e-4 rad on well-conditioned poses; states are the FP64 path's because poses
         FP32 cannot decide are re-solved in FP64 -- their count is ``n_escalated``).
+        devices: CUDA ordinals of this node to spread a HOST batch over -- contiguous slices of the batch, one
+        H2D -> K1 -> D2H pipeline per device, no inter-GPU traffic (``is_reachable_batch_host``); results are NumPy arrays.
         """
         torch = self._torch
         dt = _precision_dtype(torch, precision)
+        if devices is not None:
+            if hasattr(poses, "is_cuda") and poses.is_cuda:
+                raise ValueError("devices=[...] spreads a host batch; a CUDA tensor already lives on one device")
+            if theta is not None or previous_joints is not None:
+                raise ValueError("devices=[...] solves at theta_interval[0] with the default previous_joints")
+            want = self.HOST_FIELDS if want_joints else ("reachable", "state", "interval")
+            o = self.is_reachable_batch_host(poses, precision=precision, want=want, devices=devices)
+            npy = lambda t: None if t is None else t.numpy()   # noqa: E731
+            return BatchResult(o.reachable.numpy().astype(bool), npy(o.theta_interval), o.state.numpy(), npy(o.joints), npy(o.elbow))
         with torch.cuda.device(self._device):
             P, kind, was_cuda = normalise_poses(torch, poses, self._device, dt)
             n = P.shape[0]
@@ -205,30 +241,51 @@ class SymbolicIK:
         _native.check(rc, "r2ik_symik_solve_f32")
 
     # ------------------------------------------------------------------ host-buffer pipeline
-    def alloc_host_outputs(self, n: int, precision: str = "fp64") -> BatchResult:
-        """Pinned host output buffers for ``is_reachable_batch_host`` (reusable across calls)."""
+    HOST_FIELDS = ("reachable", "state", "interval", "joints", "elbow")
+    LEAN = ("state", "joints")   # 57 bytes per pose back: state == 0 <=> reachable (states.STATE_STRINGS)
+
+    def alloc_host_outputs(self, n: int, precision: str = "fp64", want=None) -> BatchResult:
+        """Pinned host output buffers for ``is_reachable_batch_host`` (reusable across calls); fields not in ``want``
+        (default: all five) are None."""
         torch = self._torch
         dt = _precision_dtype(torch, precision)
+        want = self.HOST_FIELDS if want is None else tuple(want)
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()   # noqa: E731
         return BatchResult(
-            reachable=torch.empty(n, dtype=torch.uint8).pin_memory(),
-            theta_interval=torch.empty((n, 2), dtype=dt).pin_memory(),
-            state=torch.empty(n, dtype=torch.uint8).pin_memory(),
-            joints=torch.empty((n, 7), dtype=dt).pin_memory(),
-            elbow=torch.empty((n, 3), dtype=dt).pin_memory())
+            reachable=pin(n, dtype=torch.uint8) if "reachable" in want else None,
+            theta_interval=pin(n, 2, dtype=dt) if "interval" in want else None,
+            state=pin(n, dtype=torch.uint8),
+            joints=pin(n, 7, dtype=dt) if "joints" in want else None,
+            elbow=pin(n, 3, dtype=dt) if "elbow" in want else None)
 
     def is_reachable_batch_host(self, poses_host, out: Optional[BatchResult] = None, chunk: Optional[int] = None,
-                                n_streams: int = 3, precision: str = "fp64") -> BatchResult:
+                                n_streams: int = 3, precision: str = "fp64", want=None, devices=None) -> BatchResult:
         """Host-to-host batched solve: ``poses_host`` is a CPU tensor (N,16)/(N,4,4)/(N,6)/(N,2,3),
         ideally pinned; results land in ``out`` (pinned CPU tensors; ``reachable`` is uint8 0/1).
         The batch is cut into chunks that flow H2D -> K1 -> D2H on ``n_streams`` CUDA streams so the
-        PCIe copies in both directions overlap the kernel.  Synchronous on return.  precision="fp32": float32
-        poses and outputs (half the PCIe bytes), the FP32 fast path of K1."""
+        PCIe copies in both directions overlap the kernel.  Synchronous on return.
+
+        precision="fp32": float32 poses and outputs (half the PCIe bytes), the FP32 fast path of K1.
+        want: which of ("reachable", "state", "interval", "joints", "elbow") to compute and bring back (``state`` always
+        is); the link is the bound of this call, so bytes are throughput: the reference's own input format (N,6) =
+        48 B / pose with ``want=SymbolicIK.LEAN`` (state + joints = 57 B / pose) moves 105 B where (N,4,4) + all
+        five outputs moves 226 B.
+        devices: CUDA ordinals to spread the batch over (contiguous slices, one pipeline per device, no exchange);
+        default = this solver's device only."""
         torch = self._torch
         dt = _precision_dtype(torch, precision)
+        want = self.HOST_FIELDS if want is None else tuple(want)
+        unknown = set(want) - set(self.HOST_FIELDS)
+        if unknown:
+            raise ValueError(f"unknown output fields {sorted(unknown)}; choose from {self.HOST_FIELDS}")
+        if precision == "fp32" and "reachable" not in want:
+            want = want + ("reachable",)     # r2ik_symik_solve_f32 always writes it
         if chunk is None:   # measured optimum on B200 / PCIe 5 (scripts/exp_e2e.py): 128 k poses (FP64), 256 k (FP32)
             chunk = 1 << 17 if precision == "fp64" else 1 << 18
         if not hasattr(poses_host, "is_cuda"):
             poses_host = torch.from_numpy(np.ascontiguousarray(poses_host))
+        if poses_host.is_cuda:
+            raise ValueError("is_reachable_batch_host takes host poses; use is_reachable_batch for CUDA tensors")
         if poses_host.dtype != dt:
             poses_host = poses_host.to(dt)
         shp = tuple(poses_host.shape)
@@ -237,17 +294,37 @@ class SymbolicIK:
             raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6); got {shp}")
         kind = _abi.POSE_MAT4 if k == 16 else _abi.POSE_EULER6
         P = poses_host.reshape(shp[0], k)
+        if not P.is_contiguous():
+            P = P.contiguous()
         n = shp[0]
         if out is None:
-            out = self.alloc_host_outputs(n, precision)
+            out = self.alloc_host_outputs(n, precision, want)
+        devices = [self._handle.device] if devices is None else [int(d) for d in devices]
+        if len(devices) == 1 and devices[0] == self._handle.device:
+            self._host_pipeline(P, kind, k, dt, precision, want, out, 0, n, chunk, n_streams, sync=True)
+            return out
+        # one pipeline per device on its contiguous slice; everything is enqueued before anything is waited for
+        from .workspace import shard_range
+
+        solvers = [self.replica(d) for d in devices]
+        for r, sv in enumerate(solvers):
+            lo, hi = shard_range(n, r, len(solvers))
+            sv._host_pipeline(P, kind, k, dt, precision, want, out, lo, hi, chunk, n_streams, sync=False)
+        for sv in solvers:
+            sv._host_pipeline_wait(chunk, n_streams, k, dt)
+        return out
+
+    def _host_pipeline(self, P, kind, k, dt, precision, want, out, begin, end, chunk, n_streams, sync):
+        torch = self._torch
         fp32 = precision == "fp32"
         with torch.cuda.device(self._device):
             pipe = self._pipeline(chunk, n_streams, k, dt)
             cur = torch.cuda.current_stream(self._device)
             for s in pipe["streams"]:
                 s.wait_stream(cur)
-            for ci, lo in enumerate(range(0, n, chunk)):
-                hi = min(n, lo + chunk)
+            w_reach, w_itv, w_j, w_e = ("reachable" in want), ("interval" in want), ("joints" in want), ("elbow" in want)
+            for ci, lo in enumerate(range(begin, end, chunk)):
+                hi = min(end, lo + chunk)
                 m = hi - lo
                 slot = ci % n_streams
                 s = pipe["streams"][slot]
@@ -255,19 +332,31 @@ class SymbolicIK:
                 with torch.cuda.stream(s):
                     b["poses"][:m].copy_(P[lo:hi], non_blocking=True)
                     if fp32:
-                        self.solve_into_f32(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
-                                            b["elbow"], b["n_esc"], stream=s.cuda_stream, scratch=b["esc"])
+                        self.solve_into_f32(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"] if w_itv else None,
+                                            b["joints"] if w_j else None, b["elbow"] if w_e else None, b["n_esc"],
+                                            stream=s.cuda_stream, scratch=b["esc"])
                     else:
-                        self.solve_into(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"], b["joints"],
-                                        b["elbow"], stream=s.cuda_stream)
-                    out.reachable[lo:hi].copy_(b["reach"][:m], non_blocking=True)
+                        self.solve_into(b["poses"][:m], kind, None, None, b["reach"] if w_reach else None, b["state"],
+                                        b["interval"] if w_itv else None, b["joints"] if w_j else None,
+                                        b["elbow"] if w_e else None, stream=s.cuda_stream)
                     out.state[lo:hi].copy_(b["state"][:m], non_blocking=True)
-                    out.theta_interval[lo:hi].copy_(b["interval"][:m], non_blocking=True)
-                    out.joints[lo:hi].copy_(b["joints"][:m], non_blocking=True)
-                    out.elbow[lo:hi].copy_(b["elbow"][:m], non_blocking=True)
-            for s in pipe["streams"]:
-                s.synchronize()
-        return out
+                    if w_reach:
+                        out.reachable[lo:hi].copy_(b["reach"][:m], non_blocking=True)
+                    if w_itv:
+                        out.theta_interval[lo:hi].copy_(b["interval"][:m], non_blocking=True)
+                    if w_j:
+                        out.joints[lo:hi].copy_(b["joints"][:m], non_blocking=True)
+                    if w_e:
+                        out.elbow[lo:hi].copy_(b["elbow"][:m], non_blocking=True)
+            if sync:
+                for s in pipe["streams"]:
+                    s.synchronize()
+
+    def _host_pipeline_wait(self, chunk, n_streams, k, dt):
+        for s in self._pipeline(chunk, n_streams, k, dt)["streams"]:
+            s.synchronize()
+
+    _PIPE_CACHE_MAX = 4   # distinct (chunk, streams, layout, dtype) pipelines kept per solver (device buffers)
 
     def _pipeline(self, chunk: int, n_streams: int, k: int, dt=None):
         dt = self._torch.float64 if dt is None else dt
@@ -278,6 +367,8 @@ class SymbolicIK:
         if key not in cache:
             torch = self._torch
             d = self._device
+            while len(cache) >= self._PIPE_CACHE_MAX:      # bounded: the oldest pipeline's buffers go back to the allocator
+                cache.pop(next(iter(cache)))
             cache[key] = {
                 "streams": [torch.cuda.Stream(device=d) for _ in range(n_streams)],
                 "bufs": [dict(poses=torch.empty((chunk, k), dtype=dt, device=d),
@@ -291,25 +382,40 @@ class SymbolicIK:
             }
         return cache[key]
 
-    def is_reachable_no_limits_batch(self, poses, theta):
-        """``is_reachable_no_limits`` + ``get_joints(theta)``: returns (joints (N,7), elbow (N,3))."""
+    def clear_caches(self) -> None:
+        """Drop the cached host-pipeline device buffers and FP32 scratch lists."""
+        self.__dict__.pop("_pipe_cache", None)
+        self.__dict__.pop("_esc_scratch", None)
+
+    def is_reachable_no_limits_batch(self, poses, theta, previous_joints=None, with_projected: bool = False):
+        """``is_reachable_no_limits`` + ``get_joints(theta, previous_joints)``: returns (joints (N,7), elbow (N,3)) and,
+        with ``with_projected``, the (N,) bool "make_elbow_projection fired" (the reference's get_joints then returns a
+        3-vector elbow instead of [x, y, z, 1]).  previous_joints: None (zeros), (7,) broadcast or (N,7)."""
         torch = self._torch
         with torch.cuda.device(self._device):
             P, kind, was_cuda = normalise_poses(torch, poses, self._device)
             n = P.shape[0]
             th = torch.as_tensor(theta, dtype=torch.float64).to(self._device).reshape(n).contiguous()
+            pj, stride = None, 0
+            if previous_joints is not None:
+                pj = torch.as_tensor(previous_joints, dtype=torch.float64).to(self._device).contiguous()
+                if pj.numel() == 7:
+                    pj = pj.reshape(7)
+                else:
+                    pj, stride = pj.reshape(n, 7), 7
             joints = torch.empty((n, 7), dtype=torch.float64, device=self._device)
             elbow = torch.empty((n, 3), dtype=torch.float64, device=self._device)
+            proj = torch.empty(n, dtype=torch.uint8, device=self._device) if with_projected else None
             s = torch.cuda.current_stream(self._device).cuda_stream
-            rc = self._handle.lib.r2ik_symik_no_limits_f64(self._handle.h, kind, _ptr(P), _ptr(th), C.c_int64(n),
-                                                           _ptr(joints), _ptr(elbow), C.c_void_p(s))
+            rc = self._handle.lib.r2ik_symik_no_limits_f64(self._handle.h, kind, _ptr(P), _ptr(th), _ptr(pj), C.c_int32(stride),
+                                                           C.c_int64(n), _ptr(joints), _ptr(elbow), _ptr(proj), C.c_void_p(s))
             _native.check(rc, "r2ik_symik_no_limits_f64")
-            if was_cuda:
-                return joints, elbow
-            return joints.cpu().numpy(), elbow.cpu().numpy()
+            res = (joints, elbow) + ((proj.bool(),) if with_projected else ())
+            return res if was_cuda else tuple(x.cpu().numpy() for x in res)
 
-    def get_elbow_position_batch(self, poses, thetas):
-        """``get_elbow_position`` for K thetas per pose after ``is_reachable``: (N,K,3), NaN if unreachable."""
+    def get_elbow_position_batch(self, poses, thetas, no_limits: bool = False, with_projected: bool = False):
+        """``get_elbow_position`` for K thetas per pose after ``is_reachable`` (or ``is_reachable_no_limits``): (N,K,3),
+        NaN where the reference would have stored no intersection circle (symbolic_ik.py:197, :114-116)."""
         torch = self._torch
         with torch.cuda.device(self._device):
             P, kind, was_cuda = normalise_poses(torch, poses, self._device)
@@ -317,11 +423,14 @@ class SymbolicIK:
             th = torch.as_tensor(thetas, dtype=torch.float64).to(self._device).reshape(n, -1).contiguous()
             K = th.shape[1]
             out = torch.empty((n, K, 3), dtype=torch.float64, device=self._device)
+            proj = torch.empty((n, K), dtype=torch.uint8, device=self._device) if with_projected else None
             s = torch.cuda.current_stream(self._device).cuda_stream
-            rc = self._handle.lib.r2ik_elbow_positions_f64(self._handle.h, kind, _ptr(P), _ptr(th), C.c_int32(K),
-                                                           C.c_int64(n), _ptr(out), C.c_void_p(s))
+            rc = self._handle.lib.r2ik_elbow_positions_f64(self._handle.h, kind, _ptr(P), _ptr(th), C.c_int32(K), C.c_int64(n),
+                                                           C.c_int32(int(bool(no_limits))), _ptr(out), _ptr(proj), C.c_void_p(s))
             _native.check(rc, "r2ik_elbow_positions_f64")
-            return out if was_cuda else out.cpu().numpy()
+            res = (out, proj.bool()) if with_projected else (out,)
+            res = res if was_cuda else tuple(x.cpu().numpy() for x in res)
+            return res if with_projected else res[0]
 
     def reach_map(self, n: int = 256, orientations_euler=None, n_orientations: int = 512, **kw):
         """Workspace reachability map: int32 CUDA tensor (n,n,n) of per-voxel reachable-orientation
@@ -338,50 +447,73 @@ class SymbolicIK:
         return workspace.task_space_test(self, arm_length=arm_length, precision=precision, **steps)
 
     # ------------------------------------------------------------------ scalar API (reference signatures)
-    @staticmethod
-    def _pose6(goal_pose) -> np.ndarray:
-        gp = np.array([np.asarray(goal_pose[0], dtype=np.float64), np.asarray(goal_pose[1], dtype=np.float64)])
-        return gp.reshape(1, 6)
+    def _scalar(self, no_limits: bool, theta=None, previous_joints=_ZERO7) -> np.void:
+        """One launch of the one-thread kernel on the stored pose: query by value, record into mapped pinned memory."""
+        torch = self._torch
+        if self._scalar_pinned is None:
+            self._scalar_pinned = torch.zeros(_abi.SCALAR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            self._scalar_view = self._scalar_pinned.numpy().view(_abi.SCALAR_RESULT_DTYPE)
+        q = self._scalar_query
+        q.goal_pose[:] = self._pose_in
+        q.no_limits = int(no_limits)
+        q.has_theta = int(theta is not None)
+        q.theta = 0.0 if theta is None else float(theta)
+        q.previous_joints[:] = [float(x) for x in previous_joints]
+        lib = self._handle.lib
+        stream = C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        _native.check(lib.r2ik_symik_scalar_f64(self._handle.h, C.byref(q), C.c_void_p(self._scalar_pinned.data_ptr()), stream),
+                      "r2ik_symik_scalar_f64")
+        _native.check(lib.r2ik_stream_synchronize(stream), "r2ik_stream_synchronize")
+        return self._scalar_view[0].copy()
+
+    def _store_pose(self, goal_pose, no_limits: bool) -> None:
+        self._pose_in = np.concatenate([np.asarray(goal_pose[0], dtype=np.float64).reshape(3),
+                                        np.asarray(goal_pose[1], dtype=np.float64).reshape(3)])
+        self._no_limits = no_limits
+
+    def _adopt_solved(self, goal_position, wrist_position) -> None:
+        """self.goal_pose / self.wrist_position as the reference leaves them (symbolic_ik.py:143-171, 711-716)."""
+        if not np.isnan(goal_position[0]):
+            self.goal_pose = np.array([goal_position, self._pose_in[3:]])
+            self.wrist_position = np.array(wrist_position)
 
     def is_reachable(self, goal_pose) -> Tuple[bool, np.ndarray, Optional[Any], str]:
         """Check if the goal pose ``[[x,y,z],[roll,pitch,yaw]]`` is reachable taking the wrist and
         elbow limits into account; returns (is_reachable, theta_interval, theta_to_joints_func, state)."""
-        P = self._pose6(goal_pose)
-        res = self.is_reachable_batch(P, want_joints=False)
-        self.goal_pose = P.reshape(2, 3).copy()
-        self._no_limits = False
-        state = STATE_STRINGS[int(res.state[0])]
-        if bool(res.reachable[0]):
-            return True, np.array(res.theta_interval[0]), self.get_joints, state
+        self._store_pose(goal_pose, False)
+        r = self._scalar(False)
+        self._adopt_solved(r["goal_position_solved"], r["wrist_position_solved"])
+        state = STATE_STRINGS[int(r["state"])]
+        if r["reachable"]:
+            return True, np.array(r["interval"]), self.get_joints, state
         return False, np.array([]), None, state
 
     def is_reachable_no_limits(self, goal_pose) -> Tuple[bool, np.ndarray, Optional[Any]]:
         """Reachability without the wrist / elbow limits (unreachable goals are projected);
-        always (True, [-pi, pi], get_joints)."""
-        P = self._pose6(goal_pose)
-        self.goal_pose = P.reshape(2, 3).copy()
-        self._no_limits = True
-        return True, np.array([-np.pi, np.pi]), self.get_joints
+        always (True, [-pi, pi], get_joints) (symbolic_ik.py:85-119)."""
+        self._store_pose(goal_pose, True)
+        r = self._scalar(True)
+        self._adopt_solved(r["goal_position_solved"], r["wrist_position_solved"])
+        if r["reachable"]:
+            return True, np.array([-np.pi, np.pi]), self.get_joints
+        return False, np.array([]), None
 
     def get_joints(self, theta: float, previous_joints: list = _ZERO7) -> Tuple[np.ndarray, np.ndarray]:
-        """Joints for the elbow angle theta on the last solved pose (fresh solve per call)."""
-        if self.goal_pose is None:
+        """Joints for the elbow angle theta on the last solved pose (fresh solve per call).  Like the reference, the
+        elbow comes back as get_elbow_position's homogeneous [x, y, z, 1], and as a 3-vector once make_elbow_projection
+        fired (symbolic_ik.py:708-714, returned at :863)."""
+        if self._pose_in is None:
             raise AttributeError("get_joints called before is_reachable / is_reachable_no_limits")
-        P = self.goal_pose.reshape(1, 6)
-        if self._no_limits:
-            joints, elbow = self.is_reachable_no_limits_batch(P, np.array([float(theta)]))
-            j, e = joints[0], elbow[0]
-        else:
-            res = self.is_reachable_batch(P, theta=np.array([float(theta)]), previous_joints=previous_joints)
-            j, e = res.joints[0], res.elbow[0]
-        self.elbow_position = np.array(e)
-        return np.array(j), self.elbow_position
+        r = self._scalar(self._no_limits, theta, previous_joints)
+        self._adopt_solved(r["goal_position"], r["wrist_position"])
+        e = np.array(r["elbow"])
+        self.elbow_position = e if r["projected"] else np.array([e[0], e[1], e[2], 1.0])
+        return np.array(r["joints"]), self.elbow_position
 
     def get_elbow_position(self, theta: float) -> np.ndarray:
-        """Elbow position [x, y, z, 1] on the elbow circle of the last solved pose."""
-        if self.goal_pose is None:
+        """Elbow position [x, y, z, 1] on the intersection circle of the last solved pose (after ``is_reachable`` or
+        ``is_reachable_no_limits``; symbolic_ik.py:684-695)."""
+        if self._pose_in is None:
             raise AttributeError("get_elbow_position called before is_reachable")
-        if self._no_limits:
-            raise NotImplementedError("get_elbow_position after is_reachable_no_limits is not exposed")
-        e = self.get_elbow_position_batch(self.goal_pose.reshape(1, 6), np.array([[float(theta)]]))[0, 0]
+        e = self._scalar(self._no_limits, theta)["elbow_on_circle"]
         return np.array([e[0], e[1], e[2], 1.0])

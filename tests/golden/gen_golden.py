@@ -249,6 +249,119 @@ def gen_symik_big_euler(n=800):
     np.savez_compressed(os.path.join(HERE, "symik_big_euler.npz"), **out)
 
 
+def gen_symik_elbow(n_fk=400, n_task=400, K=4):
+    """get_elbow_position(theta) (symbolic_ik.py:684-695, returns [x, y, z, 1]) for K thetas per pose after is_reachable
+    (whenever the intersection circle was stored, :197 -- also for "limited by wrist") AND after is_reachable_no_limits
+    (:85-119, circle stored at :114-116); get_joints(theta, previous_joints) after is_reachable_no_limits with a non-zero
+    previous_joints; the SHAPE of the elbow that get_joints returns: (4,) = get_elbow_position's homogeneous point, (3,)
+    once make_elbow_projection fired (:708-714, returned at :863); and the solver attributes the calls leave behind
+    (goal_pose / wrist_position after is_reachable, :143-171; after get_joints, :711-716)."""
+    out = dict(META)
+    named = named_poses()
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        M = np.concatenate([fk.sample_fk_poses(n_fk, arm, seed=310 + seed, min_x=0.05),
+                            fk.sample_task_space_poses(n_task, arm, seed=320 + seed)])
+        gp = np.concatenate([np.array([euler_pose_from_matrix(m) for m in M]), named[arm]])
+        n = len(gp)
+        rng = np.random.default_rng(330 + seed)
+        flag = np.zeros(n, bool)
+        state = np.zeros(n, np.uint8)
+        thetas = rng.uniform(-np.pi, np.pi, (n, K))
+        thetas[:, K - 1] = rng.uniform(-9.0, 9.0, n)
+        el_pos = np.full((n, K, 4), np.nan)          # get_elbow_position after is_reachable
+        ir_goal = np.full((n, 3), np.nan)            # goal_pose[0] / wrist_position left by is_reachable
+        ir_wrist = np.full((n, 3), np.nan)
+        gj_joints = np.full((n, K, 7), np.nan)       # get_joints(theta_k) after a fresh is_reachable
+        gj_elbow = np.full((n, K, 3), np.nan)
+        gj_elbow_len = np.zeros((n, K), np.uint8)
+        gj_goal = np.full((n, K, 3), np.nan)         # goal_pose[0] / wrist_position left by get_joints
+        gj_wrist = np.full((n, K, 3), np.nan)
+        nl_thetas = rng.uniform(-np.pi, np.pi, (n, K))
+        nl_thetas[:, K - 1] = rng.uniform(-9.0, 9.0, n)
+        nl_el_pos = np.full((n, K, 4), np.nan)       # get_elbow_position after is_reachable_no_limits
+        nl_prev = rng.uniform(-2.0, 2.0, (n, 7))
+        nl_joints = np.full((n, K, 7), np.nan)       # get_joints(theta_k, nl_prev) after a fresh is_reachable_no_limits
+        nl_elbow = np.full((n, K, 3), np.nan)
+        nl_elbow_len = np.zeros((n, K), np.uint8)
+        with _Quiet():
+            for i in range(n):
+                g = np.array(gp[i])
+                ik = SymbolicIK(arm=arm)             # fresh: attributes below are those THIS call set
+                ok, itv, fn, st = ik.is_reachable(g.copy())
+                flag[i] = ok
+                state[i] = state_code(st)
+                if st in ("reachable", "limited by wrist", "wrist out of range"):
+                    ir_goal[i] = ik.goal_pose[0]
+                    ir_wrist[i] = ik.wrist_position
+                if st in ("reachable", "limited by wrist"):
+                    if ok:
+                        width = itv[1] - itv[0] if itv[0] <= itv[1] else itv[1] + 2 * np.pi - itv[0]
+                        thetas[i, 0] = itv[0]
+                        thetas[i, 1] = itv[0] + rng.uniform(0, 1) * width
+                    for k in range(K):
+                        e = ik.get_elbow_position(thetas[i, k])
+                        assert e.shape == (4,)
+                        el_pos[i, k] = e
+                if ok:
+                    for k in range(K):
+                        ok2, _, fn2, _ = ik.is_reachable(g.copy())
+                        j, e = fn2(thetas[i, k])
+                        gj_joints[i, k] = j
+                        gj_elbow[i, k] = np.asarray(e)[:3]
+                        gj_elbow_len[i, k] = len(e)
+                        gj_goal[i, k] = ik.goal_pose[0]
+                        gj_wrist[i, k] = ik.wrist_position
+                ok, _, fn = ik.is_reachable_no_limits(g.copy())
+                assert ok
+                for k in range(K):
+                    nl_el_pos[i, k] = ik.get_elbow_position(nl_thetas[i, k])
+                for k in range(K):
+                    ok, _, fn = ik.is_reachable_no_limits(g.copy())
+                    j, e = fn(nl_thetas[i, k], list(nl_prev[i]))
+                    nl_joints[i, k] = j
+                    nl_elbow[i, k] = np.asarray(e)[:3]
+                    nl_elbow_len[i, k] = len(e)
+        pre = arm + "_"
+        out.update({pre + "goal_pose": gp, pre + "reachable": flag, pre + "state": state, pre + "thetas": thetas,
+                    pre + "elbow_position": el_pos, pre + "ir_goal": ir_goal, pre + "ir_wrist": ir_wrist,
+                    pre + "gj_joints": gj_joints, pre + "gj_elbow": gj_elbow, pre + "gj_elbow_len": gj_elbow_len,
+                    pre + "gj_goal": gj_goal, pre + "gj_wrist": gj_wrist,
+                    pre + "nl_thetas": nl_thetas, pre + "nl_elbow_position": nl_el_pos, pre + "nl_prev": nl_prev,
+                    pre + "nl_joints": nl_joints, pre + "nl_elbow": nl_elbow, pre + "nl_elbow_len": nl_elbow_len})
+        print(arm, "symik_elbow: reachable", flag.mean(), "projection fired (limits)", (gj_elbow_len[flag] == 3).mean(),
+              "(no limits)", (nl_elbow_len == 3).mean(), "limited by wrist", (state == 4).mean())
+    np.savez_compressed(os.path.join(HERE, "symik_elbow.npz"), **out)
+
+
+def gen_ctl_ctor(n_variants=6):
+    """ControlIK.previous_theta right after construction (control_ik.py:142-159): default arguments and random
+    current_joints / current_pose, standard and DVT."""
+    out = dict(META, n_variants=n_variants)
+    rng = np.random.default_rng(400)
+    variants = []
+    for v in range(n_variants):
+        cj = np.array([fk.sample_fk_joints(1, np.random.default_rng(410 + v))[0], fk.sample_fk_joints(1, np.random.default_rng(420 + v))[0]])
+        cp = np.array([fk.forward_kinematics(cj[0][None], "r_arm")[0], fk.forward_kinematics(cj[1][None], "l_arm")[0]])
+        if v == 0:                                  # identity rotations: the np.allclose snap of control_ik.py:142
+            cp[:, :3, :3] = np.eye(3)
+        variants.append((cj, cp))
+        out[f"v{v}_current_joints"] = cj
+        out[f"v{v}_current_pose"] = cp
+    for tag, dvt in (("std", False), ("dvt", True)):
+        with _Quiet():
+            ctl = new_control(is_dvt=dvt)
+        for arm in ("r_arm", "l_arm"):
+            out[f"{tag}_default_{arm}"] = ctl.previous_theta[arm]
+        for v, (cj, cp) in enumerate(variants):
+            with _Quiet():
+                ctl = ControlIK(current_joints=[list(cj[0]), list(cj[1])], current_pose=[cp[0], cp[1]], urdf_path="../config_files/reachy2.urdf",
+                                is_dvt=dvt)
+            for arm in ("r_arm", "l_arm"):
+                out[f"{tag}_v{v}_{arm}"] = ctl.previous_theta[arm]
+        print("ctl_ctor", tag, {k: float(out[k]) for k in out if k.startswith(tag)})
+    np.savez_compressed(os.path.join(HERE, "ctl_ctor.npz"), **out)
+
+
 def gen_api_surface():
     """Names, parameter names and defaults of the public methods of the reference's two classes (the drop-in boundary,
     SURVEY.md 8(b)) -> api_surface.json."""
@@ -658,7 +771,7 @@ def gen_helpers(n=2000):
 
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler", "api"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler", "elbow", "ctl_ctor", "api"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -679,6 +792,10 @@ if __name__ == "__main__":
         gen_symik_ctor()
     if "big_euler" in which:
         gen_symik_big_euler()
+    if "elbow" in which:
+        gen_symik_elbow()
+    if "ctl_ctor" in which:
+        gen_ctl_ctor()
     if "api" in which:
         gen_api_surface()
     if "task_space" in which:

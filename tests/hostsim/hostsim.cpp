@@ -335,6 +335,45 @@ void hs_ctl_continuous_phased_lanes_batch(const R2ikArmConfig *cfg, const R2ikCt
 
 // K1-f32 (r2ik_device_f32.cuh): the FP32 fast solve with FP64 escalation, mirroring k_symik_solve_f32.
 // mode: 0 = as the kernel (escalate flagged poses), 1 = never escalate (raw FP32 results, to measure them).
+// k_ctl_ctor_theta of r2ik_kernels.cu (ControlIK.__init__'s previous_theta seed, ctl:142-159)
+double hs_ctl_ctor_theta(const R2ikArmConfig *cfg, double preferred_theta, const double *rows, int n_rows, const double *current_pose) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  Solve S;
+  const double cpos[3] = {current_pose[3], current_pose[7], current_pose[11]};
+  if (!rotation_from_mat4(current_pose, true, S.R) || is_reachable_R<true>(A, cpos, S).state != R2IK_STATE_REACHABLE) return NAN;
+  return ctor_previous_theta(A, S, rows, n_rows, preferred_theta);
+}
+
+// get_elbow_position(thetas[i][k]) + the projection predicate, as k_elbow_positions<KIND, NO_LIMITS> of r2ik_kernels.cu
+void hs_elbow_positions(const R2ikArmConfig *cfg, int kind, const double *poses, const double *thetas, int K, int64_t n,
+                        int no_limits, double *elbows, uint8_t *projected) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  int stride = kind == R2IK_POSE_EULER6 ? 6 : 16;
+  for (int64_t i = 0; i < n; ++i) {
+    double pos[3];
+    Solve S;
+    bool ok = load_pose(kind, poses + i * stride, false, pos, S.R);
+    if (ok) {
+      const int st = no_limits ? is_reachable_R<true>(A, pos, S).state : is_reachable_R<false>(A, pos, S).state;
+      ok = st == R2IK_STATE_REACHABLE || (!no_limits && st == R2IK_STATE_LIMITED_BY_WRIST);
+    }
+    for (int k = 0; k < K; ++k) {
+      double E[3] = {NAN, NAN, NAN};
+      bool proj = false;
+      if (ok) {
+        double st, ct;
+        sincos_any(thetas[i * K + k], st, ct);
+        elbow_position_cs(S, ct, st, E);
+        proj = E[2] > (E[0] - A.es[0]) * A.sing_coeff + A.es[2] - A.sing_offset;
+      }
+      for (int c = 0; c < 3; ++c) elbows[(i * K + k) * 3 + c] = E[c];
+      projected[i * K + k] = proj;
+    }
+  }
+}
+
 void hs_symik_batch_f32(const R2ikArmConfig *cfg, int kind, const float *poses, const float *theta, int64_t n, int mode,
                         uint8_t *reach, uint8_t *state, float *interval, float *joints, float *elbow, uint8_t *escalated) {
   ArmConst A; R2ikArmConstants pub;

@@ -277,7 +277,7 @@ def test_discrete_analytic_search_equals_exhaustive_scan(controls, arm, K):
 
 
 @pytest.mark.parametrize("arm", ARMS)
-def test_continuous_serial_route_and_fixup(controls, arm, monkeypatch):
+def test_continuous_serial_route_and_fixup(controls, arm):
     """A waypoint whose get_joints needs the previous solution (exact singularities) stops the lane-parallel finish
     scan of its trajectory; a fixup kernel resumes it serially.  No physical pose triggers that, so the library's test
     hook sends every m-th waypoint down that route: outputs and final states must not change."""
@@ -290,9 +290,7 @@ def test_continuous_serial_route_and_fixup(controls, arm, monkeypatch):
     M[5, 7, :3, :3] = np.diag([-1.0, 1.0, 1.0])        # invalid rotation in trajectory 5
     want = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous")
     for m in (1, 7, 97):
-        monkeypatch.setenv("R2IK_DEBUG_FORCE_SERIAL", str(m))
-        got = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous")
-        monkeypatch.delenv("R2IK_DEBUG_FORCE_SERIAL")
+        got = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", _test_force_serial_mod=m)
         np.testing.assert_allclose(got[0], want[0], rtol=0, atol=1e-12)
         np.testing.assert_array_equal(got[1], want[1])
         np.testing.assert_array_equal(got[2], want[2])

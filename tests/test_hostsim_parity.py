@@ -777,3 +777,52 @@ def test_non_orthonormal_rotation_blocks(hs, oracle, kind):
     rep.close("interval", itv, want[1])
     rep.close("joints", joints, want[3])
     rep.check(max_ill_fraction=0.03)   # FK-sampled poses reach down to a straight arm: ~1.7 % move by > 1e-10 under 3e-13
+
+
+@pytest.mark.parametrize("is_dvt", [False, True])
+def test_constructor_previous_theta(hs, is_dvt):
+    """ControlIK.previous_theta as the reference's constructor seeds it (control_ik.py:142-159; ternary search over the
+    two-arm joint list) on the kernel source: default and custom current_joints / current_pose (tests/golden/ctl_ctor.npz)."""
+    g = load("ctl_ctor.npz")
+    tag = "dvt" if is_dvt else "std"
+    params = urdf_params()
+    hs.hs_ctl_ctor_theta.restype = C.c_double
+    hs.hs_ctl_ctor_theta.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+    default_cj = np.array([[0.0, 0.2617993877991494, -0.17453292519943295, 0.0, 0.0, 0.0, 0.0],
+                           [0.0, -0.2617993877991494, 0.17453292519943295, 0.0, 0.0, 0.0, 0.0]])
+    default_cp = np.array([[[1, 0, 0, 0], [0, 1, 0, -0.2], [0, 0, 1, -0.66], [0, 0, 0, 1]],
+                           [[1, 0, 0, 0], [0, 1, 0, 0.2], [0, 0, 1, -0.66], [0, 0, 0, 1]]], dtype=np.float64)
+    cases = [("default", default_cj, default_cp)] + [(f"v{v}", g[f"v{v}_current_joints"], g[f"v{v}_current_pose"])
+                                                     for v in range(int(g["n_variants"]))]
+    for name, cj, cp in cases:
+        for k, arm in enumerate(ARMS):
+            cfg = cfg_for(arm, params, 0.03 if is_dvt else -1.01)
+            pref = -4 * np.pi / 6 if arm == "r_arm" else -np.pi + 4 * np.pi / 6
+            rows = np.ascontiguousarray(cj, dtype=np.float64)
+            pose = np.ascontiguousarray(cp[k], dtype=np.float64)
+            got = hs.hs_ctl_ctor_theta(C.byref(cfg), pref, dp(rows), len(rows), dp(pose))
+            assert abs(got - float(g[f"{tag}_{name}_{arm}"])) < 1e-9, (name, arm, got, float(g[f"{tag}_{name}_{arm}"]))
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_elbow_positions(hs, oracle, arm):
+    """get_elbow_position after is_reachable / is_reachable_no_limits and the projection predicate on the kernel source
+    (tests/golden/symik_elbow.npz; the GPU twin is tests/test_gpu_api_r2.py::test_elbow_positions_entry)."""
+    g = load("symik_elbow.npz")
+    cfg = cfg_for(arm)
+    ocfg = oracle.arm_config(arm)
+    P = np.ascontiguousarray(g[f"{arm}_goal_pose"].reshape(-1, 6))
+    n, K = g[f"{arm}_thetas"].shape
+    th, nth = np.ascontiguousarray(g[f"{arm}_thetas"]), np.ascontiguousarray(g[f"{arm}_nl_thetas"])
+    run = lambda p: (oracle.elbow_positions_batch(ocfg, p.reshape(n, 2, 3), th),  # noqa: E731
+                     oracle.elbow_positions_batch(ocfg, p.reshape(n, 2, 3), nth, no_limits=True))
+    ill = ill_conditioned_mask(run, P)
+    rep = Report(f"hostsim elbow {arm}", n, ill)
+    for no_limits, thetas, want, want_len in ((0, th, g[f"{arm}_elbow_position"], g[f"{arm}_gj_elbow_len"]),
+                                              (1, nth, g[f"{arm}_nl_elbow_position"], g[f"{arm}_nl_elbow_len"])):
+        E = np.empty((n, K, 3)); proj = np.zeros((n, K), np.uint8)
+        hs.hs_elbow_positions(C.byref(cfg), _abi.POSE_EULER6, dp(P), dp(thetas), K, C.c_int64(n), no_limits, dp(E), u8(proj))
+        rep.close(f"get_elbow_position (no_limits={no_limits})", E, want[:, :, :3])
+        valid = want_len > 0
+        rep.exact(f"elbow shape of get_joints (no_limits={no_limits})", np.where(valid, np.where(proj.astype(bool), 3, 4), 0), want_len)
+    rep.check(max_ill_fraction=0.03)

@@ -107,6 +107,75 @@ def test_constructor_variants(oracle, arm, variant):
 
 
 @pytest.mark.parametrize("arm", ARMS)
+def test_elbow_positions_and_return_shape(oracle, arm):
+    """get_elbow_position(theta) after is_reachable and after is_reachable_no_limits (symbolic_ik.py:684-695, circle
+    stored at :197 / :114-116), get_joints(theta, previous_joints) after is_reachable_no_limits, and the branch that
+    decides the SHAPE of the elbow get_joints returns ((4,) [x, y, z, 1]; (3,) once make_elbow_projection fired, :714)."""
+    g = load("symik_elbow.npz")
+    cfg = oracle.arm_config(arm)
+    P = g[f"{arm}_goal_pose"]
+    n, K = g[f"{arm}_thetas"].shape
+    flat = P.reshape(n, 6)
+    th, nth = g[f"{arm}_thetas"], g[f"{arm}_nl_thetas"]
+    run = lambda p: (oracle.symik_batch(cfg, p.reshape(P.shape))[0], oracle.elbow_positions_batch(cfg, p.reshape(P.shape), th),  # noqa: E731
+                     oracle.elbow_positions_batch(cfg, p.reshape(P.shape), nth, no_limits=True))
+    ill = ill_conditioned_mask(run, flat)
+    rep = Report(f"oracle elbow {arm}", n, ill)
+    reach = g[f"{arm}_reachable"]
+    E, proj = oracle.elbow_positions_batch(cfg, P, th, with_projected=True)
+    has_circle = reach | (g[f"{arm}_state"] == 4)          # stored at sik:197, also for "limited by wrist"
+    rep.exact("circle stored (NaN rows otherwise)", np.isfinite(E).all(axis=(1, 2)), has_circle)
+    rep.close("get_elbow_position after is_reachable", E, g[f"{arm}_elbow_position"][:, :, :3])
+    assert np.all(g[f"{arm}_elbow_position"][has_circle][:, :, 3] == 1.0)
+    rep.exact("elbow shape of get_joints (3 <=> projection fired)", np.where(reach[:, None], np.where(proj, 3, 4), 0),
+              g[f"{arm}_gj_elbow_len"])
+    Enl, proj_nl = oracle.elbow_positions_batch(cfg, P, nth, no_limits=True, with_projected=True)
+    rep.close("get_elbow_position after is_reachable_no_limits", Enl, g[f"{arm}_nl_elbow_position"][:, :, :3])
+    rep.exact("elbow shape of get_joints after no_limits", np.where(proj_nl, 3, 4), g[f"{arm}_nl_elbow_len"])
+    for k in range(K):
+        _, _, _, j, e = oracle.symik_batch(cfg, P, th[:, k])
+        rep.close(f"get_joints(theta[{k}])", j, g[f"{arm}_gj_joints"][:, k])
+        rep.close(f"elbow of get_joints(theta[{k}])", e, g[f"{arm}_gj_elbow"][:, k])
+        j, e, pr = oracle.symik_no_limits_batch(cfg, P, nth[:, k], g[f"{arm}_nl_prev"], with_projected=True)
+        rep.close(f"no_limits get_joints(theta[{k}], previous_joints)", j, g[f"{arm}_nl_joints"][:, k])
+        rep.close(f"no_limits elbow of get_joints(theta[{k}])", e, g[f"{arm}_nl_elbow"][:, k])
+        assert np.array_equal(pr, proj_nl[:, k])
+    rep.check(max_ill_fraction=0.03)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_scalar_call_sequence_record(oracle, arm):
+    """orc_symik_scalar (the checker of r2ik_symik_scalar_f64) against what the reference's scalar calls return and leave
+    on the solver: goal_pose / wrist_position after is_reachable (sik:143-171) and after get_joints (sik:711-716)."""
+    g = load("symik_elbow.npz")
+    cfg = oracle.arm_config(arm)
+    P = g[f"{arm}_goal_pose"]
+    idx = np.r_[0:120, 400:520, len(P) - 24:len(P)]       # FK-sampled, task-space and the named poses
+    singular = len(P) - 24 + 10                           # the fully stretched arm: a true singularity (see test_named_poses)
+    worst = 0.0
+    for i in idx[idx != singular]:
+        for k in (0, 3):
+            th = g[f"{arm}_thetas"][i, k]
+            r = oracle.symik_scalar(cfg, P[i], theta=th)
+            assert r["state"] == g[f"{arm}_state"][i] and bool(r["reachable"]) == bool(g[f"{arm}_reachable"][i])
+            for got, want in ((r["goal_position_solved"], g[f"{arm}_ir_goal"][i]), (r["wrist_position_solved"], g[f"{arm}_ir_wrist"][i]),
+                              (r["elbow_on_circle"], g[f"{arm}_elbow_position"][i, k, :3]), (r["joints"], g[f"{arm}_gj_joints"][i, k]),
+                              (r["elbow"], g[f"{arm}_gj_elbow"][i, k]), (r["goal_position"], g[f"{arm}_gj_goal"][i, k]),
+                              (r["wrist_position"], g[f"{arm}_gj_wrist"][i, k])):
+                assert np.array_equal(np.isnan(got), np.isnan(want)), (i, k)
+                worst = max(worst, float(np.nanmax(np.abs(got - want), initial=0.0)))
+            if r["reachable"]:
+                assert (3 if r["projected"] else 4) == g[f"{arm}_gj_elbow_len"][i, k]
+            th = g[f"{arm}_nl_thetas"][i, k]
+            r = oracle.symik_scalar(cfg, P[i], no_limits=True, theta=th, previous_joints=g[f"{arm}_nl_prev"][i])
+            assert r["reachable"] and (3 if r["projected"] else 4) == g[f"{arm}_nl_elbow_len"][i, k]
+            for got, want in ((r["elbow_on_circle"], g[f"{arm}_nl_elbow_position"][i, k, :3]), (r["joints"], g[f"{arm}_nl_joints"][i, k]),
+                              (r["elbow"], g[f"{arm}_nl_elbow"][i, k])):
+                worst = max(worst, float(np.nanmax(np.abs(got - want), initial=0.0)))
+    assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("arm", ARMS)
 def test_big_euler_angles(oracle, arm):
     """Goal orientations as euler angles far outside [-pi, pi] (tests/golden/symik_big_euler.npz)."""
     g = load("symik_big_euler.npz")
