@@ -1,23 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- benchmarks of the Reachy2 symbolic IK hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload symik|discrete|continuous|reachmap]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|symik|symik_f32|discrete|continuous|reachmap]
 
-Default workload `symik` = BASELINE.json configs[1], the configuration the headline metric is quoted on:
-1 M FK-sampled poses per arm (r_arm and l_arm), FP64, reachability flag + theta interval + 7 joints at
-theta_interval[0] + elbow position.  One *step* = one pass of K1 (`r2ik_symik_solve_f64`) over both arms'
-batches = 2 M solves per GPU.  The other workloads are configs[2..4] (ControlIK discrete K=360, ControlIK
-continuous 65 536 x 1 000, reach map 256^3 x 512 with an NCCL all-reduce); they print the same JSON line.
+The headline workload `symik` = BASELINE.json configs[1], the configuration the metric is quoted on: 1 M FK-sampled poses per
+arm (r_arm and l_arm), FP64, reachability flag + theta interval + 7 joints at theta_interval[0] + elbow position.  One *step* =
+one pass of K1 (`r2ik_symik_solve_f64`) over both arms' batches = 2 M solves per GPU; exactly K steps are timed.  With the
+default `--workload all` the same JSON line also carries `workloads`: one sub-record per other BASELINE config -- `symik_f32`
+(configs[1] on the FP32 fast path), `discrete` (configs[2], K = 360), `continuous` (configs[3], 65 536 x 1 000) and `reachmap`
+(configs[4], 256^3 x 512, orientation-sharded over the ranks with the all-reduce timed separately) -- each with its own value,
+ms_per_step, roofline, parity and e2e, under torchrun too, so that the scaling run measures every config at every N.
 
-* own arm: `value` = poses/s with inputs resident in HBM (CUDA events on the launching stream, max over
-  ranks); `e2e` = the same metric through the public facade with pinned HOST buffers, H2D and D2H copies inside
-  the timed region; `roofline` (HBM form) / `roofline_fp64` for the dominant kernel; `cpu_baseline` = the C oracle
-  (a port of the reference algorithm, OpenMP on all host threads) and, when `baseline/_ref` holds the installed
-  Python reference, the reference itself on a bounded sample with one process per core.
-* `--impl reference`: the reference algorithm's CPU implementation (oracle port, all host threads) on the same
-  workload; rank 0 only.
-* N > 1: launched by torchrun, one rank per GPU, contiguous slices of the batch per rank, no data-path collective
-  (weak scaling); the reach map shards orientations and all-reduces the count volume.
+* own arm: `value` = poses/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` = the
+  same metric through the public facade with pinned HOST buffers, H2D and D2H copies inside the timed region (`e2e.lean`: the
+  reference's own (N,6) input format and the state + joints record, 105 instead of 226 bytes per pose over the link);
+  `roofline` for the dominant kernel; `cpu_baseline` = the C oracle (a port of the reference algorithm, OpenMP on all host
+  threads) and, when `baseline/_ref` holds the installed Python reference, the reference itself on a bounded sample with one
+  process per core; `scalar_latency` = what one control tick costs through the reference's scalar API.
+* `--impl reference`: the reference algorithm's CPU implementation (oracle port, all host threads) on the same workloads;
+  rank 0 only.
+* N > 1: launched by torchrun, one rank per GPU, contiguous slices of the batch per rank, no data-path collective (weak
+  scaling); the reach map shards orientations and all-reduces the count volume (strong scaling).
 """
 from __future__ import annotations
 
@@ -172,8 +175,9 @@ class Symik:
     # the batch, in the ncu source-level counts of profiles/r1_s16.  SURVEY.md 8(d)'s weighted estimate
     # for the reference's formulation (library-cost transcendentals) is 2100 flop-equivalents; it is reported beside it.
     FLOP_EQ = 874.0
-    FLOP_EQ_SURVEY = 2100.0
+    FP64_PIPE_INSTR = 604.0   # DFMA + DMUL + DADD + DSETP per pose (profiles/r1_s43_symik_ncu_full.txt): pipe slots
     kernel = "k_symik_solve<MAT4>"
+    e2e_extra_legs = ("lean", "goal_pose_input")
 
     def config(self, world):
         n = self.POSES_PER_ARM
@@ -223,36 +227,58 @@ class Symik:
     def e2e_check(self, torch):
         assert torch.equal(self.host_out["r_arm"].joints[:1000].nan_to_num(), self.outs["r_arm"]["joints"][:1000].cpu().nan_to_num())
 
-    def e2e_goal_pose(self, torch, steps):
-        """Optional extra leg (single GPU, run last, never fatal): the same solves fed in the reference's OWN input format,
-        goal_pose = (position, xyz euler) = 48 B / pose instead of the 128 B of a 4x4 matrix; outputs unchanged."""
+    def _goal_poses_pinned(self, torch):
+        """The workload in the reference's OWN input format: goal_pose = (position, xyz euler), 48 B / pose."""
         from scipy.spatial.transform import Rotation as R
 
+        if not hasattr(self, "_gp_pinned"):
+            self._gp_pinned = {}
+            for arm in ARMS:
+                M = self.poses[arm]
+                gp = np.concatenate([M[:, :3, 3], R.from_matrix(M[:, :3, :3]).as_euler("xyz")], axis=1)
+                self._gp_pinned[arm] = torch.from_numpy(np.ascontiguousarray(gp)).pin_memory()
+        return self._gp_pinned
+
+    def _e2e_leg(self, env, steps, host_in, host_out, bytes_in, bytes_out, path, **kw):
+        torch = env.torch
         n = self.POSES_PER_ARM
-        host_in = {}
-        for arm in ARMS:
-            M = self.poses[arm]
-            gp = np.concatenate([M[:, :3, 3], R.from_matrix(M[:, :3, :3]).as_euler("xyz")], axis=1)
-            host_in[arm] = torch.from_numpy(np.ascontiguousarray(gp)).pin_memory()
         for _ in range(2):
             for arm in ARMS:
-                self.solvers[arm].is_reachable_batch_host(host_in[arm], self.host_out[arm])
-        torch.cuda.synchronize()
+                self.solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm], **kw)
+        env.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             for arm in ARMS:
-                self.solvers[arm].is_reachable_batch_host(host_in[arm], self.host_out[arm])
+                self.solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm], **kw)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        got = self.host_out["r_arm"].joints[:100_000].numpy()
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        got = host_out["r_arm"].joints[:100_000].numpy()
         ref = self.outs["r_arm"]["joints"][:100_000].cpu().numpy()
         both = np.isfinite(got).all(axis=1) & np.isfinite(ref).all(axis=1)
         dj = np.abs(got[both] - ref[both]).max(axis=1)
-        return {"value": 2 * n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 48, "d2h_bytes_per_step": 2 * n * self.BYTES_OUT,
-                "steps": steps, "path": "SymbolicIK.is_reachable_batch_host on (N,6) goal poses (the reference's input format)",
+        return {"value": 2 * n * env.world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * n * bytes_in,
+                "d2h_bytes_per_step": 2 * n * bytes_out, "steps": steps, "path": path,
                 "median_abs_joint_difference_vs_mat4_input_rad": float(np.median(dj)),
-                "state_agreement_vs_mat4_input": float((self.host_out["r_arm"].state[:100_000].numpy() ==
+                "state_agreement_vs_mat4_input": float((host_out["r_arm"].state[:100_000].numpy() ==
                                                         self.outs["r_arm"]["state"][:100_000].cpu().numpy()).mean())}
+
+    def e2e_goal_pose_input(self, env, steps):
+        """The same solves fed in the reference's input format (48 B / pose instead of the 128 B of a 4x4 matrix); all five outputs."""
+        return self._e2e_leg(env, steps, self._goal_poses_pinned(env.torch), self.host_out, 48, self.BYTES_OUT,
+                             "SymbolicIK.is_reachable_batch_host on (N,6) goal poses (the reference's input format), all outputs")
+
+    def e2e_lean(self, env, steps):
+        """The lean host record: (N,6) goal poses in, state + joints out = 48 + 57 B / pose over the link."""
+        ik = self.solvers["r_arm"]
+        if not hasattr(self, "_lean_out"):
+            self._lean_out = {arm: self.solvers[arm].alloc_host_outputs(self.POSES_PER_ARM, want=ik.LEAN) for arm in ARMS}
+        return self._e2e_leg(env, steps, self._goal_poses_pinned(env.torch), self._lean_out, 48, 57,
+                             "SymbolicIK.is_reachable_batch_host((N,6) goal poses, want=SymbolicIK.LEAN): state + joints back",
+                             want=ik.LEAN)
+
+    def teardown(self):
+        for k in ("_gp_pinned", "_lean_out", "host_in", "host_out", "dpose", "outs"):
+            self.__dict__.pop(k, None)
 
     def parity(self, torch):
         from oracle import oracle as O
@@ -302,9 +328,10 @@ class SymikF32(Symik):
     # 78 FADD + 71 FSETP) + 58 FP64 of the mixed-precision front end (11 DFMA + 10 DMUL + 20 DADD + 6 DSETP)
     FLOP_EQ = 58.0       # FP64 part (roofline_fp64)
     FLOP_FP32 = 573.0    # FP32 part (roofline_fp32)
-    FLOP_EQ_SURVEY = 2100.0
     kernel = "k_symik_solve_f32<MAT4>"
     fp32 = True
+    FP64_PIPE_INSTR = None
+    e2e_extra_legs = ()
 
     def config(self, world):
         c = super().config(world)
@@ -395,10 +422,6 @@ class Discrete:
         # 65 % of the poses search (measured with the oracle)
         return 2400.0 + self.SEARCH_FRACTION * (17 * 55.0 + 200.0)
 
-    @property
-    def FLOP_EQ_SURVEY(self):
-        return 2700.0 + 100.0 * self.K
-
     def config(self, world):
         return {"workload": f"configs[2]: ControlIK discrete, 1M FK-sampled r_arm poses x {self.K} elbow-theta samples, in-kernel "
                             "best-elbow selection + joints + safety checks", "poses_per_step_per_gpu": self.N,
@@ -480,7 +503,6 @@ class Continuous:
     T, W = 65_536, 1_000
     BYTES_IN, BYTES_OUT = 128, 56 + 2
     FLOP_EQ = 2550.0          # is_reachable 900 + 10-sample search 350 + get_joints 900 + safety 300 + continuity 100
-    FLOP_EQ_SURVEY = 4500.0
     kernel = "k_ctl_continuous"
 
     def config(self, world):
@@ -585,7 +607,6 @@ class ReachMap:
     FLOP_FP32 = 0.25 * 35.0
     fp32 = True
     dtype = "f64+f32"   # FP64 front end and escalation, FP32 linking test; integer counts identical to the all-FP64 kernel
-    FLOP_EQ_SURVEY = 900.0 * 0.25
     kernel = "k_reach_map"
 
     def config(self, world):
@@ -600,6 +621,7 @@ class ReachMap:
     def setup(self, torch, dev, rank, world):
         from reachy2_symbolic_ik_b200 import SymbolicIK, fk
 
+        self._torch, self._events = torch, []
         self.ik = SymbolicIK(arm="r_arm", device=dev.index)
         self.ori = torch.from_numpy(fk.fibonacci_orientations(self.N_ORI)).to(dev)
         self.out = torch.empty((self.N,) * 3, dtype=torch.int32, device=dev)
@@ -613,8 +635,25 @@ class ReachMap:
         self.units_per_launch = self.N ** 3 * self.N_ORI // world
 
     def step(self):
-        self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out)
+        torch = self._torch
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out, mark=e[1].record)
+        e[2].record()
+        self._events.append(e)
         return 1
+
+    def phase_times(self, env, steps):
+        """Kernel and collective of the last `steps` steps, timed by events on the launching stream (max over ranks)."""
+        ev = self._events[-steps:]
+        k = env.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b, _ in ev])))
+        c = env.max_over_ranks(float(np.mean([b.elapsed_time(c_) for _, b, c_ in ev])))
+        out = {"kernel_ms": k, "collective_ms": c if env.world > 1 else 0.0, "collective_share_of_step": c / (k + c) if env.world > 1 else 0.0}
+        if env.world > 1:
+            out["collective"] = {"op": "all_reduce(SUM)", "dtype": "int32", "elements": self.N ** 3, "bytes": 4 * self.N ** 3,
+                                 "backend": "NCCL (torch.distributed), in place on the kernel's output volume",
+                                 "bus_GBps": 2 * (env.world - 1) / env.world * 4 * self.N ** 3 / (c * 1e-3) / 1e9}
+        return out
 
     def e2e_setup(self, torch):
         self.host_out = torch.empty((self.N,) * 3, dtype=torch.int32).pin_memory()
@@ -662,29 +701,49 @@ class ReachMap:
 WORKLOADS = {w.name: w for w in (Symik, SymikF32, Discrete, Continuous, ReachMap)}
 
 
-def run_reference(args, wl):
+def reference_record(wl, steps, warmup):
+    """One workload on the CPU arm: `warmup` + `steps` passes of the C port over the bounded sample cpu_port() defines."""
+    vals, secs = [], []
+    sample = cores = None
+    for _ in range(warmup):
+        wl.cpu_port(repeats=1)
+    for _ in range(steps):
+        v, dt, cores, sample = wl.cpu_port(repeats=1)
+        vals.append(v); secs.append(dt)
+    value = float(np.mean(vals))
+    return {"value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"per step: {sample}"}}
+
+
+def run_reference(args, names):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as O
 
     O.use_all_host_threads()   # torchrun exports OMP_NUM_THREADS=1
-    # a bounded sample per step: one pass of the CPU port over the (sub)workload cpu_port() defines
-    vals, secs = [], []
-    sample = cores = None
-    for _ in range(args.warmup):
-        wl.cpu_port(repeats=1)
-    for _ in range(args.steps):
-        v, dt, cores, sample = wl.cpu_port(repeats=1)
-        vals.append(v); secs.append(dt)
-    value = float(np.mean(vals))
+    head = WORKLOADS[names[0]]()
+    if isinstance(head, Symik):
+        # the headline workload honours --steps / --warmup exactly: the per-step sample shrinks instead (a step is a
+        # pass of the CPU port over the first poses of the workload, about 40 M solves for the whole run)
+        steps = args.steps or 10
+        warmup = args.warmup if args.warmup is not None else 1
+        per_arm = int(min(head.POSES_PER_ARM, max(10_000, 20_000_000 // (steps + warmup))))
+        full = head.host_poses(0)
+        head._cpu_data = {arm: full[arm][:per_arm] for arm in ARMS}
+    else:
+        # one reference step is a fraction of a second to a few seconds of all host cores: bound the run
+        steps = min(args.steps or 10, 20)
+        warmup = min(args.warmup if args.warmup is not None else 1, 2)
+    rec = reference_record(head, steps, warmup)
+    cfg = head.config(args.gpus)
+    cfg["reference_sample"] = rec["cpu_baseline"]["sample"] + " (the CPU arm times a bounded sample of the workload, not all of it)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
-        "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": wl.config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"per step: {sample}"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+        "scaling": getattr(head, "scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg, "cpu_baseline": rec["cpu_baseline"],
+        "e2e": {"value": rec["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference is pure Python (NumPy/SciPy, single-threaded, ~1e3 poses/s/core, reported as cpu_baseline.python_reference); this arm times the C port of "
                 "its algorithm (oracle/, pinned to the reference's outputs by tests/golden) on all host threads -- a much "
@@ -693,15 +752,26 @@ def run_reference(args, wl):
     # the unmodified Python reference itself (baseline/_ref), on a bounded sample, beside the port
     pr = None
     try:
-        if isinstance(wl, Symik):
+        if isinstance(head, Symik):
             from reachy2_symbolic_ik_b200 import fk
 
             m = 400 * (os.cpu_count() or 1)
-            pr = python_reference_baseline("symik", "r_arm", fk.sample_fk_poses(m, "r_arm", seed=wl.SEEDS["r_arm"]), m)
+            pr = python_reference_baseline("symik", "r_arm", fk.sample_fk_poses(m, "r_arm", seed=head.SEEDS["r_arm"]), m)
     except Exception as e:  # the installed reference is optional
         pr = {"unavailable": repr(e)}
     if pr is not None:
         line["cpu_baseline"]["python_reference"] = pr
+    subs = {}
+    for name in names[1:]:
+        try:
+            wl = WORKLOADS[name]()
+            r = reference_record(wl, 2, 1)
+            r["config"] = {"workload": wl.config(args.gpus)["workload"]}
+            subs[name] = r
+        except Exception as e:
+            subs[name] = {"error": repr(e)}
+    if subs:
+        line["workloads"] = subs
     emit(line)
     return 0
 
@@ -728,6 +798,196 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+def csrc_sha16() -> str:
+    """Identity of the kernel sources the loaded library was built from (the committed ncu captures carry the same tag)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(REPO, "reachy2_symbolic_ik_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+class Env:
+    """Process-level context shared by the workloads of one run."""
+
+    def __init__(self, torch, dist, dev, rank, world, local_rank):
+        self.torch, self.dist, self.dev, self.rank, self.world, self.local_rank = torch, dist, dev, rank, world, local_rank
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def run_workload(env: Env, wl, steps: int, warmup: int, headline: bool, cpu_baseline: bool):
+    """Time one workload: W warm-up steps, exactly K timed steps (barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks), the end-to-end leg, the parity spot check, the rooflines.  Returns the record."""
+    import contextlib
+
+    torch, dev, rank, world = env.torch, env.dev, env.rank, env.world
+    from reachy2_symbolic_ik_b200 import _native
+
+    with contextlib.redirect_stdout(sys.stderr):   # the facade prints like the reference ("Using default parameters")
+        wl.setup(torch, dev, rank, world)
+    for _ in range(warmup):
+        wl.step()
+    env.barrier()
+    launches = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(env.local_rank) as clocks:
+        ev0.record()
+        for _ in range(steps):
+            launches += wl.step()
+        ev1.record()
+        env.barrier()
+    ms_total = env.max_over_ranks(ev0.elapsed_time(ev1))
+    units_per_step = wl.units_per_step * world
+    value = units_per_step * steps / (ms_total * 1e-3)
+    kernel_ms = ms_total / launches  # a step is nothing but launches of the dominant kernel(s): average launch duration
+    rec = {"value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+           "scaling": getattr(wl, "scaling", "weak"),
+           "dtype": getattr(wl, "dtype", "f32" if getattr(wl, "fp32", False) else "f64"), "config": wl.config(world),
+           "gpu_launches": launches, "clocks": clocks.summary()}
+    if hasattr(wl, "phase_times"):
+        rec.update(wl.phase_times(env, steps))
+
+    # a sustained run of the headline kernel beside the K-step burst (the driver's K = 20 steps are 3 ms: no clock sample
+    # can fall inside, and the power limit is never reached)
+    if headline:
+        n_sus = max(steps, 1500)
+        with ClockSampler(env.local_rank) as cs:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_sus):
+                wl.step()
+            e1.record()
+            env.barrier()
+        ms_sus = env.max_over_ranks(e0.elapsed_time(e1))
+        rec["sustained"] = {"steps": n_sus, "value": units_per_step * n_sus / (ms_sus * 1e-3), "ms_per_step": ms_sus / n_sus,
+                            "clocks": cs.summary()}
+
+    # ---- end to end through the public facade with pinned host buffers (copies inside the timed region)
+    e2e_info = wl.e2e_setup(torch)
+    e2e_units = e2e_info.pop("units_per_step", wl.units_per_step) * world
+    for _ in range(2):
+        wl.e2e_step(torch)
+    env.barrier()
+    e2e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wl.e2e_step(torch)
+    torch.cuda.synchronize()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+    wl.e2e_check(torch)
+    rec["e2e"] = {"value": e2e_units * e2e_steps / e2e_s, "unit": UNIT, **e2e_info, "steps": e2e_steps}
+    for name in getattr(wl, "e2e_extra_legs", ()):
+        try:     # optional legs: can only add a key
+            rec["e2e"][name] = getattr(wl, "e2e_" + name)(env, e2e_steps)
+        except Exception as e:
+            rec["e2e"][name] = {"unavailable": repr(e)}
+
+    # ---- parity spot check against the oracle on this rank's data (not timed), CPU baselines
+    if rank == 0:
+        rec["parity"] = wl.parity(torch)
+        if world == 1 and cpu_baseline:
+            from oracle import oracle as O
+
+            O.use_all_host_threads()
+            v, dt, cores, sample = wl.cpu_port(getattr(wl, "poses", None))
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            try:
+                pr = wl.pyref()
+            except Exception as e:  # the installed reference is optional
+                pr = {"unavailable": repr(e)}
+            if pr is not None:
+                cpu["python_reference"] = pr
+            rec["cpu_baseline"] = cpu
+
+    # ---- rooflines for the dominant kernel
+    hbm_peak, peak_src = measured_peaks()
+    alg_bytes = (wl.BYTES_IN + wl.BYTES_OUT) * wl.units_per_launch
+    achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    pms, pfl = C.c_double(), C.c_double()
+    _native.check(_native.load().r2ik_dfma_probe(env.local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_dfma_probe")
+    fp64_peak = pfl.value / (pms.value * 1e-3) / 1e12
+    # dram__bytes_read + dram__bytes_write of one launch and the pipe activity, from the committed ncu --set full capture of
+    # this kernel (scripts/ncu_to_json.py -> profiles/<workload>_ncu.json); null when no capture is committed
+    traffic = ncu = None
+    tp = os.path.join(REPO, "profiles", f"{wl.name}_ncu.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            ncu = json.load(f)
+        traffic = ncu.get("dram_bytes_per_launch")
+    hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+           "traffic": traffic, "kernel": wl.kernel, "kernel_ms": kernel_ms,
+           "algorithmic_bytes_per_pose": wl.BYTES_IN + wl.BYTES_OUT, "poses_per_launch": wl.units_per_launch,
+           "peak_source": peak_src,
+           "traffic_source": None if ncu is None else {"file": f"profiles/{wl.name}_ncu.json", "capture": ncu.get("source"),
+                                                       "csrc_sha16_of_capture": ncu.get("csrc_sha16"),
+                                                       "csrc_sha16_running": csrc_sha16()}}
+    # FP64 pipe: every FP64 instruction (DFMA, DADD, DMUL, DSETP) holds the pipe for the same two cycles per warp, so the
+    # pipe roofline counts instructions (x 2 = DFMA-equivalent flops) against the measured DFMA peak.  Kernels without a
+    # counted instruction mix fall back to their flop estimate (FMA = 2).
+    slots = getattr(wl, "FP64_PIPE_INSTR", None)
+    fp64_flop = 2.0 * slots if slots is not None else wl.FLOP_EQ
+    fp64_ach = fp64_flop * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
+    fp64 = {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
+            "kernel": wl.kernel, "kernel_ms": kernel_ms,
+            "accounting": ("FP64-pipe instructions per pose x 2 (DFMA-equivalent): the pipe issues one FP64 instruction of any kind "
+                           "per two cycles per SM sub-partition" if slots is not None else "estimated FP64 flops per pose (FMA = 2)"),
+            "fp64_pipe_instructions_per_pose": slots, "flop_per_pose": fp64_flop,
+            "peak_source": "r2ik_dfma_probe measured in this run (DFMA chains, full grid)",
+            "ncu": None if ncu is None else {k: ncu.get(k) for k in (
+                "fp64_pipe_pct_of_peak", "issue_active_pct", "warps_active_pct", "registers_per_thread", "warp_instructions", "source")}}
+    # `roofline` names the limiter that actually binds: the one whose lower bound on the launch time is the larger
+    binding = hbm if hbm["frac"] >= fp64["frac"] or getattr(wl, "fp32", False) else fp64
+    other = fp64 if binding is hbm else hbm
+    rec["roofline"] = dict(binding)
+    if binding is fp64:
+        rec["roofline"]["traffic"] = traffic
+    rec["roofline"]["note"] = (f"both lower bounds are reported; `roofline` is the binding one ({binding['bound']}: frac {binding['frac']:.3f}); "
+                               f"the other is roofline_{other['bound']} (frac {other['frac']:.3f})")
+    rec["roofline_" + other["bound"]] = other
+    if getattr(wl, "fp32", False):
+        # mixed-precision kernels (K1-f32, K4): the measured FFMA peak beside the DFMA one
+        _native.check(_native.load().r2ik_ffma_probe(env.local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_ffma_probe")
+        fp32_peak = pfl.value / (pms.value * 1e-3) / 1e12
+        fp32_ach = wl.FLOP_FP32 * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
+        rec["roofline_fp32"] = {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                "frac": fp32_ach / fp32_peak, "fp32_flop_per_pose": wl.FLOP_FP32,
+                                "peak_source": "r2ik_ffma_probe measured in this run (FFMA chains, full grid)",
+                                "note": "mixed-precision kernel: the FP32 flops are counted here, the FP64 flops in "
+                                        "roofline_fp64; the two pipes issue from the same slots"}
+    if hasattr(wl, "teardown"):
+        wl.teardown()
+    del wl
+    torch.cuda.empty_cache()
+    return rec
+
+
+def scalar_latency():
+    """One control tick through the reference's scalar API (examples call it once per tick, src/example/example_control.py:9-27)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("exp_scalar", os.path.join(REPO, "scripts", "experiments", "exp_r2_scalar_latency.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.measure(200)
+
+
+SUB_STEPS = {"symik_f32": (50, 5), "discrete": (20, 5), "continuous": (3, 3), "reachmap": (3, 3)}   # (steps, warm-up) as sub-records
+
+
 def main() -> int:
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -735,26 +995,15 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="symik", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]()
-    default_steps = {"symik": 2000, "symik_f32": 2000, "discrete": 50, "continuous": 5, "reachmap": 5}[wl.name]
-    default_warm = {"symik": 20, "symik_f32": 20, "discrete": 5, "continuous": 3, "reachmap": 3}[wl.name]
+    names = ["symik", "symik_f32", "discrete", "continuous", "reachmap"] if args.workload == "all" else [args.workload]
     if args.impl == "reference":
-        if isinstance(wl, Symik):
-            # the headline workload honours --steps / --warmup exactly: the per-step sample shrinks instead (a step is a
-            # pass of the CPU port over the first poses of the workload, about 40 M solves for the whole run)
-            args.steps = args.steps or 10
-            args.warmup = args.warmup if args.warmup is not None else 1
-            per_arm = int(min(wl.POSES_PER_ARM, max(10_000, 20_000_000 // (args.steps + args.warmup))))
-            full = wl.host_poses(0)
-            wl._cpu_data = {arm: full[arm][:per_arm] for arm in ARMS}
-        else:
-            # one reference step is a fraction of a second to a few seconds of all host cores: bound the run
-            args.steps = min(args.steps or 10, 20)
-            args.warmup = min(args.warmup if args.warmup is not None else 1, 2)
-        return run_reference(args, wl)
+        return run_reference(args, names)
+    head = WORKLOADS[names[0]]()
+    default_steps = {"symik": 2000, "symik_f32": 2000, "discrete": 50, "continuous": 5, "reachmap": 5}[head.name]
+    default_warm = {"symik": 20, "symik_f32": 20, "discrete": 5, "continuous": 3, "reachmap": 3}[head.name]
     args.steps = args.steps or default_steps
     args.warmup = max(args.warmup if args.warmup is not None else default_warm, 3)
 
@@ -772,134 +1021,35 @@ def main() -> int:
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from reachy2_symbolic_ik_b200 import _native
+    from reachy2_symbolic_ik_b200 import hostmem
 
-    dev = torch.device("cuda", local_rank)
-    import contextlib
+    binding = hostmem.bind_to_gpu_numa(local_rank)     # pinned buffers and copy threads next to this rank's GPU
+    env = Env(torch, dist, torch.device("cuda", local_rank), rank, world, local_rank)
+    rec = run_workload(env, head, args.steps, args.warmup, headline=True, cpu_baseline=not args.no_cpu_baseline)
+    subs = {}
+    for name in names[1:]:
+        k, w = SUB_STEPS[name]
+        try:
+            subs[name] = run_workload(env, WORKLOADS[name](), k, w, headline=False, cpu_baseline=not args.no_cpu_baseline)
+        except Exception as e:   # a sub-record can only add a key: the headline line stands without it
+            import traceback
 
-    with contextlib.redirect_stdout(sys.stderr):   # the facade prints like the reference ("Using default parameters")
-        wl.setup(torch, dev, rank, world)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(args.warmup):
-        wl.step()
-    barrier()
-    launches = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        ev0.record()
-        for _ in range(args.steps):
-            launches += wl.step()
-        ev1.record()
-        barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    units_per_step = wl.units_per_step * world
-    value = units_per_step * args.steps / (ms_total * 1e-3)
-    kernel_ms = ms_total / launches  # a step is nothing but launches of the dominant kernel: average launch duration
-
-    # ---- end to end through the public facade with pinned host buffers (copies inside the timed region)
-    e2e_info = wl.e2e_setup(torch)
-    e2e_units = e2e_info.pop("units_per_step", wl.units_per_step) * world
-    for _ in range(2):
-        wl.e2e_step(torch)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        wl.e2e_step(torch)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = e2e_units * e2e_steps / e2e_s
-    wl.e2e_check(torch)
-
-    # ---- parity spot check against the oracle on this rank's data (not timed), CPU baselines
-    parity = cpu = None
+            traceback.print_exc()
+            subs[name] = {"error": repr(e)}
+        env.barrier()
     if rank == 0:
-        parity = wl.parity(torch)
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as O
-
-            O.use_all_host_threads()
-            v, dt, cores, sample = wl.cpu_port(getattr(wl, "poses", None))
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {"metric": METRIC, "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": world, "steps": rec.pop("steps"),
+                "warmup": rec.pop("warmup"), "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True,
+                "scaling": rec.pop("scaling"), "vs_baseline": None, "dtype": rec.pop("dtype"), "data": "synthetic",
+                "config": rec.pop("config"), **rec, "host_binding": binding}
+        if subs:
+            line["workloads"] = subs
+            line["gpu_launches_all_workloads"] = line["gpu_launches"] + sum(v.get("gpu_launches", 0) for v in subs.values())
+        if world == 1 and args.workload == "all":
             try:
-                pr = wl.pyref()
-            except Exception as e:  # the installed reference is optional
-                pr = {"unavailable": repr(e)}
-            if pr is not None:
-                cpu["python_reference"] = pr
-
-    # ---- rooflines for the dominant kernel
-    hbm_peak, peak_src = measured_peaks()
-    alg_bytes = (wl.BYTES_IN + wl.BYTES_OUT) * wl.units_per_launch
-    achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    pms, pfl = C.c_double(), C.c_double()
-    _native.check(_native.load().r2ik_dfma_probe(local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_dfma_probe")
-    fp64_peak = pfl.value / (pms.value * 1e-3) / 1e12
-    fp32_peak = None
-    if getattr(wl, "fp32", False):
-        _native.check(_native.load().r2ik_ffma_probe(local_rank, 400000, C.byref(pms), C.byref(pfl), None), "r2ik_ffma_probe")
-        fp32_peak = pfl.value / (pms.value * 1e-3) / 1e12
-    fp64_ach = wl.FLOP_EQ * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
-    # dram__bytes_read + dram__bytes_write of one launch and the FP64 pipe activity, from the committed ncu --set full
-    # capture of this kernel (scripts/ncu_to_json.py -> profiles/<workload>_ncu.json); null when no capture is committed
-    traffic = ncu = None
-    tp = os.path.join(REPO, "profiles", f"{wl.name}_ncu.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            ncu = json.load(f)
-        traffic = ncu.get("dram_bytes_per_launch")
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"),
-            "vs_baseline": None, "dtype": getattr(wl, "dtype", "f32" if getattr(wl, "fp32", False) else "f64"), "data": "synthetic", "config": wl.config(world),
-            "e2e": {"value": e2e_value, "unit": UNIT, **e2e_info, "steps": e2e_steps},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": traffic, "kernel": wl.kernel, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_pose": wl.BYTES_IN + wl.BYTES_OUT, "poses_per_launch": wl.units_per_launch,
-                         "peak_source": peak_src, "note": "the kernel is FP64-pipe bound, not HBM bound: see roofline_fp64"},
-            "roofline_fp64": {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
-                              "flop_eq_per_pose": wl.FLOP_EQ, "flop_eq_per_pose_survey_8d": wl.FLOP_EQ_SURVEY,
-                              "frac_survey_8d": wl.FLOP_EQ_SURVEY * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
-                              "peak_source": "r2ik_dfma_probe measured in this run (DFMA chains, full grid)",
-                              "note": "achieved = FP64 flops of THIS formulation per pose (counted, FMA = 2) / launch time; frac_survey_8d uses "
-                                      "SURVEY.md 8(d)'s weighted estimate of the reference's formulation instead (it exceeds 1 where the "
-                                      "restructured kernel does less arithmetic than that estimate); the executed FP64 pipe activity of "
-                                      "the committed ncu capture is in `ncu`",
-                              "ncu": None if ncu is None else {k: ncu.get(k) for k in (
-                                  "fp64_pipe_pct_of_peak", "issue_active_pct", "warps_active_pct", "registers_per_thread",
-                                  "warp_instructions", "source")}},
-            "clocks": clocks.summary(), "parity": parity,
-        }
-        if fp32_peak is not None:
-            # mixed-precision kernels (K1-f32, K4): the measured FFMA peak beside the DFMA one
-            fp32_ach = wl.FLOP_FP32 * wl.units_per_launch / (kernel_ms * 1e-3) / 1e12
-            line["roofline_fp32"] = {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                                     "frac": fp32_ach / fp32_peak, "fp32_flop_per_pose": wl.FLOP_FP32,
-                                     "peak_source": "r2ik_ffma_probe measured in this run (FFMA chains, full grid)",
-                                     "note": "mixed-precision kernel: the FP32 flops are counted here, the FP64 flops in "
-                                             "roofline_fp64; the two pipes issue from the same slots"}
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        if world == 1 and type(wl) is Symik:
-            try:     # optional, last, never fatal: the line above is complete without it
-                line["e2e"]["goal_pose_input"] = wl.e2e_goal_pose(torch, e2e_steps)
+                line["scalar_latency"] = scalar_latency()
             except Exception as e:
-                line["e2e"]["goal_pose_input"] = {"unavailable": repr(e)}
+                line["scalar_latency"] = {"unavailable": repr(e)}
         emit(line)
     if dist is not None:
         dist.barrier()

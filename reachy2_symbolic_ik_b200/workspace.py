@@ -38,21 +38,24 @@ def reach_grid(shoulder_position, max_arm_length: float, n: int):
     return origin, np.array([step, step, step]), np.array([n, n, n], dtype=np.int32)
 
 
-def sharded_sum(launch: Callable[[int, int], "object"], n_orientations: int, dist=None, group=None):
+def sharded_sum(launch: Callable[[int, int], "object"], n_orientations: int, dist=None, group=None, mark=None):
     """Run ``launch(ori_begin, ori_end)`` on this rank's orientation slice and sum the returned
-    count tensor over the ranks in place.  ``dist`` is ``torch.distributed`` (initialised) or None."""
+    count tensor over the ranks in place.  ``dist`` is ``torch.distributed`` (initialised) or None.
+    ``mark``: optional callable invoked between the kernel and the collective (benchmarks record an event there)."""
     rank, world = 0, 1
     if dist is not None and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, e = shard_range(n_orientations, rank, world)
     counts = launch(b, e)
+    if mark is not None:
+        mark()
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     return counts
 
 
 def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int = 512, origin=None, step=None,
-              dims=None, dist=None, group=None, out=None, all_fp64: bool = False):
+              dims=None, dist=None, group=None, out=None, all_fp64: bool = False, mark=None):
     """Reachability count volume of ``solver`` (a ``SymbolicIK``): int32 CUDA tensor (d0, d1, d2).
 
     orientations_euler: (n_ori, 3) xyz Euler angles (default: ``fibonacci_orientations(n_orientations)``).
@@ -88,7 +91,7 @@ def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int
             _native.check(rc, "r2ik_reach_map_u32")
             return out
 
-        return sharded_sum(launch, n_ori, dist, group)
+        return sharded_sum(launch, n_ori, dist, group, mark)
 
 
 def task_space_grid(shoulder_position, arm_length: float = 0.5, x_step: float = 0.15, y_step: float = 0.15,

@@ -235,10 +235,13 @@ def test_invalid_rotation_keeps_controller_state():
             ctl.symbolic_inverse_kinematics("r_arm", bad, mode)
     assert np.array_equal(ctl.previous_sol["r_arm"], before[0]) and ctl.previous_theta["r_arm"] == before[1]
     assert ctl.init == before[2] and ctl.last_call_t["r_arm"] == before[3]
-    j, ok, state = ctl.symbolic_inverse_kinematics("r_arm", M[0], "discrete")
-    assert len(j) == 7
-    j, ok, state = ctl.symbolic_inverse_kinematics("r_arm", M[0], "continuous")
-    np.testing.assert_allclose(j, j0, atol=1e-9)
+    twin = ControlIK(urdf_path="../config_files/reachy2.urdf")       # the same calls without the two that raised
+    twin.symbolic_inverse_kinematics("r_arm", M[0], "continuous")
+    for mode in ("discrete", "continuous", "continuous"):
+        j, ok, state = ctl.symbolic_inverse_kinematics("r_arm", M[2], mode)
+        jt, okt, statet = twin.symbolic_inverse_kinematics("r_arm", M[2], mode)
+        np.testing.assert_allclose(j, jt, atol=1e-12)
+        assert (ok, state) == (okt, statet)
 
 
 def test_f32_empty_batch_sets_the_escalation_count(solvers):
