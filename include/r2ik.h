@@ -279,6 +279,16 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par /* ho
                                    R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
                                    double *workspace, int32_t test_force_serial_mod, void *stream);
 
+/* The same computation with the joints written once: k_cont_targets and k_cont_thetas as above, then ONE kernel for
+ * the rest -- a block owns 16 trajectories and walks them 8 waypoints at a time, get_joints per waypoint and the unwrap /
+ * continuity / emergency scan (one lane per joint) alternate per tile, the tile is staged in shared memory and stored
+ * with row-contiguous requests; waypoints that need the serial get_joints are redone in order inside the scan (no fixup
+ * pass).  workspace: T*W doubles.  Same flags / states as r2ik_ctl_continuous_f64, joints equal to rounding. */
+int r2ik_ctl_continuous_tiled_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
+                                  int32_t W, const double *current_joints, const double *current_pose,
+                                  R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
+                                  double *workspace, int32_t test_force_serial_mod, void *stream);
+
 /* Workspace reachability map: counts[v] += #orientations o in [ori_begin, ori_end) with
  * is_reachable(voxel centre, orientations_euler[o]) true.  Voxel (ix,iy,iz) centre =
  * origin + (ix,iy,iz)*step, v = (ix*dims[1] + iy)*dims[2] + iz.  origin/step/dims: host.

@@ -245,7 +245,13 @@ class ControlIK:
                     joints = torch.empty((T, W, 7), dtype=torch.float64, device=self._device)
                     reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                     state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
-                if phased:
+                if phased == "tiled":
+                    ws = self._scratch(T * W, stream.value)
+                    rc = solver._handle.lib.r2ik_ctl_continuous_tiled_f64(
+                        solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
+                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
+                    _native.check(rc, "r2ik_ctl_continuous_tiled_f64")
+                elif phased:
                     ws = self._scratch(T * W, stream.value)
                     rc = solver._handle.lib.r2ik_ctl_continuous_phased_f64(
                         solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),

@@ -736,6 +736,7 @@ k_cont_finish_direct(const __grid_constant__ ArmConst A, const __grid_constant__
 }
 
 #include "r2ik_scan_lanes.cuh"
+#include "r2ik_cont_tiles.cuh"
 
 // ---------------------------------------------------------------------------------------
 // K4: workspace reachability map.  One thread per voxel.  Voxels outside the reach sphere or behind the torso plane
@@ -1194,6 +1195,30 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
       K, T, W, current_joints, st, workspace, joints, reachable, state);
   k_cont_finish_direct<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state,
                                                     true);
+  R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
+  return 0;
+}
+
+int r2ik_ctl_continuous_tiled_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                                  const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
+                                  uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
+                                  void *stream) {
+  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_tiled_f64: null handle or parameters");
+  if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_tiled_f64: bad T, W or nb_search_points_continuous");
+  if (T == 0 || W == 0) return 0;
+  if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state || !workspace)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_tiled_f64: null argument");
+  if (misaligned16(M) || misaligned16(current_pose))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_tiled_f64: M and current_pose must be 16-byte aligned");
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_wp = T * (int64_t)W;
+  k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
+  k_cont_thetas<<<(unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK), R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st,
+                                                                                               workspace, reachable);
+  k_cont_joints_finish<<<(unsigned)((T + R2IK_TILE_T - 1) / R2IK_TILE_T), R2IK_TILE_BLOCK, 0, s>>>(
+      h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state, test_force_serial_mod);
   R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
   return 0;
 }
