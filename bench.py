@@ -221,8 +221,11 @@ class Symik:
                 "path": "SymbolicIK.is_reachable_batch_host: pinned host -> chunked H2D / K1 / D2H on 3 streams"}
 
     def e2e_step(self, torch):
+        # a step = both arms' batches: both are enqueued, then both are waited for (results in host memory at step end)
         for arm in ARMS:
-            self.solvers[arm].is_reachable_batch_host(self.host_in[arm], self.host_out[arm])
+            self.solvers[arm].is_reachable_batch_host(self.host_in[arm], self.host_out[arm], wait=False)
+        for arm in ARMS:
+            self.solvers[arm].wait_host()
 
     def e2e_check(self, torch):
         assert torch.equal(self.host_out["r_arm"].joints[:1000].nan_to_num(), self.outs["r_arm"]["joints"][:1000].cpu().nan_to_num())
@@ -242,14 +245,18 @@ class Symik:
     def _e2e_leg(self, env, steps, host_in, host_out, bytes_in, bytes_out, path, **kw):
         torch = env.torch
         n = self.POSES_PER_ARM
-        for _ in range(2):
+        def step():
             for arm in ARMS:
-                self.solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm], **kw)
+                self.solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm], wait=False, **kw)
+            for arm in ARMS:
+                self.solvers[arm].wait_host()
+
+        for _ in range(2):
+            step()
         env.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            for arm in ARMS:
-                self.solvers[arm].is_reachable_batch_host(host_in[arm], host_out[arm], **kw)
+            step()
         torch.cuda.synchronize()
         dt = env.max_over_ranks(time.perf_counter() - t0)
         got = host_out["r_arm"].joints[:100_000].numpy()
@@ -376,7 +383,9 @@ class SymikF32(Symik):
 
     def e2e_step(self, torch):
         for arm in ARMS:
-            self.solvers[arm].is_reachable_batch_host(self.host_in[arm], self.host_out[arm], precision="fp32")
+            self.solvers[arm].is_reachable_batch_host(self.host_in[arm], self.host_out[arm], precision="fp32", wait=False)
+        for arm in ARMS:
+            self.solvers[arm].wait_host()
 
     def parity(self, torch):
         from oracle import oracle as O

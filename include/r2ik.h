@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define R2IK_ABI_VERSION 3 /* 3: + symik_scalar, stream_synchronize; no_limits / projected in elbow_positions, prev_joints in
+#define R2IK_ABI_VERSION 3 /* 3: + symik_scalar, stream_synchronize, host pipelines, ctl_ctor_theta, continuous_tiled; no_limits / projected in elbow_positions, prev_joints in
                               no_limits, nullable `reachable`, test hook of the phased continuous entry as a parameter */
 
 /* argument errors */
@@ -314,6 +314,33 @@ int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int6
  * host array).  Host memory should be pinned for the copy to be asynchronous. */
 int r2ik_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
                       size_t rows, void *stream);
+
+/* ---- host pipelines -------------------------------------------------------------------------------------------
+ * A batch in HOST memory, cut into chunks that flow H2D copy -> kernel -> D2H copy on three CUDA streams chained by
+ * events (both PCIe directions and the kernel overlap).  The pipeline object owns its device staging buffers, streams
+ * and events (created once for a chunk size and a number of in-flight slots); the calls enqueue and return, and
+ * r2ik_pipeline_wait blocks until the results are in host memory.  All data pointers below are HOST pointers,
+ * ideally pinned (pageable memory makes the copies synchronous).  Batched counterparts of
+ * SymbolicIK.is_reachable + get_joints (symbolic_ik.py:121-282, 697-863) and of
+ * ControlIK.symbolic_inverse_kinematics(name, M, "discrete") (control_ik.py:162-274, 409-462) for callers whose poses
+ * live in host memory -- which is every caller of the reference. */
+typedef struct r2ik_pipeline *r2ik_pipeline_t;
+int r2ik_pipeline_create(r2ik_handle h, int device, int64_t chunk_poses, int32_t n_slots /* 2 .. 16 */, r2ik_pipeline_t *out);
+int r2ik_pipeline_destroy(r2ik_pipeline_t p);
+int r2ik_pipeline_wait(r2ik_pipeline_t p);
+const char *r2ik_pipeline_last_error(void);
+
+/* Outputs as r2ik_symik_solve_f64 (theta_interval[0], default previous_joints); any output except `state` may be NULL
+ * and is then neither computed nor copied: poses n x 6 in + state + joints back is 48 + 57 bytes per pose. */
+int r2ik_pipeline_symik_f64(r2ik_pipeline_t p, int pose_kind, const double *poses_host, int64_t n, uint8_t *reachable,
+                            uint8_t *state, double *interval, double *joints, double *elbow);
+/* FP32 fast path (r2ik_symik_solve_f32): float poses and results; `reachable` is required. */
+int r2ik_pipeline_symik_f32(r2ik_pipeline_t p, int pose_kind, const float *poses_host, int64_t n, uint8_t *reachable,
+                            uint8_t *state, float *interval, float *joints, float *elbow);
+/* r2ik_ctl_discrete_f64 on host matrices M_host (n x 16); prev / current joints: 7 host doubles each. */
+int r2ik_pipeline_ctl_discrete_f64(r2ik_pipeline_t p, const R2ikCtlParams *par, const double *M_host, int64_t n,
+                                   const double *prev_joints_host, const double *current_joints_host, double *joints,
+                                   uint8_t *reachable, uint8_t *state, uint8_t *emergency /* nullable */);
 
 /* FP64 FMA peak probe used by bench.py for the compute roofline: runs `iters` dependent
  * DFMA chains (8 per thread) on a full grid and returns elapsed ms / flop count. */

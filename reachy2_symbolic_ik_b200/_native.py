@@ -29,6 +29,8 @@ EXPORTS = (
     "r2ik_symik_scalar_f64", "r2ik_stream_synchronize", "r2ik_ctl_ctor_theta_f64",
     "r2ik_ctl_discrete_f64", "r2ik_ctl_discrete_scan_f64", "r2ik_ctl_continuous_f64", "r2ik_ctl_continuous_phased_f64", "r2ik_ctl_continuous_tiled_f64", "r2ik_reach_map_u32", "r2ik_reach_map_f64_u32", "r2ik_fk_f64", "r2ik_copy2d_async",
     "r2ik_dfma_probe", "r2ik_ffma_probe",
+    "r2ik_pipeline_create", "r2ik_pipeline_destroy", "r2ik_pipeline_wait", "r2ik_pipeline_last_error", "r2ik_pipeline_symik_f64",
+    "r2ik_pipeline_symik_f32", "r2ik_pipeline_ctl_discrete_f64",
 )
 
 
@@ -75,9 +77,17 @@ def load() -> C.CDLL:
     L.r2ik_copy2d_async.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     L.r2ik_dfma_probe.argtypes = [C.c_int, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     L.r2ik_ffma_probe.argtypes = [C.c_int, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
+    L.r2ik_pipeline_create.argtypes = [vp, C.c_int, i64, i32, C.POINTER(vp)]
+    L.r2ik_pipeline_destroy.argtypes = [vp]
+    L.r2ik_pipeline_wait.argtypes = [vp]
+    L.r2ik_pipeline_last_error.restype = C.c_char_p
+    L.r2ik_pipeline_symik_f64.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp]
+    L.r2ik_pipeline_symik_f32.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp]
+    L.r2ik_pipeline_ctl_discrete_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, C.POINTER(C.c_double),
+                                                 C.POINTER(C.c_double), vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)  # AttributeError here = the library does not export what r2ik.h declares
-        if name not in ("r2ik_abi_version", "r2ik_last_error"):
+        if name not in ("r2ik_abi_version", "r2ik_last_error", "r2ik_pipeline_last_error"):
             fn.restype = C.c_int
     if L.r2ik_abi_version() != _abi.ABI_VERSION:
         raise R2ikError(f"libr2ik.so ABI {L.r2ik_abi_version()} != expected {_abi.ABI_VERSION}; rebuild")
@@ -90,6 +100,39 @@ def check(rc: int, what: str) -> None:
         msg = load().r2ik_last_error().decode(errors="replace")
         kind = "argument error" if rc > 0 else "CUDA error"
         raise R2ikError(f"{what}: {kind} {rc}: {msg}")
+
+
+def check_pipeline(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().r2ik_pipeline_last_error().decode(errors="replace")
+        kind = "argument error" if rc > 0 else "CUDA error"
+        raise R2ikError(f"{what}: {kind} {rc}: {msg}")
+
+
+class Pipeline:
+    """Owns one r2ik_pipeline (device staging buffers + three streams + events) of a handle."""
+
+    def __init__(self, handle: "Handle", chunk: int, n_slots: int):
+        self.lib = handle.lib
+        self.handle = handle          # keeps the r2ik_handle alive
+        self._p = C.c_void_p()
+        check_pipeline(self.lib.r2ik_pipeline_create(handle.h, handle.device, C.c_int64(int(chunk)), C.c_int32(int(n_slots)),
+                                                     C.byref(self._p)), "r2ik_pipeline_create")
+
+    @property
+    def p(self):
+        return self._p
+
+    def wait(self) -> None:
+        check_pipeline(self.lib.r2ik_pipeline_wait(self._p), "r2ik_pipeline_wait")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_p", None) and self._p.value:
+                self.lib.r2ik_pipeline_destroy(self._p)
+                self._p = C.c_void_p()
+        except Exception:
+            pass
 
 
 def require_cuda():

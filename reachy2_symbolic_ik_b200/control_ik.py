@@ -351,6 +351,8 @@ class ControlIK:
         for pipe in getattr(self, "_pipe_cache", {}).values():
             for s in pipe["streams"]:
                 s.synchronize()
+        for pipe in self.__dict__.pop("_native_pipes", []):
+            pipe.wait()
 
     # ------------------------------------------------------------------ host-buffer pipelines
     def alloc_host_outputs(self, control_type: str, shape) -> tuple:
@@ -397,31 +399,27 @@ class ControlIK:
             if control_type == "discrete":
                 n = M_host.shape[0]
                 P = M_host.reshape(n, 16)
-                chunk = chunk or (1 << 17)
+                chunk = chunk or (1 << 16)
                 if out is None:
                     out = self.alloc_host_outputs("discrete", n)
-                prev = self._dev(self.previous_sol[name] if previous_joints is None else previous_joints, (7,))
-                cur = prev if current_joints is None else self._dev(current_joints, (7,))
-                pipe = self._pipeline(("discrete", chunk, n_streams), lambda: dict(
-                    M=torch.empty((chunk, 16), dtype=f64, device=dev), joints=torch.empty((chunk, 7), dtype=f64, device=dev),
-                    reach=torch.empty(chunk, dtype=u8, device=dev), state=torch.empty(chunk, dtype=u8, device=dev),
-                    emg=torch.empty(chunk, dtype=u8, device=dev)), n_streams)
-                for s in pipe["streams"]:
-                    s.wait_stream(cur_stream)
-                for ci, lo in enumerate(range(0, n, chunk)):
-                    hi = min(n, lo + chunk)
-                    m = hi - lo
-                    s, b = pipe["streams"][ci % n_streams], pipe["bufs"][ci % n_streams]
-                    with torch.cuda.stream(s):
-                        b["M"][:m].copy_(P[lo:hi], non_blocking=True)
-                        rc = lib.r2ik_ctl_discrete_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(m), _ptr(prev), _ptr(cur),
-                                                       _ptr(b["joints"]), _ptr(b["reach"]), _ptr(b["state"]), _ptr(b["emg"]),
-                                                       C.c_void_p(s.cuda_stream))
-                        _native.check(rc, "r2ik_ctl_discrete_f64")
-                        out[0][lo:hi].copy_(b["joints"][:m], non_blocking=True)
-                        out[1][lo:hi].copy_(b["reach"][:m], non_blocking=True)
-                        out[2][lo:hi].copy_(b["state"][:m], non_blocking=True)
-                        out[3][lo:hi].copy_(b["emg"][:m], non_blocking=True)
+                for i, (cols, dtype) in enumerate(((7, f64), (1, u8), (1, u8), (1, u8))):
+                    o = out[i]
+                    if not hasattr(o, "is_cuda") or o.is_cuda or o.dtype != dtype or o.numel() != n * cols or not o.is_contiguous():
+                        raise ValueError(f"out[{i}] must be a contiguous CPU tensor of {n} x {cols} {dtype} (see alloc_host_outputs)")
+                prev = np.ascontiguousarray(self.previous_sol[name] if previous_joints is None else previous_joints, dtype=np.float64).reshape(7)
+                cur = prev if current_joints is None else np.ascontiguousarray(current_joints, dtype=np.float64).reshape(7)
+                pipe = solver._pipeline(chunk, n_streams)      # the native chunk loop of libr2ik.so (r2ik_pipeline_*)
+                dp = C.POINTER(C.c_double)
+                rc = lib.r2ik_pipeline_ctl_discrete_f64(pipe.p, C.byref(par), C.c_void_p(P.data_ptr()), C.c_int64(n),
+                                                        prev.ctypes.data_as(dp), cur.ctypes.data_as(dp),
+                                                        C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                                        C.c_void_p(out[2].data_ptr()), C.c_void_p(out[3].data_ptr()))
+                _native.check_pipeline(rc, "r2ik_pipeline_ctl_discrete_f64")
+                if _wait:
+                    pipe.wait()
+                else:
+                    self.__dict__.setdefault("_native_pipes", []).append(pipe)
+                return out
             elif control_type == "continuous":
                 # A trajectory is a recursion over its waypoints, so K3's run time is set by W, not by T: the
                 # pipeline therefore cuts the WAYPOINT axis.  Chunk c = waypoints [w0, w1) of every trajectory

@@ -259,7 +259,8 @@ class SymbolicIK:
             elbow=pin(n, 3, dtype=dt) if "elbow" in want else None)
 
     def is_reachable_batch_host(self, poses_host, out: Optional[BatchResult] = None, chunk: Optional[int] = None,
-                                n_streams: int = 3, precision: str = "fp64", want=None, devices=None) -> BatchResult:
+                                n_streams: int = 3, precision: str = "fp64", want=None, devices=None,
+                                wait: bool = True) -> BatchResult:
         """Host-to-host batched solve: ``poses_host`` is a CPU tensor (N,16)/(N,4,4)/(N,6)/(N,2,3),
         ideally pinned; results land in ``out`` (pinned CPU tensors; ``reachable`` is uint8 0/1).
         The batch is cut into chunks that flow H2D -> K1 -> D2H on ``n_streams`` CUDA streams so the
@@ -271,7 +272,9 @@ class SymbolicIK:
         48 B / pose with ``want=SymbolicIK.LEAN`` (state + joints = 57 B / pose) moves 105 B where (N,4,4) + all
         five outputs moves 226 B.
         devices: CUDA ordinals to spread the batch over (contiguous slices, one pipeline per device, no exchange);
-        default = this solver's device only."""
+        default = this solver's device only.
+        wait=False: enqueue and return at once; ``out`` is complete after ``wait_host()`` (several calls -- both arms, the
+        next batch -- can then share the link without a pipeline fill / drain gap between them)."""
         torch = self._torch
         dt = _precision_dtype(torch, precision)
         want = self.HOST_FIELDS if want is None else tuple(want)
@@ -280,8 +283,7 @@ class SymbolicIK:
             raise ValueError(f"unknown output fields {sorted(unknown)}; choose from {self.HOST_FIELDS}")
         if precision == "fp32" and "reachable" not in want:
             want = want + ("reachable",)     # r2ik_symik_solve_f32 always writes it
-        if chunk is None:   # measured optimum on B200 / PCIe 5 (scripts/exp_e2e.py): 128 k poses (FP64), 256 k (FP32)
-            chunk = 1 << 17 if precision == "fp64" else 1 << 18
+        chunk_auto = chunk is None
         if not hasattr(poses_host, "is_cuda"):
             poses_host = torch.from_numpy(np.ascontiguousarray(poses_host))
         if poses_host.is_cuda:
@@ -293,15 +295,31 @@ class SymbolicIK:
         if k == 6 and shp[1:] not in ((2, 3), (6,)):
             raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6); got {shp}")
         kind = _abi.POSE_MAT4 if k == 16 else _abi.POSE_EULER6
+        if chunk_auto:
+            # measured on B200 / PCIe 5 (profiles/r2_experiments.md): when the results outweigh the poses the D2H stream is
+            # the critical one and the first, exposed H2D copy should be short (64 k poses); otherwise 128 k-pose chunks
+            out_cols = 2 * ("interval" in want) + 7 * ("joints" in want) + 3 * ("elbow" in want)
+            chunk = (1 << 16 if out_cols > k else 1 << 17) * (1 if precision == "fp64" else 2)
         P = poses_host.reshape(shp[0], k)
         if not P.is_contiguous():
             P = P.contiguous()
         n = shp[0]
         if out is None:
             out = self.alloc_host_outputs(n, precision, want)
+        else:   # the native pipeline addresses raw rows of these buffers
+            for name, t, cols, tdt in (("reachable", out.reachable, 1, torch.uint8), ("state", out.state, 1, torch.uint8),
+                                       ("interval", out.theta_interval, 2, dt), ("joints", out.joints, 7, dt), ("elbow", out.elbow, 3, dt)):
+                if name != "state" and name not in want:
+                    continue
+                if (t is None or not hasattr(t, "is_cuda") or t.is_cuda or t.dtype != tdt or not t.is_contiguous()
+                        or t.numel() != n * cols):
+                    raise ValueError(f"out.{name} must be a contiguous CPU tensor of {n} x {cols} {tdt} (see alloc_host_outputs)")
         devices = [self._handle.device] if devices is None else [int(d) for d in devices]
+        self._keep_alive = P          # the copies read it until wait_host()
         if len(devices) == 1 and devices[0] == self._handle.device:
-            self._host_pipeline(P, kind, k, dt, precision, want, out, 0, n, chunk, n_streams, sync=True)
+            self._host_pipeline(P, kind, k, dt, precision, want, out, 0, n, chunk, n_streams, sync=wait)
+            if not wait:
+                self._pending = [(self, (chunk, n_streams, k, dt))]
             return out
         # one pipeline per device on its contiguous slice; everything is enqueued before anything is waited for
         from .workspace import shard_range
@@ -310,76 +328,52 @@ class SymbolicIK:
         for r, sv in enumerate(solvers):
             lo, hi = shard_range(n, r, len(solvers))
             sv._host_pipeline(P, kind, k, dt, precision, want, out, lo, hi, chunk, n_streams, sync=False)
-        for sv in solvers:
-            sv._host_pipeline_wait(chunk, n_streams, k, dt)
+        self._pending = [(sv, (chunk, n_streams, k, dt)) for sv in solvers]
+        if wait:
+            self.wait_host()
         return out
 
+    def wait_host(self) -> None:
+        """Block until the last ``is_reachable_batch_host(..., wait=False)`` has delivered its results."""
+        for sv, key in self.__dict__.pop("_pending", []):
+            sv._host_pipeline_wait(*key)
+        self.__dict__.pop("_keep_alive", None)
+
     def _host_pipeline(self, P, kind, k, dt, precision, want, out, begin, end, chunk, n_streams, sync):
-        torch = self._torch
-        fp32 = precision == "fp32"
-        with torch.cuda.device(self._device):
-            pipe = self._pipeline(chunk, n_streams, k, dt)
-            cur = torch.cuda.current_stream(self._device)
-            for s in pipe["streams"]:
-                s.wait_stream(cur)
-            w_reach, w_itv, w_j, w_e = ("reachable" in want), ("interval" in want), ("joints" in want), ("elbow" in want)
-            for ci, lo in enumerate(range(begin, end, chunk)):
-                hi = min(end, lo + chunk)
-                m = hi - lo
-                slot = ci % n_streams
-                s = pipe["streams"][slot]
-                b = pipe["bufs"][slot]
-                with torch.cuda.stream(s):
-                    b["poses"][:m].copy_(P[lo:hi], non_blocking=True)
-                    if fp32:
-                        self.solve_into_f32(b["poses"][:m], kind, None, None, b["reach"], b["state"], b["interval"] if w_itv else None,
-                                            b["joints"] if w_j else None, b["elbow"] if w_e else None, b["n_esc"],
-                                            stream=s.cuda_stream, scratch=b["esc"])
-                    else:
-                        self.solve_into(b["poses"][:m], kind, None, None, b["reach"] if w_reach else None, b["state"],
-                                        b["interval"] if w_itv else None, b["joints"] if w_j else None,
-                                        b["elbow"] if w_e else None, stream=s.cuda_stream)
-                    out.state[lo:hi].copy_(b["state"][:m], non_blocking=True)
-                    if w_reach:
-                        out.reachable[lo:hi].copy_(b["reach"][:m], non_blocking=True)
-                    if w_itv:
-                        out.theta_interval[lo:hi].copy_(b["interval"][:m], non_blocking=True)
-                    if w_j:
-                        out.joints[lo:hi].copy_(b["joints"][:m], non_blocking=True)
-                    if w_e:
-                        out.elbow[lo:hi].copy_(b["elbow"][:m], non_blocking=True)
-            if sync:
-                for s in pipe["streams"]:
-                    s.synchronize()
+        """Enqueue rows [begin, end) on this solver's native pipeline (r2ik_pipeline_*: the chunk loop, the three
+        streams and the staging buffers live in libr2ik.so)."""
+        pipe = self._pipeline(chunk, n_streams, k, dt)
+        esz = P.element_size()
+
+        def at(t, cols):
+            return C.c_void_p(None) if t is None else C.c_void_p(t.data_ptr() + begin * cols * t.element_size())
+
+        w = set(want)
+        args = (pipe.p, kind, C.c_void_p(P.data_ptr() + begin * k * esz), C.c_int64(end - begin),
+                at(out.reachable if "reachable" in w else None, 1), at(out.state, 1),
+                at(out.theta_interval if "interval" in w else None, 2), at(out.joints if "joints" in w else None, 7),
+                at(out.elbow if "elbow" in w else None, 3))
+        if precision == "fp32":
+            _native.check_pipeline(pipe.lib.r2ik_pipeline_symik_f32(*args), "r2ik_pipeline_symik_f32")
+        else:
+            _native.check_pipeline(pipe.lib.r2ik_pipeline_symik_f64(*args), "r2ik_pipeline_symik_f64")
+        if sync:
+            pipe.wait()
 
     def _host_pipeline_wait(self, chunk, n_streams, k, dt):
-        for s in self._pipeline(chunk, n_streams, k, dt)["streams"]:
-            s.synchronize()
+        self._pipeline(chunk, n_streams, k, dt).wait()
 
-    _PIPE_CACHE_MAX = 4   # distinct (chunk, streams, layout, dtype) pipelines kept per solver (device buffers)
+    _PIPE_CACHE_MAX = 4   # distinct (chunk, slots) pipelines kept per solver (each owns device staging buffers)
 
-    def _pipeline(self, chunk: int, n_streams: int, k: int, dt=None):
-        dt = self._torch.float64 if dt is None else dt
-        key = (chunk, n_streams, k, dt)
+    def _pipeline(self, chunk: int, n_streams: int, k: int = 16, dt=None):
+        key = (int(chunk), int(n_streams))
         cache = getattr(self, "_pipe_cache", None)
         if cache is None:
             cache = self._pipe_cache = {}
         if key not in cache:
-            torch = self._torch
-            d = self._device
-            while len(cache) >= self._PIPE_CACHE_MAX:      # bounded: the oldest pipeline's buffers go back to the allocator
+            while len(cache) >= self._PIPE_CACHE_MAX:      # bounded: the oldest pipeline's buffers are freed
                 cache.pop(next(iter(cache)))
-            cache[key] = {
-                "streams": [torch.cuda.Stream(device=d) for _ in range(n_streams)],
-                "bufs": [dict(poses=torch.empty((chunk, k), dtype=dt, device=d),
-                              reach=torch.empty(chunk, dtype=torch.uint8, device=d),
-                              state=torch.empty(chunk, dtype=torch.uint8, device=d),
-                              interval=torch.empty((chunk, 2), dtype=dt, device=d),
-                              joints=torch.empty((chunk, 7), dtype=dt, device=d),
-                              elbow=torch.empty((chunk, 3), dtype=dt, device=d),
-                              esc=torch.empty(chunk, dtype=torch.int32, device=d),
-                              n_esc=torch.empty(1, dtype=torch.int32, device=d)) for _ in range(n_streams)],
-            }
+            cache[key] = _native.Pipeline(self._handle, chunk, max(2, n_streams))
         return cache[key]
 
     def clear_caches(self) -> None:
