@@ -399,10 +399,12 @@ class SymikF32(Symik):
         got_j, got_i, got_s = (o[k][:m].cpu().numpy() for k in ("joints", "interval", "state"))
         ej, ei = np.nan_to_num(np.abs(got_j - want[3])).max(axis=1), np.nan_to_num(np.abs(got_i - want[1])).max(axis=1)
         ok = want[2] == 0
-        return {"checked_poses": m, "state_mismatches": int((got_s != want[2]).sum()), "tolerance_rad": 1e-4,
+        return {"checked_poses": m, "state_mismatches": int((got_s != want[2]).sum()),
+                "stated_bound": "1e-4 rad for >= 99.99 % of the poses, 3e-4 rad for all (include/r2ik.h)",
                 "max_abs_err_joints_rad": float(ej.max()), "p50_abs_err_joints_rad": float(np.median(ej[ok])),
-                "p99.9_abs_err_joints_rad": float(np.quantile(ej[ok], 0.999)), "max_abs_err_interval_rad": float(ei.max()),
-                "over_1e-4": int((ej > 1e-4).sum()), "escalated_to_fp64_fraction": esc / self.POSES_PER_ARM,
+                "p99.9_abs_err_joints_rad": float(np.quantile(ej[ok], 0.999)), "p99.99_abs_err_joints_rad": float(np.quantile(ej[ok], 0.9999)),
+                "max_abs_err_interval_rad": float(ei.max()),
+                "over_1e-4": int((ej > 1e-4).sum()), "over_3e-4": int((ej > 3e-4).sum()), "escalated_to_fp64_fraction": esc / self.POSES_PER_ARM,
                 "vs": "FP64 CPU oracle on the same float32 inputs widened to double"}
 
     def cpu_port(self, poses=None, repeats=3):
@@ -645,23 +647,43 @@ class ReachMap:
 
     def step(self):
         torch = self._torch
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        if self.world > 1:
+            t = {}
+            self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out, timing=t)
+            self._events.append(t)
+            return len(t["k"])
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         e[0].record()
-        self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out, mark=e[1].record)
-        e[2].record()
-        self._events.append(e)
+        self.ik.reach_map(n=self.N, orientations_euler=self.ori, out=self.out)
+        e[1].record()
+        self._events.append({"t0": e[0], "t1": e[1], "k": [(e[0], e[1])]})
         return 1
 
     def phase_times(self, env, steps):
-        """Kernel and collective of the last `steps` steps, timed by events on the launching stream (max over ranks)."""
+        """Kernel time (sum of the slab kernels) and what the all-reduce adds to the step beyond it, by events on the
+        launching stream (max over ranks); plus, once, the plain form: one all-reduce of the full int32 volume after the kernel."""
         ev = self._events[-steps:]
-        k = env.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b, _ in ev])))
-        c = env.max_over_ranks(float(np.mean([b.elapsed_time(c_) for _, b, c_ in ev])))
-        out = {"kernel_ms": k, "collective_ms": c if env.world > 1 else 0.0, "collective_share_of_step": c / (k + c) if env.world > 1 else 0.0}
+        step_ms = env.max_over_ranks(float(np.mean([t["t0"].elapsed_time(t["t1"]) for t in ev])))
+        k_ms = env.max_over_ranks(float(np.mean([sum(a.elapsed_time(b) for a, b in t["k"]) for t in ev])))
+        out = {"kernel_ms": k_ms, "collective_ms": max(step_ms - k_ms, 0.0) if env.world > 1 else 0.0,
+               "collective_share_of_step": max(step_ms - k_ms, 0.0) / step_ms if env.world > 1 else 0.0}
         if env.world > 1:
-            out["collective"] = {"op": "all_reduce(SUM)", "dtype": "int32", "elements": self.N ** 3, "bytes": 4 * self.N ** 3,
-                                 "backend": "NCCL (torch.distributed), in place on the kernel's output volume",
-                                 "bus_GBps": 2 * (env.world - 1) / env.world * 4 * self.N ** 3 / (c * 1e-3) / 1e9}
+            torch = self._torch
+            xb = ev[-1]["exchanged_bytes"]
+            out["collective"] = {"op": "all_reduce(SUM), one per slab, asynchronous: overlaps the next slab's kernel", "slabs": len(ev[-1]["k"]),
+                                 "wire_dtype": "uint16 counts, two per int32 lane", "bytes": xb, "full_int32_volume_bytes": 4 * self.N ** 3,
+                                 "backend": "NCCL (torch.distributed)", "collective_ms_is": "step time minus the slab kernels' time: "
+                                 "the part of the exchange that the kernels do not hide, plus the 16->32-bit widening pass"}
+            ms = []
+            for _ in range(3):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record()
+                self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out, plain_allreduce=True, mark=e[1].record)
+                e[2].record(); torch.cuda.synchronize()
+                ms.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+            out["plain_form"] = {"kernel_ms": env.max_over_ranks(float(np.mean([a for a, _ in ms[1:]]))),
+                                 "collective_ms": env.max_over_ranks(float(np.mean([b for _, b in ms[1:]]))),
+                                 "bytes": 4 * self.N ** 3, "note": "one all-reduce of the full int32 volume after the kernel (the round-1 form)"}
         return out
 
     def e2e_setup(self, torch):

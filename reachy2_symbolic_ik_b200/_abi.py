@@ -10,6 +10,7 @@ ABI_VERSION = 3
 
 POSE_EULER6 = 0
 POSE_MAT4 = 1
+POSE_MAT34 = 2
 
 EMG_SHOULDER_PITCH = 1
 EMG_ELBOW_YAW = 2

@@ -114,8 +114,15 @@ constexpr float kBandLen = 4e-6f;      // lengths and coordinates [m]
 constexpr float kBandSin = 1e-5f;      // |sin| below which an angle sits on the +-pi / 0 branch cut
 constexpr double kBandD2 = 4e-8;       // squared wrist distance [m^2] around the range / minimum-distance spheres
 constexpr float kMinH2 = 4e-6f;        // squared length under an atan2 below which the angle is ill-conditioned (2 mm)
+// The two angles whose lever collapses on ordinary poses -- shoulder pitch (the elbow near the pitch axis) and elbow
+// yaw (a nearly straight arm: lever = forearm x sin(elbow pitch)) -- amplify the FP32 noise of the frame chain (a few
+// 1e-6 m, measured) to more than 1e-4 rad well before 2 mm: they are handed to FP64 below 1.7 cm / 3.2 cm.  Host soak of
+// 1.44 M reachable FK samples (profiles/r2_experiments.md): joints over 1e-4 rad 39 -> 5, max 4.8e-4 -> 1.4e-4,
+// escalated 0.5 % -> 4.6 %.
+constexpr float kMinH2ShoulderPitch = 3e-4f;
+constexpr float kMinH2ElbowYaw = 1e-3f;
 constexpr float kMinRadius2 = 1e-9f;   // elbow-circle radius^2 below which 1 / r is not trusted (0.03 mm)
-constexpr float kMinLever2 = 1e-6f;    // (r rho sin alpha)^2 below which the interval ends are ill-conditioned (1 mm)
+constexpr float kMinLever2 = 1e-5f;    // (r rho sin alpha)^2 below which the interval ends are ill-conditioned (3 mm: interval error <= 2e-5 rad)
 
 // atan2(s, c) of a UNIT vector (see angle_of_unit in r2ik_math.cuh): asin polynomial of 5 terms on
 // |u| <= sin(pi/8), scripts/gen_atan_coeffs.py 0.3826834323650898 5 asin (max rel err 4.4e-9).
@@ -140,14 +147,14 @@ R2IK_HD float angle_of_unit_f(float c, float s) {
 
 // (cos a, sin a) and a = atan2(y, x).  esc: the vector is too short for the angle to be determined to
 // 1e-4 from FP32 coordinates, or a sits on the +-pi branch cut.
-R2IK_HD float cs_and_angle_f(float y, float x, float &c, float &s, bool &esc) {
+R2IK_HD float cs_and_angle_f(float y, float x, float &c, float &s, bool &esc, float min_h2 = kMinH2) {
   const float h2 = x * x + y * y;
   const float ih = rsqrt_f(h2);
   c = x * ih; s = y * ih;
 #ifdef R2IK_F32_DEBUG
   r2ik_f32_dbg(h2);
 #endif
-  R2IK_ESC(1, !(h2 > kMinH2) || (c < 0.0f && fabsf(s) < kBandSin));
+  R2IK_ESC(1, !(h2 > min_h2) || (c < 0.0f && fabsf(s) < kBandSin));
   return angle_of_unit_f(c, s);
 }
 
@@ -206,13 +213,17 @@ R2IK_HD void rotation_from_mat4_f(const float m[12], float R[9], bool &esc) {
 }
 
 // R.from_euler("xyz", e).as_matrix() = Rz(e2) Ry(e1) Rx(e0)
+// The six sines / cosines are taken in FP64 (the straight-line kernel of r2ik_math.cuh on the exactly widened angles) and
+// the matrix is rounded once at the end: the FP32 construction carries ~2e-7 per element, which the near-straight-arm
+// levers turn into 4e-4 rad (12 M host soak: 84 poses over 1e-4 with the FP32 matrix, against 18 for the same poses given
+// as float matrices); this costs ~90 FP64 instructions on the euler layout only.
 R2IK_HD void rot_from_euler_xyz_f(float e0, float e1, float e2, float R[9], bool &esc) {
   R2IK_ESC(3, !(fabsf(e0) <= 64.0f && fabsf(e1) <= 64.0f && fabsf(e2) <= 64.0f));
-  float sx, cx, sy, cy, sz, cz;
-  sincos_f(e0, sx, cx); sincos_f(e1, sy, cy); sincos_f(e2, sz, cz);
-  R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
-  R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
-  R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
+  double sx, cx, sy, cy, sz, cz;
+  sincos_small((double)e0, sx, cx); sincos_small((double)e1, sy, cy); sincos_small((double)e2, sz, cz);
+  R[0] = (float)(cz * cy); R[1] = (float)(cz * sy * sx - sz * cx); R[2] = (float)(cz * sy * cx + sz * sx);
+  R[3] = (float)(sz * cy); R[4] = (float)(sz * sy * sx + cz * cx); R[5] = (float)(sz * sy * cx - cz * sx);
+  R[6] = (float)(-sy);     R[7] = (float)(cy * sx);                R[8] = (float)(cy * cx);
 }
 
 R2IK_HD void wrist_from_goal_f(const ArmConstF &A, const float p[3], const float R[9], float w[3]) {
@@ -402,14 +413,14 @@ R2IK_HD void get_joints_f(const ArmConstF &A, SolveF &S, float ct, float st, flo
   const float ptw[3] = {S.R[0] * 0.1f + tipw[0], S.R[3] * 0.1f + tipw[1], S.R[6] * 0.1f + tipw[2]};
   P3f el = to_shoulder_f(A, E), wr = to_shoulder_f(A, S.w), tp = to_shoulder_f(A, tipw), pt = to_shoulder_f(A, ptw);
   float s, c, at[7];
-  at[0] = cs_and_angle_f(el.z, el.x, c, s, esc);                       // sik:751-758
+  at[0] = cs_and_angle_f(el.z, el.x, c, s, esc, kMinH2ShoulderPitch);  // sik:751-758
   rot_y_f(el, c, s); rot_y_f(wr, c, s); rot_y_f(tp, c, s); rot_y_f(pt, c, s);
   at[1] = -cs_and_angle_f(-el.y, el.x, c, s, esc);                     // sik:766-769
   rot_z_f(wr, c, s); rot_z_f(tp, c, s); rot_z_f(pt, c, s);
   wr.x -= A.L1; tp.x -= A.L1; pt.x -= A.L1;
   {
     float ca, sa;
-    at[2] = cs_and_angle_f(wr.z, -wr.y, ca, sa, esc);                  // sik:782-789
+    at[2] = cs_and_angle_f(wr.z, -wr.y, ca, sa, esc, kMinH2ElbowYaw);  // sik:782-789
     c = sa; s = -ca;
   }
   rot_x_f(wr, c, s); rot_x_f(tp, c, s); rot_x_f(pt, c, s);

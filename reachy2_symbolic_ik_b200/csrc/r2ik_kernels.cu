@@ -33,6 +33,9 @@ using namespace r2ik;
 #ifndef R2IK_K1_MINBLOCKS
 #define R2IK_K1_MINBLOCKS 4   // resident blocks / SM the register allocation of K1 is held to
 #endif
+#ifndef R2IK_K1_STAGED
+#define R2IK_K1_STAGED 0      // 1: K1's float outputs leave through shared memory as 128-bit row-contiguous stores
+#endif
 
 // ---------------------------------------------------------------------------------------
 // vectorised global memory helpers
@@ -59,6 +62,18 @@ __device__ __forceinline__ bool load_pose(const double *__restrict__ poses, int6
     pos[0] = a.x; pos[1] = a.y; pos[2] = b.x;
     rot_from_euler_xyz(b.y, c.x, c.y, R);
     return true;
+  } else if (KIND == R2IK_POSE_MAT34) {
+    // the 3x4 top of the matrix, 12 doubles per pose: every byte that crosses HBM (and PCIe) is used
+    double m[16];
+    const double *p = poses + 12 * i;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double2 a = ldg2(p + 4 * r), b = ldg2(p + 4 * r + 2);
+      m[4 * r] = a.x; m[4 * r + 1] = a.y; m[4 * r + 2] = b.x; m[4 * r + 3] = b.y;
+    }
+    m[12] = 0.0; m[13] = 0.0; m[14] = 0.0; m[15] = 1.0;
+    pos[0] = m[3]; pos[1] = m[7]; pos[2] = m[11];
+    return rotation_from_mat4(m, snap, R);
   } else {
     double m[16];
     load_mat4(poses + 16 * i, m);
@@ -74,31 +89,37 @@ __device__ __forceinline__ void store_nan(double *p, int n) {
 // ---------------------------------------------------------------------------------------
 // K1: SymbolicIK.is_reachable + theta_to_joints
 // ---------------------------------------------------------------------------------------
-template <int KIND>
+// STAGED = true: the three float outputs of a warp's 32 poses (7 + 3 + 2 doubles each) are transposed through 3 KB of
+// shared memory and leave as 128-bit row-contiguous stores (every sector written once, by one request) instead of 12
+// scalar stores of stride 56 / 24 / 16 bytes.  Needs 16-byte aligned output arrays (the launcher checks).
+template <int KIND, bool STAGED>
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
 k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ poses, const double *__restrict__ theta,
               const double *__restrict__ prev_joints, int64_t n, uint8_t *__restrict__ reachable,
               uint8_t *__restrict__ state, double *__restrict__ interval, double *__restrict__ joints,
               double *__restrict__ elbow) {
+  __shared__ double s_stage[STAGED ? R2IK_BLOCK / 32 : 1][STAGED ? 32 * 12 : 1];
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const bool active = i < n;
+  if (!STAGED && !active) return;
   double prev0 = 0.0, prev2 = 0.0;
   if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
   double pos[3];
   Solve S;
   Reach rc;
-  if (load_pose<KIND>(poses, i, false, pos, S.R)) {
-    rc = is_reachable_R<false>(A, pos, S);
-  } else {
-    rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
+  rc.state = R2IK_STATE_INVALID_ROTATION; rc.i0 = NAN; rc.i1 = NAN;
+  if (active && load_pose<KIND>(poses, i, false, pos, S.R)) rc = is_reachable_R<false>(A, pos, S);
+  bool ok = active && rc.state == R2IK_STATE_REACHABLE;
+  if (active) {
+    if (reachable) reachable[i] = ok ? 1 : 0;   // nullable: state == R2IK_STATE_REACHABLE says the same (lean host record)
+    state[i] = (uint8_t)rc.state;
   }
-  bool ok = rc.state == R2IK_STATE_REACHABLE;
-  if (reachable) reachable[i] = ok ? 1 : 0;   // nullable: state == R2IK_STATE_REACHABLE says the same (lean host record)
-  state[i] = (uint8_t)rc.state;
-  if (interval) { interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1; }
-  if (!joints && !elbow) return;
+  if (!STAGED) {
+    if (interval) { interval[2 * i] = rc.i0; interval[2 * i + 1] = rc.i1; }
+    if (!joints && !elbow) return;
+  }
   double j[7], E[3];
-  if (ok) {
+  if (ok && (joints || elbow)) {
     double ct = rc.c0, st = rc.s0;   // theta_interval[0]: its cos / sin come with the interval
     if (theta) sincos_any(theta[i], st, ct);
     get_joints_cs(A, S, ct, st, prev0, prev2, j, E);
@@ -107,11 +128,45 @@ k_symik_solve(const __grid_constant__ ArmConst A, const double *__restrict__ pos
     for (int k = 0; k < 7; ++k) j[k] = NAN;
     E[0] = NAN; E[1] = NAN; E[2] = NAN;
   }
-  if (joints) {
+  if (!STAGED) {
+    if (joints) {
 #pragma unroll
-    for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+      for (int k = 0; k < 7; ++k) joints[7 * i + k] = j[k];
+    }
+    if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+    return;
   }
-  if (elbow) { elbow[3 * i] = E[0]; elbow[3 * i + 1] = E[1]; elbow[3 * i + 2] = E[2]; }
+  // ---- staged stores: [0, 224) joints, [224, 320) elbow, [320, 384) interval of the warp's 32 poses
+  const int lane = threadIdx.x & 31;
+  double *sw = s_stage[STAGED ? threadIdx.x >> 5 : 0];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) sw[7 * lane + k] = j[k];
+  sw[224 + 3 * lane] = E[0]; sw[224 + 3 * lane + 1] = E[1]; sw[224 + 3 * lane + 2] = E[2];
+  sw[320 + 2 * lane] = rc.i0; sw[320 + 2 * lane + 1] = rc.i1;
+  __syncwarp();
+  const int64_t i0 = i - lane;                                  // first pose of the warp
+  const int64_t left = n - i0;
+  const int cnt = left < 32 ? (int)left : 32;                   // poses of this warp inside the batch (> 0 for a launched warp)
+  if (cnt <= 0) return;
+  const double2 *s2 = reinterpret_cast<const double2 *>(sw);
+  if (joints) {
+    double2 *g = reinterpret_cast<double2 *>(joints + 7 * i0);
+    const int n2 = (7 * cnt) >> 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int e = lane + 32 * q; if (e < n2) g[e] = s2[e]; }
+    if (((7 * cnt) & 1) && lane == 0) joints[7 * i0 + 7 * cnt - 1] = sw[7 * cnt - 1];
+  }
+  if (elbow) {
+    double2 *g = reinterpret_cast<double2 *>(elbow + 3 * i0);
+    const int n2 = (3 * cnt) >> 1;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const int e = lane + 32 * q; if (e < n2) g[e] = s2[112 + e]; }
+    if (((3 * cnt) & 1) && lane == 0) elbow[3 * i0 + 3 * cnt - 1] = sw[224 + 3 * cnt - 1];
+  }
+  if (interval) {
+    double2 *g = reinterpret_cast<double2 *>(interval + 2 * i0);
+    if (lane < cnt) g[lane] = s2[160 + lane];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -767,13 +822,16 @@ __device__ __forceinline__ bool voxel_live(const ArmConst &A, int64_t v, int64_t
   return reach_prechecks(A, px, py, pz) < 0;
 }
 
+// CT = uint32_t, or uint16_t for the sharded map: orientation shards of at most 65 535 orientations sum without a carry
+// when two 16-bit counts travel in one 32-bit lane of the all-reduce.  [v_begin, nv) = the voxel range of this launch
+// (slabs of the volume are launched one after the other so that the reduction of one overlaps the kernel of the next).
+template <typename CT>
 __global__ void __launch_bounds__(R2IK_BLOCK)
 k_reach_map(const __grid_constant__ ArmConst A, const __grid_constant__ f32::ArmConstF AF, double ox, double oy, double oz,
             double sx, double sy, double sz, int d0, int d1, int d2, const double *__restrict__ ori_euler, int ori_begin,
-            int ori_end, uint32_t *__restrict__ counts) {
+            int ori_end, int64_t v_begin, int64_t nv, CT *__restrict__ counts) {
   __shared__ f32::OriConst sO[R2IK_ORI_CHUNK];
-  const int64_t nv = (int64_t)d0 * d1 * d2;
-  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t v = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double px, py, pz;
   const bool live = voxel_live(A, v, nv, ox, oy, oz, sx, sy, sz, d1, d2, px, py, pz);
   if (!__syncthreads_or(live ? 1 : 0)) {
@@ -807,7 +865,7 @@ k_reach_map(const __grid_constant__ ArmConst A, const __grid_constant__ f32::Arm
       }
     }
   }
-  if (v < nv) counts[v] = count;
+  if (v < nv) counts[v] = (CT)count;
 }
 
 // The all-FP64 form (every pair through solve_core<false, true>): the cross-check of k_reach_map.
@@ -1003,7 +1061,7 @@ int r2ik_interval_limit(int side, int low_elbow, double *out) {
 int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, const double *theta, const double *prev_joints,
                          int64_t n, uint8_t *reachable, uint8_t *state, double *interval, double *joints, double *elbow,
                          void *stream) {
-  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4))
+  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4 && pose_kind != R2IK_POSE_MAT34))
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: bad n or pose_kind");
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null handle");
   if (n == 0) return 0;  // empty batch: nothing to read or write
@@ -1011,10 +1069,17 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: poses must be 16-byte aligned");
   R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
-  if (pose_kind == R2IK_POSE_MAT4)
-    k_symik_solve<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
-  else
-    k_symik_solve<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);
+  // staged (transposed, 128-bit) stores need 16-byte aligned output rows; anything else takes the scalar-store kernel
+  const bool staged = R2IK_K1_STAGED && (joints || elbow || interval) && !misaligned16(joints) && !misaligned16(elbow) && !misaligned16(interval);
+#define R2IK_LAUNCH_K1(KIND)                                                                                                          \
+  do {                                                                                                                                \
+    if (staged) k_symik_solve<KIND, true><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow); \
+    else k_symik_solve<KIND, false><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, n, reachable, state, interval, joints, elbow);       \
+  } while (0)
+  if (pose_kind == R2IK_POSE_MAT4) R2IK_LAUNCH_K1(R2IK_POSE_MAT4);
+  else if (pose_kind == R2IK_POSE_MAT34) R2IK_LAUNCH_K1(R2IK_POSE_MAT34);
+  else R2IK_LAUNCH_K1(R2IK_POSE_EULER6);
+#undef R2IK_LAUNCH_K1
   R2IK_CUDA(cudaGetLastError(), "k_symik_solve launch");
   return 0;
 }
@@ -1237,9 +1302,28 @@ static int reach_map_launch(bool all_f64, r2ik_handle h, const double *origin, c
                                                                             step[1], step[2], dims[0], dims[1], dims[2],
                                                                             orientations_euler, ori_begin, ori_end, counts);
   else
-    k_reach_map<<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, h->AF, origin[0], origin[1], origin[2], step[0],
-                                                                        step[1], step[2], dims[0], dims[1], dims[2],
-                                                                        orientations_euler, ori_begin, ori_end, counts);
+    k_reach_map<uint32_t><<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, h->AF, origin[0], origin[1], origin[2], step[0],
+                                                                                  step[1], step[2], dims[0], dims[1], dims[2],
+                                                                                  orientations_euler, ori_begin, ori_end, 0, nv, counts);
+  R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
+  return 0;
+}
+
+int r2ik_reach_map_range_u16(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
+                             const double *orientations_euler, int32_t ori_begin, int32_t ori_end, int64_t voxel_begin,
+                             int64_t voxel_end, uint16_t *counts, void *stream) {
+  if (!h || !origin || !step || !dims || !orientations_euler || !counts)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_reach_map_range_u16: null argument");
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || ori_begin < 0 || ori_end < ori_begin || ori_end - ori_begin > 65535)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_range_u16: bad dims or orientation range (at most 65 535 orientations per call)");
+  const int64_t nv = (int64_t)dims[0] * dims[1] * dims[2];
+  if (voxel_begin < 0 || voxel_end > nv || voxel_end < voxel_begin)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_range_u16: bad voxel range");
+  if (voxel_end == voxel_begin) return 0;
+  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  k_reach_map<uint16_t><<<blocks_for(voxel_end - voxel_begin), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(
+      h->A, h->AF, origin[0], origin[1], origin[2], step[0], step[1], step[2], dims[0], dims[1], dims[2], orientations_euler,
+      ori_begin, ori_end, voxel_begin, voxel_end, counts);
   R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
   return 0;
 }

@@ -148,7 +148,7 @@ enum Mode { SYMIK_F64, SYMIK_F32, DISCRETE_F64 };
 int run_chunks(r2ik_pipeline *p, Mode mode, int pose_kind, const void *poses_host, int64_t n, const R2ikCtlParams *par,
                uint8_t *reachable, uint8_t *state, void *interval, void *joints, void *elbow, uint8_t *aux) {
   const size_t esz = mode == SYMIK_F32 ? 4 : 8;
-  const size_t k = (mode == DISCRETE_F64 || pose_kind == R2IK_POSE_MAT4) ? 16 : 6;
+  const size_t k = (mode == DISCRETE_F64 || pose_kind == R2IK_POSE_MAT4) ? 16 : (pose_kind == R2IK_POSE_MAT34 ? 12 : 6);
   const char *src = static_cast<const char *>(poses_host);
   P_CUDA(cudaSetDevice(p->device), "cudaSetDevice");
   const bool direct_state = device_can_write(state), direct_reach = device_can_write(reachable), direct_aux = device_can_write(aux);
@@ -225,7 +225,8 @@ extern "C" {
 int r2ik_pipeline_symik_f64(r2ik_pipeline *p, int pose_kind, const double *poses_host, int64_t n, uint8_t *reachable,
                             uint8_t *state, double *interval, double *joints, double *elbow) {
   if (!p) return pfail(R2IK_ERR_NULL, "r2ik_pipeline_symik_f64: null pipeline");
-  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4)) return pfail(R2IK_ERR_ARG, "r2ik_pipeline_symik_f64: bad n or pose_kind");
+  if (n < 0 || (pose_kind != R2IK_POSE_EULER6 && pose_kind != R2IK_POSE_MAT4 && pose_kind != R2IK_POSE_MAT34))
+    return pfail(R2IK_ERR_ARG, "r2ik_pipeline_symik_f64: bad n or pose_kind");
   if (n == 0) return 0;
   if (!poses_host || !state) return pfail(R2IK_ERR_NULL, "r2ik_pipeline_symik_f64: null argument");
   return run_chunks(p, SYMIK_F64, pose_kind, poses_host, n, nullptr, reachable, state, interval, joints, elbow, nullptr);

@@ -72,8 +72,10 @@ def normalise_poses(torch, poses, device, dtype=None):
         kind, k = _abi.POSE_MAT4, 16
     elif len(shp) == 3 and shp[1:] == (2, 3) or len(shp) == 2 and shp[1] == 6:
         kind, k = _abi.POSE_EULER6, 6
+    elif (len(shp) == 3 and shp[1:] == (3, 4) or len(shp) == 2 and shp[1] == 12) and dtype == torch.float64:
+        kind, k = _abi.POSE_MAT34, 12       # the 3x4 top of the homogeneous matrix: 96 useful bytes of its 128
     else:
-        raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6); got {shp}")
+        raise ValueError(f"poses must be (N,4,4), (N,16), (N,3,4), (N,12), (N,2,3) or (N,6); got {shp}")
     poses = poses.reshape(shp[0], k).contiguous()
     if not was_cuda:
         poses = poses.to(device, non_blocking=True)
@@ -167,7 +169,7 @@ class SymbolicIK:
         end, ``R.from_matrix(M[:3,:3]).as_euler("xyz")``) or (N,2,3)/(N,6) reference goal poses
         ``[[x,y,z],[roll,pitch,yaw]]``.  theta: None -> ``theta_interval[0]``; else (N,).
         precision: "fp64" (the correctness reference, 1e-9 rad) or "fp32" (the fast path: float32 poses in,
-        float32 results out, within 1e-4 rad on well-conditioned poses; states are the FP64 path's because poses
+        float32 results out, within 1e-4 rad for >= 99.99 % of the poses and 3e-4 rad for all (include/r2ik.h); states are the FP64 path's because poses
         FP32 cannot decide are re-solved in FP64 -- their count is ``n_escalated``).
         devices: CUDA ordinals of this node to spread a HOST batch over -- contiguous slices of the batch, one
         H2D -> K1 -> D2H pipeline per device, no inter-GPU traffic (``is_reachable_batch_host``); results are NumPy arrays.
@@ -291,10 +293,10 @@ class SymbolicIK:
         if poses_host.dtype != dt:
             poses_host = poses_host.to(dt)
         shp = tuple(poses_host.shape)
-        k = 16 if (shp[1:] == (4, 4) or shp[1:] == (16,)) else 6
-        if k == 6 and shp[1:] not in ((2, 3), (6,)):
-            raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6); got {shp}")
-        kind = _abi.POSE_MAT4 if k == 16 else _abi.POSE_EULER6
+        k = 16 if shp[1:] in ((4, 4), (16,)) else 12 if shp[1:] in ((3, 4), (12,)) else 6
+        if k == 6 and shp[1:] not in ((2, 3), (6,)) or k == 12 and precision != "fp64":
+            raise ValueError(f"poses must be (N,4,4), (N,16), (N,2,3) or (N,6) -- or (N,3,4) / (N,12) in FP64; got {shp}")
+        kind = {16: _abi.POSE_MAT4, 12: _abi.POSE_MAT34, 6: _abi.POSE_EULER6}[k]
         if chunk_auto:
             # measured on B200 / PCIe 5 (profiles/r2_experiments.md): when the results outweigh the poses the D2H stream is
             # the critical one and the first, exposed H2D copy should be short (64 k poses); otherwise 128 k-pose chunks

@@ -6,9 +6,13 @@ voxel grid x orientation set is swept by the K4 kernel (``r2ik_reach_map_u32``):
 number of orientations for which ``SymbolicIK.is_reachable(voxel centre, orientation)`` is True.
 
 Multi-GPU: poses / trajectories are independent, so batches are cut into contiguous slices
-(``shard_range``) with no exchange.  The reach map shards the ORIENTATION set; every rank fills a
-full count volume, and one all-reduce (NCCL over NVLink / NVSwitch) sums them in place -- the only
-collective of the whole path.
+(``shard_range``) with no exchange.  The reach map shards the ORIENTATION set; every rank counts its
+shard for every voxel and the volumes are summed by an all-reduce (NCCL over NVLink / NVSwitch) -- the
+only collective of the whole path.  Three things keep it off the critical path (``reach_map_sharded``):
+only the x-range of the volume that can hold a reachable voxel is exchanged (the torso plane and the
+reach sphere do not depend on the orientation, so the rest is zero on every rank), counts are 16 bits
+on the wire, and the range is produced slab by slab so that the all-reduce of one slab overlaps the
+kernel of the next.
 """
 from __future__ import annotations
 
@@ -54,15 +58,95 @@ def sharded_sum(launch: Callable[[int, int], "object"], n_orientations: int, dis
     return counts
 
 
+def live_x_range(solver, origin, step, dims, margin: int = 1) -> Tuple[int, int]:
+    """Index range [lo, hi) along x outside which no voxel can be reachable for ANY orientation: the pre-checks of
+    ``is_reachable`` (symbolic_ik.py:284-307) reject goals behind ``backward_limit`` and outside the reach sphere before
+    the orientation is looked at.  ``margin`` indices are added on both sides (the device evaluates the same
+    comparisons on ox + ix * sx; the margin makes the host-side range a superset whatever the rounding)."""
+    x = origin[0] + np.arange(int(dims[0])) * step[0]
+    sx = float(np.asarray(solver.shoulder_position, dtype=np.float64)[0])
+    ok = (x >= solver.backward_limit) & (np.abs(x - sx) <= float(solver.max_arm_length))
+    idx = np.nonzero(ok)[0]
+    if len(idx) == 0:
+        return 0, 0
+    return max(0, int(idx[0]) - margin), min(int(dims[0]), int(idx[-1]) + 1 + margin)
+
+
+def allreduce_u16_pairs(c16, v0: int, v1: int, dist, group=None):
+    """Sum the 16-bit counts c16[v0:v1] (an int16 tensor; v0 even) over the ranks, two counts per int32 lane of the
+    all-reduce: exact as long as no total exceeds 65 535 (no carry from the low half into the high one; the sign bit of
+    the int16 storage is just the top count bit).  An odd tail takes the following (padding) element along.  Returns
+    the async work handle."""
+    v1e = v1 + (v1 - v0) % 2
+    import torch
+
+    lanes = c16[v0:v1e].view(torch.int32)
+    return dist.all_reduce(lanes, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
+def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=None, n_slabs: int = 4, timing=None):
+    """The sharded map: this rank's orientation slice, uint16 counts, live x-range only, slab-pipelined all-reduce.
+    Returns the int32 volume (every rank holds the full map).  ``timing``: optional dict that receives CUDA events
+    (``k0`` / ``k1`` around each slab's kernel, ``t0`` / ``t1`` around the whole call) for the benchmark."""
+    torch = solver._torch
+    dev = solver._device
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b, e = shard_range(ori.shape[0], rank, world)
+    d0, d1, d2 = (int(d) for d in dims)
+    plane = d1 * d2
+    lo, hi = live_x_range(solver, origin, step, dims)
+    if plane % 2:            # two 16-bit counts per int32 lane: slab boundaries must sit on even element offsets
+        lo, hi, n_slabs = 0, d0, 1
+    c16 = solver.__dict__.get("_reach_c16")
+    if c16 is None or c16.numel() != d0 * plane + (d0 * plane) % 2 or c16.device != dev:
+        c16 = solver._reach_c16 = torch.zeros(d0 * plane + (d0 * plane) % 2, dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    if timing is not None:
+        timing["t0"] = torch.cuda.Event(enable_timing=True); timing["t0"].record(stream)
+        timing["k"] = []
+    c16[:lo * plane].zero_()
+    c16[hi * plane:].zero_()
+    edges = [lo + (hi - lo) * k // n_slabs for k in range(n_slabs + 1)]
+    works = []
+    dp = C.POINTER(C.c_double)
+    for x0, x1 in zip(edges[:-1], edges[1:]):
+        if x1 <= x0:
+            continue
+        v0, v1 = x0 * plane, x1 * plane
+        if timing is not None:
+            k0 = torch.cuda.Event(enable_timing=True); k0.record(stream)
+        rc = solver._handle.lib.r2ik_reach_map_range_u16(
+            solver._handle.h, origin.ctypes.data_as(dp), step.ctypes.data_as(dp), dims.ctypes.data_as(C.POINTER(C.c_int32)),
+            C.c_void_p(ori.data_ptr()), C.c_int32(b), C.c_int32(e), C.c_int64(v0), C.c_int64(v1), C.c_void_p(c16.data_ptr()),
+            C.c_void_p(stream.cuda_stream))
+        _native.check(rc, "r2ik_reach_map_range_u16")
+        if timing is not None:
+            k1 = torch.cuda.Event(enable_timing=True); k1.record(stream)
+            timing["k"].append((k0, k1))
+        works.append(allreduce_u16_pairs(c16, v0, v1, dist, group))
+    for w in works:
+        w.wait()                                 # the current stream waits for the collective
+    if out is None:
+        out = torch.empty((d0, d1, d2), dtype=torch.int32, device=dev)
+    out.view(-1).copy_(c16[:d0 * plane])
+    if timing is not None:
+        timing["t1"] = torch.cuda.Event(enable_timing=True); timing["t1"].record(stream)
+        timing["exchanged_bytes"] = 2 * (hi - lo) * plane
+    return out
+
+
 def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int = 512, origin=None, step=None,
-              dims=None, dist=None, group=None, out=None, all_fp64: bool = False, mark=None):
+              dims=None, dist=None, group=None, out=None, all_fp64: bool = False, mark=None, plain_allreduce: bool = False,
+              timing=None):
     """Reachability count volume of ``solver`` (a ``SymbolicIK``): int32 CUDA tensor (d0, d1, d2).
 
     orientations_euler: (n_ori, 3) xyz Euler angles (default: ``fibonacci_orientations(n_orientations)``).
     With an initialised ``torch.distributed`` passed as ``dist`` the orientation set is sharded over the
     ranks and the volume is all-reduced; every rank returns the full map.
     all_fp64: decide every (voxel, orientation) pair with the FP64 flag solve instead of the mixed-precision test with
-    FP64 escalation (identical counts, slower: the cross-check)."""
+    FP64 escalation (identical counts, slower: the cross-check).
+    plain_allreduce: sum the full int32 volumes with one all-reduce after the kernel (the base form, kept as the
+    cross-check of ``reach_map_sharded``)."""
     torch = solver._torch
     if orientations_euler is None:
         orientations_euler = fibonacci_orientations(n_orientations)
@@ -78,6 +162,9 @@ def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int
         else:
             ori = torch.from_numpy(np.ascontiguousarray(orientations_euler, dtype=np.float64)).to(dev)
         n_ori = ori.shape[0]
+        sharded = dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+        if sharded and not all_fp64 and not plain_allreduce and n_ori <= 65535 * dist.get_world_size(group):
+            return reach_map_sharded(solver, ori, origin, step, dims, dist, group, out, timing=timing)
         if out is None:
             out = torch.empty(tuple(int(d) for d in dims), dtype=torch.int32, device=dev)
 

@@ -45,6 +45,24 @@ def _worker(rank, world, port, tmp):
         full = O.reach_map(cfg, origin, step, dims, ori).astype(np.int32)
         assert np.array_equal(counts.numpy(), full), "all-reduced shards differ from the full map"
 
+        # the sharded map's wire format: 16-bit counts, two per int32 lane, live x-range only, slab by slab (async)
+        from types import SimpleNamespace
+
+        solver = SimpleNamespace(shoulder_position=[0.0, -0.2, 0.0], max_arm_length=0.66, backward_limit=0.02)
+        lo, hi = workspace.live_x_range(solver, origin, step, dims)
+        assert not full[:lo].any() and not full[hi:].any() and 0 < hi - lo < int(dims[0])
+        b, e = workspace.shard_range(len(ori), rank, world)
+        mine16 = torch.from_numpy(O.reach_map(cfg, origin, step, dims, ori, b, e).astype(np.int16).reshape(-1))
+        plane = int(dims[1] * dims[2])
+        edges = [lo + (hi - lo) * k // 3 for k in range(4)]
+        works = [workspace.allreduce_u16_pairs(mine16, x0 * plane, x1 * plane, dist) for x0, x1 in zip(edges[:-1], edges[1:])]
+        for w in works:
+            w.wait()
+        assert np.array_equal(mine16.numpy().astype(np.int32).reshape(full.shape), full), "packed 16-bit all-reduce differs"
+        big = torch.full((6,), 30000 if rank == 0 else 30001, dtype=torch.int16)      # 60 001 > int16 max: the top bit is a count bit
+        workspace.allreduce_u16_pairs(big, 0, 5, dist).wait()                          # odd tail: the padding element rides along
+        assert np.array_equal(big.numpy().view(np.uint16), np.full(6, 60001, np.uint16))
+
         # pose batch: contiguous slices, no exchange; gathering the slices reproduces the full batch
         M = fk.sample_fk_poses(1001, "r_arm", seed=9)
         b, e = workspace.shard_range(len(M), rank, world)

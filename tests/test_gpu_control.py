@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from parity import Report, ill_conditioned_mask, load
+from parity import COND_TOL, PERTURB, TOL  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 ARMS = ("r_arm", "l_arm")
@@ -166,10 +167,22 @@ def test_continuous_vs_oracle_many(controls, oracle, arm):
     ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
     joints, reach, state, st = ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous")
     assert np.array_equal(reach, wr) and np.array_equal(state, ws)
-    err = np.abs(joints - wj).reshape(256, -1).max(axis=1)
-    # a trajectory is a recursion: an ill-conditioned waypoint would contaminate its tail
-    assert np.quantile(err, 0.99) < 1e-9, np.sort(err)[-5:]
-    assert (err < 1e-9).mean() > 0.99
+    # every waypoint over 1e-9 is classified, as in the K1 / K2 tests (tests/parity.py): it must be ill-conditioned -- the
+    # oracle's own answer for it moves by > 1e-10 when the trajectory is perturbed by 3e-13 (a trajectory is a recursion:
+    # one such waypoint contaminates its tail) -- else it is a genuine failure
+    err = np.abs(joints - wj).max(axis=2)
+    over = err > TOL
+    ill = np.zeros_like(over)
+    rng = np.random.default_rng(4100)
+    for _ in range(3):
+        pj, pr, ps, _ = oracle.ctl_continuous_batch(ocfg, oracle.ControlParams(arm=arm), M + rng.uniform(-PERTURB, PERTURB, size=M.shape))
+        ill |= (np.abs(pj - wj).max(axis=2) > COND_TOL) | (pr != wr) | (ps != ws)
+    genuine = over & ~ill
+    print(f"[gpu ctl continuous vs oracle {arm}] {over.size} waypoints: over {TOL:g}: {int(over.sum())} "
+          f"({int((over & ill).sum())} ill-conditioned, {int(genuine.sum())} genuine); ill-conditioned waypoints {int(ill.sum())}; "
+          f"max|err| well-conditioned {np.where(ill, 0.0, err).max():.2e} (all {err.max():.2e})")
+    assert not genuine.any(), np.argwhere(genuine)[:10]
+    assert ill.mean() <= 0.10, ill.mean()      # sinusoids sweep through the straight arm: ~6 % of the waypoints
     np.testing.assert_array_equal(st["emergency_stop"], wst["emergency_stop"])
     ok = ~st["emergency_stop"].astype(bool)
     step = np.abs(np.diff(joints[ok], axis=1))[:, 1:]  # waypoint 0 -> 1 follows the unconstrained init

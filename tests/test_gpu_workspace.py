@@ -141,3 +141,49 @@ def test_task_space_sweep_matches_reference():
         assert mism == 0 if precision == "fp64" else mism <= 40, (precision, mism)
         if precision == "fp64":
             assert np.array_equal(res.reachable, want) and int(res.reachable.sum()) == 13492
+
+
+def _sharded_worker(rank, world, port, tmp):
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from reachy2_symbolic_ik_b200 import SymbolicIK, fk
+
+        ik = SymbolicIK(arm="l_arm", device=rank)
+        for n, n_ori in ((40, 37), (33, 64)):           # even and odd plane sizes (the odd one takes the unsplit path)
+            ori = fk.fibonacci_orientations(n_ori)
+            single = ik.reach_map(n=n, orientations_euler=ori)
+            timing = {}
+            sharded = ik.reach_map(n=n, orientations_euler=ori, dist=dist, timing=timing)
+            plain = ik.reach_map(n=n, orientations_euler=ori, dist=dist, plain_allreduce=True)
+            assert torch.equal(sharded, single), f"sharded (16-bit, live range, slabs) differs from the single-GPU map ({n}, {n_ori})"
+            assert torch.equal(plain, single), "plain all-reduce differs from the single-GPU map"
+            assert timing["exchanged_bytes"] <= 2 * n ** 3
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reach_map_sharded_two_gpus(tmp_path):
+    """cfg 5 as it runs on several GPUs: orientation shards, 16-bit counts two per all-reduce lane, only the x-range that
+    can hold a reachable voxel exchanged, slab-pipelined -- equal to the single-GPU volume and to the plain all-reduce."""
+    import socket
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))
