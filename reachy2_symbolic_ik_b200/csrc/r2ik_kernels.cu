@@ -1005,6 +1005,21 @@ static int fail_cuda(cudaError_t e, const char *where) {
     if (e_ != cudaSuccess) return fail_cuda(e_, where); \
   } while (0)
 
+// Every entry runs on its handle's device and leaves the calling thread's current device as it found it (the caller --
+// torch, or any other runtime user in the process -- keeps its own notion of the current device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;     // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static inline bool misaligned16(const void *p) { return ((uintptr_t)p & 15) != 0; }
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + R2IK_BLOCK - 1) / R2IK_BLOCK); }
 
@@ -1067,7 +1082,8 @@ int r2ik_symik_solve_f64(r2ik_handle h, int pose_kind, const double *poses, cons
   if (n == 0) return 0;  // empty batch: nothing to read or write
   if (!poses || !state) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f64: null argument");
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f64: poses must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   // staged (transposed, 128-bit) stores need 16-byte aligned output rows; anything else takes the scalar-store kernel
   const bool staged = R2IK_K1_STAGED && (joints || elbow || interval) && !misaligned16(joints) && !misaligned16(elbow) && !misaligned16(interval);
@@ -1092,7 +1108,8 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
   if (!h) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null handle");
   if (n == 0) {   // the contract "the call sets n_escalated" holds for an empty batch too
     if (n_escalated) {
-      R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+      DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
       R2IK_CUDA(cudaMemsetAsync(n_escalated, 0, sizeof(uint32_t), (cudaStream_t)stream), "cudaMemsetAsync");
     }
     return 0;
@@ -1101,7 +1118,8 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
     return fail_arg(R2IK_ERR_NULL, "r2ik_symik_solve_f32: null argument");
   if (((uintptr_t)poses & (pose_kind == R2IK_POSE_MAT4 ? 15 : 7)) != 0 || ((uintptr_t)interval & 7) != 0)
     return fail_arg(R2IK_ERR_ARG, "r2ik_symik_solve_f32: poses must be 16-byte (MAT4) / 8-byte (EULER6) aligned, interval 8-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   R2IK_CUDA(cudaMemsetAsync(n_escalated, 0, sizeof(uint32_t), s), "cudaMemsetAsync");
   // second pass: a fixed modest grid striding over the (device-side) count -- a few thousand poses per million
@@ -1125,7 +1143,8 @@ int r2ik_symik_no_limits_f64(r2ik_handle h, int pose_kind, const double *poses, 
   if (n == 0) return 0;
   if (!poses || !theta || !joints) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_no_limits_f64: null argument");
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_symik_no_limits_f64: poses must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   if (pose_kind == R2IK_POSE_MAT4)
     k_symik_no_limits<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, prev_stride, n, joints, elbow, projected);
@@ -1143,7 +1162,8 @@ int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, 
   if (n == 0 || K == 0) return 0;
   if (!poses || !thetas || !elbows) return fail_arg(R2IK_ERR_NULL, "r2ik_elbow_positions_f64: null argument");
   if (misaligned16(poses)) return fail_arg(R2IK_ERR_ARG, "r2ik_elbow_positions_f64: poses must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned g = blocks_for(n);
   if (pose_kind == R2IK_POSE_MAT4) {
@@ -1159,7 +1179,8 @@ int r2ik_elbow_positions_f64(r2ik_handle h, int pose_kind, const double *poses, 
 
 int r2ik_symik_scalar_f64(r2ik_handle h, const R2ikScalarQuery *query, R2ikScalarResult *out, void *stream) {
   if (!h || !query || !out) return fail_arg(R2IK_ERR_NULL, "r2ik_symik_scalar_f64: null argument");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   k_symik_scalar<<<1, 32, 0, (cudaStream_t)stream>>>(h->A, *query, out);
   R2IK_CUDA(cudaGetLastError(), "k_symik_scalar launch");
   return 0;
@@ -1169,7 +1190,8 @@ int r2ik_ctl_ctor_theta_f64(r2ik_handle h, double preferred_theta, const double 
                             const double *current_pose, double *out_theta, void *stream) {
   if (!h || !current_joints_rows || !current_pose || !out_theta) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_ctor_theta_f64: null argument");
   if (n_rows < 0 || n_rows > 7) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_ctor_theta_f64: n_rows must be 0 .. 7 (the reference indexes joints[i] by the row)");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   CtorThetaArgs a;
   memset(&a, 0, sizeof a);
   memcpy(a.rows, current_joints_rows, sizeof(double) * 7 * (size_t)n_rows);
@@ -1195,7 +1217,8 @@ static int ctl_discrete_launch(bool scan, r2ik_handle h, const R2ikCtlParams *pa
   if (!M || !prev_joints || !current_joints || !joints || !reachable || !state)
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_f64: null argument");
   if (misaligned16(M)) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_f64: M must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   if (scan)
     k_ctl_discrete_scan<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, n, prev_joints, current_joints,
                                                                                joints, reachable, state, emergency);
@@ -1229,7 +1252,8 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const doubl
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_f64: null argument");
   if (misaligned16(M) || misaligned16(current_pose))
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_f64: M and current_pose must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   k_ctl_continuous<<<(unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK), R2IK_K3_BLOCK, 0, (cudaStream_t)stream>>>(h->A, *par, M, T, W, current_joints, current_pose, st,
                                                                           joints, reachable, state);
   R2IK_CUDA(cudaGetLastError(), "k_ctl_continuous launch");
@@ -1248,7 +1272,8 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_phased_f64: null argument");
   if (misaligned16(M) || misaligned16(current_pose))
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: M and current_pose must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_wp = T * (int64_t)W;
   const unsigned tb = (unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK);
@@ -1276,7 +1301,8 @@ int r2ik_ctl_continuous_tiled_f64(r2ik_handle h, const R2ikCtlParams *par, const
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_tiled_f64: null argument");
   if (misaligned16(M) || misaligned16(current_pose))
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_tiled_f64: M and current_pose must be 16-byte aligned");
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_wp = T * (int64_t)W;
   k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
@@ -1296,7 +1322,8 @@ static int reach_map_launch(bool all_f64, r2ik_handle h, const double *origin, c
   if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || ori_begin < 0 || ori_end < ori_begin)
     return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_u32: bad dims or orientation range");
   int64_t nv = (int64_t)dims[0] * dims[1] * dims[2];
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   if (all_f64)
     k_reach_map_f64<<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, origin[0], origin[1], origin[2], step[0],
                                                                             step[1], step[2], dims[0], dims[1], dims[2],
@@ -1320,7 +1347,8 @@ int r2ik_reach_map_range_u16(r2ik_handle h, const double *origin, const double *
   if (voxel_begin < 0 || voxel_end > nv || voxel_end < voxel_begin)
     return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_range_u16: bad voxel range");
   if (voxel_end == voxel_begin) return 0;
-  R2IK_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   k_reach_map<uint16_t><<<blocks_for(voxel_end - voxel_begin), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(
       h->A, h->AF, origin[0], origin[1], origin[2], step[0], step[1], step[2], dims[0], dims[1], dims[2], orientations_euler,
       ori_begin, ori_end, voxel_begin, voxel_end, counts);
@@ -1344,7 +1372,8 @@ int r2ik_fk_f64(const R2ikFkChain *chain, int device, const double *joints, int6
   if (n < 0) return fail_arg(R2IK_ERR_ARG, "r2ik_fk_f64: bad n");
   if (n == 0) return 0;
   if (!joints || !M) return fail_arg(R2IK_ERR_NULL, "r2ik_fk_f64: null argument");
-  R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  DeviceGuard guard_(device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   k_fk<<<blocks_for(n), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(*chain, joints, n, M);
   R2IK_CUDA(cudaGetLastError(), "k_fk launch");
   return 0;
@@ -1362,7 +1391,8 @@ int r2ik_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_p
 
 int r2ik_dfma_probe(int device, int32_t iters, double *out_ms, double *out_flop, void *stream) {
   if (!out_ms || !out_flop) return fail_arg(R2IK_ERR_NULL, "r2ik_dfma_probe: null argument");
-  R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  DeviceGuard guard_(device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaDeviceProp prop;
   R2IK_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1388,7 +1418,8 @@ int r2ik_dfma_probe(int device, int32_t iters, double *out_ms, double *out_flop,
 
 int r2ik_ffma_probe(int device, int32_t iters, double *out_ms, double *out_flop, void *stream) {
   if (!out_ms || !out_flop) return fail_arg(R2IK_ERR_NULL, "r2ik_ffma_probe: null argument");
-  R2IK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  DeviceGuard guard_(device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaDeviceProp prop;
   R2IK_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
   cudaStream_t s = (cudaStream_t)stream;

@@ -37,6 +37,21 @@ int pfail_cuda(cudaError_t e, const char *where) {
     if (e_ != cudaSuccess) return pfail_cuda(e_, where); \
   } while (0)
 
+// Every entry runs on its handle's device and leaves the calling thread's current device as it found it (the caller --
+// torch, or any other runtime user in the process -- keeps its own notion of the current device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;     // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 struct Slot {
   void *poses = nullptr;      // chunk x 16 doubles (also holds float poses and n x 6 layouts)
   uint8_t *reach = nullptr, *state = nullptr, *aux = nullptr;   // aux: emergency bits (discrete mode)
@@ -74,7 +89,7 @@ const char *r2ik_pipeline_last_error(void) { return g_perr; }
 
 int r2ik_pipeline_destroy(r2ik_pipeline *p) {
   if (!p) return 0;
-  cudaSetDevice(p->device);
+  DeviceGuard guard_(p->device);
   for (cudaStream_t q : p->s_out)
     if (q) cudaStreamSynchronize(q);
   if (p->s_k) cudaStreamSynchronize(p->s_k);
@@ -102,7 +117,8 @@ int r2ik_pipeline_create(r2ik_handle h, int device, int64_t chunk_poses, int32_t
   r2ik_pipeline *p = new (std::nothrow) r2ik_pipeline;
   if (!p) return pfail(R2IK_ERR_ARG, "r2ik_pipeline_create: out of host memory");
   p->h = h; p->device = device; p->chunk = chunk_poses;
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard guard_(device);
+  cudaError_t e = guard_.err;
   auto check = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   check(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
   check(cudaStreamCreateWithFlags(&p->s_k, cudaStreamNonBlocking));
@@ -132,7 +148,8 @@ int r2ik_pipeline_create(r2ik_handle h, int device, int64_t chunk_poses, int32_t
 
 int r2ik_pipeline_wait(r2ik_pipeline *p) {
   if (!p) return pfail(R2IK_ERR_NULL, "r2ik_pipeline_wait: null pipeline");
-  P_CUDA(cudaSetDevice(p->device), "cudaSetDevice");
+  DeviceGuard guard_(p->device);
+  P_CUDA(guard_.err, "cudaSetDevice");
   for (cudaStream_t q : p->s_out) P_CUDA(cudaStreamSynchronize(q), "cudaStreamSynchronize");
   P_CUDA(cudaStreamSynchronize(p->s_k), "cudaStreamSynchronize");     // the kernels write the byte outputs themselves
   return 0;
@@ -150,7 +167,8 @@ int run_chunks(r2ik_pipeline *p, Mode mode, int pose_kind, const void *poses_hos
   const size_t esz = mode == SYMIK_F32 ? 4 : 8;
   const size_t k = (mode == DISCRETE_F64 || pose_kind == R2IK_POSE_MAT4) ? 16 : (pose_kind == R2IK_POSE_MAT34 ? 12 : 6);
   const char *src = static_cast<const char *>(poses_host);
-  P_CUDA(cudaSetDevice(p->device), "cudaSetDevice");
+  DeviceGuard guard_(p->device);
+  P_CUDA(guard_.err, "cudaSetDevice");
   const bool direct_state = device_can_write(state), direct_reach = device_can_write(reachable), direct_aux = device_can_write(aux);
   // Chunk sizes.  The link is the bottleneck and every copy costs ~10-25 us of fixed latency on its stream
   // (scripts/experiments/exp_r2_copy_patterns.py, exp_r2_pipe_timeline.py), so the bulk moves in full-size chunks.  What
@@ -249,7 +267,8 @@ int r2ik_pipeline_ctl_discrete_f64(r2ik_pipeline *p, const R2ikCtlParams *par, c
   if (n == 0) return 0;
   if (!M_host || !prev_joints_host || !current_joints_host || !joints || !reachable || !state)
     return pfail(R2IK_ERR_NULL, "r2ik_pipeline_ctl_discrete_f64: null argument");
-  P_CUDA(cudaSetDevice(p->device), "cudaSetDevice");
+  DeviceGuard guard_(p->device);
+  P_CUDA(guard_.err, "cudaSetDevice");
   // the two 7-vectors ride the kernel stream, ordered before this call's first launch (and after the previous call's last)
   P_CUDA(cudaMemcpyAsync(p->prev, prev_joints_host, 7 * sizeof(double), cudaMemcpyHostToDevice, p->s_k), "H2D previous_sol");
   P_CUDA(cudaMemcpyAsync(p->cur, current_joints_host, 7 * sizeof(double), cudaMemcpyHostToDevice, p->s_k), "H2D current_joints");
