@@ -313,13 +313,16 @@ int r2ik_reach_map_f64_u32(r2ik_handle h, const double *origin, const double *st
                            int32_t ori_end, uint32_t *counts, void *stream);
 
 /* The same counts as r2ik_reach_map_u32 for the voxels [voxel_begin, voxel_end) only (v = (ix*dims[1] + iy)*dims[2] + iz),
- * stored as uint16 into counts[v] (counts = base of the FULL volume).  For the sharded map: the volume is produced slab by
- * slab so that the all-reduce of one slab overlaps the kernel of the next, and 16-bit counts halve the bytes on the
- * wire (two counts travel in one int32 lane; orientation shards of <= 65 535 orientations cannot carry). */
+ * stored as uint16 into counts[v] (counts = base of the FULL volume).  row_mod > 1: of the rows (ix, iy, :) of that
+ * range only those with row % row_mod == row_rem are computed (the range must then be row-aligned) -- the interleaved
+ * sharding of the multi-GPU map, where rank r owns every world-th row and the all-reduce adds the disjoint pieces.
+ * For the sharded map the volume is produced slab by slab so that the all-reduce of one slab overlaps the kernel of
+ * the next, and 16-bit counts halve the bytes on the wire (two counts travel in one int32 lane; <= 65 535
+ * orientations cannot carry). */
 int r2ik_reach_map_range_u16(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
                              const double *orientations_euler /* device, n_ori x 3 */, int32_t ori_begin,
-                             int32_t ori_end, int64_t voxel_begin, int64_t voxel_end, uint16_t *counts,
-                             void *stream);
+                             int32_t ori_end, int64_t voxel_begin, int64_t voxel_end, int32_t row_mod,
+                             int32_t row_rem, uint16_t *counts, void *stream);
 
 /* Forward kinematics: M[i] (row-major 4x4) = tip pose in the torso frame for joints[i] (7).
  * chain: host pointer.  device: CUDA ordinal to launch on. */

@@ -73,7 +73,7 @@ def load() -> C.CDLL:
     L.r2ik_ctl_continuous_tiled_f64.argtypes = [vp, C.POINTER(_abi.CtlParams), vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     L.r2ik_reach_map_u32.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), vp, i32, i32, vp, vp]
     L.r2ik_reach_map_f64_u32.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), vp, i32, i32, vp, vp]
-    L.r2ik_reach_map_range_u16.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), vp, i32, i32, i64, i64, vp, vp]
+    L.r2ik_reach_map_range_u16.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), vp, i32, i32, i64, i64, i32, i32, vp, vp]
     L.r2ik_fk_f64.argtypes = [C.POINTER(_abi.FkChain), C.c_int, vp, i64, vp, vp]
     L.r2ik_copy2d_async.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     L.r2ik_dfma_probe.argtypes = [C.c_int, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]

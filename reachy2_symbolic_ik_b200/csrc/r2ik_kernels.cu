@@ -815,9 +815,17 @@ __device__ __forceinline__ bool voxel_live(const ArmConst &A, int64_t v, int64_t
                                            double sy, double sz, int d1, int d2, double &px, double &py, double &pz) {
   px = 0; py = 0; pz = 0;
   if (v >= nv) return false;
-  int iz = (int)(v % d2);
-  int iy = (int)((v / d2) % d1);
-  int ix = (int)(v / ((int64_t)d2 * d1));
+  int ix, iy, iz;
+  if (nv <= 0x7fffffffLL) {      // 32-bit index arithmetic whenever the volume allows it (the 64-bit divisions are emulated)
+    const unsigned u = (unsigned)v, row = u / (unsigned)d2;
+    iz = (int)(u - row * (unsigned)d2);
+    ix = (int)(row / (unsigned)d1);
+    iy = (int)(row - (unsigned)ix * (unsigned)d1);
+  } else {
+    iz = (int)(v % d2);
+    iy = (int)((v / d2) % d1);
+    ix = (int)(v / ((int64_t)d2 * d1));
+  }
   px = ox + ix * sx; py = oy + iy * sy; pz = oz + iz * sz;
   return reach_prechecks(A, px, py, pz) < 0;
 }
@@ -829,9 +837,17 @@ template <typename CT>
 __global__ void __launch_bounds__(R2IK_BLOCK)
 k_reach_map(const __grid_constant__ ArmConst A, const __grid_constant__ f32::ArmConstF AF, double ox, double oy, double oz,
             double sx, double sy, double sz, int d0, int d1, int d2, const double *__restrict__ ori_euler, int ori_begin,
-            int ori_end, int64_t v_begin, int64_t nv, CT *__restrict__ counts) {
+            int ori_end, int64_t v_begin, int64_t nv, int row_mod, int row_rem, CT *__restrict__ counts) {
   __shared__ f32::OriConst sO[R2IK_ORI_CHUNK];
   int64_t v = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row_mod > 1) {
+    // interleaved sharding: of the rows (ix, iy, :) of [v_begin, nv) this launch owns those with row % row_mod == row_rem
+    // (v_begin is row-aligned); the launch index enumerates the owned rows densely
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row0 = v_begin / d2;
+    const int64_t first = row0 + ((row_rem - row0 % row_mod) + row_mod) % row_mod;
+    v = (first + (u / d2) * row_mod) * d2 + u % d2;
+  }
   double px, py, pz;
   const bool live = voxel_live(A, v, nv, ox, oy, oz, sx, sy, sz, d1, d2, px, py, pz);
   if (!__syncthreads_or(live ? 1 : 0)) {
@@ -1331,14 +1347,14 @@ static int reach_map_launch(bool all_f64, r2ik_handle h, const double *origin, c
   else
     k_reach_map<uint32_t><<<blocks_for(nv), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(h->A, h->AF, origin[0], origin[1], origin[2], step[0],
                                                                                   step[1], step[2], dims[0], dims[1], dims[2],
-                                                                                  orientations_euler, ori_begin, ori_end, 0, nv, counts);
+                                                                                  orientations_euler, ori_begin, ori_end, 0, nv, 1, 0, counts);
   R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
   return 0;
 }
 
 int r2ik_reach_map_range_u16(r2ik_handle h, const double *origin, const double *step, const int32_t *dims,
                              const double *orientations_euler, int32_t ori_begin, int32_t ori_end, int64_t voxel_begin,
-                             int64_t voxel_end, uint16_t *counts, void *stream) {
+                             int64_t voxel_end, int32_t row_mod, int32_t row_rem, uint16_t *counts, void *stream) {
   if (!h || !origin || !step || !dims || !orientations_euler || !counts)
     return fail_arg(R2IK_ERR_NULL, "r2ik_reach_map_range_u16: null argument");
   if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || ori_begin < 0 || ori_end < ori_begin || ori_end - ori_begin > 65535)
@@ -1346,12 +1362,21 @@ int r2ik_reach_map_range_u16(r2ik_handle h, const double *origin, const double *
   const int64_t nv = (int64_t)dims[0] * dims[1] * dims[2];
   if (voxel_begin < 0 || voxel_end > nv || voxel_end < voxel_begin)
     return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_range_u16: bad voxel range");
+  if (row_mod < 1 || row_rem < 0 || row_rem >= row_mod || (row_mod > 1 && (voxel_begin % dims[2] || voxel_end % dims[2])))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_reach_map_range_u16: bad row interleave (0 <= row_rem < row_mod; row-aligned range when row_mod > 1)");
   if (voxel_end == voxel_begin) return 0;
+  int64_t n_launch = voxel_end - voxel_begin;
+  if (row_mod > 1) {
+    const int64_t row0 = voxel_begin / dims[2], row1 = voxel_end / dims[2];
+    const int64_t first = row0 + ((row_rem - row0 % row_mod) + row_mod) % row_mod;
+    n_launch = first < row1 ? ((row1 - first + row_mod - 1) / row_mod) * dims[2] : 0;
+    if (n_launch == 0) return 0;
+  }
   DeviceGuard guard_(h->device);
   R2IK_CUDA(guard_.err, "cudaSetDevice");
-  k_reach_map<uint16_t><<<blocks_for(voxel_end - voxel_begin), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(
+  k_reach_map<uint16_t><<<blocks_for(n_launch), R2IK_BLOCK, 0, (cudaStream_t)stream>>>(
       h->A, h->AF, origin[0], origin[1], origin[2], step[0], step[1], step[2], dims[0], dims[1], dims[2], orientations_euler,
-      ori_begin, ori_end, voxel_begin, voxel_end, counts);
+      ori_begin, ori_end, voxel_begin, voxel_end, row_mod, row_rem, counts);
   R2IK_CUDA(cudaGetLastError(), "k_reach_map launch");
   return 0;
 }

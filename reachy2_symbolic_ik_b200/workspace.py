@@ -84,19 +84,27 @@ def allreduce_u16_pairs(c16, v0: int, v1: int, dist, group=None):
     return dist.all_reduce(lanes, op=dist.ReduceOp.SUM, group=group, async_op=True)
 
 
-def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=None, n_slabs: int = 4, timing=None):
-    """The sharded map: this rank's orientation slice, uint16 counts, live x-range only, slab-pipelined all-reduce.
-    Returns the int32 volume (every rank holds the full map).  ``timing``: optional dict that receives CUDA events
-    (``k0`` / ``k1`` around each slab's kernel, ``t0`` / ``t1`` around the whole call) for the benchmark."""
+def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=None, n_slabs: int = 4, timing=None,
+                      shard: str = "voxels"):
+    """The map over several GPUs.  Returns the int32 volume (every rank holds the full map).
+
+    Only the x-range of the volume that can hold a reachable voxel takes part (the rest is zero on every rank), counts are
+    16 bits on the wire (two per int32 lane of the all-reduce) and the work is launched slab by slab so that the all-reduce
+    of one slab overlaps the kernel of the next.  shard="voxels" (default): each rank counts ALL orientations for every
+    world-th row (ix, iy, :) of the volume and the all-reduce adds the disjoint pieces -- the per-block staging of the
+    orientation set and the per-voxel pre-checks are then divided by the number of ranks like everything else, and the
+    interleave balances the ranks statistically (contiguous ranges of equal chord length were 12 % out of balance: the
+    cost of a voxel depends on how many orientations pass the early range tests); shard="orientations": each rank
+    counts its slice of the orientation set for every voxel (BASELINE.json's wording).
+    ``timing``: optional dict that receives CUDA events (``k``: per slab kernel, ``t0`` / ``t1`` around the call)."""
     torch = solver._torch
     dev = solver._device
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    b, e = shard_range(ori.shape[0], rank, world)
     d0, d1, d2 = (int(d) for d in dims)
     plane = d1 * d2
     lo, hi = live_x_range(solver, origin, step, dims)
-    if plane % 2:            # two 16-bit counts per int32 lane: slab boundaries must sit on even element offsets
-        lo, hi, n_slabs = 0, d0, 1
+    if d2 % 2:               # two 16-bit counts per int32 lane: slab boundaries must sit on even element offsets
+        lo, hi, n_slabs, shard = 0, d0, 1, "orientations"
     c16 = solver.__dict__.get("_reach_c16")
     if c16 is None or c16.numel() != d0 * plane + (d0 * plane) % 2 or c16.device != dev:
         c16 = solver._reach_c16 = torch.zeros(d0 * plane + (d0 * plane) % 2, dtype=torch.int16, device=dev)
@@ -104,26 +112,31 @@ def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=Non
     if timing is not None:
         timing["t0"] = torch.cuda.Event(enable_timing=True); timing["t0"].record(stream)
         timing["k"] = []
-    c16[:lo * plane].zero_()
-    c16[hi * plane:].zero_()
-    edges = [lo + (hi - lo) * k // n_slabs for k in range(n_slabs + 1)]
+    if shard == "voxels":
+        c16.zero_()                                   # the other ranks' rows (and the dead ranges) are zero here
+        b, e, row_mod, row_rem = 0, ori.shape[0], world, rank
+    else:
+        b, e = shard_range(ori.shape[0], rank, world)
+        row_mod, row_rem = 1, 0
+        c16[:lo * plane].zero_()
+        c16[hi * plane:].zero_()
+    xe = [lo + (hi - lo) * k // n_slabs for k in range(n_slabs + 1)]
+    slabs = [(x0 * plane, x1 * plane, x0 * plane, x1 * plane) for x0, x1 in zip(xe[:-1], xe[1:]) if x1 > x0]
     works = []
     dp = C.POINTER(C.c_double)
-    for x0, x1 in zip(edges[:-1], edges[1:]):
-        if x1 <= x0:
-            continue
-        v0, v1 = x0 * plane, x1 * plane
-        if timing is not None:
-            k0 = torch.cuda.Event(enable_timing=True); k0.record(stream)
-        rc = solver._handle.lib.r2ik_reach_map_range_u16(
-            solver._handle.h, origin.ctypes.data_as(dp), step.ctypes.data_as(dp), dims.ctypes.data_as(C.POINTER(C.c_int32)),
-            C.c_void_p(ori.data_ptr()), C.c_int32(b), C.c_int32(e), C.c_int64(v0), C.c_int64(v1), C.c_void_p(c16.data_ptr()),
-            C.c_void_p(stream.cuda_stream))
-        _native.check(rc, "r2ik_reach_map_range_u16")
-        if timing is not None:
-            k1 = torch.cuda.Event(enable_timing=True); k1.record(stream)
-            timing["k"].append((k0, k1))
-        works.append(allreduce_u16_pairs(c16, v0, v1, dist, group))
+    for g0, g1, v0, v1 in slabs:
+        if v1 > v0:
+            if timing is not None:
+                k0 = torch.cuda.Event(enable_timing=True); k0.record(stream)
+            rc = solver._handle.lib.r2ik_reach_map_range_u16(
+                solver._handle.h, origin.ctypes.data_as(dp), step.ctypes.data_as(dp), dims.ctypes.data_as(C.POINTER(C.c_int32)),
+                C.c_void_p(ori.data_ptr()), C.c_int32(b), C.c_int32(e), C.c_int64(v0), C.c_int64(v1), C.c_int32(row_mod),
+                C.c_int32(row_rem), C.c_void_p(c16.data_ptr()), C.c_void_p(stream.cuda_stream))
+            _native.check(rc, "r2ik_reach_map_range_u16")
+            if timing is not None:
+                k1 = torch.cuda.Event(enable_timing=True); k1.record(stream)
+                timing["k"].append((k0, k1))
+        works.append(allreduce_u16_pairs(c16, g0, g1, dist, group))
     for w in works:
         w.wait()                                 # the current stream waits for the collective
     if out is None:
@@ -132,12 +145,13 @@ def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=Non
     if timing is not None:
         timing["t1"] = torch.cuda.Event(enable_timing=True); timing["t1"].record(stream)
         timing["exchanged_bytes"] = 2 * (hi - lo) * plane
+        timing["shard"] = shard
     return out
 
 
 def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int = 512, origin=None, step=None,
               dims=None, dist=None, group=None, out=None, all_fp64: bool = False, mark=None, plain_allreduce: bool = False,
-              timing=None):
+              timing=None, shard: str = "voxels"):
     """Reachability count volume of ``solver`` (a ``SymbolicIK``): int32 CUDA tensor (d0, d1, d2).
 
     orientations_euler: (n_ori, 3) xyz Euler angles (default: ``fibonacci_orientations(n_orientations)``).
@@ -163,8 +177,8 @@ def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int
             ori = torch.from_numpy(np.ascontiguousarray(orientations_euler, dtype=np.float64)).to(dev)
         n_ori = ori.shape[0]
         sharded = dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1
-        if sharded and not all_fp64 and not plain_allreduce and n_ori <= 65535 * dist.get_world_size(group):
-            return reach_map_sharded(solver, ori, origin, step, dims, dist, group, out, timing=timing)
+        if sharded and not all_fp64 and not plain_allreduce and n_ori <= 65535:
+            return reach_map_sharded(solver, ori, origin, step, dims, dist, group, out, timing=timing, shard=shard)
         if out is None:
             out = torch.empty(tuple(int(d) for d in dims), dtype=torch.int32, device=dev)
 

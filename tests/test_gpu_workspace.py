@@ -162,12 +162,13 @@ def _sharded_worker(rank, world, port, tmp):
         for n, n_ori in ((40, 37), (33, 64)):           # even and odd plane sizes (the odd one takes the unsplit path)
             ori = fk.fibonacci_orientations(n_ori)
             single = ik.reach_map(n=n, orientations_euler=ori)
-            timing = {}
-            sharded = ik.reach_map(n=n, orientations_euler=ori, dist=dist, timing=timing)
+            for shard in ("voxels", "orientations"):
+                timing = {}
+                sharded = ik.reach_map(n=n, orientations_euler=ori, dist=dist, timing=timing, shard=shard)
+                assert torch.equal(sharded, single), f"{shard}-sharded map (16-bit, live range, slabs) differs from the single-GPU map ({n}, {n_ori})"
+                assert timing["exchanged_bytes"] <= 2 * n ** 3
             plain = ik.reach_map(n=n, orientations_euler=ori, dist=dist, plain_allreduce=True)
-            assert torch.equal(sharded, single), f"sharded (16-bit, live range, slabs) differs from the single-GPU map ({n}, {n_ori})"
             assert torch.equal(plain, single), "plain all-reduce differs from the single-GPU map"
-            assert timing["exchanged_bytes"] <= 2 * n ** 3
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
