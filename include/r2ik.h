@@ -287,6 +287,17 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par /* ho
                                    R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
                                    double *workspace, int32_t test_force_serial_mod, void *stream);
 
+/* The same computation with the finish pass on winding codes: the joints kernel also emits, per waypoint, a 16-bit code
+ * (per-joint change of the winding number against the previous waypoint's raw joints, the continuity verdict, or
+ * "irregular") and stores the raw joints row-contiguously; the per-trajectory scan then walks 2 bytes per waypoint and
+ * touches a joints row only where a joint winds past +-pi or the waypoint is irregular, where it runs the reference's
+ * statements verbatim (csrc/r2ik_cont_codes.cuh).  workspace: T*W doubles (thetas) followed by T*W uint16 (codes),
+ * i.e. at least T*W + (T*W + 3) / 4 doubles.  Same flags / states as r2ik_ctl_continuous_f64, joints equal to rounding. */
+int r2ik_ctl_continuous_codes_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
+                                  int32_t W, const double *current_joints, const double *current_pose,
+                                  R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
+                                  double *workspace, int32_t test_force_serial_mod, void *stream);
+
 /* The same computation with the joints written once: k_cont_targets and k_cont_thetas as above, then ONE kernel for
  * the rest -- a block owns 16 trajectories and walks them 8 waypoints at a time, get_joints per waypoint and the unwrap /
  * continuity / emergency scan (one lane per joint) alternate per tile, the tile is staged in shared memory and stored

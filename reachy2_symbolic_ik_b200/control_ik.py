@@ -190,8 +190,10 @@ class ControlIK:
         ``exhaustive`` (discrete): False = the elbow search finds the arg-min over the nb_search_points samples from
         the crossings of the two elbow tests (cost independent of K); True = every sample is visited by the
         warp-cooperative scan kernel.  Same outputs.
-        ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans (needs T*W doubles of device
-        scratch, allocated here); False = the single one-thread-per-trajectory kernel.  Same flags / states; joints equal to rounding.
+        ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans, the finish pass on winding codes
+        (``r2ik_ctl_continuous_codes_f64``; needs 10 bytes of device scratch per waypoint, allocated here); False = the single
+        one-thread-per-trajectory kernel; "phased4" / "tiled" = the earlier forms of the phased pipeline (slower, kept as
+        cross-checks).  Same flags / states; joints equal to rounding.
         ``devices``: CUDA ordinals of this node to spread a HOST batch over (contiguous slices of the poses / of the
         trajectories, one pipeline per device, no inter-GPU traffic); results are NumPy arrays.
         """
@@ -245,13 +247,20 @@ class ControlIK:
                     joints = torch.empty((T, W, 7), dtype=torch.float64, device=self._device)
                     reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                     state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
-                if phased == "tiled":
+                if phased is True or phased == "codes":
+                    n_wp = T * W
+                    ws = self._scratch(n_wp + (n_wp + 3) // 4, stream.value)
+                    rc = solver._handle.lib.r2ik_ctl_continuous_codes_f64(
+                        solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
+                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
+                    _native.check(rc, "r2ik_ctl_continuous_codes_f64")
+                elif phased == "tiled":
                     ws = self._scratch(T * W, stream.value)
                     rc = solver._handle.lib.r2ik_ctl_continuous_tiled_f64(
                         solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
                         _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
                     _native.check(rc, "r2ik_ctl_continuous_tiled_f64")
-                elif phased:
+                elif phased == "phased4":
                     ws = self._scratch(T * W, stream.value)
                     rc = solver._handle.lib.r2ik_ctl_continuous_phased_f64(
                         solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
@@ -450,7 +459,7 @@ class ControlIK:
                 pipe = self._pipeline(("continuous", T, wc, n_slots), lambda: dict(
                     M=torch.empty((T, wc, 16), dtype=f64, device=dev), joints=torch.empty((T, wc, 7), dtype=f64, device=dev),
                     reach=torch.empty((T, wc), dtype=u8, device=dev), state=torch.empty((T, wc), dtype=u8, device=dev),
-                    ws=torch.empty((T, wc), dtype=f64, device=dev)),
+                    ws=torch.empty(T * wc + (T * wc + 3) // 4, dtype=f64, device=dev)),
                     max(3, n_slots))
                 s_in, s_k, s_out = pipe["streams"][:3]
                 for s in (s_in, s_k, s_out):
@@ -473,11 +482,11 @@ class ControlIK:
                     s_k.wait_event(e["h2d"])
                     if e["d2h"] is not None:
                         s_k.wait_event(e["d2h"])                  # this slot's previous results have left
-                    rc = lib.r2ik_ctl_continuous_phased_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
-                                                            _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]),
-                                                            _ptr(b["state"]), _ptr(b["ws"]), C.c_int32(0),
-                                                            C.c_void_p(s_k.cuda_stream))
-                    _native.check(rc, "r2ik_ctl_continuous_phased_f64")
+                    rc = lib.r2ik_ctl_continuous_codes_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
+                                                           _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]),
+                                                           _ptr(b["state"]), _ptr(b["ws"]), C.c_int32(0),
+                                                           C.c_void_p(s_k.cuda_stream))
+                    _native.check(rc, "r2ik_ctl_continuous_codes_f64")
                     e["k"] = torch.cuda.Event()
                     e["k"].record(s_k)
                     s_out.wait_event(e["k"])

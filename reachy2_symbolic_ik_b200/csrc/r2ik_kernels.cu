@@ -792,6 +792,7 @@ k_cont_finish_direct(const __grid_constant__ ArmConst A, const __grid_constant__
 
 #include "r2ik_scan_lanes.cuh"
 #include "r2ik_cont_tiles.cuh"
+#include "r2ik_cont_codes.cuh"
 
 // ---------------------------------------------------------------------------------------
 // K4: workspace reachability map.  One thread per voxel.  Voxels outside the reach sphere or behind the torso plane
@@ -1301,6 +1302,36 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
       K, T, W, current_joints, st, workspace, joints, reachable, state);
   k_cont_finish_direct<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state,
                                                     true);
+  R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
+  return 0;
+}
+
+int r2ik_ctl_continuous_codes_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                                  const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
+                                  uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
+                                  void *stream) {
+  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_codes_f64: null handle or parameters");
+  if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_codes_f64: bad T, W or nb_search_points_continuous");
+  if (T == 0 || W == 0) return 0;
+  if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state || !workspace)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_codes_f64: null argument");
+  if (misaligned16(M) || misaligned16(current_pose))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_codes_f64: M and current_pose must be 16-byte aligned");
+  const int64_t nblk = (W + R2IK_CODE_STORED - 1) / R2IK_CODE_STORED;
+  if (T * nblk > 0x7fffffffLL) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_codes_f64: T * ceil(W / 127) exceeds the grid limit");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_wp = T * (int64_t)W;
+  uint16_t *codes16 = reinterpret_cast<uint16_t *>(workspace + n_wp);       // the codes follow the T*W thetas
+  const unsigned tb = (unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK);
+  k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
+  k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
+  k_cont_raw_joints_codes<<<(unsigned)(T * nblk), R2IK_CODE_BLOCK, 0, s>>>(h->A, *par, M, W, workspace, reachable, state, joints, codes16,
+                                                                          test_force_serial_mod);
+  k_cont_finish_codes<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, codes16, joints, reachable, state);
+  k_cont_apply_windings<<<(unsigned)(((n_wp + 7) / 8 + 255) / 256), 256, 0, s>>>(n_wp, codes16, joints);
   R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
   return 0;
 }

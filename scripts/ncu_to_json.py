@@ -28,20 +28,37 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ms": 1e3, 
 
 def main():
     rep, wl, kernel, tag = sys.argv[1:5]
+    sum_all = len(sys.argv) > 5 and sys.argv[5] == "sum"      # a step of several kernels (K3): byte / instruction counts are summed
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = {"source": f"ncu --set full --clock-control none, {os.path.basename(rep)} ({tag}); per launch; under the profiler "
                      "(use for traffic / ratios, not as a timing)", "kernel": kernel}
+    additive = {"duration_us_under_ncu", "dram_bytes_read", "dram_bytes_write", "warp_instructions", "thread_dfma", "thread_dmul", "thread_dadd"}
+    seen = []
     for r in rows[2:]:
-        if kernel not in r[hdr.index("Kernel Name")]:
+        name_k = r[hdr.index("Kernel Name")]
+        if kernel not in name_k:
             continue
+        short = name_k.split("(")[0]
+        if short in seen:
+            continue
+        seen.append(short)
         for k, name in WANT.items():
             if k in hdr:
                 v = float(r[hdr.index(k)].replace(",", ""))
                 v *= UNIT_SCALE.get(units[hdr.index(k)], 1.0)
-                out[name] = v
-        break
+                if sum_all and name in additive:
+                    out[name] = out.get(name, 0.0) + v
+                elif name not in out:
+                    out[name] = v
+        if not sum_all:
+            break
+    if sum_all:
+        out["kernels_summed"] = seen
+    sha = os.path.join(os.path.dirname(rep), f"{tag}_csrc_sha16.txt")
+    if os.path.exists(sha):
+        out["csrc_sha16"] = open(sha).read().strip()
     out["dram_bytes_per_launch"] = out.get("dram_bytes_read", 0.0) + out.get("dram_bytes_write", 0.0)
     if "thread_dfma" in out:
         out["executed_fp64_flop"] = 2 * out["thread_dfma"] + out.get("thread_dmul", 0.0) + out.get("thread_dadd", 0.0)

@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "../../reachy2_symbolic_ik_b200/csrc/r2ik_control.cuh"
+#include "../../reachy2_symbolic_ik_b200/csrc/r2ik_cont_codes.cuh"
 #define R2IK_F32_DEBUG 1
 #include "../../reachy2_symbolic_ik_b200/csrc/r2ik_device_f32.cuh"
 #include "../../reachy2_symbolic_ik_b200/csrc/r2ik_host.h"
@@ -331,6 +332,73 @@ void hs_ctl_continuous_phased_lanes_batch(const R2ikArmConfig *cfg, const R2ikCt
   phased_front(A, par, M, T, W, cur_joints, cur_pose, st, joints, reach, state, ws, force_serial_mod);
   lanesim::run_finish_lanes(lanes, T, W, cur_joints, st, ws, joints, reach, state);
   finish_direct(A, par, M, T, W, cur_joints, st, ws, joints, reach, state, true);
+}
+
+// K3 with the finish pass on winding codes (csrc/r2ik_cont_codes.cuh): phases 1-2 as above, then k_cont_raw_joints_codes
+// (raw joints + the 16-bit code of every waypoint against its predecessor; the first waypoint of a trajectory is irregular) and k_cont_finish_codes (cont_finish_codes_trajectory, the same function the kernel calls).
+void hs_ctl_continuous_codes_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+                                   const double *cur_joints, const double *cur_pose, R2ikTrajState *st, double *joints,
+                                   uint8_t *reach, uint8_t *state, double *ws, uint16_t *codes, int force_serial_mod) {   // codes: in / out
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  const int64_t n_wp = T * W;
+  for (int64_t k = 0; k < n_wp; ++k) {                       // k_cont_targets
+    Solve S; double pos[3], goal; int sto;
+    int c = cont_target(A, *par, M + 16 * k, S, pos, goal, sto);
+    ws[k] = goal; reach[k] = (uint8_t)c; state[k] = (uint8_t)sto;
+  }
+  for (int64_t t = 0; t < T; ++t) {                          // k_cont_thetas
+    if (st[t].emergency_stop) continue;
+    double theta = st[t].previous_theta;
+    bool has = st[t].has_previous_sol != 0;
+    for (int32_t w = 0; w < W; ++w) {
+      size_t k = (size_t)t * W + w;
+      int c = reach[k];
+      if (c == R2IK_WP_INVALID) continue;
+      if (!has) { theta = cont_initial_theta(A, *par, cur_joints + 7 * t, cur_pose + 16 * t); has = true; }
+      theta = cont_next_theta(*par, c, ws[k], theta);
+      ws[k] = theta;
+    }
+  }
+  for (int64_t t = 0; t < T; ++t) {                          // k_cont_raw_joints_codes
+    bool prev_ordinary = false;
+    double jp[7];
+    for (int32_t w = 0; w < W; ++w) {
+      size_t k = (size_t)t * W + w;
+      int c = reach[k];
+      double j[7];
+      bool serial = false;
+      for (int q = 0; q < 7; ++q) j[q] = NAN;
+      if (c != R2IK_WP_INVALID) {
+        const double *m = M + 16 * k;
+        Solve S; double pos[3] = {m[3], m[7], m[11]};
+        rotation_from_mat4(m, true, S.R);
+        if (c == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S); else circle_of_reachable(A, pos, S);
+        double sn, cs_, E[3];
+        sincos_any(ws[k], sn, cs_);
+        serial = !get_joints_impl<false>(A, S, cs_, sn, 0.0, 0.0, j, E);
+        if (force_serial_mod > 0 && k % force_serial_mod == 0) serial = true;
+        if (!serial) limit_orbita3d_wrist(j, par->orbita3d_max_angle);
+      }
+      const bool ordinary = c != R2IK_WP_INVALID && !serial;
+      unsigned cd = (ordinary && w > 0 && prev_ordinary) ? cont_wind_code(j, jp) : cont_irregular_code(serial ? (c | R2IK_WP_SERIAL) : c);
+      codes[k] = (uint16_t)cd;
+      reach[k] = c == R2IK_WP_TARGET ? 1 : 0;
+      for (int q = 0; q < 7; ++q) { joints[7 * k + q] = j[q]; jp[q] = j[q]; }
+      prev_ordinary = ordinary;
+    }
+  }
+  for (int64_t t = 0; t < T; ++t) {                          // k_cont_finish_codes
+    const size_t base = (size_t)t * W;
+    auto serial = [&](int w, int kind, double theta, double p0, double p2, double *out) {
+      const double *m = M + 16 * (base + w);
+      Solve S; double pos[3] = {m[3], m[7], m[11]};
+      rotation_from_mat4(m, true, S.R);
+      if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
+      cont_raw_joints(A, *par, kind, pos, S, theta, p0, p2, out);
+    };
+    cont_finish_codes_trajectory(W, cur_joints + 7 * t, st[t], ws + base, codes + base, joints + 7 * base, reach + base, state + base, serial);
+  }
 }
 
 // K1-f32 (r2ik_device_f32.cuh): the FP32 fast solve with FP64 escalation, mirroring k_symik_solve_f32.

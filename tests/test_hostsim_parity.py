@@ -280,7 +280,7 @@ def test_ctl_continuous(hs, oracle, arm, variant):
     assert st2.tobytes() == st.tobytes()
 
 
-def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, lanes=0, force_serial=0):
+def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, lanes=0, force_serial=0, codes=False):
     M = np.ascontiguousarray(M, dtype=np.float64)
     T, W = M.shape[:2]
     cj = np.empty((T, 7)); cp = np.empty((T, 4, 4))
@@ -291,7 +291,12 @@ def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, lanes
         states["init"] = 1
     st = np.ascontiguousarray(states).copy()
     joints = np.empty((T, W, 7)); reach = np.zeros((T, W), np.uint8); state = np.zeros((T, W), np.uint8)
-    if lanes:   # phases 1-3, the lane-parallel finish kernel body under the warp emulation, the fixup pass
+    if codes:   # phases 1-2, the joints kernel with winding codes, the scan on codes (csrc/r2ik_cont_codes.cuh)
+        ws = np.empty((T, W)); cd = np.zeros((T, W), np.uint16)
+        hs.hs_ctl_continuous_codes_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
+                                         st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws),
+                                         cd.ctypes.data_as(C.c_void_p), C.c_int(force_serial))
+    elif lanes:   # phases 1-3, the lane-parallel finish kernel body under the warp emulation, the fixup pass
         ws = np.empty((T, W))
         hs.hs_ctl_continuous_phased_lanes_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
                                                 st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws),
@@ -437,6 +442,47 @@ def test_ctl_continuous_lane_parallel_finish_kernel(hs, oracle, arm, lanes):
         np.testing.assert_array_equal(got2[2], want2[2])
         assert got2[3].tobytes() == want2[3].tobytes()
     assert hit_clamp, "no trajectory reached the +-6 pi clamp"
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_ctl_continuous_winding_codes(hs, oracle, arm):
+    """The finish pass on winding codes (csrc/r2ik_cont_codes.cuh: cont_wind_code + cont_finish_codes_trajectory, the
+    functions the kernels call) against the serial finish scan: flags, states and controller flags identical, joints and
+    previous_sol equal to rounding (nj = j + 2 pi k instead of prev + angle_diff(j, prev)) -- on the golden trajectories
+    (continuity latch, unreachable stretches), the multi-turn ramps (windings past +-pi, the +-6 pi clamp and its
+    emergency bits), trajectories longer than a 128-waypoint block, resumed states, invalid rotations, and with the test
+    hook sending every m-th waypoint down the serial get_joints route."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    cfg = cfg_for(arm, urdf_params(), -1.01)
+    par = ctl_params(oracle, arm)
+    g, go = load(f"ctl_continuous_{arm}.npz"), load(f"ctl_overrides_{arm}.npz")
+    long = fk.sinusoidal_trajectories(5, 300, arm, seed=77)[0].copy()
+    long[1, 140:, :3, :3] = long[1, 140:, :3, :3] @ np.diag([-1.0, -1.0, 1.0])      # discontinuity -> latch
+    long[2, 129, :3, :3] = np.diag([-1.0, 1.0, 1.0])                                # invalid rotation right after a block edge
+    long[3, 127, :3, :3] = np.diag([-1.0, 1.0, 1.0])                                # ... and right before one
+    hit_clamp = wound = False
+
+    def same(got, want, what):
+        np.testing.assert_allclose(got[0], want[0], rtol=0, atol=1e-12, err_msg=f"{what} joints")
+        np.testing.assert_array_equal(got[1], want[1], err_msg=f"{what} flags")
+        np.testing.assert_array_equal(got[2], want[2], err_msg=f"{what} states")
+        for f in ("has_previous_sol", "init", "emergency_stop", "emergency_bits"):
+            np.testing.assert_array_equal(got[3][f], want[3][f], err_msg=f"{what} controller {f}")
+        np.testing.assert_allclose(got[3]["previous_sol"], want[3]["previous_sol"], rtol=0, atol=1e-12, err_msg=f"{what} previous_sol")
+        np.testing.assert_array_equal(got[3]["previous_theta"], want[3]["previous_theta"], err_msg=f"{what} previous_theta")
+
+    for name, M in (("golden", g["M"]), ("multi-turn", go["mt_M"]), ("unfreeze", go["unf_M"][None]), ("long", long)):
+        M = np.ascontiguousarray(M)
+        want = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
+        for force in (0, 1, 7, 97):
+            same(hs_continuous(hs, oracle, cfg, par, arm, M, codes=True, force_serial=force), want, f"{name} force={force}")
+        hit_clamp = hit_clamp or bool((want[3]["emergency_bits"] & 7).any())
+        wound = wound or bool((np.abs(np.nan_to_num(want[0])) > np.pi + 1e-6).any())
+        Mr = np.ascontiguousarray(M[:, ::-1])       # resume the reversed trajectories from the returned states
+        same(hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], codes=True),
+             hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], phased=True), f"{name} resumed")
+    assert hit_clamp and wound, "no trajectory wound past pi / reached the +-6 pi clamp"
 
 
 @pytest.mark.parametrize("arm", ARMS)
