@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define R2IK_ABI_VERSION 3 /* 3: + symik_scalar, stream_synchronize, host pipelines, ctl_ctor_theta, continuous_tiled; no_limits / projected in elbow_positions, prev_joints in
+#define R2IK_ABI_VERSION 3 /* 3: + symik_scalar, stream_synchronize, host pipelines, ctl_ctor_theta, reach_map_range_u16; no_limits / projected in elbow_positions, prev_joints in
                               no_limits, nullable `reachable`, test hook of the phased continuous entry as a parameter */
 
 /* argument errors */
@@ -277,36 +277,20 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, 
                             void *stream);
 
 /* The same computation as r2ik_ctl_continuous_f64 (same flags / states, joints equal to rounding), cut at its data dependences:
- * the per-waypoint work (reachability, target theta, joints for a given theta, Orbita3D limit) runs with one
- * thread per waypoint, and only the rate-limited theta and the unwrap / continuity / emergency chain run as
- * per-trajectory scans.  workspace: T*W doubles of device scratch (theta per waypoint), caller-owned.
+ * the per-waypoint work (reachability, target theta, joints for a given theta, Orbita3D limit) runs with one thread per
+ * waypoint, and only the rate-limited theta and the unwrap / continuity / emergency chain run as per-trajectory scans --
+ * the latter on 16-bit winding codes that the joints kernel emits per waypoint (per-joint change of the winding number
+ * against the previous waypoint's raw joints, the continuity verdict, or "irregular"): the scan walks 2 bytes per waypoint
+ * and touches a joints row only where the waypoint is irregular, where it runs the reference's statements verbatim; rows
+ * of joints that have wound past +-pi get their 2 pi k in a last parallel pass (csrc/r2ik_cont_codes.cuh).
+ * workspace: T*W doubles (thetas) followed by T*W uint16 (codes), i.e. at least T*W + (T*W + 3) / 4 doubles of device
+ * scratch, caller-owned.
  * test_force_serial_mod: 0 in production; m > 0 sends every m-th waypoint down the serial get_joints route (which no
  * physical pose takes) so that tests can hold that route to the ordinary result. */
 int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
                                    int32_t W, const double *current_joints, const double *current_pose,
                                    R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
                                    double *workspace, int32_t test_force_serial_mod, void *stream);
-
-/* The same computation with the finish pass on winding codes: the joints kernel also emits, per waypoint, a 16-bit code
- * (per-joint change of the winding number against the previous waypoint's raw joints, the continuity verdict, or
- * "irregular") and stores the raw joints row-contiguously; the per-trajectory scan then walks 2 bytes per waypoint and
- * touches a joints row only where a joint winds past +-pi or the waypoint is irregular, where it runs the reference's
- * statements verbatim (csrc/r2ik_cont_codes.cuh).  workspace: T*W doubles (thetas) followed by T*W uint16 (codes),
- * i.e. at least T*W + (T*W + 3) / 4 doubles.  Same flags / states as r2ik_ctl_continuous_f64, joints equal to rounding. */
-int r2ik_ctl_continuous_codes_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
-                                  int32_t W, const double *current_joints, const double *current_pose,
-                                  R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
-                                  double *workspace, int32_t test_force_serial_mod, void *stream);
-
-/* The same computation with the joints written once: k_cont_targets and k_cont_thetas as above, then ONE kernel for
- * the rest -- a block owns 16 trajectories and walks them 8 waypoints at a time, get_joints per waypoint and the unwrap /
- * continuity / emergency scan (one lane per joint) alternate per tile, the tile is staged in shared memory and stored
- * with row-contiguous requests; waypoints that need the serial get_joints are redone in order inside the scan (no fixup
- * pass).  workspace: T*W doubles.  Same flags / states as r2ik_ctl_continuous_f64, joints equal to rounding. */
-int r2ik_ctl_continuous_tiled_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t T,
-                                  int32_t W, const double *current_joints, const double *current_pose,
-                                  R2ikTrajState *st, double *joints, uint8_t *reachable, uint8_t *state,
-                                  double *workspace, int32_t test_force_serial_mod, void *stream);
 
 /* Workspace reachability map: counts[v] += #orientations o in [ori_begin, ori_end) with
  * is_reachable(voxel centre, orientations_euler[o]) true.  Voxel (ix,iy,iz) centre =

@@ -191,9 +191,8 @@ class ControlIK:
         the crossings of the two elbow tests (cost independent of K); True = every sample is visited by the
         warp-cooperative scan kernel.  Same outputs.
         ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans, the finish pass on winding codes
-        (``r2ik_ctl_continuous_codes_f64``; needs 10 bytes of device scratch per waypoint, allocated here); False = the single
-        one-thread-per-trajectory kernel; "phased4" / "tiled" = the earlier forms of the phased pipeline (slower, kept as
-        cross-checks).  Same flags / states; joints equal to rounding.
+        (``r2ik_ctl_continuous_phased_f64``; needs 10 bytes of device scratch per waypoint, allocated here); False = the single
+        one-thread-per-trajectory kernel (the cross-check).  Same flags / states; joints equal to rounding.
         ``devices``: CUDA ordinals of this node to spread a HOST batch over (contiguous slices of the poses / of the
         trajectories, one pipeline per device, no inter-GPU traffic); results are NumPy arrays.
         """
@@ -247,21 +246,9 @@ class ControlIK:
                     joints = torch.empty((T, W, 7), dtype=torch.float64, device=self._device)
                     reach = torch.empty((T, W), dtype=torch.uint8, device=self._device)
                     state = torch.empty((T, W), dtype=torch.uint8, device=self._device)
-                if phased is True or phased == "codes":
+                if phased:
                     n_wp = T * W
                     ws = self._scratch(n_wp + (n_wp + 3) // 4, stream.value)
-                    rc = solver._handle.lib.r2ik_ctl_continuous_codes_f64(
-                        solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
-                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
-                    _native.check(rc, "r2ik_ctl_continuous_codes_f64")
-                elif phased == "tiled":
-                    ws = self._scratch(T * W, stream.value)
-                    rc = solver._handle.lib.r2ik_ctl_continuous_tiled_f64(
-                        solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
-                        _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
-                    _native.check(rc, "r2ik_ctl_continuous_tiled_f64")
-                elif phased == "phased4":
-                    ws = self._scratch(T * W, stream.value)
                     rc = solver._handle.lib.r2ik_ctl_continuous_phased_f64(
                         solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(T), C.c_int32(W), _ptr(cj), _ptr(cp), _ptr(st),
                         _ptr(joints), _ptr(reach), _ptr(state), _ptr(ws), C.c_int32(int(_test_force_serial_mod)), stream)
@@ -482,11 +469,11 @@ class ControlIK:
                     s_k.wait_event(e["h2d"])
                     if e["d2h"] is not None:
                         s_k.wait_event(e["d2h"])                  # this slot's previous results have left
-                    rc = lib.r2ik_ctl_continuous_codes_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
+                    rc = lib.r2ik_ctl_continuous_phased_f64(h, C.byref(par), _ptr(b["M"]), C.c_int64(T), C.c_int32(m), _ptr(cj),
                                                            _ptr(cp), _ptr(st), _ptr(b["joints"]), _ptr(b["reach"]),
                                                            _ptr(b["state"]), _ptr(b["ws"]), C.c_int32(0),
                                                            C.c_void_p(s_k.cuda_stream))
-                    _native.check(rc, "r2ik_ctl_continuous_codes_f64")
+                    _native.check(rc, "r2ik_ctl_continuous_phased_f64")
                     e["k"] = torch.cuda.Event()
                     e["k"].record(s_k)
                     s_out.wait_event(e["k"])

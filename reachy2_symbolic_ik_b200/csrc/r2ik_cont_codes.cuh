@@ -3,7 +3,8 @@
 // The last link of ControlIK's continuous mode (ctl:393-405, utl:493-589) takes the joints of a waypoint and returns
 //     nj = previous_sol + angle_diff(j, previous_sol)                 (allow_multiturn)
 // clamped to +-6 pi (joints 0, 2, 6), checked for continuity against previous_sol, and keeps it as the next previous_sol.
-// As a scan over the raw joints this reads and rewrites 56 bytes per waypoint (2.9 ms of the 10.2 ms of cfg 4) although
+// As a scan over the raw joints (round 1: four lanes per trajectory) this reads and rewrites 56 bytes per waypoint -- 2.9 ms
+// of the 10.2 ms of cfg 4 -- although
 // nj is j itself -- to one rounding -- unless a joint has wound past +-pi.  Consecutive outputs are congruent to the raw
 // joints modulo 2 pi, so everything the recursion needs from a waypoint depends on the RAW joints of that waypoint and of
 // its predecessor only:
@@ -217,7 +218,22 @@ R2IK_HD void cont_finish_codes_trajectory(int W, const double *current_joints, R
 }  // namespace r2ik
 
 #if defined(__CUDACC__)
-// Joints of a waypoint for its theta + Orbita3D limit (as k_cont_raw_joints), the winding code against the predecessor
+// The serial get_joints of one waypoint (ctl:369-393 with previous_sol[0], [2]): out of line, the rare route.
+__device__ __noinline__ void tile_serial_joints(const r2ik::ArmConst &A, const R2ikCtlParams &par, const double *M, int kind, double theta,
+                                                double prev0, double prev2, double *j) {
+  using namespace r2ik;
+  double m[16];
+  load_mat4(M, m);
+  Solve S;
+  double pos[3] = {m[3], m[7], m[11]};
+  rotation_from_mat4(m, true, S.R);
+  if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
+  double jj[7];
+  cont_raw_joints(A, par, kind, pos, S, theta, prev0, prev2, jj);
+  for (int q = 0; q < 7; ++q) j[q] = jj[q];
+}
+
+// Joints of a waypoint for its theta + Orbita3D limit, the winding code against the predecessor
 // through shared memory, row-contiguous stores of the block's 127 x 7 raw joints.  Thread 0 of a block holds the waypoint
 // before the block's first one (computed again, not stored).
 #define R2IK_CODE_STORED (R2IK_CODE_BLOCK - 1)     // waypoints a block stores
@@ -266,7 +282,8 @@ k_cont_raw_joints_codes(const __grid_constant__ r2ik::ArmConst A, const __grid_c
       sincos_any(ws[k], st, ct);
       // straight-line get_joints only; a degenerate input (exact singularity: needs previous_sol) is left to the scan
       serial = !get_joints_impl<false>(A, S, ct, st, 0.0, 0.0, j, E);
-      // test hook (ABI parameter test_force_serial_mod = m > 0), see k_cont_raw_joints
+      // test hook (ABI parameter test_force_serial_mod = m > 0): every m-th waypoint takes the serial route although it
+      // does not need it, so that the route is exercised on ordinary data
       if (force_serial_mod > 0 && k % (size_t)force_serial_mod == 0) serial = true;
       if (!serial) limit_orbita3d_wrist(j, par.orbita3d_max_angle);
     }

@@ -5,7 +5,7 @@
 //   K1b    k_symik_no_limits, k_elbow_positions    is_reachable_no_limits, get_elbow_position
 //   K2     k_ctl_discrete                       one lane / pose, analytic arg-min over the K elbow samples
 //          k_ctl_discrete_scan                  the exhaustive warp-cooperative scan of the K samples (cross-check)
-//   K3     k_cont_targets / k_cont_thetas / k_cont_raw_joints / k_cont_finish_lanes (+ k_cont_finish_direct)
+//   K3     k_cont_targets / k_cont_thetas / k_cont_raw_joints_codes / k_cont_finish_codes / k_cont_apply_windings
 //                                               continuous mode cut at its data dependences: per-waypoint kernels
 //                                               and per-trajectory scans;  k_ctl_continuous = the one-kernel form
 //   K4     k_reach_map                          one thread / voxel, mixed-precision flag with FP64 escalation
@@ -600,18 +600,19 @@ k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2i
 }
 
 // ---------------------------------------------------------------------------------------
-// K3, phased form (needs a T x W double workspace).  See r2ik_control.cuh "Continuous mode, cut at its
-// data dependences":
-//   k_cont_targets     1 thread / waypoint    classify + target theta            -> code, state, ws = goal
-//   k_cont_thetas      1 thread / trajectory  rate-limited theta scan (tiles through shared memory) -> ws = theta
-//   k_cont_raw_joints  1 thread / waypoint    get_joints(theta) + Orbita3D limit -> joints (raw)
-//   k_cont_finish_lanes<G>  G = 4 lanes / trajectory  unwrap / continuity / emergency scan, joints split over the lanes
-//                                                                                -> joints, reachable, state, states
-//   k_cont_finish_direct<fixup>  1 thread / trajectory: finishes the trajectories the lane scan had to leave at a
-//                      waypoint that needs the serial get_joints (exact singularities; none on physical data)
-// The two per-waypoint kernels hold ~85 % of the arithmetic and run at full parallelism (T x W threads); the
-// two scans are a few dozen FP64 operations per waypoint.  `reachable` carries the waypoint code and
-// `state` the reference state between the phases, so the only scratch is the theta workspace.
+// K3, phased form (needs 10 bytes of workspace per waypoint).  See r2ik_control.cuh "Continuous mode, cut at its
+// data dependences" and r2ik_cont_codes.cuh:
+//   k_cont_targets           1 thread / waypoint    classify + target theta                       -> code, state, ws = goal
+//   k_cont_thetas            1 thread / trajectory  rate-limited theta scan (tiles through shared memory) -> ws = theta
+//   k_cont_raw_joints_codes  1 thread / waypoint    get_joints(theta) + Orbita3D limit, winding code against the predecessor
+//                                                                                                 -> joints (raw), codes16, reachable
+//   k_cont_finish_codes      1 thread / trajectory  unwrap / continuity / emergency scan on the 16-bit codes; the reference's
+//                                                   statements verbatim on irregular waypoints    -> codes16 (absolute windings),
+//                                                                                                    joints / state where irregular, states
+//   k_cont_apply_windings    1 thread / 8 waypoints j + 2 pi k on the wound rows                  -> joints
+// The two per-waypoint kernels hold ~95 % of the arithmetic and run at full parallelism (T x W threads); the scans are a
+// 1 000-step recursion per trajectory that only all trajectories in flight at once can hide.  `reachable` carries the
+// waypoint code and `state` the reference state between the phases.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
 k_cont_targets(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
@@ -684,114 +685,6 @@ k_cont_thetas(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCt
   }
 }
 
-__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
-k_cont_raw_joints(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
-                  int64_t n_wp, const double *__restrict__ ws, uint8_t *__restrict__ code, double *__restrict__ joints,
-                  int force_serial_mod) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_wp) return;
-  const int c = code[k];
-  double j[7];
-  bool serial = false;
-  if (c == R2IK_WP_INVALID) {
-#pragma unroll
-    for (int q = 0; q < 7; ++q) j[q] = NAN;
-  } else {
-    double m[16];
-    load_mat4(M + 16 * k, m);
-    Solve S;
-    double pos[3] = {m[3], m[7], m[11]};
-    rotation_from_mat4(m, true, S.R);
-    if (c == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S);
-    else circle_of_reachable(A, pos, S);   // reachable (phase 1 decided): the elbow circle is all get_joints needs
-    double st, ct, E[3];
-    sincos_any(ws[k], st, ct);
-    // straight-line get_joints only; a degenerate input (exact singularity: needs previous_sol) is left to the scan
-    serial = !get_joints_impl<false>(A, S, ct, st, 0.0, 0.0, j, E);
-    // test hook (ABI parameter test_force_serial_mod = m > 0): every m-th waypoint is sent down the serial route although it does not
-    // need it, so that the stop / fixup machinery of the finish scan is exercised on ordinary data
-    if (force_serial_mod > 0 && k % force_serial_mod == 0) serial = true;
-    if (!serial) limit_orbita3d_wrist(j, par.orbita3d_max_angle);
-  }
-  if (serial) { code[k] = (uint8_t)(c | R2IK_WP_SERIAL); return; }
-#pragma unroll
-  for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
-}
-
-// One waypoint of the finish scan on the joints j (in / out); returns the flag to store in `reachable`.
-__device__ __forceinline__ uint8_t cont_finish_waypoint(const ArmConst &A, const R2ikCtlParams &par, const double *__restrict__ M,
-                                                        const double *__restrict__ current_joints, int64_t t, size_t k, int c,
-                                                        double theta, R2ikTrajState &cs, double j[7], uint8_t *__restrict__ state) {
-  if (cs.emergency_stop) {                                   // ctl:205-210
-#pragma unroll
-    for (int q = 0; q < 7; ++q) j[q] = cs.previous_sol[q];
-    state[k] = R2IK_STATE_EMERGENCY;
-    return 0;
-  }
-  const int kind = c & 0x7f;
-  if (kind == R2IK_WP_INVALID) return 0;                     // joints are NaN, state is INVALID_ROTATION already
-  if (!cs.has_previous_sol) {                                // ctl:306-313
-#pragma unroll
-    for (int q = 0; q < 7; ++q) cs.previous_sol[q] = current_joints[7 * t + q];
-    cs.has_previous_sol = 1;
-    cs.init = 1;
-  }
-  cs.previous_theta = theta;
-  if (c & R2IK_WP_SERIAL) {                                  // exact singularity of get_joints: redo it with previous_sol
-    double m[16];
-    load_mat4(M + 16 * k, m);
-    Solve S;
-    double pos[3] = {m[3], m[7], m[11]};
-    rotation_from_mat4(m, true, S.R);
-    if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
-    cont_raw_joints(A, par, kind, pos, S, cs.previous_theta, cs.previous_sol[0], cs.previous_sol[2], j);
-  }
-  cont_finish(cs, j);
-  return kind == R2IK_WP_TARGET ? 1 : 0;
-}
-
-// Generic form: every thread reads / writes its trajectory's rows directly.  With fixup = true it only serves the
-// trajectories that k_cont_finish_lanes left at a waypoint needing the serial get_joints (code bit R2IK_WP_SERIAL still set):
-// it resumes there, from the controller state that kernel stored.
-__global__ void __launch_bounds__(R2IK_K3_BLOCK, R2IK_K3_MINBLOCKS)
-k_cont_finish_direct(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
-                     int64_t T, int W, const double *__restrict__ current_joints, R2ikTrajState *__restrict__ states,
-                     const double *__restrict__ ws, double *__restrict__ joints, uint8_t *__restrict__ reachable,
-                     uint8_t *__restrict__ state, bool fixup) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const size_t base = (size_t)t * W;
-  int w_begin = 0;
-  if (fixup) {
-    w_begin = W;
-    if (((base | (size_t)W) & 7) == 0) {      // 8 codes per load
-      const unsigned long long *c8 = reinterpret_cast<const unsigned long long *>(reachable + base);
-      for (int g = 0; g < W / 8; ++g) {
-        const unsigned long long hit = c8[g] & 0x8080808080808080ull;
-        if (hit) { w_begin = 8 * g + ((__ffsll((long long)hit) - 1) >> 3); break; }
-      }
-    } else {
-      for (int w = 0; w < W; ++w)
-        if (reachable[base + w] & R2IK_WP_SERIAL) { w_begin = w; break; }
-    }
-    if (w_begin >= W) return;
-  }
-  R2ikTrajState cs = states[t];
-  for (int w = w_begin; w < W; ++w) {
-    const size_t k = base + w;
-    double j[7];
-#pragma unroll
-    for (int q = 0; q < 7; ++q) j[q] = joints[7 * k + q];
-    const uint8_t flag = cont_finish_waypoint(A, par, M, current_joints, t, k, reachable[k], ws[k], cs, j, state);
-#pragma unroll
-    for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
-    reachable[k] = flag;
-  }
-  states[t] = cs;
-}
-
-#include "r2ik_scan_lanes.cuh"
-#include "r2ik_cont_tiles.cuh"
 #include "r2ik_cont_codes.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -1278,9 +1171,9 @@ int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const doubl
 }
 
 int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
-                                   const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
-                                   uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
-                                   void *stream) {
+                                  const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
+                                  uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
+                                  void *stream) {
   if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_phased_f64: null handle or parameters");
   if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: bad T, W or nb_search_points_continuous");
@@ -1289,37 +1182,8 @@ int r2ik_ctl_continuous_phased_f64(r2ik_handle h, const R2ikCtlParams *par, cons
     return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_phased_f64: null argument");
   if (misaligned16(M) || misaligned16(current_pose))
     return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: M and current_pose must be 16-byte aligned");
-  DeviceGuard guard_(h->device);
-  R2IK_CUDA(guard_.err, "cudaSetDevice");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t n_wp = T * (int64_t)W;
-  const unsigned tb = (unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK);
-  k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
-  k_cont_thetas<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st, workspace, reachable);
-  k_cont_raw_joints<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, joints, test_force_serial_mod);
-  const ScanConst K = {kPi, kTwoPi, 2.0 * kTwoPi, 4.0 * kTwoPi, 6.0 * kPi};
-  k_cont_finish_lanes<R2IK_FIN_LANES><<<(unsigned)((T * R2IK_FIN_LANES + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK), R2IK_FIN8_BLOCK, 0, s>>>(
-      K, T, W, current_joints, st, workspace, joints, reachable, state);
-  k_cont_finish_direct<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state,
-                                                    true);
-  R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
-  return 0;
-}
-
-int r2ik_ctl_continuous_codes_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
-                                  const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
-                                  uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
-                                  void *stream) {
-  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_codes_f64: null handle or parameters");
-  if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
-    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_codes_f64: bad T, W or nb_search_points_continuous");
-  if (T == 0 || W == 0) return 0;
-  if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state || !workspace)
-    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_codes_f64: null argument");
-  if (misaligned16(M) || misaligned16(current_pose))
-    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_codes_f64: M and current_pose must be 16-byte aligned");
   const int64_t nblk = (W + R2IK_CODE_STORED - 1) / R2IK_CODE_STORED;
-  if (T * nblk > 0x7fffffffLL) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_codes_f64: T * ceil(W / 127) exceeds the grid limit");
+  if (T * nblk > 0x7fffffffLL) return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_phased_f64: T * ceil(W / 127) exceeds the grid limit");
   DeviceGuard guard_(h->device);
   R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1332,31 +1196,6 @@ int r2ik_ctl_continuous_codes_f64(r2ik_handle h, const R2ikCtlParams *par, const
                                                                           test_force_serial_mod);
   k_cont_finish_codes<<<tb, R2IK_K3_BLOCK, 0, s>>>(h->A, *par, M, T, W, current_joints, st, workspace, codes16, joints, reachable, state);
   k_cont_apply_windings<<<(unsigned)(((n_wp + 7) / 8 + 255) / 256), 256, 0, s>>>(n_wp, codes16, joints);
-  R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
-  return 0;
-}
-
-int r2ik_ctl_continuous_tiled_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
-                                  const double *current_joints, const double *current_pose, R2ikTrajState *st, double *joints,
-                                  uint8_t *reachable, uint8_t *state, double *workspace, int32_t test_force_serial_mod,
-                                  void *stream) {
-  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_tiled_f64: null handle or parameters");
-  if (T < 0 || W < 0 || par->nb_search_points_continuous < 2)
-    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_tiled_f64: bad T, W or nb_search_points_continuous");
-  if (T == 0 || W == 0) return 0;
-  if (!M || !current_joints || !current_pose || !st || !joints || !reachable || !state || !workspace)
-    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_continuous_tiled_f64: null argument");
-  if (misaligned16(M) || misaligned16(current_pose))
-    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_continuous_tiled_f64: M and current_pose must be 16-byte aligned");
-  DeviceGuard guard_(h->device);
-  R2IK_CUDA(guard_.err, "cudaSetDevice");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t n_wp = T * (int64_t)W;
-  k_cont_targets<<<blocks_for(n_wp), R2IK_BLOCK, 0, s>>>(h->A, *par, M, n_wp, workspace, reachable, state);
-  k_cont_thetas<<<(unsigned)((T + R2IK_K3_BLOCK - 1) / R2IK_K3_BLOCK), R2IK_K3_BLOCK, 0, s>>>(h->A, *par, T, W, current_joints, current_pose, st,
-                                                                                               workspace, reachable);
-  k_cont_joints_finish<<<(unsigned)((T + R2IK_TILE_T - 1) / R2IK_TILE_T), R2IK_TILE_BLOCK, 0, s>>>(
-      h->A, *par, M, T, W, current_joints, st, workspace, joints, reachable, state, test_force_serial_mod);
   R2IK_CUDA(cudaGetLastError(), "k_cont_* launch");
   return 0;
 }

@@ -13,7 +13,7 @@ if args and args[0].endswith(".so"):
     _native.use_library(args.pop(0))
 from reachy2_symbolic_ik_b200 import ControlIK, _abi, fk  # noqa: E402
 
-modes = args or ["phased4", "codes", "serial"]
+modes = args or ["codes", "serial"]
 T, W = 65536, 1000
 ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
 dM = fk.sinusoidal_trajectories_device(T, W, "r_arm", seed=4, device=torch.device("cuda"))
@@ -21,7 +21,7 @@ st0 = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE); st0["init"] = 1
 st0 = torch.from_numpy(st0.view(np.uint8).reshape(T, -1)).cuda()
 ref = None
 for mode in modes:
-    phased = {"tiled": "tiled", "phased4": "phased4", "codes": True, "serial": False}[mode]
+    phased = {"codes": True, "serial": False}[mode]
     st = st0.clone()
     out = None
     ts = []

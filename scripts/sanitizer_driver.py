@@ -44,10 +44,10 @@ for arm in ("r_arm", "l_arm"):
     MT = fk.sinusoidal_trajectories(77, 53, arm, seed=5)[0].copy()
     MT[3, 13:, :3, :3] = MT[3, 13:, :3, :3] @ np.diag([-1.0, -1.0, 1.0])     # emergency latch
     MT[5, 7, :3, :3] = np.diag([-1.0, 1.0, 1.0])                             # invalid rotation
-    for phased in (False, True, "phased4", "tiled"):
+    for phased in (False, True):
         ctl.symbolic_inverse_kinematics_batch(arm, MT, "continuous", phased=phased)
         ctl.symbolic_inverse_kinematics_batch(arm, MT, "continuous", phased=phased, _test_force_serial_mod=7) if phased else None
-    ran.append("k_ctl_continuous, k_cont_targets / thetas / raw_joints_codes / finish_codes / apply_windings, raw_joints / finish_lanes / finish_direct, k_cont_joints_finish")
+    ran.append("k_ctl_continuous, k_cont_targets / thetas / raw_joints_codes / finish_codes / apply_windings")
     ctl.symbolic_inverse_kinematics_batch_host(arm, torch.from_numpy(MT), "continuous", chunk=16)
     fk.forward_kinematics_device(torch.zeros((333, 7), dtype=torch.float64, device="cuda"), arm); ran.append("k_fk")
 torch.cuda.synchronize()

@@ -1,7 +1,7 @@
 """Randomised soak of ControlIK's per-call parameters against the unmodified reference (build container only: imports
 /root/reference/src): discrete mode with random K / preferred_theta / constrained_mode / DVT, continuous mode with random
 d_theta_max / preferred_theta / constrained_mode / DVT incl. excursions out of the workspace.  Checked: the CPU oracle,
-the kernel source compiled for the host (serial forms) and the lane-parallel finish kernel under the warp emulation.
+the kernel source compiled for the host (the serial recursion and the phased form with its finish pass on winding codes).
 
     PYTHONDONTWRITEBYTECODE=1 python scripts/soak_control_params.py [seed] [trials]
 """
@@ -97,7 +97,7 @@ for trial in range(trials):
     cfg, par = T.cfg_for(arm, params, off), T.ctl_params(O, arm, **kw)
     runs = {"oracle": O.ctl_continuous_batch(ocfg, O.ControlParams(arm=arm, **kw), Ms),
             "hostsim serial": T.hs_continuous(hs, O, cfg, par, arm, Ms),
-            "hostsim lanes": T.hs_continuous(hs, O, cfg, par, arm, Ms, lanes=4)}
+            "hostsim phased": T.hs_continuous(hs, O, cfg, par, arm, Ms, phased=True)}
     ok = True
     for who, (jj, rr, ss, stt) in runs.items():
         for t in range(Tn):

@@ -1,6 +1,6 @@
 """Large-sample soak of the kernel SOURCE compiled for the host (tests/hostsim) against the CPU oracle -- no reference and no
 GPU needed.  K1 FP64 and FP32 on 1 M FK + 1 M task-space poses per arm, K2 on 500 k poses per arm (K = 360 and low_elbow),
-K3 (serial, phased, lane-parallel under the warp emulation) on 3 000 trajectories x 200 waypoints per arm with excursions
+K3 (serial, and phased with its finish pass on winding codes) on 3 000 trajectories x 200 waypoints per arm with excursions
 and orientation flips.  The committed tests run thousands of poses; this runs millions.
 
     python scripts/soak_host_kernels.py [seed]
@@ -95,7 +95,7 @@ for arm in ("r_arm", "l_arm"):
             M[t, int(rng.integers(5, W - 5)):, :3, :3] = M[t, -1, :3, :3] @ np.diag([-1.0, -1.0, 1.0])   # jump: emergency latch
     wj, wr, ws, wst = O.ctl_continuous_batch(ocfg, O.ControlParams(arm=arm), M)
     par = T.ctl_params(O, arm)
-    for name, kw, sl in (("serial", {}, slice(None)), ("phased", dict(phased=True), slice(None)), ("lanes4", dict(lanes=4), slice(0, 256))):
+    for name, kw, sl in (("serial", {}, slice(None)), ("phased", dict(phased=True), slice(None))):
         j, r, s, st = T.hs_continuous(hs, O, cfg, par, arm, M[sl], **kw)
         ej = np.abs(j - wj[sl]).max(axis=2)
         straight = np.abs(wj[sl][..., 3]) < 1e-3          # kinematic singularity: counted, not compared

@@ -24,71 +24,6 @@ static bool load_pose(int kind, const double *p, bool snap, double pos[3], doubl
   return rotation_from_mat4(p, snap, R);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// lanesim: csrc/r2ik_scan_lanes.cuh (k_cont_finish_lanes<G>) compiled for the host.  One host thread per CUDA thread of a
-// block; threadIdx / blockIdx / blockDim are thread-local, __ballot_sync / __all_sync meet on a barrier of the 32 threads
-// of a warp.  The kernel has no early exit, so every lane reaches every vote.
-// ---------------------------------------------------------------------------------------------------------------------
-#include <pthread.h>
-#include <thread>
-#include <vector>
-
-namespace lanesim {
-struct Dim3 { unsigned x = 0, y = 0, z = 0; };
-struct Warp { pthread_barrier_t bar; unsigned pred[32]; };
-static thread_local Dim3 threadIdx, blockIdx, blockDim;
-static thread_local Warp *warp = nullptr;
-
-static unsigned __ballot_sync(unsigned mask, bool p) {
-  warp->pred[threadIdx.x & 31] = p ? 1u : 0u;
-  pthread_barrier_wait(&warp->bar);
-  unsigned r = 0;
-  for (int i = 0; i < 32; ++i) r |= warp->pred[i] << i;
-  pthread_barrier_wait(&warp->bar);          // nobody overwrites pred[] before everybody has read it
-  return r & mask;
-}
-static bool __all_sync(unsigned mask, bool p) { return (__ballot_sync(mask, p) & mask) == mask; }
-
-#define __global__
-#define __device__
-#define __forceinline__ inline
-#define __grid_constant__
-#define __launch_bounds__(...)
-#include "../../reachy2_symbolic_ik_b200/csrc/r2ik_scan_lanes.cuh"
-#undef __global__
-#undef __device__
-#undef __forceinline__
-#undef __grid_constant__
-#undef __launch_bounds__
-
-template <int G>
-static void launch(int64_t T, int W, const double *cur_joints, R2ikTrajState *st, const double *ws, double *joints,
-                   uint8_t *reach, uint8_t *state) {
-  const ScanConst K = {kPi, kTwoPi, 2.0 * kTwoPi, 4.0 * kTwoPi, 6.0 * kPi};      // as r2ik_ctl_continuous_phased_f64 builds it
-  const unsigned blocks = (unsigned)((T * G + R2IK_FIN8_BLOCK - 1) / R2IK_FIN8_BLOCK);
-  for (unsigned b = 0; b < blocks; ++b) {
-    std::vector<Warp> warps(R2IK_FIN8_BLOCK / 32);
-    for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < R2IK_FIN8_BLOCK; ++t)
-      th.emplace_back([&, t] {
-        threadIdx.x = t; blockIdx.x = b; blockDim.x = R2IK_FIN8_BLOCK;
-        warp = &warps[t / 32];
-        k_cont_finish_lanes<G>(K, T, W, cur_joints, st, ws, joints, reach, state);
-      });
-    for (auto &x : th) x.join();
-    for (auto &w : warps) pthread_barrier_destroy(&w.bar);
-  }
-}
-
-static void run_finish_lanes(int lanes, int64_t T, int W, const double *cur_joints, R2ikTrajState *st, const double *ws,
-                             double *joints, uint8_t *reach, uint8_t *state) {
-  if (lanes == 2) launch<2>(T, W, cur_joints, st, ws, joints, reach, state);
-  else if (lanes == 8) launch<8>(T, W, cur_joints, st, ws, joints, reach, state);
-  else launch<4>(T, W, cur_joints, st, ws, joints, reach, state);
-}
-}  // namespace lanesim
-
 extern "C" {
 
 // r2ik_math.cuh: the straight-line atan2 (host build: '/' instead of the MUFU seed + Newton).
@@ -218,125 +153,10 @@ void hs_ctl_continuous_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par,
     }
 }
 
-// Mirrors the four phased kernels of r2ik_kernels.cu (k_cont_targets / k_cont_thetas / k_cont_raw_joints /
-// k_cont_finish) statement by statement, phase after phase over the whole batch.
-// The phased K3 on the host.  Phases 1-3 (k_cont_targets, k_cont_thetas, k_cont_raw_joints) are loops over the same
-// device functions; force_serial_mod mirrors the library's R2IK_DEBUG_FORCE_SERIAL test hook.
-static void phased_front(const ArmConst &A, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
-                         const double *cur_joints, const double *cur_pose, const R2ikTrajState *st, double *joints,
-                         uint8_t *reach, uint8_t *state, double *ws, int force_serial_mod) {
-  const int64_t n_wp = T * W;
-  for (int64_t k = 0; k < n_wp; ++k) {                       // k_cont_targets
-    Solve S; double pos[3], goal; int sto;
-    int c = cont_target(A, *par, M + 16 * k, S, pos, goal, sto);
-    ws[k] = goal; reach[k] = (uint8_t)c; state[k] = (uint8_t)sto;
-  }
-  for (int64_t t = 0; t < T; ++t) {                          // k_cont_thetas
-    if (st[t].emergency_stop) continue;
-    double theta = st[t].previous_theta;
-    bool has = st[t].has_previous_sol != 0;
-    for (int32_t w = 0; w < W; ++w) {
-      size_t k = (size_t)t * W + w;
-      int c = reach[k];
-      if (c == R2IK_WP_INVALID) continue;
-      if (!has) { theta = cont_initial_theta(A, *par, cur_joints + 7 * t, cur_pose + 16 * t); has = true; }
-      theta = cont_next_theta(*par, c, ws[k], theta);
-      ws[k] = theta;
-    }
-  }
-  for (int64_t k = 0; k < n_wp; ++k) {                       // k_cont_raw_joints
-    int c = reach[k];
-    double j[7];
-    bool serial = false;
-    if (c == R2IK_WP_INVALID) { for (int q = 0; q < 7; ++q) j[q] = NAN; }
-    else {
-      const double *m = M + 16 * k;
-      Solve S; double pos[3] = {m[3], m[7], m[11]};
-      rotation_from_mat4(m, true, S.R);
-      if (c == R2IK_WP_UNREACHABLE) is_reachable_R<true>(A, pos, S); else is_reachable_R<false>(A, pos, S);
-      double sn, cs_, E[3];
-      sincos_any(ws[k], sn, cs_);
-      serial = !get_joints_impl<false>(A, S, cs_, sn, 0.0, 0.0, j, E);
-      if (force_serial_mod > 0 && k % force_serial_mod == 0) serial = true;
-      if (!serial) limit_orbita3d_wrist(j, par->orbita3d_max_angle);
-    }
-    if (serial) { reach[k] = (uint8_t)(c | R2IK_WP_SERIAL); continue; }
-    for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
-  }
-}
-
-// k_cont_finish_direct: one trajectory after the other; fixup = resume at the first waypoint that still carries
-// R2IK_WP_SERIAL, from the controller state the lane scan stored.
-static void finish_direct(const ArmConst &A, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
-                          const double *cur_joints, R2ikTrajState *st, const double *ws, double *joints, uint8_t *reach,
-                          uint8_t *state, bool fixup) {
-  for (int64_t t = 0; t < T; ++t) {
-    int32_t w_begin = 0;
-    if (fixup) {
-      w_begin = W;
-      for (int32_t w = 0; w < W; ++w)
-        if (reach[(size_t)t * W + w] & R2IK_WP_SERIAL) { w_begin = w; break; }
-      if (w_begin >= W) continue;
-    }
-    R2ikTrajState cs = st[t];
-    for (int32_t w = w_begin; w < W; ++w) {
-      size_t k = (size_t)t * W + w;
-      double j[7];
-      if (cs.emergency_stop) {
-        for (int q = 0; q < 7; ++q) joints[7 * k + q] = cs.previous_sol[q];
-        reach[k] = 0; state[k] = R2IK_STATE_EMERGENCY;
-        continue;
-      }
-      int c = reach[k], kind = c & 0x7f;
-      if (kind == R2IK_WP_INVALID) { reach[k] = 0; continue; }
-      if (!cs.has_previous_sol) {
-        for (int q = 0; q < 7; ++q) cs.previous_sol[q] = cur_joints[7 * t + q];
-        cs.has_previous_sol = 1; cs.init = 1;
-      }
-      cs.previous_theta = ws[k];
-      if (c & R2IK_WP_SERIAL) {
-        const double *m = M + 16 * k;
-        Solve S; double pos[3] = {m[3], m[7], m[11]};
-        rotation_from_mat4(m, true, S.R);
-        if (kind != R2IK_WP_UNREACHABLE) is_reachable_R<false>(A, pos, S);
-        cont_raw_joints(A, *par, kind, pos, S, cs.previous_theta, cs.previous_sol[0], cs.previous_sol[2], j);
-      } else {
-        for (int q = 0; q < 7; ++q) j[q] = joints[7 * k + q];
-      }
-      cont_finish(cs, j);
-      for (int q = 0; q < 7; ++q) joints[7 * k + q] = j[q];
-      reach[k] = kind == R2IK_WP_TARGET ? 1 : 0;
-    }
-    st[t] = cs;
-  }
-}
-
-void hs_ctl_continuous_phased_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
-                                    const double *cur_joints, const double *cur_pose, R2ikTrajState *st, double *joints,
-                                    uint8_t *reach, uint8_t *state, double *ws) {
-  ArmConst A; R2ikArmConstants pub;
-  derive_constants(*cfg, A, pub);
-  phased_front(A, par, M, T, W, cur_joints, cur_pose, st, joints, reach, state, ws, 0);
-  finish_direct(A, par, M, T, W, cur_joints, st, ws, joints, reach, state, false);
-}
-
-// The phased K3 as the library launches it: phases 1-3, then the LANE-PARALLEL finish scan -- the kernel body of
-// csrc/r2ik_scan_lanes.cuh itself, run by one host thread per CUDA thread with the warp votes emulated (lanesim below)
-// -- then the fixup pass for the trajectories that scan left at a waypoint needing the serial get_joints.
-void hs_ctl_continuous_phased_lanes_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T,
-                                          int32_t W, const double *cur_joints, const double *cur_pose, R2ikTrajState *st,
-                                          double *joints, uint8_t *reach, uint8_t *state, double *ws, int lanes,
-                                          int force_serial_mod) {
-  ArmConst A; R2ikArmConstants pub;
-  derive_constants(*cfg, A, pub);
-  phased_front(A, par, M, T, W, cur_joints, cur_pose, st, joints, reach, state, ws, force_serial_mod);
-  lanesim::run_finish_lanes(lanes, T, W, cur_joints, st, ws, joints, reach, state);
-  finish_direct(A, par, M, T, W, cur_joints, st, ws, joints, reach, state, true);
-}
-
-// K3 with the finish pass on winding codes (csrc/r2ik_cont_codes.cuh): phases 1-2 as above, then k_cont_raw_joints_codes
+// The phased K3 on the host, phase after phase over the whole batch with the device functions the kernels call:
+// k_cont_targets, k_cont_thetas, then k_cont_raw_joints_codes
 // (raw joints + the 16-bit code of every waypoint against its predecessor; the first waypoint of a trajectory is irregular) and k_cont_finish_codes (cont_finish_codes_trajectory, the same function the kernel calls).
-void hs_ctl_continuous_codes_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
+void hs_ctl_continuous_phased_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,
                                    const double *cur_joints, const double *cur_pose, R2ikTrajState *st, double *joints,
                                    uint8_t *reach, uint8_t *state, double *ws, uint16_t *codes, int force_serial_mod) {   // codes: in / out
   ArmConst A; R2ikArmConstants pub;

@@ -271,8 +271,6 @@ def test_continuous_phased_equals_serial_kernel(controls, arm, W):
         np.testing.assert_allclose(p[3]["previous_sol"], q[3]["previous_sol"], rtol=0, atol=1e-12)
 
     same(a, b)
-    for form in ("phased4", "tiled"):      # the earlier forms of the phased pipeline stay in the library as cross-checks
-        same(ctl.symbolic_inverse_kinematics_batch(arm, M, "continuous", phased=form), b)
     assert a[3]["emergency_stop"][3] == 1 and (a[2][3, -10:] == 8).all()
     # resume from the returned states
     a2 = ctl.symbolic_inverse_kinematics_batch(arm, M[:, ::-1].copy(), "continuous", states=a[3], phased=True)

@@ -268,19 +268,30 @@ def test_ctl_continuous(hs, oracle, arm, variant):
         rep.check()
     np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
     np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
-    # the phased form (per-waypoint phases + per-trajectory scans) is the same arithmetic regrouped: bit-identical
+    # the phased form (per-waypoint phases + per-trajectory scans on winding codes)
     st2 = np.zeros(T, dtype=_abi.TRAJ_STATE_DTYPE)
     st2["init"] = 1
     j2 = np.empty((T, W, 7)); r2 = np.zeros((T, W), np.uint8); s2 = np.zeros((T, W), np.uint8); ws = np.empty((T, W))
+    cd = np.zeros((T, W), np.uint16)
     hs.hs_ctl_continuous_phased_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
-                                      st2.ctypes.data_as(C.c_void_p), dp(j2), u8(r2), u8(s2), dp(ws))
-    np.testing.assert_array_equal(j2, joints)
-    np.testing.assert_array_equal(r2, reach)
-    np.testing.assert_array_equal(s2, state)
-    assert st2.tobytes() == st.tobytes()
+                                      st2.ctypes.data_as(C.c_void_p), dp(j2), u8(r2), u8(s2), dp(ws), cd.ctypes.data_as(C.c_void_p), C.c_int(0))
+    assert_phased_equals_serial((j2, r2, s2, st2), (joints, reach, state, st), f"{arm} {variant}")
 
 
-def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, lanes=0, force_serial=0, codes=False):
+def assert_phased_equals_serial(phased, serial, what=""):
+    """The phased form against the serial recursion: flags, states and the integer controller state identical, joints /
+    previous_sol equal to rounding (an ordinary waypoint's joints are its raw joints plus whole turns in the phased form,
+    prev + angle_diff(j, prev) in the serial one), previous_theta identical."""
+    np.testing.assert_allclose(phased[0], serial[0], rtol=0, atol=1e-12, err_msg=f"{what} joints")
+    np.testing.assert_array_equal(phased[1], serial[1], err_msg=f"{what} flags")
+    np.testing.assert_array_equal(phased[2], serial[2], err_msg=f"{what} states")
+    for f in ("has_previous_sol", "init", "emergency_stop", "emergency_bits"):
+        np.testing.assert_array_equal(phased[3][f], serial[3][f], err_msg=f"{what} controller {f}")
+    np.testing.assert_allclose(phased[3]["previous_sol"], serial[3]["previous_sol"], rtol=0, atol=1e-12, err_msg=f"{what} previous_sol")
+    np.testing.assert_array_equal(phased[3]["previous_theta"], serial[3]["previous_theta"], err_msg=f"{what} previous_theta")
+
+
+def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, force_serial=0):
     M = np.ascontiguousarray(M, dtype=np.float64)
     T, W = M.shape[:2]
     cj = np.empty((T, 7)); cp = np.empty((T, 4, 4))
@@ -291,20 +302,11 @@ def hs_continuous(hs, oracle, cfg, par, arm, M, states=None, phased=False, lanes
         states["init"] = 1
     st = np.ascontiguousarray(states).copy()
     joints = np.empty((T, W, 7)); reach = np.zeros((T, W), np.uint8); state = np.zeros((T, W), np.uint8)
-    if codes:   # phases 1-2, the joints kernel with winding codes, the scan on codes (csrc/r2ik_cont_codes.cuh)
+    if phased:   # phases 1-2, the joints kernel with winding codes, the scan on codes (csrc/r2ik_cont_codes.cuh)
         ws = np.empty((T, W)); cd = np.zeros((T, W), np.uint16)
-        hs.hs_ctl_continuous_codes_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
-                                         st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws),
-                                         cd.ctypes.data_as(C.c_void_p), C.c_int(force_serial))
-    elif lanes:   # phases 1-3, the lane-parallel finish kernel body under the warp emulation, the fixup pass
-        ws = np.empty((T, W))
-        hs.hs_ctl_continuous_phased_lanes_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
-                                                st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws),
-                                                C.c_int(lanes), C.c_int(force_serial))
-    elif phased:
-        ws = np.empty((T, W))
         hs.hs_ctl_continuous_phased_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
-                                          st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws))
+                                          st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state), dp(ws),
+                                          cd.ctypes.data_as(C.c_void_p), C.c_int(force_serial))
     else:
         hs.hs_ctl_continuous_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(T), C.c_int32(W), dp(cj), dp(cp),
                                    st.ctypes.data_as(C.c_void_p), dp(joints), u8(reach), u8(state))
@@ -330,11 +332,7 @@ def test_ctl_continuous_overrides(hs, oracle, arm, variant):
         rep.check()
     np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g[pre + "emergency"])
     np.testing.assert_allclose(st["previous_theta"], g[pre + "final_theta"], atol=1e-9)
-    j2, r2, s2, st2 = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
-    np.testing.assert_array_equal(j2, joints)
-    np.testing.assert_array_equal(r2, reach)
-    np.testing.assert_array_equal(s2, state)
-    assert st2.tobytes() == st.tobytes()
+    assert_phased_equals_serial(hs_continuous(hs, oracle, cfg, par, arm, M, phased=True), (joints, reach, state, st))
 
 
 @pytest.mark.parametrize("arm", ARMS)
@@ -405,49 +403,13 @@ def test_ctl_continuous_multiturn(hs, oracle, arm):
         rep.check()
     np.testing.assert_array_equal(st["emergency_stop"].astype(bool), g["mt_emergency"])
     np.testing.assert_allclose(st["previous_theta"], g["mt_final_theta"], atol=1e-9)
-    j2, r2, s2, st2 = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
-    np.testing.assert_array_equal(j2, joints)
-    np.testing.assert_array_equal(r2, reach)
-    np.testing.assert_array_equal(s2, state)
-    assert st2.tobytes() == st.tobytes()
-
-
-@pytest.mark.parametrize("arm", ARMS)
-@pytest.mark.parametrize("lanes", [2, 4, 8])
-def test_ctl_continuous_lane_parallel_finish_kernel(hs, oracle, arm, lanes):
-    """k_cont_finish_lanes<G> -- the kernel body of csrc/r2ik_scan_lanes.cuh itself, run on the host by one thread per CUDA
-    thread with emulated warp votes -- against the serial finish scan: identical joints, flags, states and controller
-    states on the golden trajectories (continuity latch, unreachable stretches), on the multi-turn ramps (the +-6 pi clamp
-    and its emergency bits), when resumed from returned states, and when the test hook sends every m-th waypoint down the
-    serial get_joints route (stop + fixup pass)."""
-    cfg = cfg_for(arm, urdf_params(), -1.01)
-    par = ctl_params(oracle, arm)
-    g, go = load(f"ctl_continuous_{arm}.npz"), load(f"ctl_overrides_{arm}.npz")
-    hit_clamp = False
-    for name, M in (("golden", g["M"]), ("multi-turn", go["mt_M"]), ("unfreeze", go["unf_M"][None])):
-        M = np.ascontiguousarray(M)
-        want = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
-        for force in (0, 1, 7, 97):
-            got = hs_continuous(hs, oracle, cfg, par, arm, M, lanes=lanes, force_serial=force)
-            np.testing.assert_array_equal(got[0], want[0], err_msg=f"{name} joints, force={force}")
-            np.testing.assert_array_equal(got[1], want[1], err_msg=f"{name} flags, force={force}")
-            np.testing.assert_array_equal(got[2], want[2], err_msg=f"{name} states, force={force}")
-            assert got[3].tobytes() == want[3].tobytes(), f"{name} controller states, force={force}"
-        hit_clamp = hit_clamp or bool((want[3]["emergency_bits"] & 7).any())
-        # resume the reversed trajectories from the returned states (latched and unlatched alike)
-        Mr = np.ascontiguousarray(M[:, ::-1])
-        want2 = hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], phased=True)
-        got2 = hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], lanes=lanes)
-        np.testing.assert_array_equal(got2[0], want2[0])
-        np.testing.assert_array_equal(got2[2], want2[2])
-        assert got2[3].tobytes() == want2[3].tobytes()
-    assert hit_clamp, "no trajectory reached the +-6 pi clamp"
+    assert_phased_equals_serial(hs_continuous(hs, oracle, cfg, par, arm, M, phased=True), (joints, reach, state, st))
 
 
 @pytest.mark.parametrize("arm", ARMS)
 def test_ctl_continuous_winding_codes(hs, oracle, arm):
-    """The finish pass on winding codes (csrc/r2ik_cont_codes.cuh: cont_wind_code + cont_finish_codes_trajectory, the
-    functions the kernels call) against the serial finish scan: flags, states and controller flags identical, joints and
+    """The phased K3 with its finish pass on winding codes (csrc/r2ik_cont_codes.cuh: cont_wind_code +
+    cont_finish_codes_trajectory, the functions the kernels call) against the serial recursion: flags, states and controller flags identical, joints and
     previous_sol equal to rounding (nj = j + 2 pi k instead of prev + angle_diff(j, prev)) -- on the golden trajectories
     (continuity latch, unreachable stretches), the multi-turn ramps (windings past +-pi, the +-6 pi clamp and its
     emergency bits), trajectories longer than a 128-waypoint block, resumed states, invalid rotations, and with the test
@@ -463,25 +425,18 @@ def test_ctl_continuous_winding_codes(hs, oracle, arm):
     long[3, 127, :3, :3] = np.diag([-1.0, 1.0, 1.0])                                # ... and right before one
     hit_clamp = wound = False
 
-    def same(got, want, what):
-        np.testing.assert_allclose(got[0], want[0], rtol=0, atol=1e-12, err_msg=f"{what} joints")
-        np.testing.assert_array_equal(got[1], want[1], err_msg=f"{what} flags")
-        np.testing.assert_array_equal(got[2], want[2], err_msg=f"{what} states")
-        for f in ("has_previous_sol", "init", "emergency_stop", "emergency_bits"):
-            np.testing.assert_array_equal(got[3][f], want[3][f], err_msg=f"{what} controller {f}")
-        np.testing.assert_allclose(got[3]["previous_sol"], want[3]["previous_sol"], rtol=0, atol=1e-12, err_msg=f"{what} previous_sol")
-        np.testing.assert_array_equal(got[3]["previous_theta"], want[3]["previous_theta"], err_msg=f"{what} previous_theta")
+    same = assert_phased_equals_serial
 
     for name, M in (("golden", g["M"]), ("multi-turn", go["mt_M"]), ("unfreeze", go["unf_M"][None]), ("long", long)):
         M = np.ascontiguousarray(M)
-        want = hs_continuous(hs, oracle, cfg, par, arm, M, phased=True)
+        want = hs_continuous(hs, oracle, cfg, par, arm, M)
         for force in (0, 1, 7, 97):
-            same(hs_continuous(hs, oracle, cfg, par, arm, M, codes=True, force_serial=force), want, f"{name} force={force}")
+            same(hs_continuous(hs, oracle, cfg, par, arm, M, phased=True, force_serial=force), want, f"{name} force={force}")
         hit_clamp = hit_clamp or bool((want[3]["emergency_bits"] & 7).any())
         wound = wound or bool((np.abs(np.nan_to_num(want[0])) > np.pi + 1e-6).any())
         Mr = np.ascontiguousarray(M[:, ::-1])       # resume the reversed trajectories from the returned states
-        same(hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], codes=True),
-             hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], phased=True), f"{name} resumed")
+        same(hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3], phased=True),
+             hs_continuous(hs, oracle, cfg, par, arm, Mr, states=want[3]), f"{name} resumed")
     assert hit_clamp and wound, "no trajectory wound past pi / reached the +-6 pi clamp"
 
 
@@ -783,7 +738,8 @@ def test_reference_example_matrices(hs, oracle, arm):
         args = [C.byref(cfg), C.byref(par), dp(MT), C.c_int64(n), C.c_int32(W), dp(cj), dp(cp), st.ctypes.data_as(C.c_void_p),
                 dp(j), u8(r), u8(s_)]
         if entry.endswith("phased_batch"):
-            ws = np.empty((n, W)); args.append(dp(ws))
+            ws = np.empty((n, W)); cd = np.zeros((n, W), np.uint16)
+            args += [dp(ws), cd.ctypes.data_as(C.c_void_p), C.c_int(0)]
         getattr(hs, entry)(*args)
         assert np.array_equal(s_, g[f"{arm}_con_state"]) and np.array_equal(r.astype(bool), g[f"{arm}_con_reachable"]), entry
         np.testing.assert_allclose(j, g[f"{arm}_con_joints"], atol=1e-9)
