@@ -514,7 +514,7 @@ class Continuous:
     T, W = 65_536, 1_000
     BYTES_IN, BYTES_OUT = 128, 56 + 2
     FLOP_EQ = 2550.0          # is_reachable 900 + 10-sample search 350 + get_joints 900 + safety 300 + continuity 100
-    kernel = "k_ctl_continuous"
+    kernel = "k_cont_targets + k_cont_thetas + k_cont_raw_joints_codes + k_cont_finish_codes + k_cont_apply_windings"
 
     def config(self, world):
         return {"workload": f"configs[3]: ControlIK continuous, {self.T} trajectories x {self.W} waypoints (joint-space sinusoids "
@@ -556,7 +556,8 @@ class Continuous:
         self.ctl.symbolic_inverse_kinematics_batch_host("r_arm", self.host_in, "continuous", out=self.e2e_out)
 
     def e2e_check(self, torch):
-        assert np.array_equal(np.asarray(self.e2e_out[0][:16]), self.out[0][:16].cpu().numpy())
+        # the host pipeline cuts the waypoint axis: joints agree with the one-shot call to rounding (tests/test_gpu_control.py)
+        assert np.allclose(np.asarray(self.e2e_out[0][:16]), self.out[0][:16].cpu().numpy(), rtol=0, atol=1e-12, equal_nan=True)
 
     def _oracle(self, M):
         from oracle import oracle as O
