@@ -515,6 +515,7 @@ class Continuous:
     BYTES_IN, BYTES_OUT = 128, 56 + 2
     FLOP_EQ = 2550.0          # is_reachable 900 + 10-sample search 350 + get_joints 900 + safety 300 + continuity 100
     kernel = "k_cont_targets + k_cont_thetas + k_cont_raw_joints_codes + k_cont_finish_codes + k_cont_apply_windings"
+    KERNELS_PER_PASS = 5      # the roofline's "launch" is the five-kernel pass (plus torch's 2 MB state reset copy, not counted)
 
     def config(self, world):
         return {"workload": f"configs[3]: ControlIK continuous, {self.T} trajectories x {self.W} waypoints (joint-space sinusoids "
@@ -900,7 +901,7 @@ def run_workload(env: Env, wl, steps: int, warmup: int, headline: bool, cpu_base
     rec = {"value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
            "scaling": getattr(wl, "scaling", "weak"),
            "dtype": getattr(wl, "dtype", "f32" if getattr(wl, "fp32", False) else "f64"), "config": wl.config(world),
-           "gpu_launches": launches, "clocks": clocks.summary()}
+           "gpu_launches": launches * getattr(wl, "KERNELS_PER_PASS", 1), "clocks": clocks.summary()}
     if hasattr(wl, "phase_times"):
         rec.update(wl.phase_times(env, steps))
 
