@@ -422,16 +422,17 @@ class Discrete:
     N = 1_000_000
     K = 360
     BYTES_IN, BYTES_OUT = 128, 56 + 3
-    kernel = "k_ctl_discrete"
+    kernel = "k_disc_consts + k_disc_classify + k_disc_search + k_disc_finish"
+    KERNELS_PER_PASS = 4      # the roofline's "launch" is the four-kernel pass of r2ik_ctl_discrete_compact_f64
 
-    SEARCH_FRACTION = 0.65   # share of the FK-sampled poses whose preferred theta fails and that run the elbow search
+    SEARCH_FRACTION = 0.80   # share of the FK-sampled poses whose preferred theta fails and that run the elbow search
 
     @property
     def FLOP_EQ(self):
-        # solve + joints + safety chain ~2400 flops per pose; the analytic search evaluates 17 candidate samples (sincos 35,
-        # two half-plane tests 8, theta_k 2, wrapped cost 10) plus 4 atan2 + 2 roots to locate them (~200): independent of K;
-        # 65 % of the poses search (measured with the oracle)
-        return 2400.0 + self.SEARCH_FRACTION * (17 * 55.0 + 200.0)
+        # solve + joints + safety chain ~2400 flops per pose; the analytic search evaluates 17 candidate samples (7 sincos of
+        # 35 shared by the neighbours, two half-plane tests 8, theta_k 2, wrapped cost 10) plus 4 atan2 + 2 roots to locate them (~200): independent of K;
+        # 80 % of the poses search (length of the search list, profiles/r2_experiments.md)
+        return 2400.0 + self.SEARCH_FRACTION * (7 * 35.0 + 17 * 20.0 + 200.0)
 
     def config(self, world):
         return {"workload": f"configs[2]: ControlIK discrete, 1M FK-sampled r_arm poses x {self.K} elbow-theta samples, in-kernel "

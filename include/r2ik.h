@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define R2IK_ABI_VERSION 3 /* 3: + symik_scalar, stream_synchronize, host pipelines, ctl_ctor_theta, reach_map_range_u16; no_limits / projected in elbow_positions, prev_joints in
+#define R2IK_ABI_VERSION 4 /* 4: + ctl_discrete_compact; 3: + symik_scalar, stream_synchronize, host pipelines, ctl_ctor_theta, reach_map_range_u16; no_limits / projected in elbow_positions, prev_joints in
                               no_limits, nullable `reachable`, test hook of the phased continuous entry as a parameter */
 
 /* argument errors */
@@ -268,6 +268,17 @@ int r2ik_ctl_discrete_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, co
 int r2ik_ctl_discrete_scan_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t n,
                                const double *prev_joints, const double *current_joints, double *joints,
                                uint8_t *reachable, uint8_t *state, uint8_t *emergency, void *stream);
+
+/* r2ik_ctl_discrete_f64 for large batches, same results: the three sections of the call (is_reachable + preferred-theta
+ * shortcut for every pose / elbow search for the poses the shortcut fails on / get_joints + safety chain for the poses
+ * with a valid theta) run as separate kernels over compacted index lists, so no warp carries idle lanes through a
+ * section its poses do not need.  workspace: r2ik_ctl_discrete_workspace_bytes(n) bytes of device memory, 16-byte
+ * aligned, owned by the call until it has completed on `stream`; n < 2^31. */
+int64_t r2ik_ctl_discrete_workspace_bytes(int64_t n);
+int r2ik_ctl_discrete_compact_f64(r2ik_handle h, const R2ikCtlParams *par /* host */, const double *M, int64_t n,
+                                  const double *prev_joints, const double *current_joints, double *joints,
+                                  uint8_t *reachable, uint8_t *state, uint8_t *emergency, void *workspace,
+                                  int64_t workspace_bytes, void *stream);
 
 /* ControlIK continuous mode: T trajectories x W waypoints, M is T x W x 16.  current_joints
  * (T x 7) and current_pose (T x 16) feed the (re)initialisation; st: T states, in/out. */

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 POSE_EULER6 = 0
 POSE_MAT4 = 1

@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libr2ik.so")
 SOURCES = ["r2ik_kernels.cu", "r2ik_pipeline.cu"]
-HEADERS = ["r2ik_math.cuh", "r2ik_device.cuh", "r2ik_device_f32.cuh", "r2ik_control.cuh", "r2ik_cont_codes.cuh", "r2ik_host.h", os.path.join("..", "..", "include", "r2ik.h")]
+HEADERS = ["r2ik_math.cuh", "r2ik_device.cuh", "r2ik_device_f32.cuh", "r2ik_control.cuh", "r2ik_cont_codes.cuh", "r2ik_discrete_compact.cuh", "r2ik_host.h", os.path.join("..", "..", "include", "r2ik.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -176,7 +176,8 @@ class ControlIK:
                                           constrained_mode: str = "unconstrained", current_pose=None,
                                           d_theta_max: float = 0.01, preferred_theta: float = -4 * np.pi / 6,
                                           previous_joints=None, states=None, out=None, phased: bool = True,
-                                          exhaustive: bool = False, devices=None, _test_force_serial_mod: int = 0):
+                                          exhaustive: bool = False, devices=None, compact=None,
+                                          _test_force_serial_mod: int = 0):
         """Batched ``symbolic_inverse_kinematics``.
 
         discrete:   M (N,4,4) -> joints (N,7), reachable (N,), state (N,) uint8, emergency bits (N,).
@@ -190,6 +191,9 @@ class ControlIK:
         ``exhaustive`` (discrete): False = the elbow search finds the arg-min over the nb_search_points samples from
         the crossings of the two elbow tests (cost independent of K); True = every sample is visited by the
         warp-cooperative scan kernel.  Same outputs.
+        ``compact`` (discrete): True = the three dense passes over compacted index lists
+        (``r2ik_ctl_discrete_compact_f64``; 80 bytes of device scratch per pose, allocated here), False = the single
+        kernel, None = by batch size (``COMPACT_MIN_POSES``).  Same outputs.
         ``phased`` (continuous): True = per-waypoint kernels + per-trajectory scans, the finish pass on winding codes
         (``r2ik_ctl_continuous_phased_f64``; needs 10 bytes of device scratch per waypoint, allocated here); False = the single
         one-thread-per-trajectory kernel (the cross-check).  Same flags / states; joints equal to rounding.
@@ -219,10 +223,21 @@ class ControlIK:
                     reach = torch.empty(n, dtype=torch.uint8, device=self._device)
                     state = torch.empty(n, dtype=torch.uint8, device=self._device)
                     emg = torch.empty(n, dtype=torch.uint8, device=self._device)
-                entry = solver._handle.lib.r2ik_ctl_discrete_scan_f64 if exhaustive else solver._handle.lib.r2ik_ctl_discrete_f64
-                rc = entry(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(n),
-                           _ptr(prev), _ptr(cur), _ptr(joints), _ptr(reach), _ptr(state), _ptr(emg), stream)
-                _native.check(rc, "r2ik_ctl_discrete_f64")
+                lib = solver._handle.lib
+                if compact is None:
+                    compact = n >= self.COMPACT_MIN_POSES
+                if compact and not exhaustive and n > 0:
+                    nbytes = lib.r2ik_ctl_discrete_workspace_bytes(C.c_int64(n))
+                    ws = self._scratch((nbytes + 7) // 8, stream.value)
+                    rc = lib.r2ik_ctl_discrete_compact_f64(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(n), _ptr(prev),
+                                                           _ptr(cur), _ptr(joints), _ptr(reach), _ptr(state), _ptr(emg),
+                                                           _ptr(ws), C.c_int64(ws.numel() * 8), stream)
+                    _native.check(rc, "r2ik_ctl_discrete_compact_f64")
+                else:
+                    entry = lib.r2ik_ctl_discrete_scan_f64 if exhaustive else lib.r2ik_ctl_discrete_f64
+                    rc = entry(solver._handle.h, C.byref(par), _ptr(Md), C.c_int64(n),
+                               _ptr(prev), _ptr(cur), _ptr(joints), _ptr(reach), _ptr(state), _ptr(emg), stream)
+                    _native.check(rc, "r2ik_ctl_discrete_f64")
                 res = (joints, reach.view(torch.bool), state, emg)
                 return res if was_cuda else tuple(x.cpu().numpy() for x in res)
             if control_type == "continuous":
@@ -264,8 +279,10 @@ class ControlIK:
                 return (*res, st_out)
             raise ValueError(f"Unknown type {control_type}")
 
+    COMPACT_MIN_POSES = 1 << 18      # measured crossover (scripts/experiments/exp_r2_k2.py): 65 536 poses 39 vs 47 us, 262 144 poses 84 vs 79 us, 1M poses 253 vs 203 us
+
     def _scratch(self, n: int, stream_key=0):
-        """Device scratch of n doubles for the phased continuous kernels, one buffer per CUDA stream (launches on one
+        """Device scratch of n doubles for the phased continuous / compacted discrete kernels, one buffer per CUDA stream (launches on one
         stream are ordered; two streams, or two threads on two streams, must not share it), grown on demand."""
         torch = self._torch
         cache = self.__dict__.setdefault("_scratch_bufs", {})

@@ -76,18 +76,15 @@ R2IK_HD void search_strided(const SearchPlan &P, int nb, int k0, int stride, dou
 // The valid samples therefore form a few runs of consecutive indices, and on a run the cheapest sample is
 // either next to the preferred point or at an end of the run -- i.e. next to a crossing of one of the two
 // tests or at an end of the range.  Candidates: the 3 samples around each of the <= 4 crossings, the 3
-// around the preferred point, the first and the last sample; each is evaluated exactly like a visited
-// sample (theta_k from linspace, sincos, the two tests, the wrapped cost) and the minimum is taken in
+// around the preferred point, the first and the last sample; each is evaluated like a visited sample
+// (theta_k from linspace, its cos / sin, the two tests, the wrapped cost) and the minimum is taken in
 // (cost, index) order = the reference's strict-< scan.  17 evaluations instead of K, no cooperation
 // between lanes.  Returns false when an atan2 argument is outside the fast routine's range (the caller
 // scans instead).
-R2IK_HD void search_eval(const SearchPlan &P, int nb, int k, double &best, int &best_k) {
+R2IK_HD void search_eval_cs(const SearchPlan &P, int nb, int k, double c, double s, double &best, int &best_k) {
   if (k < 0 || k >= nb) return;
-  const double th = linspace_value(P.L, k);
-  double s, c;
-  sincos_any(th, s, c);
   if (!elbow_ok_cs(P.T, c, s)) return;
-  const double cost = fabs(angle_diff(th, P.preferred_theta));
+  const double cost = fabs(angle_diff(linspace_value(P.L, k), P.preferred_theta));
   if (cost < best || (cost == best && k < best_k)) { best = cost; best_k = k; }
 }
 R2IK_HD bool search_analytic(const SearchPlan &P, int nb, double &best, int &best_k) {
@@ -117,22 +114,31 @@ R2IK_HD bool search_analytic(const SearchPlan &P, int nb, double &best, int &bes
     cand[2 * t + 1] = cross ? phi - alpha : NAN;
   }
   cand[4] = P.preferred_theta;
-  // One copy of the sample evaluation in the instruction stream, visited 17 times (unrolled it is ~2000
-  // instructions and the kernel no longer fits the instruction cache).
+  // cos / sin of a candidate's two neighbours follow from its own by the fixed rotation of one sample step -- the way
+  // search_strided walks the samples -- so the 17 evaluations take 7 sincos (+ 1 for the step).  One copy of the body
+  // in the instruction stream (unrolled the kernel no longer fits the instruction cache).
+  double sd, cd;
+  sincos_any(P.L.step, sd, cd);
 #pragma unroll 1
-  for (int q = 0; q < 17; ++q) {
+  for (int g = 0; g < 7; ++g) {
     int k;
-    if (q < 15) {
-      const double theta = cand[q / 3];
-      // sample position of the angle congruent to theta in [start, start + 2 pi)
+    if (g < 5) {
+      // sample position of the angle congruent to the candidate in [start, start + 2 pi)
       // (+ 4 pi keeps the argument inside pymod_2pi's exact fast range; the candidate index tolerates the rounding)
-      const double x = pymod_2pi((theta - P.L.start) + 2.0 * kTwoPi) * inv_step;
+      const double x = pymod_2pi((cand[g] - P.L.start) + 2.0 * kTwoPi) * inv_step;
       if (!(x <= (double)nb)) continue;                  // NaN, or beyond the last sample (ranges shorter than 2 pi)
-      k = (int)rint(x) + (q % 3) - 1;
+      k = (int)rint(x);
+      if (k >= nb) k = nb - 1;                           // x rounded up past the last sample: its neighbourhood is the range's end
     } else {
-      k = q == 15 ? 0 : nb - 1;
+      k = g == 5 ? 0 : nb - 1;
     }
-    search_eval(P, nb, k, best, best_k);
+    double s, c;
+    sincos_any(linspace_value(P.L, k), s, c);
+    search_eval_cs(P, nb, k, c, s, best, best_k);
+    if (g < 5) {
+      search_eval_cs(P, nb, k - 1, c * cd + s * sd, s * cd - c * sd, best, best_k);
+      search_eval_cs(P, nb, k + 1, c * cd - s * sd, s * cd + c * sd, best, best_k);
+    }
   }
   return ok;
 }

@@ -218,6 +218,7 @@ k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ 
                   uint8_t *__restrict__ reachable, uint8_t *__restrict__ state, float *__restrict__ interval,
                   float *__restrict__ joints, float *__restrict__ elbow, uint32_t *__restrict__ esc_list,
                   unsigned *__restrict__ n_escalated) {
+  asm volatile("griddepcontrol.launch_dependents;");   // k_symik_escalated_f32 may be scheduled under this kernel's tail
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < n;
   bool esc = false;
@@ -248,6 +249,8 @@ k_symik_escalated_f32(const __grid_constant__ ArmConst A64, const float *__restr
                       const float *__restrict__ prev_joints, uint8_t *__restrict__ reachable, uint8_t *__restrict__ state,
                       float *__restrict__ interval, float *__restrict__ joints, float *__restrict__ elbow,
                       const uint32_t *__restrict__ esc_list, const unsigned *__restrict__ n_escalated) {
+  // launched as a programmatic dependent of k_symik_solve_f32: its blocks may be resident before that kernel has drained
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned count = *n_escalated;
   float prev0 = 0.0f, prev2 = 0.0f;
   if (prev_joints) { prev0 = prev_joints[0]; prev2 = prev_joints[2]; }
@@ -686,6 +689,7 @@ k_cont_thetas(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCt
 }
 
 #include "r2ik_cont_codes.cuh"
+#include "r2ik_discrete_compact.cuh"
 
 // ---------------------------------------------------------------------------------------
 // K4: workspace reachability map.  One thread per voxel.  Voxels outside the reach sphere or behind the torso plane
@@ -1034,12 +1038,22 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
   R2IK_CUDA(cudaMemsetAsync(n_escalated, 0, sizeof(uint32_t), s), "cudaMemsetAsync");
   // second pass: a fixed modest grid striding over the (device-side) count -- a few thousand poses per million
   const unsigned eb = (unsigned)(blocks_for(n) < 592u ? blocks_for(n) : 592u);
+  // the second pass is a programmatic dependent of the first: it is scheduled under the first kernel's tail and waits
+  // (griddepcontrol.wait) for its list
+  cudaLaunchAttribute eattr[1];
+  eattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  eattr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t ecfg = {};
+  ecfg.gridDim = dim3(eb); ecfg.blockDim = dim3(R2IK_BLOCK); ecfg.dynamicSmemBytes = 0; ecfg.stream = s;
+  ecfg.attrs = eattr; ecfg.numAttrs = 1;
+  const uint32_t *esc_c = escalated_idx;
+  const unsigned *nesc_c = n_escalated;
   if (pose_kind == R2IK_POSE_MAT4) {
     k_symik_solve_f32<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, n, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
-    k_symik_escalated_f32<R2IK_POSE_MAT4><<<eb, R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
+    R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_escalated_f32<R2IK_POSE_MAT4>, h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, esc_c, nesc_c), "k_symik_escalated_f32 launch");
   } else {
     k_symik_solve_f32<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, n, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
-    k_symik_escalated_f32<R2IK_POSE_EULER6><<<eb, R2IK_BLOCK, 0, s>>>(h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
+    R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_escalated_f32<R2IK_POSE_EULER6>, h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, esc_c, nesc_c), "k_symik_escalated_f32 launch");
   }
   R2IK_CUDA(cudaGetLastError(), "k_symik_solve_f32 launch");
   return 0;
@@ -1149,6 +1163,52 @@ int r2ik_ctl_discrete_scan_f64(r2ik_handle h, const R2ikCtlParams *par, const do
                                const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
                                uint8_t *emergency, void *stream) {
   return ctl_discrete_launch(true, h, par, M, n, prev_joints, current_joints, joints, reachable, state, emergency, stream);
+}
+
+#ifndef R2IK_K2C_PDL
+#define R2IK_K2C_PDL 1
+#endif
+int64_t r2ik_ctl_discrete_workspace_bytes(int64_t n) { return n < 0 ? -1 : (int64_t)disc_ws_bytes(n); }
+
+int r2ik_ctl_discrete_compact_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t n, const double *prev_joints,
+                                  const double *current_joints, double *joints, uint8_t *reachable, uint8_t *state,
+                                  uint8_t *emergency, void *workspace, int64_t workspace_bytes, void *stream) {
+  if (!h || !par) return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_compact_f64: null handle or parameters");
+  if (n < 0 || n >= ((int64_t)1 << 31) || par->nb_search_points < 2)
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_compact_f64: bad n or nb_search_points");
+  if (n == 0) return 0;
+  if (!M || !prev_joints || !current_joints || !joints || !reachable || !state || !workspace)
+    return fail_arg(R2IK_ERR_NULL, "r2ik_ctl_discrete_compact_f64: null argument");
+  if (misaligned16(M) || misaligned16(workspace))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_compact_f64: M and workspace must be 16-byte aligned");
+  if (workspace_bytes < (int64_t)disc_ws_bytes(n))
+    return fail_arg(R2IK_ERR_ARG, "r2ik_ctl_discrete_compact_f64: workspace smaller than r2ik_ctl_discrete_workspace_bytes(n)");
+  DeviceGuard guard_(h->device);
+  R2IK_CUDA(guard_.err, "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  const DiscWs w = disc_ws_carve(workspace, n);
+  const unsigned lb = blocks_for(n);   // the list passes: sized for n entries, blocks past the device-side counts leave at once
+  // consts is an ordinary launch (it waits for everything before it on the stream); the three passes are programmatic
+  // dependents of their predecessors (r2ik_discrete_compact.cuh)
+  k_disc_consts<<<1, 32, 0, s>>>(*par, prev_joints, current_joints, w.hdr);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = R2IK_K2C_PDL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(lb); cfg.blockDim = dim3(R2IK_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const double *Mc = M, *prevc = prev_joints;
+  const double *planc = w.plan, *thetac = w.finish_theta;
+  const uint32_t *sidxc = w.search_idx, *fidxc = w.finish_idx;
+  const DiscHeader *hdrc = w.hdr;
+  R2IK_CUDA(cudaLaunchKernelEx(&cfg, k_disc_classify, h->A, *par, Mc, n, w.hdr, w.plan, w.finish_theta, w.search_idx, w.finish_idx,
+                               joints, reachable, state, emergency), "k_disc_classify launch");
+  R2IK_CUDA(cudaLaunchKernelEx(&cfg, k_disc_search, *par, w.hdr, planc, w.finish_theta, sidxc, w.finish_idx, joints, reachable, state,
+                               emergency), "k_disc_search launch");
+  R2IK_CUDA(cudaLaunchKernelEx(&cfg, k_disc_finish, h->A, *par, Mc, prevc, hdrc, thetac, fidxc, joints, reachable, state, emergency),
+            "k_disc_finish launch");
+  R2IK_CUDA(cudaGetLastError(), "k_disc_* launch");
+  return 0;
 }
 
 int r2ik_ctl_continuous_f64(r2ik_handle h, const R2ikCtlParams *par, const double *M, int64_t T, int32_t W,

@@ -265,3 +265,65 @@ def test_constructor_previous_theta(is_dvt):
                         urdf_path="../config_files/reachy2.urdf", is_dvt=is_dvt)
         for arm in ARMS:
             assert abs(ctl.previous_theta[arm] - float(g[f"{tag}_v{v}_{arm}"])) < 1e-9, (v, arm)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("n", [1, 33, 5_000, 300_001])
+def test_discrete_compacted_passes_equal_single_kernel(arm, n):
+    """r2ik_ctl_discrete_compact_f64 (classify / search / finish over compacted index lists) against the one-kernel
+    r2ik_ctl_discrete_f64: the same per-pose device functions on the same inputs -> identical bytes, every pose written
+    exactly once (poisoned outputs), invalid rotation blocks and a wound previous solution included."""
+    import torch
+
+    from reachy2_symbolic_ik_b200 import ControlIK, fk
+
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    M = np.concatenate([fk.sample_fk_poses(n - n // 4, arm, seed=77 + n), fk.sample_task_space_poses(n // 4, arm, seed=78 + n)]) if n > 3 \
+        else fk.sample_fk_poses(n, arm, seed=77)
+    rng = np.random.default_rng(n)
+    bad = rng.integers(0, n, size=max(1, n // 50)) if n > 1 else []
+    for b in bad:
+        M[b, :3, :3] = np.diag([1.0, 1.0, -1.0])           # det < 0: no rotation
+    Md = torch.from_numpy(M).cuda()
+    for prev in (None, np.array([0.3, -0.2, 7.0, -1.0, 0.1, 0.2, -6.5])):
+        for K, mode in ((20, "unconstrained"), (360, "unconstrained"), (20, "low_elbow")):
+            ctl.nb_search_points = K
+            outs = {}
+            for compact in (False, True):
+                out = (torch.full((n, 7), 123.0, dtype=torch.float64, device="cuda"), torch.full((n,), 7, dtype=torch.uint8, device="cuda").view(torch.bool),
+                       torch.full((n,), 77, dtype=torch.uint8, device="cuda"), torch.full((n,), 99, dtype=torch.uint8, device="cuda"))
+                res = ctl.symbolic_inverse_kinematics_batch(arm, Md, "discrete", constrained_mode=mode, previous_joints=prev,
+                                                            out=out, compact=compact)
+                outs[compact] = [x.view(torch.uint8).cpu().numpy() if x.dtype == torch.bool else x.cpu().numpy() for x in res]
+            for a, b in zip(outs[False], outs[True]):
+                np.testing.assert_array_equal(a, b)
+            assert not (outs[True][2] == 77).any() and not (outs[True][3] == 99).any()
+            if n > 1000:
+                assert (outs[True][2] == 9).sum() == len(set(bad)) and 0.2 < outs[True][1].mean() < 0.9
+
+
+def test_discrete_compact_entry_argument_checks():
+    import torch
+
+    from reachy2_symbolic_ik_b200 import ControlIK
+
+    ctl = ControlIK(urdf_path="../config_files/reachy2.urdf")
+    solver = ctl.symbolic_ik_solver["r_arm"]
+    lib = solver._handle.lib
+    assert lib.r2ik_ctl_discrete_workspace_bytes(C.c_int64(1000)) == 256 + 80 * 1000
+    assert lib.r2ik_ctl_discrete_workspace_bytes(C.c_int64(-1)) == -1
+    par = ctl._ctl_params("r_arm", "unconstrained", -4 * np.pi / 6, 0.01)
+    n = 64
+    M = torch.eye(4, dtype=torch.float64, device="cuda").repeat(n, 1, 1).reshape(n, 16)
+    j = torch.empty((n, 7), dtype=torch.float64, device="cuda")
+    b = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    prev = torch.zeros(7, dtype=torch.float64, device="cuda")
+    ws = torch.empty(256 + 80 * n, dtype=torch.uint8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    call = lambda wsp, nbytes: lib.r2ik_ctl_discrete_compact_f64(solver._handle.h, C.byref(par), p(M), C.c_int64(n), p(prev), p(prev), p(j),  # noqa: E731
+                                                                 p(b[0]), p(b[1]), p(b[2]), wsp, C.c_int64(nbytes), None)
+    assert call(p(ws), ws.numel() - 1) != 0 and "workspace smaller" in lib.r2ik_last_error().decode()
+    assert call(None, ws.numel()) != 0
+    assert call(C.c_void_p(ws.data_ptr() + 8), ws.numel()) != 0 and "aligned" in lib.r2ik_last_error().decode()
+    assert call(p(ws), ws.numel()) == 0
+    torch.cuda.synchronize()
