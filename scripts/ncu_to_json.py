@@ -36,6 +36,7 @@ def main():
                      "(use for traffic / ratios, not as a timing)", "kernel": kernel}
     additive = {"duration_us_under_ncu", "dram_bytes_read", "dram_bytes_write", "warp_instructions", "thread_dfma", "thread_dmul", "thread_dadd"}
     seen = []
+    parts = []      # sum mode: the per-kernel figures, for the duration-weighted means of the percentages
     for r in rows[2:]:
         name_k = r[hdr.index("Kernel Name")]
         if kernel not in name_k:
@@ -44,6 +45,11 @@ def main():
         if short in seen:
             continue
         seen.append(short)
+        part = {"kernel": short}
+        for k, name in WANT.items():
+            if k in hdr:
+                part[name] = float(r[hdr.index(k)].replace(",", "")) * UNIT_SCALE.get(units[hdr.index(k)], 1.0)
+        parts.append(part)
         for k, name in WANT.items():
             if k in hdr:
                 v = float(r[hdr.index(k)].replace(",", ""))
@@ -56,6 +62,13 @@ def main():
             break
     if sum_all:
         out["kernels_summed"] = seen
+        total = sum(p_["duration_us_under_ncu"] for p_ in parts)
+        for name in ("fp64_pipe_pct_of_peak", "issue_active_pct", "warps_active_pct"):      # duration-weighted over the pass
+            out[name] = sum(p_.get(name, 0.0) * p_["duration_us_under_ncu"] for p_ in parts) / total
+        out["registers_per_thread"] = max(p_.get("registers_per_thread", 0.0) for p_ in parts)
+        out["per_kernel"] = [{k: p_.get(k) for k in ("kernel", "duration_us_under_ncu", "warp_instructions", "issue_active_pct",
+                                                      "fp64_pipe_pct_of_peak", "warps_active_pct", "registers_per_thread",
+                                                      "dram_bytes_read", "dram_bytes_write")} for p_ in parts]
     sha = os.path.join(os.path.dirname(rep), f"{tag}_csrc_sha16.txt")
     if os.path.exists(sha):
         out["csrc_sha16"] = open(sha).read().strip()

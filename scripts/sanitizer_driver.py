@@ -36,7 +36,8 @@ for arm in ("r_arm", "l_arm"):
     ik.is_reachable_batch_host(Mh, chunk=700); ik.is_reachable_batch_host(torch.from_numpy(gp).pin_memory(), chunk=512, want=ik.LEAN)
     ik.is_reachable_batch_host(Mh.float(), chunk=700, precision="fp32"); ran.append("r2ik_pipeline_symik_f64 / f32")
     ctl = ControlIK(urdf_path="../config_files/reachy2.urdf"); ran.append("k_ctl_ctor_theta")
-    ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete"); ran.append("k_ctl_discrete")
+    ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete", compact=False); ran.append("k_ctl_discrete")
+    ctl.symbolic_inverse_kinematics_batch(arm, M, "discrete", compact=True); ran.append("k_disc_consts/classify/search/finish")
     ctl.nb_search_points = 360
     ctl.symbolic_inverse_kinematics_batch(arm, M[:1100], "discrete", exhaustive=True); ran.append("k_ctl_discrete_scan")
     ctl.symbolic_inverse_kinematics_batch_host(arm, Mh, "discrete", chunk=600); ran.append("r2ik_pipeline_ctl_discrete_f64")
