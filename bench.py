@@ -674,7 +674,7 @@ class ReachMap:
             torch = self._torch
             xb = ev[-1]["exchanged_bytes"]
             out["collective"] = {"op": "all_reduce(SUM), one per slab, asynchronous: overlaps the next slab's kernel", "slabs": 4,
-                                 "sharding": "every world-th voxel row per rank (all orientations each); the all-reduce adds disjoint pieces",
+                                 "sharding": "orientation slices (every rank counts its slice of the orientation set for every voxel)",
                                  "wire_dtype": "uint16 counts, two per int32 lane", "bytes": xb, "full_int32_volume_bytes": 4 * self.N ** 3,
                                  "backend": "NCCL (torch.distributed)", "collective_ms_is": "step time minus the slab kernels' time: "
                                  "the part of the exchange that the kernels do not hide, plus the 16->32-bit widening pass"}
@@ -688,13 +688,13 @@ class ReachMap:
             oms = []
             for _ in range(3):
                 t = {}
-                self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out, timing=t, shard="orientations")
+                self.ik.reach_map(n=self.N, orientations_euler=self.ori, dist=self.dist, out=self.out, timing=t, shard="voxels")
                 torch.cuda.synchronize()
                 oms.append((t["t0"].elapsed_time(t["t1"]), sum(a.elapsed_time(b) for a, b in t["k"])))
-            out["orientation_sharded_form"] = {"step_ms": env.max_over_ranks(float(np.mean([a for a, _ in oms[1:]]))),
-                                               "kernel_ms": env.max_over_ranks(float(np.mean([b for _, b in oms[1:]]))),
-                                               "note": "each rank counts its slice of the orientation set for every voxel (BASELINE.json's wording); same "
-                                                       "16-bit, live-range, slab-pipelined exchange"}
+            out["voxel_row_sharded_form"] = {"step_ms": env.max_over_ranks(float(np.mean([a for a, _ in oms[1:]]))),
+                                             "kernel_ms": env.max_over_ranks(float(np.mean([b for _, b in oms[1:]]))),
+                                             "note": "each rank counts all orientations for every world-th voxel row, the all-reduce adds disjoint "
+                                                     "pieces; same 16-bit, live-range, slab-pipelined exchange"}
             out["plain_form"] = {"kernel_ms": env.max_over_ranks(float(np.mean([a for a, _ in ms[1:]]))),
                                  "collective_ms": env.max_over_ranks(float(np.mean([b for _, b in ms[1:]]))),
                                  "bytes": 4 * self.N ** 3, "note": "one all-reduce of the full int32 volume after the kernel (the round-1 form)"}

@@ -85,17 +85,18 @@ def allreduce_u16_pairs(c16, v0: int, v1: int, dist, group=None):
 
 
 def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=None, n_slabs: int = 4, timing=None,
-                      shard: str = "voxels"):
+                      shard: str = "orientations"):
     """The map over several GPUs.  Returns the int32 volume (every rank holds the full map).
 
     Only the x-range of the volume that can hold a reachable voxel takes part (the rest is zero on every rank), counts are
     16 bits on the wire (two per int32 lane of the all-reduce) and the work is launched slab by slab so that the all-reduce
-    of one slab overlaps the kernel of the next.  shard="voxels" (default): each rank counts ALL orientations for every
-    world-th row (ix, iy, :) of the volume and the all-reduce adds the disjoint pieces -- the per-block staging of the
-    orientation set and the per-voxel pre-checks are then divided by the number of ranks like everything else, and the
-    interleave balances the ranks statistically (contiguous ranges of equal chord length were 12 % out of balance: the
-    cost of a voxel depends on how many orientations pass the early range tests); shard="orientations": each rank
-    counts its slice of the orientation set for every voxel (BASELINE.json's wording).
+    of one slab overlaps the kernel of the next.  shard="orientations" (default, BASELINE.json's wording): each rank
+    counts its slice of the orientation set for every voxel.  shard="voxels": each rank counts ALL orientations for every
+    world-th row (ix, iy, :) of the volume and the all-reduce adds the disjoint pieces -- the per-voxel pre-checks are
+    then divided by the number of ranks too, but the ranks end up less evenly loaded (the cost of a row depends on how
+    many of its voxels and orientations pass the early range tests) and the step is the slowest rank's: measured
+    5.66 / 3.07 / 1.90 ms against 5.59 / 2.99 / 1.75 ms for orientation shards on 2 / 4 / 8 GPUs (contiguous voxel
+    ranges of equal chord length were 12 % out of balance).
     ``timing``: optional dict that receives CUDA events (``k``: per slab kernel, ``t0`` / ``t1`` around the call)."""
     torch = solver._torch
     dev = solver._device
@@ -151,7 +152,7 @@ def reach_map_sharded(solver, ori, origin, step, dims, dist, group=None, out=Non
 
 def reach_map(solver, n: int = 256, orientations_euler=None, n_orientations: int = 512, origin=None, step=None,
               dims=None, dist=None, group=None, out=None, all_fp64: bool = False, mark=None, plain_allreduce: bool = False,
-              timing=None, shard: str = "voxels"):
+              timing=None, shard: str = "orientations"):
     """Reachability count volume of ``solver`` (a ``SymbolicIK``): int32 CUDA tensor (d0, d1, d2).
 
     orientations_euler: (n_ori, 3) xyz Euler angles (default: ``fibonacci_orientations(n_orientations)``).
