@@ -769,9 +769,44 @@ def gen_helpers(n=2000):
                         ad_a=a, ad_b=b, ad=ad, lt_theta=th, lt_interval=itv, lt_out=lt, rmfv_v=v, rmfv=rm)
 
 
+def gen_legacy_theta(n_fk=120, n_task=60):
+    """get_best_continuous_theta, the first version of the continuous policy (utils.py:130-217, still imported by
+    src/example/placo/movement_memory.py:51 and test_limits.py:31), and tend_to_preferred_theta (utils.py:115-127):
+    flag, theta and the debug text for reachable poses x previous thetas x step limits, with the solver's own
+    get_elbow_position as the callback."""
+    from reachy2_symbolic_ik.utils import get_best_continuous_theta, tend_to_preferred_theta
+    out = dict(META)
+    for arm, seed in (("r_arm", 0), ("l_arm", 1)):
+        rng = np.random.default_rng(910 + seed)
+        M = np.concatenate([fk.sample_fk_poses(n_fk, arm, seed=900 + seed, min_x=0.05), fk.sample_task_space_poses(n_task, arm, seed=905 + seed)])
+        ik = SymbolicIK(arm=arm)
+        preferred = -4 * np.pi / 6 if arm == "r_arm" else -np.pi + 4 * np.pi / 6
+        rows, texts = [], []
+        for m in M:
+            gp = euler_pose_from_matrix(m)
+            ok, interval, _, _ = ik.is_reachable(gp)
+            if not ok:
+                continue
+            for prev, d in ((rng.uniform(-np.pi, np.pi), 0.01), (rng.uniform(-np.pi, np.pi), 0.6), (preferred + rng.uniform(-0.005, 0.005), 0.01),
+                            ((interval[0] + interval[1]) / 2 + rng.uniform(-0.3, 0.3), 0.2)):
+                flag, theta, text = get_best_continuous_theta(prev, interval, ik.get_elbow_position, d, preferred, arm, ik.singularity_offset,
+                                                              ik.singularity_limit_coeff, ik.elbow_singularity_position)
+                t_flag, t_theta = tend_to_preferred_theta(prev, interval, None, d, preferred)
+                rows.append([*np.concatenate(gp), interval[0], interval[1], prev, d, preferred, float(flag), theta, float(t_flag), t_theta])
+                texts.append(text)
+        out[f"{arm}_rows"] = np.array(rows)
+        out[f"{arm}_text"] = np.array(texts)
+        out[f"{arm}_elbow_singularity_position"] = np.array(ik.elbow_singularity_position, dtype=np.float64)
+        out[f"{arm}_singularity"] = np.array([ik.singularity_offset, ik.singularity_limit_coeff])
+    out["columns"] = np.array(["x", "y", "z", "roll", "pitch", "yaw", "interval0", "interval1", "previous_theta", "d_theta_max", "preferred_theta",
+                               "flag", "theta", "tend_flag", "tend_theta"])
+    np.savez_compressed(os.path.join(HERE, "legacy_theta.npz"), **out)
+    print("legacy_theta", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler", "elbow", "ctl_ctor", "api"]
+    which = sys.argv[1:] or ["named", "random", "urdf", "discrete", "continuous", "helpers", "examples", "task_space", "overrides", "ctor", "big_euler", "elbow", "ctl_ctor", "api", "legacy"]
     if "named" in which:
         gen_symik_named()
     if "helpers" in which:
@@ -798,6 +833,8 @@ if __name__ == "__main__":
         gen_ctl_ctor()
     if "api" in which:
         gen_api_surface()
+    if "legacy" in which:
+        gen_legacy_theta()
     if "task_space" in which:
         gen_task_space()
     print(f"done in {time.time() - t0:.1f}s")

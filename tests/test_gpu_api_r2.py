@@ -327,3 +327,27 @@ def test_discrete_compact_entry_argument_checks():
     assert call(C.c_void_p(ws.data_ptr() + 8), ws.numel()) != 0 and "aligned" in lib.r2ik_last_error().decode()
     assert call(p(ws), ws.numel()) == 0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_legacy_continuous_theta_policy_on_the_scalar_api(arm):
+    """The reference's example scripts drive get_best_continuous_theta (utils.py:130-217) with the solver's own
+    get_elbow_position; here the callback is the scalar kernel.  Flag and theta as in the reference's fixture."""
+    from reachy2_symbolic_ik_b200 import SymbolicIK, legacy
+
+    g = load("legacy_theta.npz")
+    rows, texts = g[f"{arm}_rows"], g[f"{arm}_text"]
+    ik = SymbolicIK(arm=arm)
+    np.testing.assert_allclose(ik.elbow_singularity_position, g[f"{arm}_elbow_singularity_position"], atol=1e-15)
+    checked = 0
+    for row, want_text in list(zip(rows, texts))[::5]:
+        ok, interval, _, _ = ik.is_reachable([row[:3], row[3:6]])
+        assert ok
+        np.testing.assert_allclose(interval, row[6:8], atol=1e-9)
+        flag, theta, text = legacy.get_best_continuous_theta(row[8], interval, ik.get_elbow_position, row[9], row[10], arm,
+                                                             ik.singularity_offset, ik.singularity_limit_coeff,
+                                                             ik.elbow_singularity_position)
+        assert bool(flag) == bool(row[11]) and abs(theta - row[12]) < 1e-9
+        assert text.split("\n")[-1] == str(want_text).split("\n")[-1]
+        checked += 1
+    assert checked > 80

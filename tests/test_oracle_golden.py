@@ -441,3 +441,30 @@ def test_task_space_sweep(oracle, tmp_path):
     workspace.save_reach_map(f, counts, [0.1, 0.2, 0.3], [0.01] * 3, np.zeros((8, 3)), arm="r_arm")
     d = workspace.load_reach_map(f)
     assert np.array_equal(d["counts"], counts) and d["arm"] == "r_arm" and d["fraction"].max() == 23 / 8
+
+
+@pytest.mark.parametrize("arm", ["r_arm", "l_arm"])
+def test_legacy_continuous_theta_policy(oracle, arm):
+    """reachy2_symbolic_ik_b200.legacy.get_best_continuous_theta / tend_to_preferred_theta (the reference's first
+    continuous policy, utils.py:130-217 / :115-127, still imported by its example scripts) against the reference's own
+    flag, theta and debug text; the elbow callback here is the oracle's get_elbow_position (on the GPU box it is
+    SymbolicIK.get_elbow_position, tests/test_gpu_api_r2.py)."""
+    from reachy2_symbolic_ik_b200 import legacy
+
+    g = load("legacy_theta.npz")
+    rows, texts = g[f"{arm}_rows"], g[f"{arm}_text"]
+    cfg = oracle.arm_config(arm)
+    n_text = 0
+    for row, want_text in zip(rows, texts):
+        pose, interval, prev, d, pref = row[:6], row[6:8], row[8], row[9], row[10]
+        elbow = lambda th: np.append(oracle.elbow_positions_batch(cfg, pose[None, :], np.array([[th]]))[0, 0], 1.0)  # noqa: E731
+        flag, theta, text = legacy.get_best_continuous_theta(prev, interval, elbow, d, pref, arm, *g[f"{arm}_singularity"],
+                                                             g[f"{arm}_elbow_singularity_position"])
+        assert bool(flag) == bool(row[11]) and theta == row[12], (row, flag, theta)
+        n_text += text == str(want_text)
+        t_flag, t_theta = legacy.tend_to_preferred_theta(prev, interval, None, d, pref)
+        assert bool(t_flag) == bool(row[13]) and t_theta == row[14]
+    assert n_text == len(rows), f"{len(rows) - n_text} debug texts differ from the reference's"
+    # every branch of the policy is in the fixture
+    last = {str(t).split("\n")[-1].rstrip("TrueFalse") for t in texts}
+    assert len(last) >= 5, last
