@@ -220,6 +220,14 @@ __device__ __forceinline__ void store_pose_f32(int64_t i, int st, const float ou
   if (elbow) { elbow[3 * i] = out[9]; elbow[3 * i + 1] = out[10]; elbow[3 * i + 2] = out[11]; }
 }
 
+// resets the escalation count (a kernel instead of a memset node, so that the three launches of a call and the last
+// launch of the previous call form one chain of programmatic dependents)
+__global__ void k_zero_u32(unsigned *p) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0 && blockIdx.x == 0) *p = 0u;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1F_MINBLOCKS)
 k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ f32::ArmConstF A,
@@ -228,6 +236,7 @@ k_symik_solve_f32(const __grid_constant__ ArmConst A64, const __grid_constant__ 
                   float *__restrict__ joints, float *__restrict__ elbow, uint32_t *__restrict__ esc_list,
                   unsigned *__restrict__ n_escalated) {
   asm volatile("griddepcontrol.launch_dependents;");   // k_symik_escalated_f32 may be scheduled under this kernel's tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // k_zero_u32 (and whatever preceded it) has completed
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < n;
   bool esc = false;
@@ -259,6 +268,7 @@ k_symik_escalated_f32(const __grid_constant__ ArmConst A64, const float *__restr
                       float *__restrict__ interval, float *__restrict__ joints, float *__restrict__ elbow,
                       const uint32_t *__restrict__ esc_list, const unsigned *__restrict__ n_escalated) {
   // launched as a programmatic dependent of k_symik_solve_f32: its blocks may be resident before that kernel has drained
+  asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned count = *n_escalated;
   float prev0 = 0.0f, prev2 = 0.0f;
@@ -1051,26 +1061,32 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
   DeviceGuard guard_(h->device);
   R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
-  R2IK_CUDA(cudaMemsetAsync(n_escalated, 0, sizeof(uint32_t), s), "cudaMemsetAsync");
   // second pass: a fixed modest grid striding over the (device-side) count -- a few thousand poses per million
   const unsigned eb = (unsigned)(blocks_for(n) < 592u ? blocks_for(n) : 592u);
-  // the second pass is a programmatic dependent of the first: it is scheduled under the first kernel's tail and waits
-  // (griddepcontrol.wait) for its list
+  // count reset, first pass and second pass are a chain of programmatic dependents: each is scheduled under its
+  // predecessor's tail and waits (griddepcontrol.wait) before it touches memory
   cudaLaunchAttribute eattr[1];
   eattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   eattr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t ecfg = {};
-  ecfg.gridDim = dim3(eb); ecfg.blockDim = dim3(R2IK_BLOCK); ecfg.dynamicSmemBytes = 0; ecfg.stream = s;
+  ecfg.gridDim = dim3(1); ecfg.blockDim = dim3(32); ecfg.dynamicSmemBytes = 0; ecfg.stream = s;
   ecfg.attrs = eattr; ecfg.numAttrs = 1;
+  R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_zero_u32, n_escalated), "k_zero_u32 launch");
   const uint32_t *esc_c = escalated_idx;
   const unsigned *nesc_c = n_escalated;
-  if (pose_kind == R2IK_POSE_MAT4) {
-    k_symik_solve_f32<R2IK_POSE_MAT4><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, n, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
-    R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_escalated_f32<R2IK_POSE_MAT4>, h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, esc_c, nesc_c), "k_symik_escalated_f32 launch");
-  } else {
-    k_symik_solve_f32<R2IK_POSE_EULER6><<<blocks_for(n), R2IK_BLOCK, 0, s>>>(h->A, h->AF, poses, theta, n, reachable, state, interval, joints, elbow, escalated_idx, n_escalated);
-    R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_escalated_f32<R2IK_POSE_EULER6>, h->A, poses, theta, prev_joints, reachable, state, interval, joints, elbow, esc_c, nesc_c), "k_symik_escalated_f32 launch");
-  }
+  ecfg.blockDim = dim3(R2IK_BLOCK);
+#define R2IK_LAUNCH_K1F(KIND)                                                                                                       \
+  do {                                                                                                                              \
+    ecfg.gridDim = dim3(blocks_for(n));                                                                                             \
+    R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_solve_f32<KIND>, h->A, h->AF, poses, theta, n, reachable, state, interval, joints,  \
+                                 elbow, escalated_idx, n_escalated), "k_symik_solve_f32 launch");                                    \
+    ecfg.gridDim = dim3(eb);                                                                                                        \
+    R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_escalated_f32<KIND>, h->A, poses, theta, prev_joints, reachable, state, interval,   \
+                                 joints, elbow, esc_c, nesc_c), "k_symik_escalated_f32 launch");                                     \
+  } while (0)
+  if (pose_kind == R2IK_POSE_MAT4) R2IK_LAUNCH_K1F(R2IK_POSE_MAT4);
+  else R2IK_LAUNCH_K1F(R2IK_POSE_EULER6);
+#undef R2IK_LAUNCH_K1F
   R2IK_CUDA(cudaGetLastError(), "k_symik_solve_f32 launch");
   return 0;
 }
