@@ -507,6 +507,7 @@ struct Reach {
   double i0, i1;    // theta interval (i0 > i1 means wrapped); NaN when unreachable
   double c0, s0;    // cos(i0), sin(i0): lets get_joints(theta_interval[0]) skip a sincos
   bool degenerate;  // LIT = false only: the result is not valid, solve again with LIT = true
+  bool literal;     // set by solve_core: the literal instantiation produced this result (and S)
 };
 
 constexpr double kSinMinusPi = -1.2246467991473532e-16;  // np.sin(-np.pi)
@@ -544,7 +545,7 @@ R2IK_HD int reach_prechecks(const ArmConst &A, double &px, double &py, double &p
 template <bool NO_LIMITS, bool FLAG_ONLY, bool LIT, bool CIRCLE_ONLY = false>
 R2IK_HD Reach solve_core_impl(const ArmConst &A, Solve &S) {
   Reach out;
-  out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false;
+  out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false; out.literal = false;
   wrist_from_goal(A, S.p, S.R, S.w);
   // --- sik:146-153 / sik:94-98 keep the wrist in front of the torso plane
   if (S.w[0] < A.backward_limit) {
@@ -771,6 +772,7 @@ R2IK_HD Reach solve_core(const ArmConst &A, Solve &S) {
     solve_core_literal<NO_LIMITS, FLAG_ONLY>(A, &T, &lit);
     S = T;
     out = lit;
+    out.literal = true;
   }
   return out;
 }
@@ -788,7 +790,7 @@ R2IK_HD Reach is_reachable_R(const ArmConst &A, const double pos[3], Solve &S) {
   int pre_state = reach_prechecks(A, px, py, pz);
   if (!NO_LIMITS && pre_state >= 0) {
     Reach out;
-    out.state = pre_state; out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false;
+    out.state = pre_state; out.i0 = NAN; out.i1 = NAN; out.c0 = NAN; out.s0 = NAN; out.degenerate = false; out.literal = false;
     return out;
   }
   S.p[0] = px; S.p[1] = py; S.p[2] = pz;

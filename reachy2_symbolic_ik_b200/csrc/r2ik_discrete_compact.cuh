@@ -13,7 +13,7 @@
 //                    otherwise -> search list with the search plan (interval + the six elbow half-plane coefficients)
 //   k_disc_search    search list: search_analytic (r2ik_control.cuh) from the stored plan.
 //                    a sample found -> finish list (theta of the sample);  none -> final result (limited by shoulder)
-//   k_disc_finish    finish list: is_reachable again from the pose (carrying the 200-byte solve through memory instead
+//   k_disc_finish    finish list: the elbow circle again from the pose (carrying the 200-byte solve through memory instead
 //                    would add 330 MB of traffic per 1M poses to save 15 M of 95 M warp instructions), get_joints, safety chain
 //
 // The per-pose device functions are the ones k_ctl_discrete calls, on the same inputs: results are identical.
@@ -33,6 +33,8 @@ struct DiscHeader {
   double pad3_[8];
 };
 static_assert(sizeof(DiscHeader) == 256, "DiscHeader is two 128-byte lines");
+
+constexpr uint32_t kDiscLiteral = 0x80000000u;   // flag bit of a list entry (n < 2^31)
 
 struct DiscWs {
   DiscHeader *hdr;
@@ -110,6 +112,9 @@ __global__ void k_disc_consts(const __grid_constant__ R2ikCtlParams par, const d
   hdr->n_finish = 0;
 }
 
+#ifndef R2IK_K2C_CIRCLE_ONLY
+#define R2IK_K2C_CIRCLE_ONLY 1
+#endif
 #ifndef R2IK_K2C_CLASSIFY_MINBLOCKS
 #define R2IK_K2C_CLASSIFY_MINBLOCKS 6
 #endif
@@ -132,11 +137,13 @@ k_disc_classify(const __grid_constant__ ArmConst A, const __grid_constant__ R2ik
   int st = R2IK_STATE_INVALID_ROTATION;
   bool shortcut = false, need_search = false;
   double i0 = 0.0, i1 = 0.0;
+  uint32_t tag = (uint32_t)i;      // list entry: pose index, bit 31 = the solve took the literal instantiation
   if (active) {
     double pos[3];
     if (load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R)) {
       Reach rc = is_reachable_R<false>(A, pos, S);
       st = rc.state; i0 = rc.i0; i1 = rc.i1;
+      if (rc.literal) tag |= kDiscLiteral;
       if (st == R2IK_STATE_REACHABLE) {
         shortcut = preferred_theta_works(A, S, i0, i1, par.preferred_theta);
         need_search = !shortcut;
@@ -147,7 +154,7 @@ k_disc_classify(const __grid_constant__ ArmConst A, const __grid_constant__ R2ik
   const unsigned slot = disc_append2(need_search, shortcut, &hdr->n_search, &hdr->n_finish);
   if (need_search) {
     const ElbowTest T = make_elbow_test(A, S);
-    search_idx[slot] = (uint32_t)i;
+    search_idx[slot] = tag;
     double2 *p = reinterpret_cast<double2 *>(plan + 8 * (size_t)slot);
     p[0] = make_double2(i0, i1);
     p[1] = make_double2(T.A1, T.B1);
@@ -155,7 +162,7 @@ k_disc_classify(const __grid_constant__ ArmConst A, const __grid_constant__ R2ik
     p[3] = make_double2(T.B2, T.C2);
   }
   if (shortcut) {
-    finish_idx[slot] = (uint32_t)i;
+    finish_idx[slot] = tag;
     finish_theta[slot] = par.preferred_theta;
   }
   if (active && !need_search && !shortcut) disc_store_final(hdr, i, st, joints, reachable, state, emergency);
@@ -198,7 +205,7 @@ k_disc_search(const __grid_constant__ R2ikCtlParams par, DiscHeader *hdr, const 
     finish_idx[kf] = i;
     finish_theta[kf] = theta;
   } else if (active) {
-    disc_store_final(hdr, (int64_t)i, R2IK_STATE_LIMITED_BY_SHOULDER, joints, reachable, state, emergency);
+    disc_store_final(hdr, (int64_t)(i & ~kDiscLiteral), R2IK_STATE_LIMITED_BY_SHOULDER, joints, reachable, state, emergency);
   }
 }
 
@@ -217,12 +224,16 @@ k_disc_finish(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCt
   double prev[7];
 #pragma unroll
   for (int q = 0; q < 7; ++q) prev[q] = prev_joints[q];
-  const int64_t i = finish_idx[k];
+  const uint32_t tag = finish_idx[k];
+  const int64_t i = tag & ~kDiscLiteral;
   const double theta = finish_theta[k];
   Solve S;
   double pos[3], j[7];
   load_pose<R2IK_POSE_MAT4>(M, i, true, pos, S.R);       // valid and reachable: k_disc_classify listed it
-  is_reachable_R<false>(A, pos, S);
+  // the elbow circle is all get_joints needs of the solve: the circle linking (a quarter of is_reachable) is not redone,
+  // except for the rare pose whose solve took the literal instantiation (its S is that instantiation's)
+  if (!R2IK_K2C_CIRCLE_ONLY || (tag & kDiscLiteral)) is_reachable_R<false>(A, pos, S);
+  else circle_of_reachable(A, pos, S);
   const int bits = discrete_finish(A, par, S, true, theta, prev, prev, j);
 #pragma unroll
   for (int q = 0; q < 7; ++q) joints[7 * i + q] = j[q];
