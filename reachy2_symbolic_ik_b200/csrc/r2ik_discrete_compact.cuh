@@ -83,8 +83,7 @@ __device__ __forceinline__ unsigned disc_append2(bool p0, bool p1, unsigned *cou
   const int l = p1 ? 1 : 0;
   unsigned slot = s_base[l] + __popc((l ? m1 : m0) & ((1u << lane) - 1));
   for (int w = 0; w < warp; ++w) slot += s_warp[l][w];
-  __syncthreads();      // the shared counters are reused by the caller's next round
-  return slot;
+  return slot;          // one call per block (the shared counters are not reused)
 }
 
 // the result of a pose without a valid theta (or NaN joints for an invalid rotation block)
