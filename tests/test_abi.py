@@ -49,6 +49,18 @@ def test_argument_errors_do_not_need_a_device(lib):
     h = C.c_void_p()
     assert lib.r2ik_create(None, 0, C.byref(h)) == 1  # R2IK_ERR_NULL
     assert b"null" in lib.r2ik_last_error()
+    # argument checks come before any CUDA call
+    assert lib.r2ik_ctl_discrete_compact_f64(None, None, None, C.c_int64(4), None, None, None, None, None, None, None, C.c_int64(0), None) == 1
+    assert b"r2ik_ctl_discrete_compact_f64" in lib.r2ik_last_error()
+
+
+def test_discrete_workspace_size_is_a_host_function(lib):
+    """r2ik_ctl_discrete_workspace_bytes: header (two 128-byte lines) + per pose a 64-byte search plan, a theta and two
+    list entries."""
+    lib.r2ik_ctl_discrete_workspace_bytes.restype = C.c_int64
+    for n in (0, 1, 1000, (1 << 31) - 1):
+        assert lib.r2ik_ctl_discrete_workspace_bytes(C.c_int64(n)) == 256 + 80 * n
+    assert lib.r2ik_ctl_discrete_workspace_bytes(C.c_int64(-5)) == -1
 
 
 def test_no_cpu_fallback():
