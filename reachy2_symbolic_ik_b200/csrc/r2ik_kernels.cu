@@ -1061,8 +1061,11 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
   DeviceGuard guard_(h->device);
   R2IK_CUDA(guard_.err, "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
-  // second pass: a fixed modest grid striding over the (device-side) count -- a few thousand poses per million
-  const unsigned eb = (unsigned)(blocks_for(n) < 592u ? blocks_for(n) : 592u);
+  // second pass: a fixed grid striding over the (device-side) count -- a few percent of the poses.  One-warp blocks: the
+  // FP64 solver takes 188 registers (10 warps / SM), and 46 k escalated poses per million are 1 438 warps -- as blocks of
+  // 32 threads they are all resident in one wave, as blocks of 128 they needed two (296 of 360 blocks at a time).
+  const int64_t ew = (n + 31) / 32;
+  const unsigned eb = (unsigned)(ew < 2368 ? ew : 2368);
   // count reset, first pass and second pass are a chain of programmatic dependents: each is scheduled under its
   // predecessor's tail and waits (griddepcontrol.wait) before it touches memory
   cudaLaunchAttribute eattr[1];
@@ -1080,7 +1083,7 @@ int r2ik_symik_solve_f32(r2ik_handle h, int pose_kind, const float *poses, const
     ecfg.gridDim = dim3(blocks_for(n));                                                                                             \
     R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_solve_f32<KIND>, h->A, h->AF, poses, theta, n, reachable, state, interval, joints,  \
                                  elbow, escalated_idx, n_escalated), "k_symik_solve_f32 launch");                                    \
-    ecfg.gridDim = dim3(eb);                                                                                                        \
+    ecfg.gridDim = dim3(eb); ecfg.blockDim = dim3(32);                                                                              \
     R2IK_CUDA(cudaLaunchKernelEx(&ecfg, k_symik_escalated_f32<KIND>, h->A, poses, theta, prev_joints, reachable, state, interval,   \
                                  joints, elbow, esc_c, nesc_c), "k_symik_escalated_f32 launch");                                     \
   } while (0)

@@ -10,9 +10,9 @@ mkdir -p $out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $out/${tag}_pytest.log
 tail -3 $out/${tag}_pytest.log
 declare -A KRE=( [symik]=k_symik_solve [symik_f32]=k_symik_.*_f32 [discrete]=k_disc_ [continuous]=k_cont_ [reachmap]=k_reach_map )
-declare -A KNAME=( [symik]=k_symik_solve [symik_f32]=k_symik_solve_f32 [discrete]=k_disc_ [continuous]=k_cont_ [reachmap]=k_reach_map )
+declare -A KNAME=( [symik]=k_symik_solve [symik_f32]=k_symik_ [discrete]=k_disc_ [continuous]=k_cont_ [reachmap]=k_reach_map )
 declare -A NCAP=( [continuous]=5 [symik_f32]=2 [discrete]=4 )
-declare -A SUM=( [continuous]=sum [discrete]=sum )
+declare -A SUM=( [continuous]=sum [discrete]=sum [symik_f32]=sum )
 python -c "import bench; print(bench.csrc_sha16())" > $out/${tag}_csrc_sha16.txt 2>/dev/null
 if [ "${BENCH:-per}" = all ]; then
   python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_all.json 2> $out/${tag}_bench_all.err
