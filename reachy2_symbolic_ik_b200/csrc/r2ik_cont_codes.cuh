@@ -238,7 +238,7 @@ __device__ __noinline__ void tile_serial_joints(const r2ik::ArmConst &A, const R
 // before the block's first one (computed again, not stored).
 #define R2IK_CODE_STORED (R2IK_CODE_BLOCK - 1)     // waypoints a block stores
 #ifndef R2IK_CODE_MINBLOCKS
-#define R2IK_CODE_MINBLOCKS 6
+#define R2IK_CODE_MINBLOCKS 8   // 64 registers + 136 B of spills: 4 / 5 / 6 / 7 / 8 blocks -> 7.91 / 7.91 / 7.70 / 7.74 / 7.66 ms for cfg 4 (s46)
 #endif
 __global__ void __launch_bounds__(R2IK_CODE_BLOCK, R2IK_CODE_MINBLOCKS)
 k_cont_raw_joints_codes(const __grid_constant__ r2ik::ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,

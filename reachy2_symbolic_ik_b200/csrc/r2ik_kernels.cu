@@ -636,7 +636,10 @@ k_ctl_continuous(const __grid_constant__ ArmConst A, const __grid_constant__ R2i
 // 1 000-step recursion per trajectory that only all trajectories in flight at once can hide.  `reachable` carries the
 // waypoint code and `state` the reference state between the phases.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K1_MINBLOCKS)
+#ifndef R2IK_K3T_MINBLOCKS
+#define R2IK_K3T_MINBLOCKS 6    // 80 registers: 4 / 5 (96 registers) / 6 / 7 / 8 blocks -> 7.70 / 7.71 / 7.51 / 7.58 / 7.63 ms for cfg 4 (s46)
+#endif
+__global__ void __launch_bounds__(R2IK_BLOCK, R2IK_K3T_MINBLOCKS)
 k_cont_targets(const __grid_constant__ ArmConst A, const __grid_constant__ R2ikCtlParams par, const double *__restrict__ M,
                int64_t n_wp, double *__restrict__ ws, uint8_t *__restrict__ code, uint8_t *__restrict__ state) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
