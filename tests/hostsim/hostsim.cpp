@@ -3,6 +3,7 @@
 // kernel *logic* is checked against the golden fixtures in the GPU-less CI.  It is not part
 // of libr2ik.so, is never imported by the package, and is no fallback for anything.
 #include <cstring>
+#include <vector>
 #include <cstdint>
 
 #include "../../reachy2_symbolic_ik_b200/csrc/r2ik_control.cuh"
@@ -138,6 +139,101 @@ void hs_ctl_discrete_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, c
     }
     emg[i] = (uint8_t)discrete_finish(A, *par, S, ok, theta, prev, cur, joints + 7 * i);
     reach[i] = ok; state[i] = (uint8_t)st;
+  }
+}
+
+// (the CUDA header r2ik_discrete_compact.cuh is device-only; its two host-visible definitions are mirrored here)
+struct DiscHeader { unsigned n_search, n_finish; int nf_bits; double nf_joints[7]; };
+constexpr uint32_t kDiscLiteral = 0x80000000u;
+
+// Host twin of r2ik_ctl_discrete_compact_f64 (csrc/r2ik_discrete_compact.cuh): the three passes run one after the other
+// over the same lists -- entries with the literal-solve flag in bit 31, the 64-byte search plan, the finish pass redoing
+// only the elbow circle -- with the appends in `order` (0: ascending, 1: descending pose index) to show that the result
+// does not depend on the order the blocks arrive in.  n_lists[0..2] receive the list lengths and the number of finish
+// entries that carry the literal-solve flag.
+void hs_ctl_discrete_compact_batch(const R2ikArmConfig *cfg, const R2ikCtlParams *par, const double *M, int64_t n,
+                                   const double *prev, const double *cur, int order, double *joints, uint8_t *reach,
+                                   uint8_t *state, uint8_t *emg, int64_t *n_lists) {
+  ArmConst A; R2ikArmConstants pub;
+  derive_constants(*cfg, A, pub);
+  DiscHeader hdr;
+  {   // k_disc_consts
+    double j[7];
+    for (int k = 0; k < 7; ++k) j[k] = cur[k];
+    hdr.nf_bits = safety_checks(j, prev, par->orbita3d_max_angle);
+    for (int k = 0; k < 7; ++k) hdr.nf_joints[k] = j[k];
+    hdr.n_search = 0; hdr.n_finish = 0;
+  }
+  std::vector<uint32_t> search_idx((size_t)n), finish_idx((size_t)n);
+  std::vector<double> plan(8 * (size_t)n), finish_theta((size_t)n);
+  auto store_final = [&](int64_t i, int st) {
+    const bool invalid = st == R2IK_STATE_INVALID_ROTATION;
+    for (int k = 0; k < 7; ++k) joints[7 * i + k] = invalid ? NAN : hdr.nf_joints[k];
+    reach[i] = 0; state[i] = (uint8_t)st; emg[i] = invalid ? 0 : (uint8_t)hdr.nf_bits;
+  };
+  for (int64_t q = 0; q < n; ++q) {   // k_disc_classify
+    const int64_t i = order ? n - 1 - q : q;
+    double pos[3];
+    Solve S;
+    int st = R2IK_STATE_INVALID_ROTATION;
+    bool shortcut = false, need_search = false;
+    double i0 = 0.0, i1 = 0.0;
+    uint32_t tag = (uint32_t)i;
+    if (load_pose(R2IK_POSE_MAT4, M + 16 * i, true, pos, S.R)) {
+      Reach rc = is_reachable_R<false>(A, pos, S);
+      st = rc.state; i0 = rc.i0; i1 = rc.i1;
+      if (rc.literal) tag |= kDiscLiteral;
+      if (st == R2IK_STATE_REACHABLE) {
+        shortcut = preferred_theta_works(A, S, i0, i1, par->preferred_theta);
+        need_search = !shortcut;
+      }
+    }
+    if (need_search) {
+      const ElbowTest T = make_elbow_test(A, S);
+      const size_t k = hdr.n_search++;
+      search_idx[k] = tag;
+      double *p = &plan[8 * k];
+      p[0] = i0; p[1] = i1; p[2] = T.A1; p[3] = T.B1; p[4] = T.C1; p[5] = T.A2; p[6] = T.B2; p[7] = T.C2;
+    } else if (shortcut) {
+      const size_t k = hdr.n_finish++;
+      finish_idx[k] = tag; finish_theta[k] = par->preferred_theta;
+    } else {
+      store_final(i, st);
+    }
+  }
+  n_lists[0] = hdr.n_search;
+  for (size_t k = 0; k < hdr.n_search; ++k) {   // k_disc_search
+    const uint32_t tag = search_idx[k];
+    const double *p = &plan[8 * k];
+    SearchPlan P;
+    P.preferred_theta = par->preferred_theta;
+    double start, stop;
+    search_range(p[0], p[1], start, stop);
+    P.L = make_linspace(start, stop, par->nb_search_points);
+    P.T.A1 = p[2]; P.T.B1 = p[3]; P.T.C1 = p[4]; P.T.A2 = p[5]; P.T.B2 = p[6]; P.T.C2 = p[7];
+    double best;
+    int best_k;
+    if (!search_analytic(P, par->nb_search_points, best, best_k)) search_strided(P, par->nb_search_points, 0, 1, best, best_k);
+    if (best < INFINITY) {
+      const size_t f = hdr.n_finish++;
+      finish_idx[f] = tag; finish_theta[f] = linspace_value(P.L, best_k);
+    } else {
+      store_final((int64_t)(tag & ~kDiscLiteral), R2IK_STATE_LIMITED_BY_SHOULDER);
+    }
+  }
+  n_lists[1] = hdr.n_finish;
+  n_lists[2] = 0;
+  for (size_t k = 0; k < hdr.n_finish; ++k) {   // k_disc_finish
+    const uint32_t tag = finish_idx[k];
+    n_lists[2] += (tag & kDiscLiteral) != 0;
+    const int64_t i = tag & ~kDiscLiteral;
+    Solve S;
+    double pos[3];
+    load_pose(R2IK_POSE_MAT4, M + 16 * i, true, pos, S.R);
+    if (tag & kDiscLiteral) is_reachable_R<false>(A, pos, S);
+    else circle_of_reachable(A, pos, S);
+    emg[i] = (uint8_t)discrete_finish(A, *par, S, true, finish_theta[k], prev, prev, joints + 7 * i);
+    reach[i] = 1; state[i] = R2IK_STATE_REACHABLE;
   }
 }
 

@@ -281,6 +281,14 @@ def test_discrete_compacted_passes_equal_single_kernel(arm, n):
     M = np.concatenate([fk.sample_fk_poses(n - n // 4, arm, seed=77 + n), fk.sample_task_space_poses(n // 4, arm, seed=78 + n)]) if n > 3 \
         else fk.sample_fk_poses(n, arm, seed=77)
     rng = np.random.default_rng(n)
+    if n > 1000:
+        # tool axis along +-e_x: the solver's literal instantiation (flagged list entries, full re-solve in the finish pass)
+        from scipy.spatial.transform import Rotation
+
+        m = 400
+        for q in range(m):
+            M[q, :3, :3] = (Rotation.from_euler("y", (np.pi / 2) * (1 if q % 2 else -1)) * Rotation.from_euler("z", rng.uniform(-np.pi, np.pi))).as_matrix()
+        M[:m, :3, 3] = np.array([0.38, -0.2 if arm == "r_arm" else 0.2, -0.12]) + rng.uniform(-0.12, 0.12, (m, 3))
     bad = rng.integers(0, n, size=max(1, n // 50)) if n > 1 else []
     for b in bad:
         M[b, :3, :3] = np.diag([1.0, 1.0, -1.0])           # det < 0: no rotation

@@ -828,3 +828,50 @@ def test_elbow_positions(hs, oracle, arm):
         valid = want_len > 0
         rep.exact(f"elbow shape of get_joints (no_limits={no_limits})", np.where(valid, np.where(proj.astype(bool), 3, 4), 0), want_len)
     rep.check(max_ill_fraction=0.03)
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("variant", ["k20", "k360", "low", "dvt"])
+def test_ctl_discrete_three_passes_equal_one_pass(hs, oracle, arm, variant):
+    """The three passes of r2ik_ctl_discrete_compact_f64 (classify -> search list -> finish list, the finish pass redoing
+    only the elbow circle unless the solve was the literal one) on the host, against the one-pass form: the same bytes,
+    whatever order the list entries arrive in; invalid rotation blocks and a wound previous solution included."""
+    from reachy2_symbolic_ik_b200 import fk
+
+    params = urdf_params()
+    off = 0.03 if variant == "dvt" else -1.01
+    kw = dict(nb_search_points=360 if variant == "k360" else 20,
+              constrained_mode="low_elbow" if variant == "low" else "unconstrained")
+    cfg = cfg_for(arm, params, off)
+    par = ctl_params(oracle, arm, **kw)
+    g = load(f"ctl_discrete_{arm}.npz")
+    M = np.ascontiguousarray(np.concatenate([g["M"], fk.sample_fk_poses(6000, arm, seed=123), fk.sample_task_space_poses(3000, arm, seed=124),
+                                             np.eye(4)[None]]))
+    # tool axis along +-e_x: the wrist-limit plane normal hits rotation_matrix_from_vector's special cases (utils.py:66-70),
+    # which the solver hands to its literal instantiation -- the list entries that carry the flag
+    from scipy.spatial.transform import Rotation
+    s_pos = np.array(oracle.arm_config(arm, ik_parameters=params, singularity_offset=off).shoulder_position)
+    rng = np.random.default_rng(5)
+    ahead = np.tile(np.eye(4), (400, 1, 1))
+    for q in range(400):
+        ahead[q, :3, :3] = (Rotation.from_euler("y", (np.pi / 2) * (1 if q % 2 else -1)) * Rotation.from_euler("z", rng.uniform(-np.pi, np.pi))).as_matrix()
+    ahead[:, :3, 3] = s_pos + np.array([0.38, 0.0, -0.12]) + rng.uniform(-0.12, 0.12, (400, 3))
+    M = np.ascontiguousarray(np.concatenate([M, ahead]))
+    M[::97, :3, :3] = np.diag([1.0, 1.0, -1.0])        # det < 0
+    n = len(M)
+    n_literal = 0
+    for prev, cur in ((np.array(oracle.DEFAULT_PREV_JOINTS[arm]),) * 2,
+                      (np.array([0.3, -0.2, 7.0, -1.0, 0.1, 0.2, -6.5]), np.array([0.1, 0.2, 0.3, -0.4, 0.5, 0.6, 19.5]))):
+        one = [np.full((n, 7), 5.0), np.full(n, 9, np.uint8), np.full(n, 99, np.uint8), np.full(n, 99, np.uint8)]
+        hs.hs_ctl_discrete_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(n), dp(prev), dp(cur), dp(one[0]), u8(one[1]), u8(one[2]), u8(one[3]))
+        for order in (0, 1):
+            three = [np.full((n, 7), 5.0), np.full(n, 9, np.uint8), np.full(n, 99, np.uint8), np.full(n, 99, np.uint8)]
+            lists = np.zeros(3, np.int64)
+            hs.hs_ctl_discrete_compact_batch(C.byref(cfg), C.byref(par), dp(M), C.c_int64(n), dp(prev), dp(cur), C.c_int(order), dp(three[0]),
+                                             u8(three[1]), u8(three[2]), u8(three[3]), lists.ctypes.data_as(C.POINTER(C.c_int64)))
+            for a, b in zip(one, three):
+                assert np.array_equal(a, b, equal_nan=True)
+            assert 0 < lists[0] < n and lists[0] * 0.2 < lists[1] < n
+            assert int(three[1].sum()) == lists[1] and int((three[2] == 9).sum()) == len(M[::97])
+            n_literal += int(lists[2])
+    assert n_literal > 0, "no pose of the sample took the literal solve: the flag path of the finish pass was not exercised"
